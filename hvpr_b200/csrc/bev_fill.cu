@@ -1,0 +1,144 @@
+// K4 — BEV canvas gather-fill: PointPillarScatter_Agg_Memory_1_scale.forward eval branch
+// (pcdet/models/backbones_2d/map_to_bev/pointpillar_scatter.py:169-220) and PointPillarScatter.forward (:14-37).
+//
+// The reference zero-fills both canvases, then scatters 160 strided 4-byte stores per pillar and finally copies
+// everything again in torch.stack.  Here the canvas is walked in its final NCHW layout and every element is written
+// exactly once — feature or 0 — with 128-bit streaming stores; the pillar row for a cell comes from the dense
+// cell->row map that the voxelizer already produced (or hvpr_build_cell_map for foreign coords).
+// Each (frame, cell) holds at most one pillar, so the result is order-independent and bitwise reproducible.
+#include "common.cuh"
+
+namespace hvpr {
+
+struct BevSrc {
+    const float *feat;   // (rows, C)
+    float *out;          // (B, Ctot, cells) canvas this source writes into
+    int C;               // channels of this source
+    int Ctot;            // channels of the destination canvas
+    int c_off;           // first destination channel
+};
+struct BevArgs {
+    BevSrc src[3];
+    int chunk_src[16];   // channel chunk -> source
+    int chunk_c0[16];    // channel chunk -> first channel within the source
+    int chunk_nc[16];    // channels in the chunk (multiple of 4)
+};
+constexpr int kBevChunk = 32;
+
+// grid (ceil(cells/4/256), B, n_chunks)
+__global__ void __launch_bounds__(256) bev_fill_kernel(const __grid_constant__ BevArgs A,
+                                                       const int32_t *__restrict__ cell_map, int64_t cells) {
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // group of 4 consecutive cells
+    const int64_t groups = cells >> 2;
+    const int f = blockIdx.y, ch = blockIdx.z;
+    const bool live = g < groups;
+    int4 m = make_int4(-1, -1, -1, -1);
+    if (live) m = __ldg(reinterpret_cast<const int4 *>(cell_map + (int64_t)f * cells) + g);
+    const BevSrc &s = A.src[A.chunk_src[ch]];
+    const int c0 = A.chunk_c0[ch], nc = A.chunk_nc[ch];
+    float4 *out = reinterpret_cast<float4 *>(s.out + ((int64_t)f * s.Ctot + s.c_off + c0) * cells) + g;
+    const bool occupied = (m.x & m.y & m.z & m.w) != -1;   // row ids are >= 0, empties are exactly -1
+    if (!__any_sync(0xffffffffu, occupied)) {
+        if (live) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+            for (int c = 0; c < nc; ++c) st_stream_f4(out + (int64_t)c * groups, z);
+        }
+        return;
+    }
+    if (!live) return;
+    const float *fa = s.feat + c0;
+    const int C = s.C;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (int c = 0; c < nc; c += 4) {
+        const float4 ra = m.x >= 0 ? __ldg(reinterpret_cast<const float4 *>(fa + (int64_t)m.x * C + c)) : z4;
+        const float4 rb = m.y >= 0 ? __ldg(reinterpret_cast<const float4 *>(fa + (int64_t)m.y * C + c)) : z4;
+        const float4 rc = m.z >= 0 ? __ldg(reinterpret_cast<const float4 *>(fa + (int64_t)m.z * C + c)) : z4;
+        const float4 rd = m.w >= 0 ? __ldg(reinterpret_cast<const float4 *>(fa + (int64_t)m.w * C + c)) : z4;
+        st_stream_f4(out + (int64_t)(c + 0) * groups, make_float4(ra.x, rb.x, rc.x, rd.x));
+        st_stream_f4(out + (int64_t)(c + 1) * groups, make_float4(ra.y, rb.y, rc.y, rd.y));
+        st_stream_f4(out + (int64_t)(c + 2) * groups, make_float4(ra.z, rb.z, rc.z, rd.z));
+        st_stream_f4(out + (int64_t)(c + 3) * groups, make_float4(ra.w, rb.w, rc.w, rd.w));
+    }
+}
+
+// generic fallback (cells or channel counts not multiples of 4): one thread per (cell), scalar stores
+__global__ void __launch_bounds__(256) bev_fill_scalar_kernel(const float *__restrict__ feat, int C, int Ctot, int c_off,
+                                                              float *__restrict__ outp,
+                                                              const int32_t *__restrict__ cell_map, int64_t cells) {
+    const int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
+    if (cell >= cells) return;
+    const int32_t r = cell_map[(int64_t)f * cells + cell];
+    float *out = outp + ((int64_t)f * Ctot + c_off) * cells + cell;
+    for (int c = 0; c < C; ++c) out[(int64_t)c * cells] = r >= 0 ? __ldg(feat + (int64_t)r * C + c) : 0.0f;
+}
+
+__global__ void cell_map_kernel(const int32_t *__restrict__ coords, const int32_t *__restrict__ n_pillars_dev,
+                                int64_t n_rows_max, int B, int nx, int ny, int32_t *__restrict__ cell_map) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t nP = n_pillars_dev ? (int64_t)*n_pillars_dev : n_rows_max;
+    if (nP > n_rows_max) nP = n_rows_max;
+    if (r >= nP) return;
+    const int4 c = __ldg(reinterpret_cast<const int4 *>(coords) + r);      // [b, z, y, x]
+    if (c.x < 0 || c.x >= B || c.z < 0 || c.z >= ny || c.w < 0 || c.w >= nx) return;
+    const int64_t idx = (int64_t)c.y + (int64_t)c.z * nx + c.w;            // pointpillar_scatter.py:192 (nz == 1 -> z == 0)
+    if (idx < 0 || idx >= (int64_t)nx * ny) return;
+    cell_map[(int64_t)c.x * nx * ny + idx] = (int32_t)r;
+}
+
+}  // namespace hvpr
+
+using namespace hvpr;
+
+extern "C" int hvpr_bev_fill(const float *feat_a, int ca, const float *feat_b, int cb, const float *feat_s, int cs,
+                             const int32_t *cell_map, int n_frames, int nx, int ny,
+                             float *spatial, float *spatial_scale, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!cell_map || !spatial || !feat_a || ca <= 0 || cb < 0 || cs < 0 || n_frames <= 0 || nx <= 0 || ny <= 0) return HVPR_ERR_ARG;
+    if ((cb > 0 && !feat_b) || (cs > 0 && (!feat_s || !spatial_scale))) return HVPR_ERR_ARG;
+    const int64_t cells = (int64_t)nx * ny;
+    const bool fast = (cells % 4 == 0) && (ca % 4 == 0) && (cb % 4 == 0) && (cs % 4 == 0) &&
+                      (((uintptr_t)feat_a | (uintptr_t)feat_b | (uintptr_t)feat_s | (uintptr_t)cell_map |
+                        (uintptr_t)spatial | (uintptr_t)spatial_scale) % 16 == 0);
+    if (fast) {
+        BevArgs A;
+        A.src[0] = BevSrc{feat_a, spatial, ca, ca + cb, 0};
+        A.src[1] = BevSrc{feat_b, spatial, cb, ca + cb, ca};
+        A.src[2] = BevSrc{feat_s, spatial_scale, cs, cs, 0};
+        int n = 0;
+        for (int s = 0; s < 3; ++s)
+            for (int c0 = 0; c0 < A.src[s].C; c0 += kBevChunk) {
+                if (n >= 16) return HVPR_ERR_UNSUPPORTED;
+                A.chunk_src[n] = s; A.chunk_c0[n] = c0;
+                A.chunk_nc[n] = A.src[s].C - c0 < kBevChunk ? A.src[s].C - c0 : kBevChunk;
+                ++n;
+            }
+        for (int i = n; i < 16; ++i) { A.chunk_src[i] = 0; A.chunk_c0[i] = 0; A.chunk_nc[i] = 0; }
+        dim3 grid((unsigned)ceil_div64(cells / 4, 256), (unsigned)n_frames, (unsigned)n);
+        bev_fill_kernel<<<grid, 256, 0, stream>>>(A, cell_map, cells);
+        HVPR_CHECK_LAUNCH();
+    } else {
+        dim3 grid((unsigned)ceil_div64(cells, 256), (unsigned)n_frames);
+        bev_fill_scalar_kernel<<<grid, 256, 0, stream>>>(feat_a, ca, ca + cb, 0, spatial, cell_map, cells);
+        HVPR_CHECK_LAUNCH();
+        if (cb > 0) { bev_fill_scalar_kernel<<<grid, 256, 0, stream>>>(feat_b, cb, ca + cb, ca, spatial, cell_map, cells); HVPR_CHECK_LAUNCH(); }
+        if (cs > 0) { bev_fill_scalar_kernel<<<grid, 256, 0, stream>>>(feat_s, cs, cs, 0, spatial_scale, cell_map, cells); HVPR_CHECK_LAUNCH(); }
+    }
+    return HVPR_OK;
+}
+
+extern "C" int hvpr_build_cell_map(const int32_t *coords, const int32_t *n_pillars_dev, int64_t n_rows_max,
+                                   int n_frames, int nx, int ny, int32_t *cell_map, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!cell_map || n_rows_max < 0 || n_frames <= 0 || nx <= 0 || ny <= 0) return HVPR_ERR_ARG;
+    if (n_rows_max > 0 && (!coords || (uintptr_t)coords % 16)) return HVPR_ERR_ARG;
+    HVPR_CHECK_CUDA(cudaMemsetAsync(cell_map, 0xFF, sizeof(int32_t) * (size_t)n_frames * nx * ny, stream));
+    if (n_rows_max > 0) {
+        cell_map_kernel<<<(unsigned)ceil_div64(n_rows_max, 256), 256, 0, stream>>>(coords, n_pillars_dev, n_rows_max,
+                                                                                  n_frames, nx, ny, cell_map);
+        HVPR_CHECK_LAUNCH();
+    }
+    return HVPR_OK;
+}

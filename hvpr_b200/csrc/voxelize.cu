@@ -1,0 +1,443 @@
+// K1 — point -> pillar voxelization, bit-exact with the serial first-seen loop of spconv's VoxelGenerator
+// (call site pcdet/datasets/processor/data_processor.py:50-67; loop witness tools/vis.py:23-50) and collated as
+// pcdet/datasets/dataset.py:159-166.
+//
+// Parallel restatement (validated against the serial loop in NumPy: oracle/voxelize.py::voxelize_np):
+//   hash    per point: cell = floor((p-lo)/vs) per axis in IEEE fp32 (no FMA, no reciprocal);  dense per-frame table
+//           (a perfect hash for nz=1 pillar grids):  first[cell] = atomicMin(point index), cnt[cell] += 1
+//   count   per block: #first points and sum of their cell counts
+//   assign  exclusive scan in point order -> first-seen voxel rank + CSR segment offset; caps applied on the rank
+//   fill    unordered CSR fill of point indices per kept voxel
+//   gather  one warp per voxel: keep the 32 lowest point indices (bitonic sort / merge in registers) = arrival
+//           order of the serial loop; write the 512-byte zero-padded voxel row, coords, count and the cell->row map
+// All atomics are integer min/add, so the result does not depend on scheduling.
+#include "common.cuh"
+#include <limits.h>
+
+namespace hvpr {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;                       // points per thread in count/assign
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+struct VoxWorkspace {
+    int2 *table;        // [B*cells] {first, cnt}
+    int32_t *cellbuf;   // [n_total]
+    int2 *agg;          // [B*blocks_per_frame] {n_first, sum_cnt}
+    int32_t *vox_cell;  // [B*max_vox]
+    int32_t *seg_off;   // [B*max_vox]
+    int32_t *cursor;    // [B*max_vox]
+    int32_t *csr;       // [n_total]
+    int32_t *frame_nvox;// [B]
+    int32_t *istar;     // [B]
+    size_t bytes;
+};
+
+static VoxWorkspace carve(void *base, int64_t n_total, int B, int64_t cells, int max_vox, int64_t blocks_per_frame) {
+    VoxWorkspace w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void *p = base ? (char *)base + off : nullptr; off += align_up(bytes, 256); return p; };
+    w.table = (int2 *)take(sizeof(int2) * (size_t)B * cells);
+    w.cellbuf = (int32_t *)take(sizeof(int32_t) * (size_t)n_total);
+    w.agg = (int2 *)take(sizeof(int2) * (size_t)B * blocks_per_frame);
+    w.vox_cell = (int32_t *)take(sizeof(int32_t) * (size_t)B * max_vox);
+    w.seg_off = (int32_t *)take(sizeof(int32_t) * (size_t)B * max_vox);
+    w.cursor = (int32_t *)take(sizeof(int32_t) * (size_t)B * max_vox);
+    w.csr = (int32_t *)take(sizeof(int32_t) * (size_t)n_total);
+    w.frame_nvox = (int32_t *)take(sizeof(int32_t) * (size_t)B);
+    w.istar = (int32_t *)take(sizeof(int32_t) * (size_t)B);
+    w.bytes = off;
+    return w;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void vox_init_kernel(int2 *table, int64_t n_table, int32_t *cell_map, int64_t n_map,
+                                int32_t *cursor, int64_t n_cursor, int32_t *frame_nvox, int32_t *istar, int B) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // table entries are 8 B; write two per thread as one 16-B store
+    int4 *t4 = reinterpret_cast<int4 *>(table);
+    int64_t n4 = n_table / 2;
+    for (int64_t j = i; j < n4; j += stride) t4[j] = make_int4(INT_MAX, 0, INT_MAX, 0);
+    if (i == 0 && (n_table & 1)) table[n_table - 1] = make_int2(INT_MAX, 0);
+    if (cell_map) {
+        int4 *m4 = reinterpret_cast<int4 *>(cell_map);
+        int64_t nm4 = n_map / 4;
+        for (int64_t j = i; j < nm4; j += stride) m4[j] = make_int4(-1, -1, -1, -1);
+        for (int64_t j = nm4 * 4 + i; j < n_map; j += stride) cell_map[j] = -1;
+    }
+    for (int64_t j = i; j < n_cursor; j += stride) cursor[j] = 0;
+    if (i < B) { frame_nvox[i] = 0; istar[i] = INT_MAX; }
+}
+
+// cell index of one point; -1 when outside the grid.  IEEE fp32 sub, div, floor — exactly the CPU arithmetic.
+__device__ __forceinline__ int32_t point_cell(float x, float y, float z, const HvprGeom &g) {
+    float cx = floorf(__fdiv_rn(__fsub_rn(x, g.lo[0]), g.vs[0]));
+    float cy = floorf(__fdiv_rn(__fsub_rn(y, g.lo[1]), g.vs[1]));
+    float cz = floorf(__fdiv_rn(__fsub_rn(z, g.lo[2]), g.vs[2]));
+    bool ok = (cx >= 0.0f) && (cx < (float)g.grid[0]) && (cy >= 0.0f) && (cy < (float)g.grid[1]) &&
+              (cz >= 0.0f) && (cz < (float)g.grid[2]);   // NaN fails every comparison -> rejected
+    if (!ok) return -1;
+    return ((int32_t)cz * g.grid[1] + (int32_t)cy) * g.grid[0] + (int32_t)cx;
+}
+
+// grid: (blocks over max_frame_points, B).  Point index stored in the table is frame-local.
+template <bool kVec4>
+__global__ void __launch_bounds__(256) vox_hash_kernel(const float *__restrict__ pts, int stride, int xyz_col,
+                                                       const int32_t *__restrict__ frame_off, HvprGeom g,
+                                                       int64_t cells, int2 *table, int32_t *__restrict__ cellbuf) {
+    const int f = blockIdx.y;
+    const int32_t start = frame_off[f], n = frame_off[f + 1] - start;
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t gi = (int64_t)start + i;
+    float x, y, z;
+    if (kVec4) {
+        float4 p = __ldg(reinterpret_cast<const float4 *>(pts) + gi);
+        x = p.x; y = p.y; z = p.z;
+    } else {
+        const float *p = pts + gi * stride + xyz_col;
+        x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+    }
+    int32_t c = point_cell(x, y, z, g);
+    cellbuf[gi] = c;
+    if (c >= 0) {
+        int2 *e = table + (int64_t)f * cells + c;
+        atomicMin(&e->x, i);
+        atomicAdd(&e->y, 1);
+    }
+}
+
+// block-wide sums of (is_first, cnt-of-first)
+__global__ void __launch_bounds__(kScanThreads) vox_count_kernel(const int32_t *__restrict__ frame_off, int64_t cells,
+                                                                 const int2 *__restrict__ table,
+                                                                 const int32_t *__restrict__ cellbuf,
+                                                                 int2 *__restrict__ agg, int blocks_per_frame) {
+    const int f = blockIdx.y;
+    const int32_t start = frame_off[f], n = frame_off[f + 1] - start;
+    const int32_t base = blockIdx.x * kScanTile;
+    if (base >= n) return;   // agg entries of blocks past the frame end are never read
+    int nf = 0, sc = 0;
+    const int2 *tab = table + (int64_t)f * cells;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        int32_t i = base + threadIdx.x * kScanItems + k;
+        if (i < n) {
+            int32_t c = cellbuf[(int64_t)start + i];
+            if (c >= 0) {
+                int2 e = tab[c];
+                if (e.x == i) { nf += 1; sc += e.y; }
+            }
+        }
+    }
+    __shared__ int s_nf[kScanThreads / 32], s_sc[kScanThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { nf += __shfl_xor_sync(0xffffffffu, nf, o); sc += __shfl_xor_sync(0xffffffffu, sc, o); }
+    if ((threadIdx.x & 31) == 0) { s_nf[threadIdx.x >> 5] = nf; s_sc[threadIdx.x >> 5] = sc; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int a = 0, b = 0;
+#pragma unroll
+        for (int w = 0; w < kScanThreads / 32; ++w) { a += s_nf[w]; b += s_sc[w]; }
+        agg[(int64_t)f * blocks_per_frame + blockIdx.x] = make_int2(a, b);
+    }
+}
+
+// exclusive scan in point order -> voxel rank / CSR offset for every first point
+__global__ void __launch_bounds__(kScanThreads) vox_assign_kernel(const int32_t *__restrict__ frame_off, int64_t cells,
+                                                                  int2 *table, const int32_t *__restrict__ cellbuf,
+                                                                  const int2 *__restrict__ agg, int blocks_per_frame,
+                                                                  int max_vox, int32_t *__restrict__ vox_cell,
+                                                                  int32_t *__restrict__ seg_off,
+                                                                  int32_t *__restrict__ frame_nvox,
+                                                                  int32_t *__restrict__ istar) {
+    const int f = blockIdx.y;
+    const int32_t start = frame_off[f], n = frame_off[f + 1] - start;
+    const int32_t base = blockIdx.x * kScanTile;
+    if (base >= n) return;
+    __shared__ int s_a[kScanThreads / 32], s_b[kScanThreads / 32];
+    __shared__ int s_pref_a, s_pref_b;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // prefix over preceding blocks of this frame (at most a few hundred entries)
+    {
+        int a = 0, b = 0;
+        for (int j = threadIdx.x; j < (int)blockIdx.x; j += kScanThreads) {
+            int2 v = agg[(int64_t)f * blocks_per_frame + j];
+            a += v.x; b += v.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        if (lane == 0) { s_a[warp] = a; s_b[warp] = b; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int ta = 0, tb = 0;
+#pragma unroll
+            for (int w = 0; w < kScanThreads / 32; ++w) { ta += s_a[w]; tb += s_b[w]; }
+            s_pref_a = ta; s_pref_b = tb;
+        }
+        __syncthreads();
+    }
+    const int pref_a = s_pref_a, pref_b = s_pref_b;
+    __syncthreads();
+
+    int2 *tab = table + (int64_t)f * cells;
+    int32_t cell[kScanItems];
+    int cnt[kScanItems];
+    bool isf[kScanItems];
+    int ta = 0, tb = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        int32_t i = base + threadIdx.x * kScanItems + k;
+        isf[k] = false; cnt[k] = 0; cell[k] = -1;
+        if (i < n) {
+            int32_t c = cellbuf[(int64_t)start + i];
+            if (c >= 0) {
+                int2 e = tab[c];
+                if (e.x == i) { isf[k] = true; cnt[k] = e.y; cell[k] = c; ta += 1; tb += e.y; }
+            }
+        }
+    }
+    // block exclusive scan of (ta, tb)
+    int ia = ta, ib = tb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int va = __shfl_up_sync(0xffffffffu, ia, o), vb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += va; ib += vb; }
+    }
+    if (lane == 31) { s_a[warp] = ia; s_b[warp] = ib; }
+    __syncthreads();
+    int wa = 0, wb = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w) {
+        if (w < warp) { wa += s_a[w]; wb += s_b[w]; }
+    }
+    int rank = pref_a + wa + (ia - ta);
+    int off = pref_b + wb + (ib - tb);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (isf[k]) {
+            int32_t i = base + threadIdx.x * kScanItems + k;
+            if (rank < max_vox) {
+                vox_cell[(int64_t)f * max_vox + rank] = cell[k];
+                seg_off[(int64_t)f * max_vox + rank] = off;
+                tab[cell[k]].x = -(rank + 1);         // cell -> voxel id, read by fill (next launch)
+            } else if (rank == max_vox) {
+                istar[f] = i;                          // first point that would open voxel #max_vox (break mode)
+            }
+            rank += 1; off += cnt[k];
+        }
+    }
+    // the block holding the frame's last point publishes the (capped) voxel count
+    if (base + kScanTile >= n && threadIdx.x == kScanThreads - 1) {
+        int total = rank;   // last thread's running rank == inclusive total
+        frame_nvox[f] = total < max_vox ? total : max_vox;
+    }
+}
+
+__global__ void __launch_bounds__(256) vox_fill_kernel(const int32_t *__restrict__ frame_off, int64_t cells,
+                                                       const int2 *__restrict__ table,
+                                                       const int32_t *__restrict__ cellbuf, int max_vox,
+                                                       const int32_t *__restrict__ seg_off, int32_t *cursor,
+                                                       int32_t *__restrict__ csr, const int32_t *__restrict__ istar,
+                                                       int break_mode) {
+    const int f = blockIdx.y;
+    const int32_t start = frame_off[f], n = frame_off[f + 1] - start;
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (break_mode && i >= istar[f]) return;
+    int32_t c = cellbuf[(int64_t)start + i];
+    if (c < 0) return;
+    int32_t e = table[(int64_t)f * cells + c].x;
+    if (e >= 0) return;                                   // cell belongs to a voxel beyond the cap
+    int32_t v = -e - 1;
+    int pos = atomicAdd(&cursor[(int64_t)f * max_vox + v], 1);
+    csr[(int64_t)start + seg_off[(int64_t)f * max_vox + v] + pos] = i;
+}
+
+__device__ __forceinline__ int32_t bitonic_sort32_asc(int32_t x, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            int32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+            bool up = ((lane & k) == 0);          // ascending block
+            bool lower = ((lane & j) == 0);
+            x = (lower == up) ? min(x, y) : max(x, y);
+        }
+    }
+    return x;
+}
+// x holds a bitonic sequence across the warp -> ascending
+__device__ __forceinline__ int32_t bitonic_merge32_asc(int32_t x, int lane) {
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        int32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+        x = ((lane & j) == 0) ? min(x, y) : max(x, y);
+    }
+    return x;
+}
+
+// one warp per voxel (grid-stride over B*max_vox slots)
+template <bool kVec4>
+__global__ void __launch_bounds__(256) vox_gather_kernel(const float *__restrict__ pts, int stride, int xyz_col,
+                                                         const int32_t *__restrict__ frame_off, int B, HvprGeom g,
+                                                         int64_t cells, int max_vox, int max_points,
+                                                         const int32_t *__restrict__ vox_cell,
+                                                         const int32_t *__restrict__ seg_off,
+                                                         const int32_t *__restrict__ cursor,
+                                                         const int32_t *__restrict__ csr,
+                                                         const int32_t *__restrict__ frame_nvox,
+                                                         float *__restrict__ voxels, int32_t *__restrict__ coords,
+                                                         int32_t *__restrict__ num_points,
+                                                         int32_t *__restrict__ voxel_offsets,
+                                                         int32_t *__restrict__ cell_map) {
+    __shared__ int32_t s_base[65];
+    const int lane = threadIdx.x & 31;
+    // every block recomputes the tiny exclusive prefix of per-frame voxel counts (B <= 64)
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int f = 0; f < B; ++f) { s_base[f] = acc; acc += frame_nvox[f]; }
+        s_base[B] = acc;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x <= B) voxel_offsets[threadIdx.x] = s_base[threadIdx.x];
+
+    const int64_t total_slots = (int64_t)B * max_vox;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = warp0; w < total_slots; w += nwarps) {
+        const int f = (int)(w / max_vox);
+        const int v = (int)(w - (int64_t)f * max_vox);
+        if (v >= frame_nvox[f]) continue;
+        const int32_t start = frame_off[f];
+        const int n = cursor[w];
+        const int32_t *seg = csr + (int64_t)start + seg_off[w];
+        int32_t best = (lane < n) ? seg[lane] : INT_MAX;
+        best = bitonic_sort32_asc(best, lane);
+        for (int c0 = 32; c0 < n; c0 += 32) {           // more than 32 candidates: keep the 32 lowest indices
+            int32_t e = (c0 + lane < n) ? seg[c0 + lane] : INT_MAX;
+            int32_t worst = __shfl_sync(0xffffffffu, best, 31);
+            if (!__any_sync(0xffffffffu, e < worst)) continue;
+            e = bitonic_sort32_asc(e, lane);
+            int32_t er = __shfl_sync(0xffffffffu, e, 31 - lane);   // descending
+            best = bitonic_merge32_asc(min(best, er), lane);
+        }
+        const int kept = n < max_points ? n : max_points;
+        const int64_t row = (int64_t)s_base[f] + v;
+        if (lane < max_points) {
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < kept) {
+                const int64_t gi = (int64_t)start + best;
+                if (kVec4) p = __ldg(reinterpret_cast<const float4 *>(pts) + gi);
+                else {
+                    const float *q = pts + gi * stride + xyz_col;
+                    p = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+                }
+            }
+            reinterpret_cast<float4 *>(voxels)[row * max_points + lane] = p;
+        }
+        if (lane == 0) {
+            const int32_t c = vox_cell[w];
+            const int32_t cx = c % g.grid[0];
+            const int32_t cy = (c / g.grid[0]) % g.grid[1];
+            const int32_t cz = c / (g.grid[0] * g.grid[1]);
+            reinterpret_cast<int4 *>(coords)[row] = make_int4(f, cz, cy, cx);
+            num_points[row] = kept;
+            if (cell_map) cell_map[(int64_t)f * cells + c] = (int32_t)row;
+        }
+    }
+}
+
+__global__ void frame_offsets_kernel(const float *__restrict__ pts, int64_t n, int stride, int B,
+                                     int32_t *__restrict__ off) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i > n) return;
+    // boundary between point i-1 and i: every frame id in (b_prev, b_cur] starts at i
+    int b_prev = (i == 0) ? -1 : (int)pts[(i - 1) * stride];
+    int b_cur = (i == n) ? B : (int)pts[i * stride];
+    if (b_cur > B) b_cur = B;
+    for (int f = b_prev + 1; f <= b_cur; ++f)
+        if (f >= 0 && f <= B) off[f] = (int32_t)i;
+}
+
+}  // namespace hvpr
+
+using namespace hvpr;
+
+extern "C" size_t hvpr_voxelize_workspace_bytes(int64_t n_total, int n_frames, const HvprGeom *geom, int max_voxels) {
+    if (!geom || n_total < 0 || n_frames < 0 || max_voxels < 0) return 0;
+    int64_t cells = (int64_t)geom->grid[0] * geom->grid[1] * geom->grid[2];
+    int64_t bpf = ceil_div64(n_total > 0 ? n_total : 1, kScanTile);
+    return carve(nullptr, n_total, n_frames, cells, max_voxels, bpf).bytes + 256;
+}
+
+extern "C" int hvpr_voxelize(const float *points, int64_t n_total, int pts_stride, int xyz_col,
+                             const int32_t *frame_offsets, int n_frames, int64_t max_frame_points,
+                             const HvprGeom *geom, int max_points, int max_voxels, int overflow_mode,
+                             float *voxels, int32_t *coords, int32_t *num_points, int32_t *voxel_offsets,
+                             int32_t *cell_map, void *workspace, size_t workspace_bytes, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!geom || !frame_offsets || !voxels || !coords || !num_points || !voxel_offsets || !workspace) return HVPR_ERR_ARG;
+    if (n_total < 0 || n_frames <= 0 || pts_stride < 4 || xyz_col < 0 || xyz_col + 4 > pts_stride) return HVPR_ERR_ARG;
+    if (n_total > 0 && !points) return HVPR_ERR_ARG;
+    if (max_points < 1 || max_points > 32 || max_voxels < 1) return HVPR_ERR_UNSUPPORTED;
+    if (n_frames > 64) return HVPR_ERR_UNSUPPORTED;
+    if (overflow_mode != HVPR_OVERFLOW_CONTINUE && overflow_mode != HVPR_OVERFLOW_BREAK) return HVPR_ERR_ARG;
+    const int64_t cells = (int64_t)geom->grid[0] * geom->grid[1] * geom->grid[2];
+    if (cells <= 0 || cells > INT_MAX || n_total > INT_MAX) return HVPR_ERR_UNSUPPORTED;
+    if (max_frame_points <= 0 || max_frame_points > n_total) max_frame_points = n_total;
+
+    const int64_t bpf_ws = ceil_div64(n_total > 0 ? n_total : 1, kScanTile);
+    // 256-B align the caller's pointer
+    uintptr_t basep = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+    VoxWorkspace w = carve((void *)basep, n_total, n_frames, cells, max_voxels, bpf_ws);
+    if (w.bytes + (basep - (uintptr_t)workspace) > workspace_bytes) return HVPR_ERR_WORKSPACE;
+
+    {
+        int64_t work = (int64_t)n_frames * cells / 2;
+        int blocks = (int)(ceil_div64(work, 256) < 148 * 8 ? (ceil_div64(work, 256) > 0 ? ceil_div64(work, 256) : 1) : 148 * 8);
+        vox_init_kernel<<<blocks, 256, 0, stream>>>(w.table, (int64_t)n_frames * cells, cell_map,
+                                                   (int64_t)n_frames * cells, w.cursor,
+                                                   (int64_t)n_frames * max_voxels, w.frame_nvox, w.istar, n_frames);
+        HVPR_CHECK_LAUNCH();
+    }
+    const bool vec4 = (pts_stride == 4 && xyz_col == 0 && ((uintptr_t)points % 16 == 0));
+    if (max_frame_points > 0) {
+        dim3 gridp((unsigned)ceil_div64(max_frame_points, 256), (unsigned)n_frames);
+        if (vec4) vox_hash_kernel<true><<<gridp, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, *geom, cells, w.table, w.cellbuf);
+        else vox_hash_kernel<false><<<gridp, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, *geom, cells, w.table, w.cellbuf);
+        HVPR_CHECK_LAUNCH();
+        const int bpf = (int)ceil_div64(max_frame_points, kScanTile);
+        dim3 grids((unsigned)bpf, (unsigned)n_frames);
+        vox_count_kernel<<<grids, kScanThreads, 0, stream>>>(frame_offsets, cells, w.table, w.cellbuf, w.agg, (int)bpf_ws);
+        HVPR_CHECK_LAUNCH();
+        vox_assign_kernel<<<grids, kScanThreads, 0, stream>>>(frame_offsets, cells, w.table, w.cellbuf, w.agg, (int)bpf_ws,
+                                                             max_voxels, w.vox_cell, w.seg_off, w.frame_nvox, w.istar);
+        HVPR_CHECK_LAUNCH();
+        vox_fill_kernel<<<gridp, 256, 0, stream>>>(frame_offsets, cells, w.table, w.cellbuf, max_voxels, w.seg_off,
+                                                  w.cursor, w.csr, w.istar, overflow_mode == HVPR_OVERFLOW_BREAK);
+        HVPR_CHECK_LAUNCH();
+    }
+    {
+        int64_t slots = (int64_t)n_frames * max_voxels;
+        int64_t want = ceil_div64(slots, 8);   // 8 warps per block
+        int blocks = (int)(want < 148 * 16 ? (want > 0 ? want : 1) : 148 * 16);
+        if (vec4) vox_gather_kernel<true><<<blocks, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, n_frames, *geom, cells, max_voxels, max_points, w.vox_cell, w.seg_off, w.cursor, w.csr, w.frame_nvox, voxels, coords, num_points, voxel_offsets, cell_map);
+        else vox_gather_kernel<false><<<blocks, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, n_frames, *geom, cells, max_voxels, max_points, w.vox_cell, w.seg_off, w.cursor, w.csr, w.frame_nvox, voxels, coords, num_points, voxel_offsets, cell_map);
+        HVPR_CHECK_LAUNCH();
+    }
+    return HVPR_OK;
+}
+
+extern "C" int hvpr_frame_offsets(const float *points5, int64_t n_total, int pts_stride, int n_frames,
+                                  int32_t *frame_offsets, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!frame_offsets || n_total < 0 || n_frames <= 0 || pts_stride < 1) return HVPR_ERR_ARG;
+    if (n_total > 0 && !points5) return HVPR_ERR_ARG;
+    if (n_total >= INT_MAX) return HVPR_ERR_UNSUPPORTED;
+    int blocks = (int)ceil_div64(n_total + 1, 256);
+    frame_offsets_kernel<<<blocks, 256, 0, stream>>>(points5, n_total, pts_stride, n_frames, frame_offsets);
+    HVPR_CHECK_LAUNCH();
+    return HVPR_OK;
+}

@@ -1,0 +1,124 @@
+"""The whole accelerated path as one object: raw LiDAR frames -> BEV pseudo-image, device-resident, CUDA-graph replayed.
+
+    points -> hvpr_voxelize -> hvpr_pfn -> hvpr_mem_attn -> hvpr_bev_fill
+           -> spatial_features (B,128,ny,nx), spatial_scale_features (B,32,ny,nx)
+
+This is the composition the reference performs across a DataLoader worker (spconv voxelizer,
+pcdet/datasets/processor/data_processor.py:43-75), collate (dataset.py:148-180), H2D, and two nn.Modules
+(pillar_vfe.py:184-221, pointpillar_scatter.py:169-220).  Buffers are allocated once for a fixed batch shape, no
+host synchronisation happens inside `run()`, and the kernel chain is captured into a CUDA graph on first use.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .config import HVPR_BEV_CFG, HVPR_VFE_CFG, Cfg
+from .geometry import Geometry
+from .map_to_bev import PointPillarScatter_Agg_Memory_1_scale
+from .vfe import PillarVFE_Scale
+from .voxelizer import Voxelizer
+
+
+class HybridFrontEnd(torch.nn.Module):
+    def __init__(self, geom: Geometry, vfe_cfg: Cfg = HVPR_VFE_CFG, bev_cfg: Cfg = HVPR_BEV_CFG,
+                 overflow: str = "continue", mem_precision: str = "fp32", device="cuda"):
+        super().__init__()
+        self.geom = geom
+        self.dev = torch.device(device)
+        self.vfe = PillarVFE_Scale(vfe_cfg, 4, list(geom.voxel_size), geom.range_f32)
+        self.map_to_bev_module = PointPillarScatter_Agg_Memory_1_scale(bev_cfg, grid_size=geom.grid_size)
+        self.map_to_bev_module.memory.precision = mem_precision
+        self.voxelizer = Voxelizer(geom, overflow, self.dev)
+        self.to(self.dev)
+        self.eval()
+        self._plan = None
+
+    def load_reference_weights(self, w: dict):
+        """w: reference state_dict names ('vfe.*', 'map_to_bev_module.memory.weight')."""
+        sd = {k: v for k, v in w.items() if k.startswith("vfe.") or k.startswith("map_to_bev_module.")}
+        missing, unexpected = self.load_state_dict(sd, strict=False)
+        missing = [m for m in missing if "num_batches_tracked" not in m]
+        assert not missing and not unexpected, (missing, unexpected)
+        return self
+
+    # ---------------------------------------------------------------------------------------------------------
+    class _Plan:
+        pass
+
+    def plan(self, n_frames: int, n_total_points: int, max_frame_points: int = 0, use_graph: bool = True):
+        """Allocate every buffer for a fixed batch shape (sized for 180 GB HBM: capacity rows = B * max_voxels)."""
+        g, dev = self.geom, self.dev
+        nx, ny, _ = g.grid_size
+        p = self._Plan()
+        p.B, p.n_total, p.max_frame_points = n_frames, n_total_points, max_frame_points
+        p.points = torch.empty((n_total_points, 4), dtype=torch.float32, device=dev)
+        p.frame_offsets = torch.zeros((n_frames + 1,), dtype=torch.int32, device=dev)
+        p.vox = self.voxelizer.alloc_output(n_frames)
+        rows = p.vox.max_rows
+        p.pillar_features = torch.empty((rows, 64), dtype=torch.float32, device=dev)
+        p.pillar_scale = torch.empty((rows, 32), dtype=torch.float32, device=dev)
+        p.readout = torch.empty((rows, 64), dtype=torch.float32, device=dev)
+        p.spatial = torch.empty((n_frames, 128, ny, nx), dtype=torch.float32, device=dev)
+        p.spatial_scale = torch.empty((n_frames, 32, ny, nx), dtype=torch.float32, device=dev)
+        p.graph = None
+        p.use_graph = use_graph
+        self._plan = p
+        return p
+
+    def _enqueue(self, p):
+        vox = self.voxelizer.run(p.points, p.frame_offsets, p.B, p.max_frame_points, out=p.vox)
+        nP = vox.n_pillars_dev
+        self.vfe.run(vox.voxels, vox.num_points, vox.coords, nP, out=p.pillar_features, scale_out=p.pillar_scale)
+        self.map_to_bev_module.run(p.pillar_features, p.pillar_scale, vox.cell_map, p.B, nP, readout=p.readout,
+                                   spatial=p.spatial, spatial_scale=p.spatial_scale)
+
+    def kernel_launches_per_run(self) -> int:
+        # init, hash, count, assign, fill, gather | pfn | mem_attn | bev_fill
+        return 9 if self.map_to_bev_module.memory.precision == "fp32" else 9
+
+    @torch.no_grad()
+    def run(self):
+        """One pass over the planned batch whose points / frame_offsets are already resident in p.points."""
+        p = self._plan
+        _lib.init_device()
+        if not p.use_graph:
+            self._enqueue(p)
+            return p
+        if p.graph is None:
+            self.vfe._weights()                         # host-side folding happens outside capture
+            if self.map_to_bev_module.memory.precision == "bf16_rescore":
+                self.map_to_bev_module.memory._packed_bf16()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._enqueue(p)                        # warm-up (workspace allocation, lazy init)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                self._enqueue(p)
+            p.graph = gr
+        p.graph.replay()
+        return p
+
+    @torch.no_grad()
+    def run_host(self, points_pinned: torch.Tensor, frame_offsets_pinned: torch.Tensor, counts_pinned: torch.Tensor):
+        """End-to-end call with HOST buffers: H2D of the frame batch, the kernel chain, D2H of the per-frame pillar
+        offsets (the data-dependent sizes a caller needs to shape `voxels`); all asynchronous on the current stream."""
+        p = self._plan
+        p.points.copy_(points_pinned, non_blocking=True)
+        p.frame_offsets.copy_(frame_offsets_pinned, non_blocking=True)
+        self.run()
+        counts_pinned.copy_(p.vox.voxel_offsets, non_blocking=True)
+        return p
+
+    @torch.no_grad()
+    def forward(self, batch_dict: dict) -> dict:
+        """batch_dict API: consumes 'points' (sum N,5) [b,x,y,z,r] + 'batch_size', fills every key the reference's
+        voxelizer + VFE + map_to_bev would (exact-shaped tensors; one 4-byte D2H read for the pillar count)."""
+        batch_dict = self.voxelizer.voxelize_batch(batch_dict, exact_shapes=True)
+        batch_dict.pop("num_pillars_dev", None)
+        batch_dict = self.vfe(batch_dict)
+        batch_dict = self.map_to_bev_module(batch_dict)
+        return batch_dict

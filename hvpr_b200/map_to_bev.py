@@ -1,0 +1,175 @@
+"""Drop-in boundary #2b — map_to_bev modules with the reference's constructor signature, parameter names and
+batch_dict contract (pcdet/models/backbones_2d/map_to_bev/pointpillar_scatter.py:5-222, memory_module.py:11-82,
+map_to_bev/__init__.py:1-8).  Inference (eval) path only.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+from torch.nn.parameter import Parameter
+
+from . import _lib
+
+
+class MemoryUnit_Agg(nn.Module):
+    """Parameter container (memory_module.py:11-27); eval forward runs hvpr_mem_attn."""
+
+    def __init__(self, mem_dim, fea_dim, shrink_thres=0.0025):
+        super().__init__()
+        self.mem_dim, self.fea_dim = mem_dim, fea_dim
+        self.weight = Parameter(torch.Tensor(self.mem_dim, self.fea_dim))
+        self.bias = None
+        self.shrink_thres = shrink_thres
+        self.precision = "fp32"      # "fp32" | "bf16_rescore"
+        self._bf16 = None
+        self._bf16_key = None
+        self._ws = None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        stdv = 1.0 / math.sqrt(self.weight.size(1))
+        self.weight.data.uniform_(-stdv, stdv)
+
+    def _packed_bf16(self):
+        w = self.weight
+        key = (w.data_ptr(), w._version)
+        if self._bf16 is None or key != self._bf16_key:
+            mpad = (self.mem_dim + 255) // 256 * 256
+            self._bf16 = torch.empty((mpad, self.fea_dim), dtype=torch.bfloat16, device=w.device)
+            _lib.check(_lib.lib().hvpr_mem_pack_bf16(_lib.ptr(w.detach()), self.mem_dim, self.fea_dim,
+                                                     _lib.ptr(self._bf16), _lib.cur_stream()), "hvpr_mem_pack_bf16")
+            self._bf16_key = key
+        return self._bf16
+
+    def run(self, pillars, k, n_pillars_dev=None, out=None, topk_idx_out=None):
+        _lib.init_device()
+        rows = pillars.shape[0]
+        if out is None:
+            out = torch.empty((rows, self.fea_dim), dtype=torch.float32, device=pillars.device)
+        mode = {"fp32": _lib.MEM_FP32, "bf16_rescore": _lib.MEM_BF16_RESCORE}[self.precision]
+        bf16 = self._packed_bf16() if mode == _lib.MEM_BF16_RESCORE else None
+        nbytes = _lib.lib().hvpr_mem_attn_workspace_bytes(rows, self.mem_dim, mode)
+        if nbytes and (self._ws is None or self._ws.numel() < nbytes or self._ws.device != pillars.device):
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=pillars.device)
+        st = _lib.lib().hvpr_mem_attn(
+            _lib.ptr(pillars), _lib.ptr(n_pillars_dev), rows, _lib.ptr(self.weight.detach()), _lib.ptr(bf16),
+            self.mem_dim, self.fea_dim, int(k), mode, _lib.ptr(out), _lib.ptr(topk_idx_out),
+            _lib.ptr(self._ws) if nbytes else None, int(nbytes), _lib.cur_stream())
+        _lib.check(st, "hvpr_mem_attn")
+        return out
+
+    def forward(self, input1, input2, k):
+        if self.training:
+            raise NotImplementedError("hvpr_b200 implements the eval branch (memory_module.py:60-77) only")
+        out = self.run(input1.contiguous().float(), k)
+        return {"output": out, "att": None}   # `att` (nv, M) is never read at eval (pointpillar_scatter.py:201,212)
+
+    def extra_repr(self):
+        return "mem_dim={}, fea_dim={}".format(self.mem_dim, self.fea_dim is not None)
+
+
+def _batch_size(batch_dict, coords):
+    if "batch_size" in batch_dict:                      # set by collate_batch, dataset.py:179 — no device sync (E9)
+        return int(batch_dict["batch_size"])
+    return int(coords[:, 0].max().int().item()) + 1     # the reference's formula, pointpillar_scatter.py:17,176
+
+
+def _cell_map(batch_dict, coords_i, B, nx, ny):
+    cm = batch_dict.get("cell_map")
+    if cm is not None and cm.shape[0] == B and cm.shape[1] == nx * ny:
+        return cm                                       # produced by hvpr_b200.Voxelizer together with these coords
+    cm = torch.empty((B, nx * ny), dtype=torch.int32, device=coords_i.device)
+    st = _lib.lib().hvpr_build_cell_map(_lib.ptr(coords_i), _lib.ptr(batch_dict.get("num_pillars_dev")),
+                                        coords_i.shape[0], B, nx, ny, _lib.ptr(cm), _lib.cur_stream())
+    _lib.check(st, "hvpr_build_cell_map")
+    return cm
+
+
+class PointPillarScatter(nn.Module):
+    """pointpillar_scatter.py:5-37"""
+
+    def __init__(self, model_cfg, grid_size, **kwargs):
+        super().__init__()
+        self.model_cfg = model_cfg
+        self.num_bev_features = self.model_cfg.NUM_BEV_FEATURES
+        self.nx, self.ny, self.nz = [int(v) for v in grid_size]
+        assert self.nz == 1
+
+    def forward(self, batch_dict, **kwargs):
+        pf, coords = batch_dict["pillar_features"], batch_dict["voxel_coords"]
+        if not pf.is_cuda:
+            raise _lib.HvprError("hvpr_b200 has no CPU path: batch_dict tensors must be on a CUDA device")
+        _lib.init_device()
+        coords_i = (coords if coords.dtype == torch.int32 else coords.to(torch.int32)).contiguous()
+        B = _batch_size(batch_dict, coords)
+        cm = _cell_map(batch_dict, coords_i, B, self.nx, self.ny)
+        pf = pf.contiguous().float()
+        C = pf.shape[1]
+        out = torch.empty((B, C * self.nz, self.ny, self.nx), dtype=torch.float32, device=pf.device)
+        st = _lib.lib().hvpr_bev_fill(_lib.ptr(pf), C, None, 0, None, 0, _lib.ptr(cm), B, self.nx, self.ny,
+                                      _lib.ptr(out), None, _lib.cur_stream())
+        _lib.check(st, "hvpr_bev_fill")
+        batch_dict["spatial_features"] = out
+        return batch_dict
+
+
+class PointPillarScatter_Agg_Memory_1_scale(nn.Module):
+    """pointpillar_scatter.py:39-222 (eval branch :169-220)"""
+
+    def __init__(self, model_cfg, grid_size, **kwargs):
+        super().__init__()
+        self.model_cfg = model_cfg
+        self.num_bev_features = self.model_cfg.NUM_BEV_FEATURES
+        self.num_coord_points = self.model_cfg.NUM_COORD_POINTS
+        self.num_pt_features = self.model_cfg.NUM_PT_FEATURES
+        self.num_scale_features = self.model_cfg.NUM_SCALE_FEATURES
+        self.k = self.model_cfg.NUM_K
+        self.mem_size = self.model_cfg.NUM_M
+        self.shrink_thres = self.model_cfg.SHRINK_TH
+        self.nx, self.ny, self.nz = [int(v) for v in grid_size]
+        self.memory = MemoryUnit_Agg(self.mem_size, self.num_pt_features, self.shrink_thres)
+        prec = model_cfg.get("MEM_PRECISION", None) if hasattr(model_cfg, "get") else None
+        if prec:
+            self.memory.precision = prec
+        assert self.nz == 1
+
+    def run(self, pillar_features, pillar_scale_features, cell_map, B, n_pillars_dev=None, readout=None,
+            spatial=None, spatial_scale=None):
+        """Memory attention + gather-fill of both canvases on the current stream (graph-capturable)."""
+        dev = pillar_features.device
+        C, Cs = pillar_features.shape[1], pillar_scale_features.shape[1]
+        readout = self.memory.run(pillar_features, self.k, n_pillars_dev, out=readout)
+        if spatial is None:
+            spatial = torch.empty((B, 2 * C * self.nz, self.ny, self.nx), dtype=torch.float32, device=dev)
+        if spatial_scale is None:
+            spatial_scale = torch.empty((B, Cs * self.nz, self.ny, self.nx), dtype=torch.float32, device=dev)
+        st = _lib.lib().hvpr_bev_fill(_lib.ptr(pillar_features), C, _lib.ptr(readout), C,
+                                      _lib.ptr(pillar_scale_features), Cs, _lib.ptr(cell_map), B, self.nx, self.ny,
+                                      _lib.ptr(spatial), _lib.ptr(spatial_scale), _lib.cur_stream())
+        _lib.check(st, "hvpr_bev_fill")
+        return spatial, spatial_scale, readout
+
+    def forward(self, batch_dict, **kwargs):
+        if self.training:
+            raise NotImplementedError("hvpr_b200 implements the eval branch (pointpillar_scatter.py:169-220) only")
+        pf, psf, coords = batch_dict["pillar_features"], batch_dict["pillar_scale_features"], batch_dict["voxel_coords"]
+        if not pf.is_cuda:
+            raise _lib.HvprError("hvpr_b200 has no CPU path: batch_dict tensors must be on a CUDA device")
+        _lib.init_device()
+        coords_i = (coords if coords.dtype == torch.int32 else coords.to(torch.int32)).contiguous()
+        B = _batch_size(batch_dict, coords)
+        cm = _cell_map(batch_dict, coords_i, B, self.nx, self.ny)
+        sp, sps, ro = self.run(pf.contiguous().float(), psf.contiguous().float(), cm, B,
+                               batch_dict.get("num_pillars_dev"))
+        batch_dict["spatial_features"] = sp
+        batch_dict["spatial_scale_features"] = sps
+        batch_dict["memory_readout"] = ro
+        return batch_dict
+
+
+__all__ = {
+    "PointPillarScatter": PointPillarScatter,
+    "PointPillarScatter_Agg_Memory_1_scale": PointPillarScatter_Agg_Memory_1_scale,
+}

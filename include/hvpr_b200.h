@@ -1,0 +1,133 @@
+/*
+ * hvpr_b200 — C ABI of the B200-native hybrid voxel-point encoding front end.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.
+ * Every entry point
+ *   - takes DEVICE pointers unless a parameter says "host";
+ *   - enqueues all its work on `stream` (a cudaStream_t passed as void*), never synchronises the device,
+ *     never allocates device memory, keeps no global state -> safe inside CUDA-graph capture and re-entrant
+ *     across streams / devices (one process per GPU);
+ *   - returns HVPR_OK (0) or a negative HvprStatus; it never throws.
+ * The caller (hvpr_b200/*.py through ctypes, or any C/C++ host) owns every buffer.
+ *
+ * Reference interfaces replaced (file:line under the reference tree):
+ *   hvpr_voxelize        spconv VoxelGenerator.generate() as called at pcdet/datasets/processor/data_processor.py:50-67
+ *                        + the collate of pcdet/datasets/dataset.py:159-166 (rows frame-major, coords [b,z,y,x])
+ *   hvpr_pfn             PillarVFE_Scale.forward  pcdet/models/backbones_3d/vfe/pillar_vfe.py:184-221
+ *                        (PillarVFE.forward :94-124 when scale_out == NULL), PFNLayer.forward :29-49
+ *   hvpr_mem_attn        MemoryUnit_Agg.forward eval branch  pcdet/models/backbones_2d/map_to_bev/memory_module.py:60-77
+ *   hvpr_bev_fill        PointPillarScatter_Agg_Memory_1_scale.forward eval branch
+ *                        pcdet/models/backbones_2d/map_to_bev/pointpillar_scatter.py:169-220
+ *                        (PointPillarScatter.forward :14-37 when readout == NULL and scale == NULL)
+ *   hvpr_build_cell_map  the index arithmetic at pointpillar_scatter.py:190-193 for externally supplied voxel_coords
+ */
+#ifndef HVPR_B200_H
+#define HVPR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum HvprStatus {
+    HVPR_OK = 0,
+    HVPR_ERR_ARG = -1,          /* null pointer / negative size / inconsistent arguments */
+    HVPR_ERR_UNSUPPORTED = -2,  /* configuration outside what the kernels are built for */
+    HVPR_ERR_WORKSPACE = -3,    /* workspace too small */
+    HVPR_ERR_CUDA = -4          /* a CUDA launch failed; cudaGetLastError text via hvpr_last_cuda_error() */
+} HvprStatus;
+
+/* Pillar grid.  lo/vs are the fp32 roundings of the YAML numbers; grid = (nx, ny, nz). */
+typedef struct HvprGeom {
+    float lo[3];      /* range min x,y,z */
+    float vs[3];      /* voxel size x,y,z */
+    int32_t grid[3];  /* nx, ny, nz */
+} HvprGeom;
+
+enum { HVPR_OVERFLOW_CONTINUE = 0, HVPR_OVERFLOW_BREAK = 1 };
+enum { HVPR_MEM_FP32 = 0,          /* exact fp32 SIMT path */
+       HVPR_MEM_BF16_RESCORE = 1   /* tcgen05 bf16 GEMM -> candidate set -> exact fp32 re-score (default) */ };
+
+/* Folded (eval-mode BN merged into the bias-free Linear) weights of PillarVFE_Scale — HOST struct, passed by value
+ * into the kernel's constant bank.  Layer sizes are the shipped cfg's (hvpr.yaml:69-75):
+ * 10 -> 16 (first PFN, out//2) ; [16 | 16] -> 64 (last PFN) ; scale MLP 5 -> 16 -> 32.                         */
+typedef struct HvprPfnWeights {
+    float w0[16][10];   /* pfn_layers.0.linear.weight * bn scale */
+    float b0[16];       /* bn shift of layer 0 (= value of a zero-padded row before ReLU) */
+    float w1a[64][16];  /* pfn_layers.1: columns 0..15  (per-point activations) */
+    float w1b[64][16];  /* pfn_layers.1: columns 16..31 (broadcast per-pillar max) */
+    float b1[64];
+    float ws0[16][5];   /* pfn_scale_layers.0 */
+    float bs0[16];
+    float ws1[32][16];  /* pfn_scale_layers.1 */
+    float bs1[32];
+} HvprPfnWeights;
+
+const char *hvpr_strerror(int status);
+const char *hvpr_last_cuda_error(void);
+int hvpr_version(void);
+/* One-time per-process/per-device kernel attribute setup (opt-in shared memory).  Call before graph capture. */
+int hvpr_init(void);
+
+/* ---- K1 voxelize -------------------------------------------------------------------------------------------------
+ * points        (n_total, pts_stride) fp32; x,y,z,intensity at columns xyz_col..xyz_col+3 (4 features are copied)
+ * frame_offsets (n_frames+1) int32: frame f owns points [off[f], off[f+1])
+ * max_frame_points  upper bound on any frame's point count (sizes the grid; 0 -> n_total)
+ * outputs (rows frame-major, first-seen order inside a frame, exactly as dataset.py:159-166 would collate):
+ *   voxels        (>= n_frames*max_voxels rows, max_points, 4) fp32, zero-padded rows
+ *   coords        (rows, 4) int32 [b, z, y, x]
+ *   num_points    (rows) int32
+ *   voxel_offsets (n_frames+1) int32: frame f owns rows [vo[f], vo[f+1]);  vo[n_frames] = total pillar count
+ *   cell_map      (n_frames, nz*ny*nx) int32: cell -> row, -1 where empty (consumed by hvpr_bev_fill); may be NULL
+ * workspace: hvpr_voxelize_workspace_bytes() bytes, contents undefined on entry.                                     */
+size_t hvpr_voxelize_workspace_bytes(int64_t n_total, int n_frames, const HvprGeom *geom, int max_voxels);
+int hvpr_voxelize(const float *points, int64_t n_total, int pts_stride, int xyz_col,
+                  const int32_t *frame_offsets, int n_frames, int64_t max_frame_points,
+                  const HvprGeom *geom, int max_points, int max_voxels, int overflow_mode,
+                  float *voxels, int32_t *coords, int32_t *num_points, int32_t *voxel_offsets, int32_t *cell_map,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
+/* frame_offsets from the leading batch-index column of a collated (n_total,5) points tensor (dataset.py:161-166). */
+int hvpr_frame_offsets(const float *points5, int64_t n_total, int pts_stride, int n_frames,
+                       int32_t *frame_offsets, void *stream);
+
+/* ---- K2 fused PFN ------------------------------------------------------------------------------------------------
+ * voxels (rows,max_points,4), num_points (rows), coords (rows,4) as produced above.
+ * n_pillars_dev: device int32 holding the live row count (e.g. &voxel_offsets[n_frames]); NULL -> n_rows_max rows.
+ * x_off/y_off/z_off: voxel/2 + range_min built by the caller with the reference's expression (pillar_vfe.py:169-171).
+ * pillar_features (rows,64); scale_out (rows,32) or NULL; mask_out (rows,max_points) or NULL.                        */
+int hvpr_pfn(const float *voxels, const int32_t *num_points, const int32_t *coords,
+             const int32_t *n_pillars_dev, int64_t n_rows_max, int max_points,
+             const HvprPfnWeights *weights_host, const HvprGeom *geom, float x_off, float y_off, float z_off,
+             float *pillar_features, float *scale_out, float *mask_out, void *stream);
+
+/* ---- K3 memory attention -----------------------------------------------------------------------------------------
+ * pillars (rows,64) fp32; mem_weight (M,64) fp32; readout (rows,64) fp32.
+ * mem_weight_bf16: (M_pad,64) bf16 copy made by hvpr_mem_pack_bf16 (M_pad = M rounded up to 256); required for
+ *                  HVPR_MEM_BF16_RESCORE, ignored for HVPR_MEM_FP32.
+ * topk_idx_out: optional (rows,k) int32 — the selected memory items (unordered set), for tests.                      */
+size_t hvpr_mem_attn_workspace_bytes(int64_t n_rows_max, int M, int precision_mode);
+int hvpr_mem_pack_bf16(const float *mem_weight, int M, int C, void *mem_weight_bf16, void *stream);
+int hvpr_mem_attn(const float *pillars, const int32_t *n_pillars_dev, int64_t n_rows_max,
+                  const float *mem_weight, const void *mem_weight_bf16, int M, int C, int k, int precision_mode,
+                  float *readout, int32_t *topk_idx_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- K4 BEV canvas gather-fill -----------------------------------------------------------------------------------
+ * Writes every canvas element exactly once (feature or 0), NCHW, x fastest (pointpillar_scatter.py:192,217-218):
+ *   spatial       (n_frames, ca+cb, ny, nx)  channels [feat_a (pillar) | feat_b (memory readout)]
+ *   spatial_scale (n_frames, cs, ny, nx)     or NULL when cs == 0
+ * cell_map (n_frames, ny*nx) int32: cell -> pillar row or -1.                                                        */
+int hvpr_bev_fill(const float *feat_a, int ca, const float *feat_b, int cb, const float *feat_s, int cs,
+                  const int32_t *cell_map, int n_frames, int nx, int ny,
+                  float *spatial, float *spatial_scale, void *stream);
+
+/* cell_map from externally supplied coords (rows,4) int32 [b,z,y,x] (module API fed by a foreign voxelizer).         */
+int hvpr_build_cell_map(const int32_t *coords, const int32_t *n_pillars_dev, int64_t n_rows_max,
+                        int n_frames, int nx, int ny, int32_t *cell_map, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HVPR_B200_H */

@@ -1,0 +1,17 @@
+"""ORACLE — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A CPU restatement of the reference's algorithm for the hybrid voxel-point encoding front end
+(voxelize -> PillarVFE[_Scale] -> MemoryUnit_Agg eval -> PointPillarScatter[_Agg_Memory_1_scale] eval).
+
+Who may import / execute this package:  tests/,  __graft_entry__.smoke(),  bench.py's `cpu_baseline`
+leg and `bench.py --impl reference`.  Nothing under hvpr_b200/ imports it; the product path fails loudly
+when its CUDA extension is missing instead of falling back to anything here.
+
+Pinning status:
+  * voxelizer          — PARITY UNPINNED against upstream spconv (not vendored, not pinned, not installed; the
+                         reference has no tests).  Pinned against an independent dict-based model and the in-tree
+                         loop witness tools/vis.py:23-50.
+  * VFE / memory / BEV — pinned against the reference's OWN Python modules imported from /root/reference in the
+                         build container (oracle/ref_loader.py, 3 in-memory patches) — see oracle/make_golden.py and
+                         tests/golden/*.npz, and tests/test_oracle_vs_reference.py (runs wherever /root/reference exists).
+"""

@@ -1,0 +1,173 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/hvpr_b200.h declares (no compute calls),
+and the host-side mirror of the reference interface behaves (cfg shim, registries, state_dict names, BN folding,
+loud failure without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import hvpr_b200
+from hvpr_b200 import _lib, config
+from hvpr_b200.geometry import G1, G2
+from oracle import hybrid
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    hdr = open(os.path.join(ROOT, "include", "hvpr_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(hvpr_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations parsed"
+    assert sorted(_lib.SYMBOLS) == declared
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for s in declared:
+        assert hasattr(L, s), s
+    assert _lib.lib().hvpr_version() >= 100
+    assert _lib.lib().hvpr_strerror(0) == b"ok" and b"workspace" in _lib.lib().hvpr_strerror(-3)
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.HvprGeom) == 36
+    assert ctypes.sizeof(_lib.HvprPfnWeights) == 4 * (160 + 16 + 1024 + 1024 + 64 + 80 + 16 + 512 + 32)
+
+
+def test_workspace_query_needs_no_gpu():
+    g = _lib.make_geom(G2.range_f32, G2.voxel_f32, G2.grid_size)
+    n = _lib.lib().hvpr_voxelize_workspace_bytes(8 * 120000, 8, ctypes.byref(g), 40000)
+    assert 8 * 432 * 496 * 8 < n < 200 * 2 ** 20
+    assert _lib.lib().hvpr_voxelize_workspace_bytes(-1, 8, ctypes.byref(g), 40000) == 0
+
+
+def test_argument_validation_without_gpu():
+    L = _lib.lib()
+    g = _lib.make_geom(G2.range_f32, G2.voxel_f32, G2.grid_size)
+    # null pointers / bad sizes are rejected before any CUDA call
+    assert L.hvpr_voxelize(None, 10, 4, 0, None, 1, 0, ctypes.byref(g), 32, 100, 0, None, None, None, None, None, None, 0, None) == -1
+    assert L.hvpr_bev_fill(None, 64, None, 0, None, 0, None, 1, 432, 496, None, None, None) == -1
+    assert L.hvpr_mem_attn(None, None, -1, None, None, 2000, 64, 20, 0, None, None, None, 0, None) == -1
+
+
+def test_registries_and_state_dict_names():
+    from hvpr_b200 import map_to_bev, vfe
+    assert set(vfe.__all__) >= {"VFETemplate", "PillarVFE", "PillarVFE_Scale"}
+    assert set(map_to_bev.__all__) >= {"PointPillarScatter", "PointPillarScatter_Agg_Memory_1_scale"}
+    m = vfe.__all__["PillarVFE_Scale"](model_cfg=config.HVPR_VFE_CFG, num_point_features=4,
+                                       point_cloud_range=G1.range_f32, voxel_size=list(G1.voxel_size))
+    assert m.get_output_feature_dim() == 64
+    b = map_to_bev.__all__["PointPillarScatter_Agg_Memory_1_scale"](model_cfg=config.HVPR_BEV_CFG, grid_size=G1.grid_size)
+    assert b.num_bev_features == 128
+    w = hybrid.random_weights(0)
+    names = {k[4:] for k in w if k.startswith("vfe.")}
+    assert names <= set(m.state_dict().keys())
+    assert set(b.state_dict().keys()) == {"memory.weight"}
+    assert tuple(b.memory.weight.shape) == (2000, 64)
+    assert float(b.memory.weight.detach().abs().max()) <= 0.125 + 1e-6          # memory_module.py:23-25
+    # shapes of the reference's parameters
+    sd = m.state_dict()
+    assert tuple(sd["pfn_layers.0.linear.weight"].shape) == (16, 10)
+    assert tuple(sd["pfn_layers.1.linear.weight"].shape) == (64, 32)
+    assert tuple(sd["pfn_scale_layers.0.0.weight"].shape) == (16, 5)
+    assert tuple(sd["pfn_scale_layers.1.0.weight"].shape) == (32, 16)
+
+
+def test_unsupported_cfg_is_loud():
+    from hvpr_b200 import vfe
+    bad = config.Cfg(config.HVPR_VFE_CFG); bad["NUM_FILTERS"] = [64]
+    with pytest.raises(NotImplementedError):
+        vfe.PillarVFE(bad, 4, list(G1.voxel_size), G1.range_f32)
+
+
+def test_bn_folding_matches_oracle():
+    """The folded (W', b') the kernel receives reproduce the oracle's Linear+BN on CPU."""
+    from hvpr_b200 import vfe
+    w = hybrid.random_weights(5)
+    m = vfe.PillarVFE_Scale(config.HVPR_VFE_CFG, 4, list(G1.voxel_size), G1.range_f32).eval()
+    m.load_state_dict({k[4:]: v for k, v in w.items() if k.startswith("vfe.")}, strict=False)
+    W = m._weights()
+    w0 = torch.tensor(list(W.w0)).view(16, 10); b0 = torch.tensor(list(W.b0))
+    x = torch.randn(100, 10)
+    ref = hybrid._bn_eval(torch.nn.functional.linear(x, w["vfe.pfn_layers.0.linear.weight"]).unsqueeze(-1), w,
+                          "vfe.pfn_layers.0.norm").squeeze(-1)
+    torch.testing.assert_close(x @ w0.t() + b0, ref, rtol=1e-5, atol=1e-5)
+    w1 = torch.cat([torch.tensor(list(W.w1a)).view(64, 16), torch.tensor(list(W.w1b)).view(64, 16)], 1)
+    x = torch.randn(100, 32)
+    ref = hybrid._bn_eval(torch.nn.functional.linear(x, w["vfe.pfn_layers.1.linear.weight"]).unsqueeze(-1), w,
+                          "vfe.pfn_layers.1.norm").squeeze(-1)
+    torch.testing.assert_close(x @ w1.t() + torch.tensor(list(W.b1)), ref, rtol=1e-5, atol=1e-5)
+    # cache invalidation on weight update
+    with torch.no_grad():
+        m.pfn_layers[0].linear.weight.mul_(2.0)      # (raw `.data` edits bypass version counters: call invalidate_weights())
+    W2 = m._weights()
+    assert abs(W2.w0[0] - 2 * w0.view(-1)[0].item()) < 1e-6
+
+
+def test_virtual_padded_row_restatement():
+    """Host model of the kernel's formulation (real points only + one virtual padded row + split W1) equals the oracle."""
+    from helpers import load_small
+    z, geom, frames, overflow, wseed = load_small("tiny_continue")
+    w = hybrid.random_weights(wseed)
+    vox = torch.from_numpy(z["voxels"]); n = torch.from_numpy(z["voxel_num_points"]); c = torch.from_numpy(z["voxel_coords"])
+    ref, _, _ = hybrid.pillar_vfe(vox, n, c, w, list(geom.voxel_size), geom.range_f32)
+    from hvpr_b200 import vfe
+    m = vfe.PillarVFE_Scale(config.HVPR_VFE_CFG, 4, list(geom.voxel_size), geom.range_f32).eval()
+    m.load_state_dict({k[4:]: v for k, v in w.items() if k.startswith("vfe.")}, strict=False)
+    W = m._weights()
+    w0 = torch.tensor(list(W.w0)).view(16, 10); b0 = torch.tensor(list(W.b0))
+    w1a = torch.tensor(list(W.w1a)).view(64, 16); w1b = torch.tensor(list(W.w1b)).view(64, 16); b1 = torch.tensor(list(W.b1))
+    out = torch.empty_like(ref)
+    for p in range(vox.shape[0]):
+        k = int(n[p]); pts = vox[p, :k]
+        mean = vox[p, :, :3].sum(0) / k
+        ctr = torch.tensor([c[p, 3] * geom.voxel_size[0] + m.x_offset, c[p, 2] * geom.voxel_size[1] + m.y_offset,
+                            c[p, 1] * geom.voxel_size[2] + m.z_offset], dtype=torch.float32)
+        f = torch.cat([pts, pts[:, :3] - mean, pts[:, :3] - ctr], 1)
+        x0 = torch.relu(f @ w0.t() + b0)
+        rb0 = torch.relu(b0)
+        xmax = x0.max(0)[0] if k == 32 else torch.maximum(x0.max(0)[0], rb0)
+        c1 = w1b @ xmax + b1
+        y = torch.relu(x0 @ w1a.t() + c1).max(0)[0]
+        if k < 32:
+            y = torch.maximum(y, torch.relu(w1a @ rb0 + c1))
+        out[p] = y
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_cpu_tensors_fail_loudly():
+    from hvpr_b200 import map_to_bev, vfe
+    m = vfe.PillarVFE_Scale(config.HVPR_VFE_CFG, 4, list(G1.voxel_size), G1.range_f32).eval()
+    bd = dict(voxels=torch.zeros(3, 32, 4), voxel_num_points=torch.ones(3), voxel_coords=torch.zeros(3, 4))
+    with pytest.raises(_lib.HvprError):
+        m(bd)
+    b = map_to_bev.PointPillarScatter(config.Cfg(NUM_BEV_FEATURES=64), grid_size=G1.grid_size)
+    with pytest.raises(_lib.HvprError):
+        b(dict(pillar_features=torch.zeros(3, 64), voxel_coords=torch.zeros(3, 4), batch_size=1))
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(bd)
+
+
+def test_yaml_cfg_loader(tmp_path):
+    y = tmp_path / "m.yaml"
+    y.write_text("DATA_CONFIG:\n  POINT_CLOUD_RANGE: [0, -19.84, -2.5, 47.36, 19.84, 0.5]\n  DATA_PROCESSOR:\n"
+                 "    - NAME: transform_points_to_voxels\n      VOXEL_SIZE: [0.16, 0.16, 3]\n      MAX_POINTS_PER_VOXEL: 32\n"
+                 "      MAX_NUMBER_OF_VOXELS: {train: 16000, test: 40000}\n"
+                 "MODEL:\n  VFE: {NAME: PillarVFE_Scale, WITH_DISTANCE: false, USE_ABSLOTE_XYZ: true, USE_NORM: true,"
+                 " NUM_FILTERS: [32, 64], NUM_SCALE_FEATURES: [16, 32]}\n"
+                 "  MAP_TO_BEV: {NAME: PointPillarScatter_Agg_Memory_1_scale, NUM_BEV_FEATURES: 128, NUM_PT_FEATURES: 64,"
+                 " NUM_SCALE_FEATURES: 32, NUM_COORD_POINTS: 3, NUM_K: 20, NUM_M: 2000, SHRINK_TH: 0.0025}\n")
+    c = config.load_yaml_model_cfg(str(y))
+    assert c["VFE"].NUM_FILTERS == [32, 64] and c["MAP_TO_BEV"].NUM_K == 20
+    assert c["VOXELIZER"].MAX_NUMBER_OF_VOXELS["test"] == 40000
+
+
+def test_synth_generators_are_deterministic():
+    from hvpr_b200 import synth
+    a = synth.make_frame("L", 5000, G2.point_cloud_range, 1024)
+    b = synth.make_frame("L", 5000, G2.point_cloud_range, 1024)
+    assert a.dtype == np.float32 and a.shape == (5000, 4) and np.array_equal(a, b)
+    c = synth.collate_points([a, b])
+    assert c.shape == (10000, 5) and c[4999, 0] == 0 and c[5000, 0] == 1

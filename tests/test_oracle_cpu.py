@@ -1,0 +1,152 @@
+"""CPU suite: pins the ORACLE (oracle/) — three independent voxelizer statements against each other, against the
+committed golden fixtures, and (where /root/reference exists) against the reference's own Python modules."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from hvpr_b200 import synth
+from hvpr_b200.geometry import G1, G2, G3, Geometry
+from oracle import hybrid, ref_loader
+from oracle import voxelize as ov
+
+from helpers import GOLDEN, load_small, sha
+
+SMALL = ["tiny_continue", "tiny_break_cap", "tiny_t5"]
+
+
+def _eq(a, b):
+    return all(np.array_equal(x.view(np.int32) if x.dtype == np.float32 else x,
+                              y.view(np.int32) if y.dtype == np.float32 else y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("mode", ["continue", "break"])
+@pytest.mark.parametrize("max_vox,max_pts", [(50, 32), (100000, 3), (100000, 32)])
+def test_c_vs_dict_model(mode, max_vox, max_pts):
+    g = Geometry((0.0, -3.2, -3.0, 6.4, 3.2, 1.0), (0.16, 0.16, 4.0))
+    f = synth.make_frame("L", 2500, g.point_cloud_range, 7, edge_cases=True)
+    a = ov.voxelize_c(f, g.range_f32, g.voxel_f32, max_pts, max_vox, mode)
+    b = ov.voxelize_py(f, g.range_f32, g.voxel_f32, max_pts, max_vox, mode)
+    assert _eq(a, b)
+
+
+@pytest.mark.parametrize("mode", ["continue", "break"])
+@pytest.mark.parametrize("gname,dist", [("G1", "U"), ("G1", "L"), ("G2", "U"), ("G2", "L")])
+def test_parallel_formulation_equals_serial_loop(gname, dist, mode):
+    g = {"G1": G1, "G2": G2}[gname]
+    f = synth.make_frame(dist, 60000, g.point_cloud_range, 3, edge_cases=True)
+    for mv in (5000, 40000):
+        a = ov.voxelize_c(f, g.range_f32, g.voxel_f32, 32, mv, mode)
+        b = ov.voxelize_np(f, g.range_f32, g.voxel_f32, 32, mv, mode)
+        assert _eq(a, b)
+
+
+def test_edge_cases_semantics():
+    g = G2
+    r = g.range_f32
+    pts = np.array([
+        [r[3], 0.0, 0.0, 0.5],                          # x == hi -> rejected
+        [0.0, r[1], 0.0, 0.5],                          # y == lo -> cell y=0
+        [1.0, 0.0, r[5], 0.5],                          # z == hi -> rejected
+        [1.0, 0.0, r[2], 0.5],                          # z == lo -> kept
+        [np.nan, 0.0, 0.0, 0.5],                        # NaN -> rejected
+        [np.inf, 0.0, 0.0, 0.5],
+        [-0.001, 0.0, 0.0, 0.5],                        # just outside
+        [0.0, r[1], 0.5, 0.7],                          # duplicate cell of row 1 -> same voxel, slot 1
+    ], dtype=np.float32)
+    v, c, n = ov.voxelize_c(pts, r, g.voxel_f32, 32, 10, "continue")
+    assert len(n) == 2 and list(n) == [2, 1]
+    assert list(c[0]) == [0, 0, 0]
+    assert np.array_equal(v[0, 0], pts[1]) and np.array_equal(v[0, 1], pts[7]) and np.array_equal(v[1, 0], pts[3])
+    assert not v[0, 2:].any()
+    # empty input
+    v, c, n = ov.voxelize_c(np.zeros((0, 4), np.float32), r, g.voxel_f32, 32, 10, "continue")
+    assert v.shape == (0, 32, 4) and len(n) == 0
+
+
+def test_grid_sizes():
+    assert G1.grid_size == (296, 248, 1) and G2.grid_size == (432, 496, 1) and G3.grid_size == (640, 640, 1)
+    for g in (G1, G2, G3):
+        assert ov.grid_size(g.range_f32, g.voxel_f32) == g.grid_size
+
+
+def test_voxel_hashes_golden():
+    """full-size frames: the C restatement reproduces the committed sha256 of (voxels bits, coords, counts)."""
+    with open(os.path.join(GOLDEN, "voxel_hashes.json")) as fh:
+        gold = json.load(fh)
+    G = {"G1": G1, "G2": G2, "G3": G3}
+    for key, ref in gold.items():
+        gname, dist, n, mode = key.split("/")
+        g = G[gname]
+        f = synth.make_frame(dist, int(n), g.point_cloud_range, 1024, edge_cases=True)
+        v, c, k = ov.voxelize_c(f, g.range_f32, g.voxel_f32, 32, g.max_voxels, mode)
+        assert (len(k), int(k.sum())) == (ref["P"], ref["K"]), key
+        assert sha(v.view(np.int32), c, k) == ref["sha256"], key
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_oracle_matches_reference_fixture(name):
+    """oracle/hybrid.py + C voxelizer vs tensors produced by the REFERENCE'S OWN modules (tests/golden, committed)."""
+    z, geom, frames, overflow, wseed = load_small(name)
+    w = hybrid.random_weights(wseed)
+    o = hybrid.frontend(frames, geom, w, overflow)
+    assert np.array_equal(o["voxels"].numpy().view(np.int32), z["voxels"].view(np.int32))
+    assert np.array_equal(o["voxel_coords"].numpy(), z["voxel_coords"])
+    assert np.array_equal(o["voxel_num_points"].numpy(), z["voxel_num_points"])
+    for k in ("pillar_features", "pillar_scale_features", "memory_readout", "spatial_features",
+              "spatial_scale_features"):
+        ref = torch.from_numpy(z[k])
+        assert o[k].shape == ref.shape, k
+        # same torch ops as the reference -> bitwise on the machine that made the fixture; allow last-ulp noise
+        # from different CPU kernels (AVX2 vs AVX512) elsewhere
+        torch.testing.assert_close(o[k], ref, rtol=2e-6, atol=2e-6, msg=k)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present on this box")
+def test_oracle_vs_live_reference():
+    """Where the reference tree exists: run its own modules (3 in-memory patches) against the restatement."""
+    ns = ref_loader.load()
+    g = G1
+    frames = synth.make_batch("L", 30000, g.point_cloud_range, 2, first_frame=7, edge_cases=True)
+    w = hybrid.random_weights(11)
+    o = hybrid.frontend(frames, g, w)
+    vfe = ns.PillarVFE_Scale(ref_loader.VFE_CFG, 4, list(g.voxel_size), g.range_f32).eval()
+    bev = ns.PointPillarScatter_Agg_Memory_1_scale(ref_loader.BEV_CFG, grid_size=g.grid_size).eval()
+    vfe.load_state_dict({k[4:]: v for k, v in w.items() if k.startswith("vfe.")}, strict=False)
+    bev.load_state_dict({"memory.weight": w["map_to_bev_module.memory.weight"]})
+    bd = dict(voxels=o["voxels"].clone(), voxel_num_points=o["voxel_num_points"].float(),
+              voxel_coords=o["voxel_coords"].float())
+    with torch.no_grad():
+        bd = bev(vfe(bd))
+    for k in ("pillar_features", "pillar_scale_features", "spatial_features", "spatial_scale_features"):
+        assert torch.equal(bd[k], o[k]), k
+    # vanilla siblings
+    pv = ns.PillarVFE(ref_loader.VFE_CFG, 4, list(g.voxel_size), g.range_f32).eval()
+    pv.load_state_dict({k[4:]: v for k, v in w.items() if k.startswith("vfe.pfn_layers")}, strict=False)
+    bd2 = dict(voxels=o["voxels"].clone(), voxel_num_points=o["voxel_num_points"].float(),
+               voxel_coords=o["voxel_coords"].float())
+    with torch.no_grad():
+        bd2 = pv(bd2)
+        ps = ns.PointPillarScatter(ref_loader.Cfg(NUM_BEV_FEATURES=64), grid_size=g.grid_size)(bd2)
+    feats, _, _ = hybrid.pillar_vfe(o["voxels"], o["voxel_num_points"], o["voxel_coords"], w, list(g.voxel_size),
+                                    g.range_f32, scale=False)
+    assert torch.equal(bd2["pillar_features"], feats)
+    assert torch.equal(ps["spatial_features"], hybrid.scatter_plain(feats, o["voxel_coords"], 2, g.grid_size[0], g.grid_size[1]))
+
+
+def test_padded_row_term_is_not_optional():
+    """E7: ignoring the zero-padded slots changes the result — guards the virtual-row logic the kernel relies on."""
+    z, geom, frames, overflow, wseed = load_small("tiny_continue")
+    w = hybrid.random_weights(wseed)
+    vox = torch.from_numpy(z["voxels"]); n = torch.from_numpy(z["voxel_num_points"]); c = torch.from_numpy(z["voxel_coords"])
+    full, _, _ = hybrid.pillar_vfe(vox, n, c, w, list(geom.voxel_size), geom.range_f32)
+    # real points only: evaluate each pillar with exactly n slots
+    sel = (n < 32).nonzero()[:50, 0]
+    diff = 0
+    for p in sel.tolist():
+        k = int(n[p])
+        only, _, _ = hybrid.pillar_vfe(vox[p:p + 1, :k], n[p:p + 1], c[p:p + 1], w, list(geom.voxel_size), geom.range_f32)
+        diff += int(not torch.allclose(only, full[p:p + 1], rtol=1e-5, atol=1e-6))
+    assert diff > 0
