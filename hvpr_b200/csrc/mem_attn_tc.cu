@@ -1,28 +1,596 @@
-// K3 (tensor-core variant, HVPR_MEM_BF16_RESCORE) — placeholder until the tcgen05 kernel lands:
-// reports HVPR_ERR_UNSUPPORTED so callers fail loudly instead of silently using another path.
+// K3 (tensor-core variant, HVPR_MEM_BF16_RESCORE) — MemoryUnit_Agg.forward eval branch
+// (pcdet/models/backbones_2d/map_to_bev/memory_module.py:60-77) as a persistent, warp-specialised tcgen05 kernel.
+//
+//   logits (bf16 x bf16 -> fp32, TMEM)   :64     tcgen05.mma cta_group::1, M128 x N256 x K16, 4 k-steps per chunk,
+//                                                8 chunks of 256 memory items; W chunks stream through a 4-stage
+//                                                cp.async.bulk (TMA engine) ring from a pre-swizzled bf16 image
+//   top-k (softmax is monotone)          :65-66  two sweeps over the accumulators, one row per thread:
+//                                                sweep 1: maxima of 16-column groups -> the 24th largest group maximum
+//                                                         tau is a lower bound of the 24th largest logit (24 distinct
+//                                                         elements are >= tau) and is tight (~25 elements pass);
+//                                                sweep 2: sign-bit masks of (logit - tau) -> candidate list
+//   exact re-score of the candidates     :70-71  fp32 FFMA against the fp32 memory rows (warp per row, coalesced)
+//   top-20, softmax, weighted readout    :72-74  fp32
+// The (rows, M) score matrix (`att`, never read at eval: pointpillar_scatter.py:201,212) never leaves TMEM.
+// The bf16 GEMM only nominates candidates; every number that reaches the output is computed in fp32, so the result
+// equals the exact-fp32 kernel (mem_attn_fp32.cu) whenever the candidate set contains the true top-20
+// (measured: always, SURVEY.md §7 K3 probe; checked in tests/test_gpu_parity.py).
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <math.h>
 
 namespace hvpr {
-__global__ void pack_bf16_kernel(const float *__restrict__ W, int M, int C, int Mpad, __nv_bfloat16 *__restrict__ out) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= (int64_t)Mpad * C) return;
-    int r = (int)(i / C);
-    out[i] = __float2bfloat16_rn(r < M ? W[i] : 0.0f);
+
+constexpr int kTcTileM = 128;          // pillar rows per tile (UMMA M)
+constexpr int kTcChunkN = 256;         // memory items per MMA (UMMA N)
+constexpr int kTcK = 64;               // feature dim
+constexpr int kTcMaxChunks = 8;        // M_pad <= 2048
+constexpr int kTcWStages = 4;
+constexpr int kTcChunkBytes = kTcChunkN * kTcK * 2;      // 32 KB
+constexpr int kTcATileBytes = kTcTileM * kTcK * 2;       // 16 KB
+constexpr int kTcCandCap = 32;         // candidates per row handled by the fast tail
+constexpr int kTcKPrime = 24;          // tau = kTcKPrime-th largest group maximum
+constexpr int kTcThreads = 512;        // warp 0 TMA, warp 1 MMA, warps 2-3 A loaders, 4-7 filter, 8-15 tail
+constexpr int kTcTailWarps = 8;
+constexpr int kTcSlowScratch = 2048;   // floats per tail warp (global workspace) for the overflow path
+
+struct TcSmem {
+    uint8_t w[kTcWStages][kTcChunkBytes];     // 1024-aligned
+    uint8_t a[2][kTcATileBytes];
+    uint16_t cand[2][kTcCandCap][kTcTileM];
+    int32_t cand_cnt[2][kTcTileM];
+    uint64_t w_full[kTcWStages], w_empty[kTcWStages];
+    uint64_t a_full[2], a_empty[2];
+    uint64_t t_full[2], t_empty[2];
+    uint64_t c_full[2], c_empty[2];
+    uint32_t tmem_base;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+    const uint32_t a = smem_u32(b);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (spin > (1u << 27)) __trap();      // watchdog: a protocol bug must not hang the GPU
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, 128-byte swizzle, rows of 128 B, 8-row atoms 1024 B apart (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address
+    d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major) = 1
+    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset
+    d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---------------------------------------------------------------------------------------------- register sorting nets
+__device__ __forceinline__ void cex_desc(float &a, float &b) {   // a >= b afterwards
+    const float hi = fmaxf(a, b), lo = fminf(a, b);
+    a = hi; b = lo;
+}
+template <int N>
+__device__ __forceinline__ void bitonic_sort_desc(float (&x)[N]) {
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    if ((i & k) == 0) cex_desc(x[i], x[l]);
+                    else cex_desc(x[l], x[i]);
+                }
+            }
+        }
+    }
+}
+template <int N>
+__device__ __forceinline__ void bitonic_merge_desc(float (&x)[N]) {   // x bitonic -> descending
+#pragma unroll
+    for (int j = N >> 1; j > 0; j >>= 1) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int l = i ^ j;
+            if (l > i) cex_desc(x[i], x[l]);
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t float_key(float f) {   // order-preserving float -> uint
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+// ---------------------------------------------------------------------------------------------- tail: one warp, one row
+// exact fp32 path over ALL items (candidate overflow: massive ties in the bf16 logits, e.g. an all-zero pillar row)
+__device__ __noinline__ void tail_slow_row(const float *__restrict__ prow, const float *__restrict__ W, int M, int k,
+                                           float *__restrict__ scratch, float *__restrict__ out_row,
+                                           int32_t *__restrict__ idx_row, int lane) {
+    float p[kTcK];
+#pragma unroll
+    for (int c4 = 0; c4 < kTcK / 4; ++c4) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(prow) + c4);
+        p[4 * c4] = v.x; p[4 * c4 + 1] = v.y; p[4 * c4 + 2] = v.z; p[4 * c4 + 3] = v.w;
+    }
+    const int Mpad = (M + 31) & ~31;
+    for (int j = lane; j < Mpad; j += 32) {
+        float acc = -INFINITY;
+        if (j < M) {
+            acc = 0.0f;
+            const float4 *wr = reinterpret_cast<const float4 *>(W + (int64_t)j * kTcK);
+#pragma unroll
+            for (int c4 = 0; c4 < kTcK / 4; ++c4) {
+                const float4 v = __ldg(wr + c4);
+                acc = fmaf(v.x, p[4 * c4], acc); acc = fmaf(v.y, p[4 * c4 + 1], acc);
+                acc = fmaf(v.z, p[4 * c4 + 2], acc); acc = fmaf(v.w, p[4 * c4 + 3], acc);
+            }
+        }
+        scratch[j] = acc;
+    }
+    __syncwarp();
+    float my_val = -INFINITY; int my_idx = 0;
+    for (int kk = 0; kk < k; ++kk) {
+        float bv = -INFINITY; int bi = 0x7fffffff;
+        for (int j = lane; j < Mpad; j += 32) {
+            const float v = scratch[j];
+            if (v > bv) { bv = v; bi = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (bi == 0x7fffffff) bi = 0;
+        if (lane == (bi & 31)) scratch[bi] = -INFINITY;
+        if (lane == kk) { my_val = bv; my_idx = bi; }
+        __syncwarp();
+    }
+    float mx = my_val;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e = (lane < k) ? expf(my_val - mx) : 0.0f;
+    float sum = e;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float a = e / sum;
+    float o0 = 0.0f, o1 = 0.0f;
+    for (int kk = 0; kk < k; ++kk) {
+        const float ak = __shfl_sync(0xffffffffu, a, kk);
+        const int ik = __shfl_sync(0xffffffffu, my_idx, kk);
+        const float2 w2 = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)ik * kTcK) + lane);
+        o0 = fmaf(ak, w2.x, o0); o1 = fmaf(ak, w2.y, o1);
+    }
+    reinterpret_cast<float2 *>(out_row)[lane] = make_float2(o0, o1);
+    if (idx_row && lane < k) idx_row[lane] = my_idx;
+}
+
+// fast path: <= 32 candidates.  Lane (hf = lane>>4, h = lane&15) ends up owning candidate 2h + hf.
+__device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, const float *__restrict__ W, int k, int cnt,
+                                              const uint16_t *__restrict__ cand_col /* stride kTcTileM */,
+                                              float *__restrict__ out_row, int32_t *__restrict__ idx_row, int lane) {
+    const int hf = lane >> 4, h = lane & 15;
+    const float4 p4 = __ldg(reinterpret_cast<const float4 *>(prow) + h);
+    float s[16];
+    int my_j = 0;
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+        s[it] = 0.0f;
+        if (2 * it < cnt) {                                   // warp-uniform
+            const int ci = 2 * it + hf;
+            const int j = (ci < cnt) ? (int)cand_col[ci * kTcTileM] : 0;
+            const float4 w4 = __ldg(reinterpret_cast<const float4 *>(W + (int64_t)j * kTcK) + h);
+            s[it] = fmaf(w4.w, p4.w, fmaf(w4.z, p4.z, fmaf(w4.y, p4.y, w4.x * p4.x)));
+            if (it == h) my_j = j;
+        }
+    }
+    // multi-value butterfly over the 16 lanes of each half: 15 shuffles, lane h ends with the total of value h
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool up = (h & 8) != 0;
+        const float send = up ? s[i] : s[i + 8];
+        const float keep = up ? s[i + 8] : s[i];
+        s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool up = (h & 4) != 0;
+        const float send = up ? s[i] : s[i + 4];
+        const float keep = up ? s[i + 4] : s[i];
+        s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const bool up = (h & 2) != 0;
+        const float send = up ? s[i] : s[i + 2];
+        const float keep = up ? s[i + 2] : s[i];
+        s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    {
+        const bool up = (h & 1) != 0;
+        const float send = up ? s[0] : s[1];
+        const float keep = up ? s[1] : s[0];
+        s[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+    const float logit = s[0];                                  // exact fp32 logit of candidate 2h + hf
+    bool valid = (2 * h + hf) < cnt;
+    uint32_t key = valid ? float_key(logit) : 0xFFFFFFFFu;
+    // drop the (cnt - k) smallest
+    for (int e = cnt; e > k; --e) {
+        const uint32_t alive = __ballot_sync(0xffffffffu, valid);
+        const uint32_t mn = __reduce_min_sync(0xffffffffu, key);
+        const uint32_t who = __ballot_sync(0xffffffffu, valid && key == mn);
+        const int victim = __ffs(who) - 1;
+        (void)alive;
+        if (lane == victim) { valid = false; key = 0xFFFFFFFFu; }
+    }
+    const uint32_t kept = __ballot_sync(0xffffffffu, valid);
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, valid ? key : 0u);
+    const float mx = key_float(kmax);
+    const float ex = valid ? expf(logit - mx) : 0.0f;
+    float sum = ex;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float a = ex / sum;
+    // readout: gather the kept items' rows, 2 channels per lane
+    float2 w2[20];
+    float ak[20];
+    const int nk = __popc(kept);
+#pragma unroll
+    for (int q = 0; q < 20; ++q) {
+        const int src = (q < nk) ? (int)__fns(kept, 0, q + 1) : 0;
+        const int jj = __shfl_sync(0xffffffffu, my_j, src);
+        ak[q] = (q < nk) ? __shfl_sync(0xffffffffu, a, src) : 0.0f;
+        w2[q] = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)jj * kTcK) + lane);
+    }
+    float o0 = 0.0f, o1 = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 20; ++q) { o0 = fmaf(ak[q], w2[q].x, o0); o1 = fmaf(ak[q], w2[q].y, o1); }
+    reinterpret_cast<float2 *>(out_row)[lane] = make_float2(o0, o1);
+    if (idx_row && valid) idx_row[__popc(kept & ((1u << lane) - 1u))] = my_j;
+    (void)k;
+}
+
+// ---------------------------------------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float *__restrict__ pillars,
+                                                                    const int32_t *__restrict__ n_pillars_dev,
+                                                                    int64_t n_rows_max, const float *__restrict__ W,
+                                                                    const uint8_t *__restrict__ Wpk, int M, int nchunks,
+                                                                    int k, float *__restrict__ readout,
+                                                                    int32_t *__restrict__ topk_idx_out,
+                                                                    float *__restrict__ slow_scratch,
+                                                                    float *__restrict__ dbg_logits) {
+    extern __shared__ uint8_t smem_raw[];
+    TcSmem &S = *reinterpret_cast<TcSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int64_t nP = n_pillars_dev ? (int64_t)*n_pillars_dev : n_rows_max;
+    if (nP > n_rows_max) nP = n_rows_max;
+    const int ntiles = (int)((nP + kTcTileM - 1) / kTcTileM);
+
+    if (tid == 0) {
+        for (int s = 0; s < kTcWStages; ++s) { mbar_init(&S.w_full[s], 1); mbar_init(&S.w_empty[s], 1); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&S.a_full[b], 2); mbar_init(&S.a_empty[b], 1);
+            mbar_init(&S.t_full[b], 1); mbar_init(&S.t_empty[b], 4);
+            mbar_init(&S.c_full[b], 4); mbar_init(&S.c_empty[b], kTcTailWarps);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = S.tmem_base;
+
+    if (warp == 0) {
+        // ===== W producer: bulk-copy pre-swizzled bf16 chunks (two sweeps per tile) ================================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
+                for (int sweep = 0; sweep < 2; ++sweep)
+                    for (int c = 0; c < nchunks; ++c, ++it) {
+                        const int s = it % kTcWStages;
+                        mbar_wait(&S.w_empty[s], ((it / kTcWStages) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&S.w_full[s], kTcChunkBytes);
+                        bulk_g2s(S.w[s], Wpk + (size_t)c * kTcChunkBytes, kTcChunkBytes, &S.w_full[s]);
+                    }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer ==========================================================================================
+        if (lane == 0) {
+            // idesc: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcChunkN >> 3) << 17) |
+                                   ((uint32_t)(kTcTileM >> 4) << 24);
+            uint32_t it = 0, ti = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+                const int ab = ti & 1;
+                mbar_wait(&S.a_full[ab], (ti >> 1) & 1);
+                tc_fence_after();
+                const uint64_t adesc = umma_desc_sw128(smem_u32(S.a[ab]));
+                for (int sweep = 0; sweep < 2; ++sweep)
+                    for (int c = 0; c < nchunks; ++c, ++it) {
+                        const int s = it % kTcWStages, tb = it & 1;
+                        mbar_wait(&S.w_full[s], (it / kTcWStages) & 1);
+                        mbar_wait(&S.t_empty[tb], ((it >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        const uint64_t bdesc = umma_desc_sw128(smem_u32(S.w[s]));
+                        const uint32_t d = tmem_base + (uint32_t)tb * kTcChunkN;
+#pragma unroll
+                        for (int kk = 0; kk < kTcK / 16; ++kk)      // +32 B along K inside the 128-B swizzle atom
+                            umma_bf16(d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, kk > 0);
+                        umma_commit(&S.w_empty[s]);
+                        umma_commit(&S.t_full[tb]);
+                    }
+                umma_commit(&S.a_empty[ab]);
+            }
+        }
+    } else if (warp < 4) {
+        // ===== A loaders: fp32 pillar rows -> bf16, 128-B-swizzled K-major tile ======================================
+        const int lt = tid - 64;       // 0..63
+        uint32_t ti = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+            const int ab = ti & 1;
+            mbar_wait(&S.a_empty[ab], ((ti >> 1) & 1) ^ 1);
+            const int64_t row0 = (int64_t)t * kTcTileM;
+#pragma unroll 4
+            for (int i = lt; i < kTcTileM * 8; i += 64) {
+                const int r = i >> 3, j = i & 7;
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                if (row0 + r < nP) {
+                    const float4 *src = reinterpret_cast<const float4 *>(pillars + (row0 + r) * kTcK + j * 8);
+                    v0 = __ldg(src); v1 = __ldg(src + 1);
+                }
+                __nv_bfloat162 b0 = __floats2bfloat162_rn(v0.x, v0.y), b1 = __floats2bfloat162_rn(v0.z, v0.w);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(v1.x, v1.y), b3 = __floats2bfloat162_rn(v1.z, v1.w);
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t *>(&b0); pk.y = *reinterpret_cast<uint32_t *>(&b1);
+                pk.z = *reinterpret_cast<uint32_t *>(&b2); pk.w = *reinterpret_cast<uint32_t *>(&b3);
+                const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+                *reinterpret_cast<uint4 *>(S.a[ab] + off) = pk;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.a_full[ab]);
+        }
+    } else if (warp < 8) {
+        // ===== filter: one accumulator row per thread ===============================================================
+        const int q = warp & 3;                 // TMEM lane quadrant of this warp
+        const int row = q * 32 + lane;          // row within the tile
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t it = 0, ti = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+            const int cb = ti & 1;
+            // ---- sweep 1: group maxima -> tau ----
+            float top[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) top[i] = -INFINITY;
+            for (int c = 0; c < nchunks; ++c, ++it) {
+                const int tb = it & 1;
+                mbar_wait(&S.t_full[tb], (it >> 1) & 1);
+                tc_fence_after();
+                float g[16];
+                const int col0 = c * kTcChunkN;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    float v[32];
+                    tmem_ld32(lane_addr + (uint32_t)(tb * kTcChunkN + b * 32), v);
+                    if (col0 + b * 32 + 32 > M) {             // warp-uniform: chunk straddles the end of the memory
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = (col0 + b * 32 + i < M) ? v[i] : -INFINITY;
+                    }
+                    if (dbg_logits) {
+                        const int64_t grow = (int64_t)t * kTcTileM + row;
+                        if (grow < nP)
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) dbg_logits[grow * (nchunks * kTcChunkN) + col0 + b * 32 + i] = v[i];
+                    }
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        float m = v[h2 * 16];
+#pragma unroll
+                        for (int i = 1; i < 16; ++i) m = fmaxf(m, v[h2 * 16 + i]);
+                        g[b * 2 + h2] = m;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.t_empty[tb]);
+                // merge the 16 new group maxima into the running top-32 (descending)
+                bitonic_sort_desc<16>(g);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) top[16 + i] = fmaxf(top[16 + i], g[15 - i]);
+                bitonic_merge_desc<32>(top);
+            }
+            const float tau = top[kTcKPrime - 1];
+            // ---- sweep 2: candidates = { j : logit_j >= tau } ----
+            mbar_wait(&S.c_empty[cb], ((ti >> 1) & 1) ^ 1);
+            int cnt = 0;
+            for (int c = 0; c < nchunks; ++c, ++it) {
+                const int tb = it & 1;
+                mbar_wait(&S.t_full[tb], (it >> 1) & 1);
+                tc_fence_after();
+                const int col0 = c * kTcChunkN;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    float v[32];
+                    tmem_ld32(lane_addr + (uint32_t)(tb * kTcChunkN + b * 32), v);
+                    uint32_t neg = 0;                           // bit (31 - i) = sign of (v[i] - tau)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) neg = __funnelshift_l(__float_as_uint(v[i] - tau), neg, 1);
+                    uint32_t m = ~neg;
+                    const int base = col0 + b * 32;
+                    if (base + 32 > M) m = (base >= M) ? 0u : (m & ~(0xFFFFFFFFu >> (M - base)));
+                    while (m) {
+                        const int bit = 31 - __clz((int)m);     // highest set bit = lowest column first
+                        m &= ~(1u << bit);
+                        if (cnt < kTcCandCap) S.cand[cb][cnt][row] = (uint16_t)(base + 31 - bit);
+                        ++cnt;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.t_empty[tb]);
+            }
+            S.cand_cnt[cb][row] = cnt;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.c_full[cb]);          // mbarrier arrive has release semantics (cta scope)
+        }
+    } else {
+        // ===== tail: exact fp32 re-score, top-k, softmax, readout — one warp per row ===================================
+        const int tw = warp - 8;
+        float *scratch = slow_scratch + ((size_t)blockIdx.x * kTcTailWarps + tw) * kTcSlowScratch;
+        uint32_t ti = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+            const int cb = ti & 1;
+            mbar_wait(&S.c_full[cb], (ti >> 1) & 1);
+            for (int r = tw; r < kTcTileM; r += kTcTailWarps) {
+                const int64_t grow = (int64_t)t * kTcTileM + r;
+                if (grow >= nP) break;
+                const int cnt = S.cand_cnt[cb][r];
+                const float *prow = pillars + grow * kTcK;
+                int32_t *idx_row = topk_idx_out ? topk_idx_out + grow * k : nullptr;
+                if (cnt >= k && cnt <= kTcCandCap)
+                    tail_fast_row(prow, W, k, cnt, &S.cand[cb][0][r], readout + grow * kTcK, idx_row, lane);
+                else
+                    tail_slow_row(prow, W, M, k, scratch, readout + grow * kTcK, idx_row, lane);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.c_empty[cb]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// W (M,64) fp32 -> bf16 image of nchunks x [256 rows x 128 B], rows padded with zeros, 128-B swizzled (ready to bulk-copy)
+__global__ void pack_bf16_kernel(const float *__restrict__ W, int M, int Mpad, uint8_t *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // one 16-byte piece (8 bf16) per thread
+    if (i >= Mpad * 8) return;
+    const int row = i >> 3, j = i & 7;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (row < M) ? W[(int64_t)row * kTcK + j * 8 + e] : 0.0f;
+    __nv_bfloat162 b0 = __floats2bfloat162_rn(v[0], v[1]), b1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 b2 = __floats2bfloat162_rn(v[4], v[5]), b3 = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 pk;
+    pk.x = *reinterpret_cast<uint32_t *>(&b0); pk.y = *reinterpret_cast<uint32_t *>(&b1);
+    pk.z = *reinterpret_cast<uint32_t *>(&b2); pk.w = *reinterpret_cast<uint32_t *>(&b3);
+    const int c = row / kTcChunkN, r = row % kTcChunkN;
+    const size_t off = (size_t)c * kTcChunkBytes + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 + (size_t)((j ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4 *>(out + off) = pk;
+}
+
 }  // namespace hvpr
 using namespace hvpr;
 
-int hvpr_mem_attn_tc_init() { return HVPR_OK; }
-size_t hvpr_mem_attn_tc_workspace_bytes(int64_t, int) { return 0; }
+static size_t tc_smem_bytes() { return sizeof(TcSmem) + 1024; }
+
+int hvpr_mem_attn_tc_init() {
+    cudaError_t e = cudaFuncSetAttribute(mem_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes());
+    if (e != cudaSuccess) { set_cuda_error(e); return HVPR_ERR_CUDA; }
+    return HVPR_OK;
+}
+
+size_t hvpr_mem_attn_tc_workspace_bytes(int64_t, int) {
+    return (size_t)kNumSMs * kTcTailWarps * kTcSlowScratch * sizeof(float) + 256;
+}
+
 int hvpr_mem_pack_bf16_impl(const float *W, int M, int C, void *out, cudaStream_t stream) {
-    int Mpad = (M + 255) / 256 * 256;
-    int64_t n = (int64_t)Mpad * C;
-    pack_bf16_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, stream>>>(W, M, C, Mpad, (__nv_bfloat16 *)out);
+    if (C != kTcK) return HVPR_ERR_UNSUPPORTED;
+    const int Mpad = (M + kTcChunkN - 1) / kTcChunkN * kTcChunkN;
+    if (Mpad > kTcMaxChunks * kTcChunkN) return HVPR_ERR_UNSUPPORTED;
+    if ((uintptr_t)out % 16) return HVPR_ERR_ARG;
+    pack_bf16_kernel<<<(Mpad * 8 + 255) / 256, 256, 0, stream>>>(W, M, Mpad, (uint8_t *)out);
     HVPR_CHECK_LAUNCH();
     return HVPR_OK;
 }
-int hvpr_mem_attn_tc(const float *, const int32_t *, int64_t, const float *, const void *, int, int, int, float *,
-                     int32_t *, void *, size_t, cudaStream_t) {
-    return HVPR_ERR_UNSUPPORTED;
+
+static int tc_launch(const float *pillars, const int32_t *n_pillars_dev, int64_t n_rows_max, const float *W,
+                     const void *Wpk, int M, int C, int k, float *readout, int32_t *topk_idx_out, void *workspace,
+                     size_t workspace_bytes, float *dbg_logits, cudaStream_t stream) {
+    if (C != kTcK || k != 20 || M < 16 * kTcKPrime || M > kTcMaxChunks * kTcChunkN) return HVPR_ERR_UNSUPPORTED;
+    if (((uintptr_t)W | (uintptr_t)Wpk | (uintptr_t)pillars | (uintptr_t)readout) % 16) return HVPR_ERR_ARG;
+    if (!workspace || workspace_bytes < hvpr_mem_attn_tc_workspace_bytes(n_rows_max, M)) return HVPR_ERR_WORKSPACE;
+    float *scratch = (float *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    const int nchunks = (M + kTcChunkN - 1) / kTcChunkN;
+    int64_t tiles = (n_rows_max + kTcTileM - 1) / kTcTileM;
+    int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+    if (grid < 1) grid = 1;
+    mem_attn_tc_kernel<<<grid, kTcThreads, tc_smem_bytes(), stream>>>(pillars, n_pillars_dev, n_rows_max, W,
+                                                                      (const uint8_t *)Wpk, M, nchunks, k, readout,
+                                                                      topk_idx_out, scratch, dbg_logits);
+    HVPR_CHECK_LAUNCH();
+    return HVPR_OK;
+}
+
+int hvpr_mem_attn_tc(const float *pillars, const int32_t *n_pillars_dev, int64_t n_rows_max, const float *W,
+                     const void *Wpk, int M, int C, int k, float *readout, int32_t *topk_idx_out, void *workspace,
+                     size_t workspace_bytes, cudaStream_t stream) {
+    return tc_launch(pillars, n_pillars_dev, n_rows_max, W, Wpk, M, C, k, readout, topk_idx_out, workspace,
+                     workspace_bytes, nullptr, stream);
+}
+
+// debug entry (not part of the public header): also dumps the bf16-GEMM logits (rows, nchunks*256) for unit tests
+extern "C" int hvpr_dbg_mem_attn_logits(const float *pillars, int64_t n_rows, const float *W, const void *Wpk, int M,
+                                        float *readout, int32_t *topk_idx_out, void *workspace, size_t workspace_bytes,
+                                        float *dbg_logits, void *stream) {
+    return tc_launch(pillars, nullptr, n_rows, W, Wpk, M, 64, 20, readout, topk_idx_out, workspace, workspace_bytes,
+                     dbg_logits, (cudaStream_t)stream);
 }

@@ -18,7 +18,7 @@ from hvpr_b200.geometry import G1, G2, G3, Geometry
 from oracle import hybrid
 from oracle import voxelize as ov
 
-from helpers import GOLDEN, TOL_BF16, TOL_FP32, load_small, rel_err, sha, to_dev
+from helpers import GOLDEN, TOL_BF16, TOL_FP32, load_small, rel_err, sha, tie_aware_readout_check, to_dev
 
 pytestmark = pytest.mark.gpu
 
@@ -102,7 +102,7 @@ def test_voxelize_ragged_and_empty_frames():
 
 def test_voxelize_all_points_one_pillar_and_tiny_caps():
     g = Geometry(G2.point_cloud_range, G2.voxel_size, 32, 40000)
-    p = synth.make_frame("U", 20000, (10.0, 1.0, -1.0, 10.15, 1.15, 0.0), 5)       # inside one 0.16 m cell
+    p = synth.make_frame("U", 20000, (10.09, 0.97, -1.0, 10.23, 1.11, 0.0), 5)     # inside one 0.16 m cell
     v, c, n = _assert_vox_equal([p], g, "continue")
     assert len(n) == 1 and n[0] == 32 and np.array_equal(v[0], p[:32])              # first 32 in arrival order
     # max_voxels = 1, max_points = 1
@@ -199,7 +199,7 @@ def test_pfn_dense_pillars_and_single_pillar():
     (rf, rs, rm), bd = _pfn_case(g, [dense], 8)
     assert int((torch.from_numpy(ov.voxelize_c(dense, g.range_f32, g.voxel_f32)[2]) == 32).sum()) > 50
     assert rel_err(bd["pillar_features"], rf)[0] <= TOL_FP32
-    one = synth.make_frame("U", 7, (10.0, 1.0, -1.0, 10.15, 1.15, 0.0), 5)
+    one = synth.make_frame("U", 7, (10.09, 0.97, -1.0, 10.23, 1.11, 0.0), 5)
     (rf, rs, rm), bd = _pfn_case(g, [one], 8)
     assert tuple(bd["pillar_features"].shape) == (1, 64)
     assert rel_err(bd["pillar_features"], rf)[0] <= TOL_FP32 and rel_err(bd["pillar_scale_features"], rs)[0] <= TOL_FP32
@@ -229,7 +229,7 @@ def _mem_inputs(P, seed):
     return pil, W
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("bf16_rescore", TOL_BF16)])
+@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("bf16_rescore", TOL_FP32)])
 def test_mem_attn_vs_oracle(precision, tol):
     from hvpr_b200.map_to_bev import MemoryUnit_Agg
     pil, W = _mem_inputs(20011, 3)
@@ -240,20 +240,48 @@ def test_mem_attn_vs_oracle(precision, tol):
     with torch.no_grad():
         m.weight.copy_(W)
     idx = torch.full((pil.shape[0], 20), -1, dtype=torch.int32, device="cuda")
-    try:
-        out = m.run(pil.cuda(), 20, topk_idx_out=idx)
-    except Exception as e:
-        if precision == "bf16_rescore" and "unsupported" in str(e):
-            pytest.xfail("tcgen05 memory-attention kernel not built yet")
-        raise
+    out = m.run(pil.cuda(), 20, topk_idx_out=idx)
     torch.cuda.synchronize()
-    e1, e2 = rel_err(out, ref)
-    assert e1 <= tol and e2 <= tol, (e1, e2)
-    # selected index SETS: fraction of rows that differ from the oracle (ties / last-ulp logits only)
+    # top-k is discontinuous: rows whose 20th/21st logits tie within fp32 noise may legitimately pick the other item
+    err, frac = tie_aware_readout_check(out, ref, pil, W, tol, idx=idx, ref_idx=ridx)
+    assert err <= tol
+    assert rel_err(out, ref)[1] <= 5e-3              # L2 over the whole tensor, tie rows included
     a = torch.sort(idx.cpu().long(), 1)[0]
     b = torch.sort(ridx, 1)[0]
-    frac = float((a != b).any(1).float().mean())
-    assert frac <= (1e-3 if precision == "fp32" else 5e-3), frac
+    assert float((a != b).any(1).float().mean()) <= 2e-3
+    assert bool((a[:, 1:] != a[:, :-1]).all()) and int(a.min()) >= 0 and int(a.max()) < 2000   # 20 distinct valid items
+
+
+def test_mem_attn_tc_gemm_logits():
+    """tcgen05 plumbing in isolation: the TMEM accumulators equal a bf16-input / fp32-accumulate matmul
+    (descriptors, 128-B swizzle, instruction descriptor, tcgen05.ld lane mapping)."""
+    import ctypes
+    from hvpr_b200 import _lib
+    _lib.init_device()
+    L = _lib.lib()
+    pil, W = _mem_inputs(1000, 5)            # 7.8 tiles: exercises the ragged last tile
+    pd, Wd = pil.cuda(), W.cuda()
+    wpk = torch.empty((2048, 64), dtype=torch.bfloat16, device="cuda")
+    _lib.check(L.hvpr_mem_pack_bf16(_lib.ptr(Wd), 2000, 64, _lib.ptr(wpk), _lib.cur_stream()))
+    nb = L.hvpr_mem_attn_workspace_bytes(1000, 2000, 1)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    logits = torch.full((1000, 2048), float("nan"), device="cuda")
+    out = torch.empty((1000, 64), device="cuda")
+    idx = torch.full((1000, 20), -1, dtype=torch.int32, device="cuda")
+    L.hvpr_dbg_mem_attn_logits.restype = ctypes.c_int
+    L.hvpr_dbg_mem_attn_logits.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                           ctypes.c_void_p, ctypes.c_void_p]
+    _lib.check(L.hvpr_dbg_mem_attn_logits(_lib.ptr(pd), 1000, _lib.ptr(Wd), _lib.ptr(wpk), 2000, _lib.ptr(out),
+                                          _lib.ptr(idx), _lib.ptr(ws), nb, _lib.ptr(logits), _lib.cur_stream()))
+    torch.cuda.synchronize()
+    ref = pil.bfloat16().float() @ W.bfloat16().float().t()
+    got = logits.cpu()
+    assert bool(torch.isinf(got[:, 2000:]).all()) and bool((got[:, 2000:] < 0).all())      # padded items masked
+    assert float((got[:, :2000] - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+    with torch.no_grad():
+        r = hybrid.memory_attention(pil, W, 20)
+    tie_aware_readout_check(out, r, pil, W, TOL_FP32, idx=idx)
 
 
 def test_mem_attn_module_forward_signature():
@@ -365,9 +393,15 @@ def test_frontend_planned_graph_vs_oracle(gname, dist):
     assert torch.equal(p.vox.num_points[:P].cpu(), o["voxel_num_points"])
     assert torch.equal(p.vox.voxels[:P].cpu().view(torch.int32), o["voxels"].view(torch.int32))
     for a, k in ((p.pillar_features[:P], "pillar_features"), (p.pillar_scale[:P], "pillar_scale_features"),
-                 (p.readout[:P], "memory_readout"), (p.spatial, "spatial_features"), (p.spatial_scale, "spatial_scale_features")):
-        e1, e2 = rel_err(a, o[k])
+                 (p.spatial_scale, "spatial_scale_features"), (p.spatial[:, :64], "spatial_features")):
+        ref = o[k][:, :64] if k == "spatial_features" else o[k]
+        e1, e2 = rel_err(a, ref)
         assert e1 <= TOL_FP32 and e2 <= TOL_FP32, (k, e1, e2)
+    # memory readout (canvas channels 64..127): tie-aware, see helpers.tie_aware_readout_check
+    err, frac = tie_aware_readout_check(p.readout[:P], o["memory_readout"], o["pillar_features"],
+                                        w["map_to_bev_module.memory.weight"], TOL_FP32)
+    assert err <= TOL_FP32
+    assert rel_err(p.spatial[:, 64:], o["spatial_features"][:, 64:])[1] <= 1e-2
     # size-independent properties: canvas is zero exactly off the occupied cells, and occupied columns equal the rows
     nx, ny, _ = g.grid_size
     sp = p.spatial.view(B, 128, -1)
