@@ -28,7 +28,7 @@ constexpr int kTcMaxChunks = 8;        // M_pad <= 2048
 constexpr int kTcWStages = 4;
 constexpr int kTcChunkBytes = kTcChunkN * kTcK * 2;      // 32 KB
 constexpr int kTcATileBytes = kTcTileM * kTcK * 2;       // 16 KB
-constexpr int kTcCandCap = 32;         // candidates per row handled by the fast tail
+constexpr int kTcCandCap = 64;         // candidate slots per row (<= 32: fast tail, <= 64: two-round tail)
 constexpr int kTcKPrime = 24;          // tau = kTcKPrime-th largest group maximum
 constexpr int kTcThreads = 512;        // warp 0 TMA, warp 1 MMA, warps 2-3 A loaders, 4-7 filter, 8-15 tail
 constexpr int kTcTailWarps = 8;
@@ -57,13 +57,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *b) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *b, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
+template <bool kBackoff = false>
 __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
     const uint32_t a = smem_u32(b);
     uint32_t done = 0;
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(a), "r"(parity) : "memory");
-        if (spin > (1u << 27)) __trap();      // watchdog: a protocol bug must not hang the GPU
+        if (!done) {
+            if (kBackoff) __nanosleep(64);    // waiters off the critical path must not steal issue slots
+            if (spin > (1u << 26)) __trap();  // watchdog: a protocol bug must not hang the GPU
+        }
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -214,90 +218,138 @@ __device__ __noinline__ void tail_slow_row(const float *__restrict__ prow, const
     if (idx_row && lane < k) idx_row[lane] = my_idx;
 }
 
-// fast path: <= 32 candidates.  Lane (hf = lane>>4, h = lane&15) ends up owning candidate 2h + hf.
+// fast path: <= 32 candidates.  Every lane loads 2 channels of EVERY candidate row (one coalesced 256-B request per
+// candidate, a single L2 round trip); the 32 per-candidate partial dots are transpose-reduced across the warp with 31
+// shuffles so that lane c ends up with the exact fp32 logit of candidate c; the rows stay in registers for the readout.
 __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, const float *__restrict__ W, int k, int cnt,
                                               const uint16_t *__restrict__ cand_col /* stride kTcTileM */,
                                               float *__restrict__ out_row, int32_t *__restrict__ idx_row, int lane) {
-    const int hf = lane >> 4, h = lane & 15;
-    const float4 p4 = __ldg(reinterpret_cast<const float4 *>(prow) + h);
-    float s[16];
-    int my_j = 0;
+    const float2 p2 = __ldg(reinterpret_cast<const float2 *>(prow) + lane);
+    const int my_j = (lane < cnt) ? (int)cand_col[lane * kTcTileM] : 0;
+    float2 w2[32];
+    float s[32];
 #pragma unroll
-    for (int it = 0; it < 16; ++it) {
-        s[it] = 0.0f;
-        if (2 * it < cnt) {                                   // warp-uniform
-            const int ci = 2 * it + hf;
-            const int j = (ci < cnt) ? (int)cand_col[ci * kTcTileM] : 0;
-            const float4 w4 = __ldg(reinterpret_cast<const float4 *>(W + (int64_t)j * kTcK) + h);
-            s[it] = fmaf(w4.w, p4.w, fmaf(w4.z, p4.z, fmaf(w4.y, p4.y, w4.x * p4.x)));
-            if (it == h) my_j = j;
+    for (int c = 0; c < 32; ++c) {
+        w2[c] = make_float2(0.f, 0.f);
+        if (c < cnt) {                                        // warp-uniform
+            const int j = __shfl_sync(0xffffffffu, my_j, c);
+            w2[c] = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)j * kTcK) + lane);
         }
     }
-    // multi-value butterfly over the 16 lanes of each half: 15 shuffles, lane h ends with the total of value h
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const bool up = (h & 8) != 0;
-        const float send = up ? s[i] : s[i + 8];
-        const float keep = up ? s[i + 8] : s[i];
-        s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
+    for (int c = 0; c < 32; ++c) s[c] = fmaf(w2[c].y, p2.y, w2[c].x * p2.x);
+    // transpose-reduce: after the stage with xor-distance d, a lane keeps the half of the values selected by its bit d
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const bool up = (h & 4) != 0;
-        const float send = up ? s[i] : s[i + 4];
-        const float keep = up ? s[i + 4] : s[i];
-        s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
+    for (int d = 16; d > 0; d >>= 1) {
+        const bool up = (lane & d) != 0;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const bool up = (h & 2) != 0;
-        const float send = up ? s[i] : s[i + 2];
-        const float keep = up ? s[i + 2] : s[i];
-        s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        for (int i = 0; i < d; ++i) {
+            const float send = up ? s[i] : s[i + d];
+            const float keep = up ? s[i + d] : s[i];
+            s[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+        }
     }
-    {
-        const bool up = (h & 1) != 0;
-        const float send = up ? s[0] : s[1];
-        const float keep = up ? s[1] : s[0];
-        s[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    const float logit = s[0];                                  // exact fp32 logit of candidate `lane`
+    const bool valid = lane < cnt;
+    const uint32_t key = valid ? float_key(logit) : 0u;
+    // rank among the candidates (ties -> lower lane first); keep rank < k
+    int rank = 0;
+#pragma unroll
+    for (int m = 0; m < 32; ++m) {
+        const uint32_t km = __shfl_sync(0xffffffffu, key, m);
+        rank += (km > key || (km == key && m < lane)) ? 1 : 0;
     }
-    const float logit = s[0];                                  // exact fp32 logit of candidate 2h + hf
-    bool valid = (2 * h + hf) < cnt;
-    uint32_t key = valid ? float_key(logit) : 0xFFFFFFFFu;
-    // drop the (cnt - k) smallest
-    for (int e = cnt; e > k; --e) {
-        const uint32_t alive = __ballot_sync(0xffffffffu, valid);
-        const uint32_t mn = __reduce_min_sync(0xffffffffu, key);
-        const uint32_t who = __ballot_sync(0xffffffffu, valid && key == mn);
-        const int victim = __ffs(who) - 1;
-        (void)alive;
-        if (lane == victim) { valid = false; key = 0xFFFFFFFFu; }
-    }
-    const uint32_t kept = __ballot_sync(0xffffffffu, valid);
-    const uint32_t kmax = __reduce_max_sync(0xffffffffu, valid ? key : 0u);
+    const bool keep = valid && rank < k;
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
     const float mx = key_float(kmax);
-    const float ex = valid ? expf(logit - mx) : 0.0f;
+    const float ex = keep ? expf(logit - mx) : 0.0f;
     float sum = ex;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float a = ex / sum;
-    // readout: gather the kept items' rows, 2 channels per lane
-    float2 w2[20];
-    float ak[20];
-    const int nk = __popc(kept);
-#pragma unroll
-    for (int q = 0; q < 20; ++q) {
-        const int src = (q < nk) ? (int)__fns(kept, 0, q + 1) : 0;
-        const int jj = __shfl_sync(0xffffffffu, my_j, src);
-        ak[q] = (q < nk) ? __shfl_sync(0xffffffffu, a, src) : 0.0f;
-        w2[q] = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)jj * kTcK) + lane);
-    }
     float o0 = 0.0f, o1 = 0.0f;
 #pragma unroll
-    for (int q = 0; q < 20; ++q) { o0 = fmaf(ak[q], w2[q].x, o0); o1 = fmaf(ak[q], w2[q].y, o1); }
+    for (int c = 0; c < 32; ++c) {
+        const float ac = __shfl_sync(0xffffffffu, a, c);       // 0 for dropped / absent candidates
+        o0 = fmaf(ac, w2[c].x, o0); o1 = fmaf(ac, w2[c].y, o1);
+    }
     reinterpret_cast<float2 *>(out_row)[lane] = make_float2(o0, o1);
-    if (idx_row && valid) idx_row[__popc(kept & ((1u << lane) - 1u))] = my_j;
-    (void)k;
+    if (idx_row && keep) idx_row[rank] = my_j;
+}
+
+// exact fp32 logits of up to 32 candidates: lane c <- logit of candidate c (0 <= c < n), rows are not retained
+__device__ __forceinline__ float cand_logits32(const float2 p2, const float *__restrict__ W, int my_j, int n, int lane) {
+    float s[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        s[c] = 0.0f;
+        if (c < n) {                                          // warp-uniform
+            const int j = __shfl_sync(0xffffffffu, my_j, c);
+            const float2 w = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)j * kTcK) + lane);
+            s[c] = fmaf(w.y, p2.y, w.x * p2.x);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const bool up = (lane & d) != 0;
+#pragma unroll
+        for (int i = 0; i < d; ++i) {
+            const float send = up ? s[i] : s[i + d];
+            const float keep = up ? s[i + d] : s[i];
+            s[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+        }
+    }
+    return s[0];
+}
+
+// 33..64 candidates (about 1 % of rows at kTcKPrime = 24): two rounds of 32, then the kept rows are gathered again
+__device__ __noinline__ void tail_medium_row(const float *__restrict__ prow, const float *__restrict__ W, int k, int cnt,
+                                             const uint16_t *__restrict__ cand_col, float *__restrict__ out_row,
+                                             int32_t *__restrict__ idx_row, int lane) {
+    const float2 p2 = __ldg(reinterpret_cast<const float2 *>(prow) + lane);
+    const int j0 = (int)cand_col[lane * kTcTileM];
+    const int n1 = cnt - 32;
+    const int j1 = (lane < n1) ? (int)cand_col[(32 + lane) * kTcTileM] : 0;
+    const float l0 = cand_logits32(p2, W, j0, 32, lane);
+    const float l1 = cand_logits32(p2, W, j1, n1, lane);
+    const uint32_t k0 = float_key(l0), k1 = (lane < n1) ? float_key(l1) : 0u;
+    int r0 = 0, r1 = 0;                                        // ranks among all candidates; ties -> lower position first
+    for (int m = 0; m < 32; ++m) {
+        const uint32_t a0 = __shfl_sync(0xffffffffu, k0, m), a1 = __shfl_sync(0xffffffffu, k1, m);
+        r0 += (a0 > k0 || (a0 == k0 && m < lane)) ? 1 : 0;
+        r0 += (a1 > k0) ? 1 : 0;
+        r1 += (a0 >= k1) ? 1 : 0;
+        r1 += (a1 > k1 || (a1 == k1 && m < lane)) ? 1 : 0;
+    }
+    const bool keep0 = r0 < k, keep1 = (lane < n1) && r1 < k;
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, k0 > k1 ? k0 : k1);
+    const float mx = key_float(kmax);
+    const float e0 = keep0 ? expf(l0 - mx) : 0.0f, e1 = keep1 ? expf(l1 - mx) : 0.0f;
+    float sum = e0 + e1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float a0 = e0 / sum, a1 = e1 / sum;
+    float o0 = 0.0f, o1 = 0.0f;
+    uint32_t m0 = __ballot_sync(0xffffffffu, keep0), m1 = __ballot_sync(0xffffffffu, keep1);
+    while (m0) {
+        const int src = __ffs(m0) - 1; m0 &= m0 - 1;
+        const int jj = __shfl_sync(0xffffffffu, j0, src);
+        const float aa = __shfl_sync(0xffffffffu, a0, src);
+        const float2 w = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)jj * kTcK) + lane);
+        o0 = fmaf(aa, w.x, o0); o1 = fmaf(aa, w.y, o1);
+    }
+    while (m1) {
+        const int src = __ffs(m1) - 1; m1 &= m1 - 1;
+        const int jj = __shfl_sync(0xffffffffu, j1, src);
+        const float aa = __shfl_sync(0xffffffffu, a1, src);
+        const float2 w = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)jj * kTcK) + lane);
+        o0 = fmaf(aa, w.x, o0); o1 = fmaf(aa, w.y, o1);
+    }
+    reinterpret_cast<float2 *>(out_row)[lane] = make_float2(o0, o1);
+    if (idx_row) {
+        if (keep0) idx_row[r0] = j0;
+        if (keep1) idx_row[r1] = j1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
@@ -342,7 +394,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
                 for (int sweep = 0; sweep < 2; ++sweep)
                     for (int c = 0; c < nchunks; ++c, ++it) {
                         const int s = it % kTcWStages;
-                        mbar_wait(&S.w_empty[s], ((it / kTcWStages) & 1) ^ 1);
+                        mbar_wait<true>(&S.w_empty[s], ((it / kTcWStages) & 1) ^ 1);
                         mbar_arrive_expect_tx(&S.w_full[s], kTcChunkBytes);
                         bulk_g2s(S.w[s], Wpk + (size_t)c * kTcChunkBytes, kTcChunkBytes, &S.w_full[s]);
                     }
@@ -382,7 +434,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
         uint32_t ti = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
             const int ab = ti & 1;
-            mbar_wait(&S.a_empty[ab], ((ti >> 1) & 1) ^ 1);
+            mbar_wait<true>(&S.a_empty[ab], ((ti >> 1) & 1) ^ 1);
             const int64_t row0 = (int64_t)t * kTcTileM;
 #pragma unroll 4
             for (int i = lt; i < kTcTileM * 8; i += 64) {
@@ -455,7 +507,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
             }
             const float tau = top[kTcKPrime - 1];
             // ---- sweep 2: candidates = { j : logit_j >= tau } ----
-            mbar_wait(&S.c_empty[cb], ((ti >> 1) & 1) ^ 1);
+            mbar_wait<true>(&S.c_empty[cb], ((ti >> 1) & 1) ^ 1);
             int cnt = 0;
             for (int c = 0; c < nchunks; ++c, ++it) {
                 const int tb = it & 1;
@@ -494,15 +546,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
         uint32_t ti = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
             const int cb = ti & 1;
-            mbar_wait(&S.c_full[cb], (ti >> 1) & 1);
+            mbar_wait<true>(&S.c_full[cb], (ti >> 1) & 1);
             for (int r = tw; r < kTcTileM; r += kTcTailWarps) {
                 const int64_t grow = (int64_t)t * kTcTileM + r;
                 if (grow >= nP) break;
                 const int cnt = S.cand_cnt[cb][r];
                 const float *prow = pillars + grow * kTcK;
                 int32_t *idx_row = topk_idx_out ? topk_idx_out + grow * k : nullptr;
-                if (cnt >= k && cnt <= kTcCandCap)
+                if (cnt >= k && cnt <= 32)
                     tail_fast_row(prow, W, k, cnt, &S.cand[cb][0][r], readout + grow * kTcK, idx_row, lane);
+                else if (cnt > 32 && cnt <= kTcCandCap)
+                    tail_medium_row(prow, W, k, cnt, &S.cand[cb][0][r], readout + grow * kTcK, idx_row, lane);
                 else
                     tail_slow_row(prow, W, M, k, scratch, readout + grow * kTcK, idx_row, lane);
             }
