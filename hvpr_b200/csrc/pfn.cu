@@ -13,7 +13,8 @@
 namespace hvpr {
 
 constexpr int kPfnThreads = 128;
-constexpr int kPfnG = 32;   // pillars per block
+constexpr int kPfnG = 32;        // pillars per block
+constexpr int kPfnStride = 84;   // floats per staged point row: 64 layer-1 pre-activations + 16 layer-0 activations (+pad)
 
 struct PfnParams {
     HvprPfnWeights w;
@@ -28,10 +29,9 @@ struct PfnSmem {
     float ctr[kPfnG][4];
     float part[4][kPfnG][3];
     float h[kPfnG][17];
-    float xmax[kPfnG][17];
-    float c1[kPfnG][65];
-    float ymax[kPfnG][64];
-    float buf[kPfnThreads * 65];
+    alignas(16) float xmax[kPfnG][20];   // running max of the layer-0 activations (16 used; float4 rows)
+    alignas(16) float m1[kPfnG][68];     // running max of W1a.x (64 used; padded: lane = pillar access is conflict-free)
+    alignas(16) float buf[kPfnThreads * kPfnStride];
 };
 
 __device__ __forceinline__ int find_pillar(const int *poff, int q) {
@@ -42,6 +42,63 @@ __device__ __forceinline__ int find_pillar(const int *poff, int q) {
     return lo;
 }
 
+
+// Per-pillar phases run with lane = pillar and the channel range split over the 4 warps.  The warp index is folded
+// into a template parameter so every weight index is a compile-time constant (uniform-register operands, no LDC).
+template <int Q>
+__device__ __forceinline__ void pfn_seed(const PfnParams &P, PfnSmem &S, int pl, bool padded) {
+#pragma unroll
+    for (int cc = 0; cc < 16; ++cc) S.m1[pl][Q * 16 + cc] = padded ? P.v1[Q * 16 + cc] : -INFINITY;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) S.xmax[pl][Q * 4 + kk] = padded ? P.rb0[Q * 4 + kk] : 0.0f;
+}
+template <int Q>
+__device__ __forceinline__ void pfn_scale_hidden(const PfnParams &P, PfnSmem &S, int pl, const float (&in)[5]) {
+#pragma unroll
+    for (int uu = 0; uu < 4; ++uu) {
+        float a = P.w.bs0[Q * 4 + uu];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) a = fmaf(P.w.ws0[Q * 4 + uu][i], in[i], a);
+        S.h[pl][Q * 4 + uu] = fmaxf(a, 0.0f);
+    }
+}
+template <int Q>
+__device__ __forceinline__ void pfn_scale_out(const PfnParams &P, PfnSmem &S, int pl, float (&o)[8]) {
+    float hh[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) hh[u] = S.h[pl][u];
+#pragma unroll
+    for (int oo = 0; oo < 8; ++oo) {
+        float a = P.w.bs1[Q * 8 + oo];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) a = fmaf(P.w.ws1[Q * 8 + oo][u], hh[u], a);
+        o[oo] = fmaxf(a, 0.0f);
+    }
+}
+template <int Q>
+__device__ __forceinline__ void pfn_finish(const PfnParams &P, PfnSmem &S, int pl, float (&o)[16]) {
+    float xm[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) xm[k] = S.xmax[pl][k];
+#pragma unroll
+    for (int cc = 0; cc < 16; ++cc) {
+        float a = P.w.b1[Q * 16 + cc];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a = fmaf(P.w.w1b[Q * 16 + cc][k], xm[k], a);
+        o[cc] = fmaxf(S.m1[pl][Q * 16 + cc] + a, 0.0f);
+    }
+}
+#define PFN_DISPATCH_Q(q, CALL)            \
+    switch (q) {                           \
+        case 0: { constexpr int Q = 0; CALL; } break; \
+        case 1: { constexpr int Q = 1; CALL; } break; \
+        case 2: { constexpr int Q = 2; CALL; } break; \
+        default: { constexpr int Q = 3; CALL; } break; \
+    }
+
+// max over a pillar's points commutes with the per-pillar constant and the ReLU:
+//     max_p ReLU(W1a.x_p + c) = ReLU(max_p(W1a.x_p) + c),      c = b1 + W1b.x_max
+// so ONE pass over the real points produces both x_max (layer 0) and max_p(W1a.x_p); c is applied per pillar afterwards.
 template <bool kScale>
 __global__ void __launch_bounds__(kPfnThreads) pfn_kernel(const __grid_constant__ PfnParams P,
                                                           const float *__restrict__ voxels,
@@ -99,6 +156,9 @@ __global__ void __launch_bounds__(kPfnThreads) pfn_kernel(const __grid_constant_
         S.part[q4][pl][0] = sx; S.part[q4][pl][1] = sy; S.part[q4][pl][2] = sz;
         if (mask_out && p < nP)
             for (int j = q4; j < T; j += 4) mask_out[p * T + j] = (j < n) ? 1.0f : 0.0f;
+        // seeds of the running maxima: the virtual zero-padded row when the pillar has padding, else the identity
+        const bool padded = n < T;
+        PFN_DISPATCH_Q(q4, pfn_seed<Q>(P, S, pl, padded));
     }
     __syncthreads();
     if (t < kPfnG) {
@@ -108,8 +168,6 @@ __global__ void __launch_bounds__(kPfnThreads) pfn_kernel(const __grid_constant_
             float s = ((S.part[0][t][a] + S.part[1][t][a]) + S.part[2][t][a]) + S.part[3][t][a];
             S.mean[t][a] = __fdiv_rn(s, nf);                    // pillar_vfe.py:187 (no guard, as the reference)
         }
-#pragma unroll
-        for (int k = 0; k < 16; ++k) S.xmax[t][k] = (S.n[t] < T) ? P.rb0[k] : 0.0f;
     }
     __syncthreads();
 
@@ -118,24 +176,10 @@ __global__ void __launch_bounds__(kPfnThreads) pfn_kernel(const __grid_constant_
         const int pl = lane;
         const float mx = S.mean[pl][0], my = S.mean[pl][1], mz = S.mean[pl][2];
         const float in[5] = {(float)S.n[pl], sqrtf(mx * mx + my * my + mz * mz), mx, my, mz};
-#pragma unroll
-        for (int uu = 0; uu < 4; ++uu) {
-            const int u = q4 * 4 + uu;
-            float a = P.w.bs0[u];
-#pragma unroll
-            for (int i = 0; i < 5; ++i) a = fmaf(P.w.ws0[u][i], in[i], a);
-            S.h[pl][u] = fmaxf(a, 0.0f);
-        }
+        PFN_DISPATCH_Q(q4, pfn_scale_hidden<Q>(P, S, pl, in));
         __syncthreads();
         float o[8];
-#pragma unroll
-        for (int oo = 0; oo < 8; ++oo) {
-            const int c = q4 * 8 + oo;
-            float a = P.w.bs1[c];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) a = fmaf(P.w.ws1[c][u], S.h[pl][u], a);
-            o[oo] = fmaxf(a, 0.0f);
-        }
+        PFN_DISPATCH_Q(q4, pfn_scale_out<Q>(P, S, pl, o));
         const int64_t p = g0 + pl;
         if (p < nP) {
             float4 *dst = reinterpret_cast<float4 *>(scale_out + p * 32 + q4 * 8);
@@ -144,96 +188,76 @@ __global__ void __launch_bounds__(kPfnThreads) pfn_kernel(const __grid_constant_
         }
     }
 
-    // ---- pass A: layer 0 on real points -> per-pillar max of the 16 activations ------------------------------
-    auto layer0 = [&](int qpt, int &pl_out, float (&x0)[16]) {
-        const int pl = find_pillar(S.poff, qpt);
-        pl_out = pl;
-        const int j = qpt - S.poff[pl];
-        const float4 v = __ldg(vox4 + (g0 + pl) * T + j);
-        float f[10];
-        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
-        f[4] = v.x - S.mean[pl][0]; f[5] = v.y - S.mean[pl][1]; f[6] = v.z - S.mean[pl][2];
-        f[7] = v.x - S.ctr[pl][0];  f[8] = v.y - S.ctr[pl][1];  f[9] = v.z - S.ctr[pl][2];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            float a = P.w.b0[k];
-#pragma unroll
-            for (int i = 0; i < 10; ++i) a = fmaf(P.w.w0[k][i], f[i], a);
-            x0[k] = fmaxf(a, 0.0f);
-        }
-    };
-
+    // ---- single pass over the real points: layer 0 (10->16, ReLU) and W1a.x (16->64), staged for the pillar max -----
     for (int c0 = 0; c0 < total; c0 += kPfnThreads) {
         const int qpt = c0 + t;
         if (qpt < total) {
-            int pl; float x0[16];
-            layer0(qpt, pl, x0);
+            const int pl = find_pillar(S.poff, qpt);
+            const int j = qpt - S.poff[pl];
+            const float4 v = __ldg(vox4 + (g0 + pl) * T + j);
+            float f[10];
+            f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+            f[4] = v.x - S.mean[pl][0]; f[5] = v.y - S.mean[pl][1]; f[6] = v.z - S.mean[pl][2];
+            f[7] = v.x - S.ctr[pl][0];  f[8] = v.y - S.ctr[pl][1];  f[9] = v.z - S.ctr[pl][2];
+            float x0[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) S.buf[t * 17 + k] = x0[k];
+            for (int k = 0; k < 16; ++k) {
+                float a = P.w.b0[k];
+#pragma unroll
+                for (int i = 0; i < 10; ++i) a = fmaf(P.w.w0[k][i], f[i], a);
+                x0[k] = fmaxf(a, 0.0f);
+            }
+            float4 *row = reinterpret_cast<float4 *>(S.buf + t * kPfnStride);
+#pragma unroll
+            for (int c4 = 0; c4 < 16; ++c4) {
+                float y[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float a = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) a = fmaf(P.w.w1a[c4 * 4 + e][k], x0[k], a);
+                    y[e] = a;
+                }
+                row[c4] = make_float4(y[0], y[1], y[2], y[3]);
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) row[16 + k4] = make_float4(x0[4 * k4], x0[4 * k4 + 1], x0[4 * k4 + 2], x0[4 * k4 + 3]);
         }
         __syncthreads();
         const int c1e = min(c0 + kPfnThreads, total);
         const int p_lo = find_pillar(S.poff, c0), p_hi = find_pillar(S.poff, c1e - 1);
-        for (int it = t; it < (p_hi - p_lo + 1) * 16; it += kPfnThreads) {
-            const int pl = p_lo + (it >> 4), k = it & 15;
-            const int a = max(S.poff[pl], c0), b = min(S.poff[pl + 1], c1e);
-            float m = S.xmax[pl][k];
-            for (int j = a; j < b; ++j) m = fmaxf(m, S.buf[(j - c0) * 17 + k]);
-            S.xmax[pl][k] = m;
-        }
-        __syncthreads();
-    }
-
-    // ---- per-pillar part of layer 1: c1 = b1 + W1b . x_max ; seed the running max with the virtual padded row --
-    {
-        const int pl = lane;
-        float xm[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) xm[k] = S.xmax[pl][k];
-        const bool padded = S.n[pl] < T;
-#pragma unroll
-        for (int cc = 0; cc < 16; ++cc) {
-            const int c = q4 * 16 + cc;
-            float a = P.w.b1[c];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) a = fmaf(P.w.w1b[c][k], xm[k], a);
-            S.c1[pl][c] = a;
-            S.ymax[pl][c] = padded ? fmaxf(a + P.v1[c], 0.0f) : 0.0f;
-        }
-    }
-    __syncthreads();
-
-    // ---- pass B: layer 1 on real points -> per-pillar max of the 64 activations ------------------------------
-    for (int c0 = 0; c0 < total; c0 += kPfnThreads) {
-        const int qpt = c0 + t;
-        if (qpt < total) {
-            int pl; float x0[16];
-            layer0(qpt, pl, x0);
-#pragma unroll
-            for (int c = 0; c < 64; ++c) {
-                float a = S.c1[pl][c];
-#pragma unroll
-                for (int k = 0; k < 16; ++k) a = fmaf(P.w.w1a[c][k], x0[k], a);
-                S.buf[t * 65 + c] = fmaxf(a, 0.0f);
+        // pillar maxima: 20 float4 columns (16 x layer-1 pre-activations, 4 x layer-0 activations) x 6 pillar slices
+        if (t < 120) {
+            const int col4 = t % 20, slice = t / 20;
+            const int np = p_hi - p_lo + 1, pps = (np + 5) / 6;
+            const int pa = p_lo + slice * pps, pb = min(pa + pps, p_hi + 1);
+            for (int pl = pa; pl < pb; ++pl) {
+                const int a = max(S.poff[pl], c0), b = min(S.poff[pl + 1], c1e);
+                float4 *dst = (col4 < 16) ? reinterpret_cast<float4 *>(&S.m1[pl][col4 * 4])
+                                          : reinterpret_cast<float4 *>(&S.xmax[pl][(col4 - 16) * 4]);
+                float4 m = *dst;
+                const float4 *src = reinterpret_cast<const float4 *>(S.buf + (a - c0) * kPfnStride) + col4;
+                for (int j = a; j < b; ++j, src += kPfnStride / 4) {
+                    const float4 v = *src;
+                    m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+                }
+                *dst = m;
             }
         }
         __syncthreads();
-        const int c1e = min(c0 + kPfnThreads, total);
-        const int p_lo = find_pillar(S.poff, c0), p_hi = find_pillar(S.poff, c1e - 1);
-        for (int it = t; it < (p_hi - p_lo + 1) * 64; it += kPfnThreads) {
-            const int pl = p_lo + (it >> 6), c = it & 63;
-            const int a = max(S.poff[pl], c0), b = min(S.poff[pl + 1], c1e);
-            float m = S.ymax[pl][c];
-            for (int j = a; j < b; ++j) m = fmaxf(m, S.buf[(j - c0) * 65 + c]);
-            S.ymax[pl][c] = m;
-        }
-        __syncthreads();
     }
 
-    // ---- write pillar_features (G x 64, coalesced) -----------------------------------------------------------
-    for (int it = t; it < kPfnG * 64; it += kPfnThreads) {
-        const int pl = it >> 6, c = it & 63;
-        if (g0 + pl < nP) feats[(g0 + pl) * 64 + c] = S.ymax[pl][c];
+    // ---- per pillar: c = b1 + W1b.x_max ; pillar_features = ReLU(max + c) -------------------------------------------
+    {
+        const int pl = lane;
+        float o[16];
+        PFN_DISPATCH_Q(q4, pfn_finish<Q>(P, S, pl, o));
+        const int64_t p = g0 + pl;
+        if (p < nP) {
+            float4 *dst = reinterpret_cast<float4 *>(feats + p * 64 + q4 * 16);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) dst[c4] = make_float4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
+        }
     }
 }
 
@@ -259,7 +283,7 @@ extern "C" int hvpr_pfn(const float *voxels, const int32_t *num_points, const in
     if (n_rows_max == 0) return HVPR_OK;
     if (!voxels || !num_points || !coords || !pillar_features) return HVPR_ERR_ARG;
     if (max_points < 1 || max_points > 32) return HVPR_ERR_UNSUPPORTED;
-    if (((uintptr_t)voxels | (uintptr_t)coords | (uintptr_t)scale_out) % 16) return HVPR_ERR_ARG;
+    if (((uintptr_t)voxels | (uintptr_t)coords | (uintptr_t)scale_out | (uintptr_t)pillar_features) % 16) return HVPR_ERR_ARG;
     PfnParams P;
     P.w = *weights_host;
     for (int k = 0; k < 16; ++k) P.rb0[k] = P.w.b0[k] > 0.f ? P.w.b0[k] : 0.f;
