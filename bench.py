@@ -325,7 +325,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mem-precision", default=os.environ.get("HVPR_MEM_PRECISION", "fp32"), choices=["fp32", "bf16_rescore"])
+    ap.add_argument("--mem-precision", default=os.environ.get("HVPR_MEM_PRECISION", "bf16_rescore"), choices=["fp32", "bf16_rescore"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -21,6 +21,29 @@
 
 namespace hvpr {
 
+// Optional cycle accounting (compile with -DHVPR_TC_PROFILE): per CTA, per role, cycles spent at each wait site / work
+// section, dumped to `dbg_logits` reinterpreted as long long [grid][16].  Never enabled in the shipped library.
+#ifdef HVPR_TC_PROFILE
+#define TCP_DECL long long tcp_t0 = 0, tcp_acc[4] = {0, 0, 0, 0}
+#define TCP_ROW_ARG , long long *tcp_row
+#define TCP_ROW_PASS , tcp_row_acc
+#define TCP_ROW_T(i) do { long long n_ = clock64(); tcp_row[i] += n_ - tcp_rt; tcp_rt = n_; } while (0)
+#define TCP_ROW_START long long tcp_rt = clock64()
+#define TCP_BEGIN() tcp_t0 = clock64()
+#define TCP_END(i) tcp_acc[i] += clock64() - tcp_t0
+#define TCP_DUMP(base) do { if (lane == 0 && dbg_logits) { long long *o_ = reinterpret_cast<long long *>(dbg_logits) + (size_t)blockIdx.x * 16 + (base); \
+    for (int i_ = 0; i_ < 4; ++i_) atomicAdd(reinterpret_cast<unsigned long long *>(o_ + i_), (unsigned long long)tcp_acc[i_]); } } while (0)
+#else
+#define TCP_DECL
+#define TCP_ROW_ARG
+#define TCP_ROW_PASS
+#define TCP_ROW_T(i)
+#define TCP_ROW_START
+#define TCP_BEGIN()
+#define TCP_END(i)
+#define TCP_DUMP(base)
+#endif
+
 constexpr int kTcTileM = 128;          // pillar rows per tile (UMMA M)
 constexpr int kTcChunkN = 256;         // memory items per MMA (UMMA N)
 constexpr int kTcK = 64;               // feature dim
@@ -30,8 +53,8 @@ constexpr int kTcChunkBytes = kTcChunkN * kTcK * 2;      // 32 KB
 constexpr int kTcATileBytes = kTcTileM * kTcK * 2;       // 16 KB
 constexpr int kTcCandCap = 64;         // candidate slots per row (<= 32: fast tail, <= 64: two-round tail)
 constexpr int kTcKPrime = 24;          // tau = kTcKPrime-th largest group maximum
-constexpr int kTcThreads = 512;        // warp 0 TMA, warp 1 MMA, warps 2-3 A loaders, 4-7 filter, 8-15 tail
-constexpr int kTcTailWarps = 8;
+constexpr int kTcThreads = 512;        // warp 0 TMA, warp 1 MMA, warps 4-7 filter, warps 2-3 + 8-15 tail (+ A-tile loads)
+constexpr int kTcTailWarps = 10;
 constexpr int kTcSlowScratch = 2048;   // floats per tail warp (global workspace) for the overflow path
 
 struct TcSmem {
@@ -39,6 +62,7 @@ struct TcSmem {
     uint8_t a[2][kTcATileBytes];
     uint16_t cand[2][kTcCandCap][kTcTileM];
     int32_t cand_cnt[2][kTcTileM];
+    float gm[16][kTcTileM];                   // group maxima of the current chunk, one column per filter thread
     uint64_t w_full[kTcWStages], w_empty[kTcWStages];
     uint64_t a_full[2], a_empty[2];
     uint64_t t_full[2], t_empty[2];
@@ -60,14 +84,12 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *b, uint32_t byte
 template <bool kBackoff = false>
 __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
     const uint32_t a = smem_u32(b);
+    const uint32_t hint_ns = kBackoff ? 20000u : 2000u;       // the thread sleeps in hardware until the phase completes
     uint32_t done = 0;
     for (uint32_t spin = 0; !done; ++spin) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
-        if (!done) {
-            if (kBackoff) __nanosleep(64);    // waiters off the critical path must not steal issue slots
-            if (spin > (1u << 26)) __trap();  // watchdog: a protocol bug must not hang the GPU
-        }
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity), "r"(hint_ns) : "memory");
+        if (!done && spin > (1u << 24)) __trap();             // watchdog: a protocol bug must not hang the GPU
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -97,8 +119,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
     return d;
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// tcgen05.ld is asynchronous: tmem_ld32_issue starts it, tmem_ld32_wait makes the 32 registers valid.  The empty asm
+// with "+r" operands ties the registers to the wait so the compiler cannot hoist their uses above it.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                  "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -107,9 +130,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
                    "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                      "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                      "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                      "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
 }
 
 // ---------------------------------------------------------------------------------------------- register sorting nets
@@ -223,21 +250,22 @@ __device__ __noinline__ void tail_slow_row(const float *__restrict__ prow, const
 // shuffles so that lane c ends up with the exact fp32 logit of candidate c; the rows stay in registers for the readout.
 __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, const float *__restrict__ W, int k, int cnt,
                                               const uint16_t *__restrict__ cand_col /* stride kTcTileM */,
-                                              float *__restrict__ out_row, int32_t *__restrict__ idx_row, int lane) {
+                                              float *__restrict__ out_row, int32_t *__restrict__ idx_row, int lane TCP_ROW_ARG) {
+    TCP_ROW_START;
     const float2 p2 = __ldg(reinterpret_cast<const float2 *>(prow) + lane);
-    const int my_j = (lane < cnt) ? (int)cand_col[lane * kTcTileM] : 0;
+    // slots past cnt replay candidate 0 (an L1 hit) so that all 32 gathers are unconditional and issue back to back:
+    // any branch here makes the compiler merge registers per group and serialises the L2 round trips
+    const int my_j = (int)cand_col[((lane < cnt) ? lane : 0) * kTcTileM];
     float2 w2[32];
-    float s[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
-        w2[c] = make_float2(0.f, 0.f);
-        if (c < cnt) {                                        // warp-uniform
-            const int j = __shfl_sync(0xffffffffu, my_j, c);
-            w2[c] = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)j * kTcK) + lane);
-        }
+        const int j = __shfl_sync(0xffffffffu, my_j, c);
+        w2[c] = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)j * kTcK) + lane);
     }
+    float s[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) s[c] = fmaf(w2[c].y, p2.y, w2[c].x * p2.x);
+    TCP_ROW_T(0);
     // transpose-reduce: after the stage with xor-distance d, a lane keeps the half of the values selected by its bit d
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -250,23 +278,24 @@ __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, co
         }
     }
     const float logit = s[0];                                  // exact fp32 logit of candidate `lane`
-    const bool valid = lane < cnt;
-    const uint32_t key = valid ? float_key(logit) : 0u;
-    // rank among the candidates (ties -> lower lane first); keep rank < k
+    TCP_ROW_T(1);
+    const uint32_t key = (lane < cnt) ? float_key(logit) : 0u;
+    // rank among the candidates (32 independent shuffles; ties -> lower lane first); keep rank < k
     int rank = 0;
 #pragma unroll
     for (int m = 0; m < 32; ++m) {
         const uint32_t km = __shfl_sync(0xffffffffu, key, m);
         rank += (km > key || (km == key && m < lane)) ? 1 : 0;
     }
-    const bool keep = valid && rank < k;
+    const bool valid = (lane < cnt) && rank < k;
     const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
     const float mx = key_float(kmax);
-    const float ex = keep ? expf(logit - mx) : 0.0f;
+    const float ex = valid ? expf(logit - mx) : 0.0f;
     float sum = ex;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float a = ex / sum;
+    TCP_ROW_T(2);
     float o0 = 0.0f, o1 = 0.0f;
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
@@ -274,20 +303,19 @@ __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, co
         o0 = fmaf(ac, w2[c].x, o0); o1 = fmaf(ac, w2[c].y, o1);
     }
     reinterpret_cast<float2 *>(out_row)[lane] = make_float2(o0, o1);
-    if (idx_row && keep) idx_row[rank] = my_j;
+    TCP_ROW_T(3);
+    if (idx_row && valid) idx_row[rank] = my_j;
 }
 
 // exact fp32 logits of up to 32 candidates: lane c <- logit of candidate c (0 <= c < n), rows are not retained
 __device__ __forceinline__ float cand_logits32(const float2 p2, const float *__restrict__ W, int my_j, int n, int lane) {
     float s[32];
+    (void)n;                                                  // slots past n hold a valid (replayed) row index
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
-        s[c] = 0.0f;
-        if (c < n) {                                          // warp-uniform
-            const int j = __shfl_sync(0xffffffffu, my_j, c);
-            const float2 w = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)j * kTcK) + lane);
-            s[c] = fmaf(w.y, p2.y, w.x * p2.x);
-        }
+        const int j = __shfl_sync(0xffffffffu, my_j, c);
+        const float2 w = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)j * kTcK) + lane);
+        s[c] = fmaf(w.y, p2.y, w.x * p2.x);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -371,7 +399,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
     if (tid == 0) {
         for (int s = 0; s < kTcWStages; ++s) { mbar_init(&S.w_full[s], 1); mbar_init(&S.w_empty[s], 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&S.a_full[b], 2); mbar_init(&S.a_empty[b], 1);
+            mbar_init(&S.a_full[b], kTcTailWarps); mbar_init(&S.a_empty[b], 1);
             mbar_init(&S.t_full[b], 1); mbar_init(&S.t_empty[b], 4);
             mbar_init(&S.c_full[b], 4); mbar_init(&S.c_empty[b], kTcTailWarps);
         }
@@ -406,16 +434,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcChunkN >> 3) << 17) |
                                    ((uint32_t)(kTcTileM >> 4) << 24);
             uint32_t it = 0, ti = 0;
+            TCP_DECL;
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
                 const int ab = ti & 1;
+                TCP_BEGIN();
                 mbar_wait(&S.a_full[ab], (ti >> 1) & 1);
+                TCP_END(0);
                 tc_fence_after();
                 const uint64_t adesc = umma_desc_sw128(smem_u32(S.a[ab]));
                 for (int sweep = 0; sweep < 2; ++sweep)
                     for (int c = 0; c < nchunks; ++c, ++it) {
                         const int s = it % kTcWStages, tb = it & 1;
+                        TCP_BEGIN();
                         mbar_wait(&S.w_full[s], (it / kTcWStages) & 1);
+                        TCP_END(1);
+                        TCP_BEGIN();
                         mbar_wait(&S.t_empty[tb], ((it >> 1) & 1) ^ 1);
+                        TCP_END(2);
                         tc_fence_after();
                         const uint64_t bdesc = umma_desc_sw128(smem_u32(S.w[s]));
                         const uint32_t d = tmem_base + (uint32_t)tb * kTcChunkN;
@@ -427,18 +462,161 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
                     }
                 umma_commit(&S.a_empty[ab]);
             }
+            TCP_DUMP(0);
         }
-    } else if (warp < 4) {
-        // ===== A loaders: fp32 pillar rows -> bf16, 128-B-swizzled K-major tile ======================================
-        const int lt = tid - 64;       // 0..63
-        uint32_t ti = 0;
+    } else if (warp >= 4 && warp < 8) {
+        // ===== filter: one accumulator row per thread ===============================================================
+        const int q = warp & 3;                 // TMEM lane quadrant of this warp
+        const int row = q * 32 + lane;          // row within the tile
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t it = 0, ti = 0;
+        TCP_DECL;
+#ifdef HVPR_TC_PROFILE
+        long long fl_acc[3] = {0, 0, 0}, fl_t = 0;
+#define FL_B() fl_t = clock64()
+#define FL_E(i) fl_acc[i] += clock64() - fl_t
+#else
+#define FL_B()
+#define FL_E(i)
+#endif
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
-            const int ab = ti & 1;
-            mbar_wait<true>(&S.a_empty[ab], ((ti >> 1) & 1) ^ 1);
-            const int64_t row0 = (int64_t)t * kTcTileM;
-#pragma unroll 4
-            for (int i = lt; i < kTcTileM * 8; i += 64) {
-                const int r = i >> 3, j = i & 7;
+            const int cb = ti & 1;
+            // ---- sweep 1: group maxima -> tau ----
+            float top[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) top[i] = -INFINITY;
+            for (int c = 0; c < nchunks; ++c, ++it) {
+                const int tb = it & 1;
+                TCP_BEGIN();
+                mbar_wait(&S.t_full[tb], (it >> 1) & 1);
+                TCP_END(0);
+                tc_fence_after();
+                const int col0 = c * kTcChunkN;
+                FL_B();
+                auto s1_block = [&](const uint32_t (&r)[32], int b) {
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                    if (col0 + b * 32 + 32 > M) {             // warp-uniform: chunk straddles the end of the memory
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = (col0 + b * 32 + i < M) ? v[i] : -INFINITY;
+                    }
+#ifndef HVPR_TC_PROFILE
+                    if (dbg_logits) {
+                        const int64_t grow = (int64_t)t * kTcTileM + row;
+                        if (grow < nP)
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) dbg_logits[grow * (nchunks * kTcChunkN) + col0 + b * 32 + i] = v[i];
+                    }
+#endif
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {          // tree max of 16
+                        float m8[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) m8[i] = fmaxf(v[h2 * 16 + i], v[h2 * 16 + 8 + i]);
+                        const float a0 = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+                        const float a1 = fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7]));
+                        S.gm[b * 2 + h2][row] = fmaxf(a0, a1);
+                    }
+                };
+                {
+                    // single-buffered here: top[32] is live in this sweep, a second 32-register buffer would spill
+                    const uint32_t cbase = lane_addr + (uint32_t)(tb * kTcChunkN);
+#pragma unroll 1
+                    for (int b = 0; b < 8; ++b) {               // rolled: keeps the hot code inside the instruction cache
+                        uint32_t ra[32];
+                        tmem_ld32_issue(cbase + (uint32_t)(b * 32), ra);
+                        tmem_ld32_wait(ra);
+                        s1_block(ra, b);
+                    }
+                }
+                FL_E(0);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.t_empty[tb]);
+                FL_B();
+                // merge the 16 new group maxima into the running top-32 (descending)
+                float g[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) g[i] = S.gm[i][row];
+                bitonic_sort_desc<16>(g);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) top[16 + i] = fmaxf(top[16 + i], g[15 - i]);
+                bitonic_merge_desc<32>(top);
+                FL_E(1);
+            }
+            const float tau = top[kTcKPrime - 1];
+            // ---- sweep 2: candidates = { j : logit_j >= tau } ----
+            TCP_BEGIN();
+            mbar_wait<true>(&S.c_empty[cb], ((ti >> 1) & 1) ^ 1);
+            TCP_END(2);
+            int cnt = 0;
+            for (int c = 0; c < nchunks; ++c, ++it) {
+                const int tb = it & 1;
+                TCP_BEGIN();
+                mbar_wait(&S.t_full[tb], (it >> 1) & 1);
+                TCP_END(1);
+                tc_fence_after();
+                const int col0 = c * kTcChunkN;
+                FL_B();
+                auto s2_block = [&](const uint32_t (&r)[32], int b) {
+                    // bit (31 - i) of `neg` = sign of (logit_i - tau); four independent 8-deep funnel-shift chains
+                    uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        n0 = __funnelshift_l(__float_as_uint(__uint_as_float(r[i]) - tau), n0, 1);
+                        n1 = __funnelshift_l(__float_as_uint(__uint_as_float(r[8 + i]) - tau), n1, 1);
+                        n2 = __funnelshift_l(__float_as_uint(__uint_as_float(r[16 + i]) - tau), n2, 1);
+                        n3 = __funnelshift_l(__float_as_uint(__uint_as_float(r[24 + i]) - tau), n3, 1);
+                    }
+                    uint32_t m = ~((n0 << 24) | (n1 << 16) | (n2 << 8) | n3);
+                    const int base = col0 + b * 32;
+                    if (base + 32 > M) m = (base >= M) ? 0u : (m & ~(0xFFFFFFFFu >> (M - base)));
+                    while (m) {
+                        const int bit = 31 - __clz((int)m);     // highest set bit = lowest column first
+                        m &= ~(1u << bit);
+                        if (cnt < kTcCandCap) S.cand[cb][cnt][row] = (uint16_t)(base + 31 - bit);
+                        ++cnt;
+                    }
+                };
+                {
+                    uint32_t ra[32], rb[32];
+                    const uint32_t cbase = lane_addr + (uint32_t)(tb * kTcChunkN);
+                    tmem_ld32_issue(cbase, ra);
+#pragma unroll 1
+                    for (int b = 0; b < 8; b += 2) {
+                        tmem_ld32_wait(ra);
+                        tmem_ld32_issue(cbase + (uint32_t)((b + 1) * 32), rb);
+                        s2_block(ra, b);
+                        tmem_ld32_wait(rb);
+                        if (b + 2 < 8) tmem_ld32_issue(cbase + (uint32_t)((b + 2) * 32), ra);
+                        s2_block(rb, b + 1);
+                    }
+                }
+                FL_E(2);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.t_empty[tb]);
+            }
+            S.cand_cnt[cb][row] = cnt;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.c_full[cb]);          // mbarrier arrive has release semantics (cta scope)
+        }
+        if (q == 0) { TCP_DUMP(4); }
+#ifdef HVPR_TC_PROFILE
+        if (q == 0 && lane == 0 && dbg_logits) { reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 16 + 7] = fl_acc[0]; reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 16 + 3] = fl_acc[1]; reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 16 + 14] = fl_acc[2]; }
+#endif
+    } else {
+        // ===== tail: A-tile loads + exact fp32 re-score, top-k, softmax, readout — one warp per row =================
+        const int tw = (warp < 4) ? (warp - 2) : (warp - 6);    // 0..9
+        float *scratch = slow_scratch + ((size_t)blockIdx.x * kTcTailWarps + tw) * kTcSlowScratch;
+        // fp32 pillar rows -> bf16, 128-B-swizzled K-major tile; this warp converts rows tw, tw+10, ...
+        auto load_a_tile = [&](int t_load, uint32_t ti_load) {
+            const int ab = ti_load & 1;
+            mbar_wait<true>(&S.a_empty[ab], ((ti_load >> 1) & 1) ^ 1);
+            const int64_t row0 = (int64_t)t_load * kTcTileM;
+            const int j = lane & 7, rsub = lane >> 3;               // 4 rows x 8 sixteen-byte pieces per pass
+            for (int r = tw * 4 + rsub; r < kTcTileM; r += kTcTailWarps * 4) {
                 float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
                 if (row0 + r < nP) {
                     const float4 *src = reinterpret_cast<const float4 *>(pillars + (row0 + r) * kTcK + j * 8);
@@ -455,98 +633,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.a_full[ab]);
+        };
+        // prologue: the first two tiles of this CTA
+        {
+            int t0 = blockIdx.x;
+            if (t0 < ntiles) load_a_tile(t0, 0);
+            if (t0 + (int)gridDim.x < ntiles) load_a_tile(t0 + gridDim.x, 1);
         }
-    } else if (warp < 8) {
-        // ===== filter: one accumulator row per thread ===============================================================
-        const int q = warp & 3;                 // TMEM lane quadrant of this warp
-        const int row = q * 32 + lane;          // row within the tile
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        uint32_t it = 0, ti = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
-            const int cb = ti & 1;
-            // ---- sweep 1: group maxima -> tau ----
-            float top[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) top[i] = -INFINITY;
-            for (int c = 0; c < nchunks; ++c, ++it) {
-                const int tb = it & 1;
-                mbar_wait(&S.t_full[tb], (it >> 1) & 1);
-                tc_fence_after();
-                float g[16];
-                const int col0 = c * kTcChunkN;
-#pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    float v[32];
-                    tmem_ld32(lane_addr + (uint32_t)(tb * kTcChunkN + b * 32), v);
-                    if (col0 + b * 32 + 32 > M) {             // warp-uniform: chunk straddles the end of the memory
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = (col0 + b * 32 + i < M) ? v[i] : -INFINITY;
-                    }
-                    if (dbg_logits) {
-                        const int64_t grow = (int64_t)t * kTcTileM + row;
-                        if (grow < nP)
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) dbg_logits[grow * (nchunks * kTcChunkN) + col0 + b * 32 + i] = v[i];
-                    }
-#pragma unroll
-                    for (int h2 = 0; h2 < 2; ++h2) {
-                        float m = v[h2 * 16];
-#pragma unroll
-                        for (int i = 1; i < 16; ++i) m = fmaxf(m, v[h2 * 16 + i]);
-                        g[b * 2 + h2] = m;
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.t_empty[tb]);
-                // merge the 16 new group maxima into the running top-32 (descending)
-                bitonic_sort_desc<16>(g);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) top[16 + i] = fmaxf(top[16 + i], g[15 - i]);
-                bitonic_merge_desc<32>(top);
-            }
-            const float tau = top[kTcKPrime - 1];
-            // ---- sweep 2: candidates = { j : logit_j >= tau } ----
-            mbar_wait<true>(&S.c_empty[cb], ((ti >> 1) & 1) ^ 1);
-            int cnt = 0;
-            for (int c = 0; c < nchunks; ++c, ++it) {
-                const int tb = it & 1;
-                mbar_wait(&S.t_full[tb], (it >> 1) & 1);
-                tc_fence_after();
-                const int col0 = c * kTcChunkN;
-#pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    float v[32];
-                    tmem_ld32(lane_addr + (uint32_t)(tb * kTcChunkN + b * 32), v);
-                    uint32_t neg = 0;                           // bit (31 - i) = sign of (v[i] - tau)
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) neg = __funnelshift_l(__float_as_uint(v[i] - tau), neg, 1);
-                    uint32_t m = ~neg;
-                    const int base = col0 + b * 32;
-                    if (base + 32 > M) m = (base >= M) ? 0u : (m & ~(0xFFFFFFFFu >> (M - base)));
-                    while (m) {
-                        const int bit = 31 - __clz((int)m);     // highest set bit = lowest column first
-                        m &= ~(1u << bit);
-                        if (cnt < kTcCandCap) S.cand[cb][cnt][row] = (uint16_t)(base + 31 - bit);
-                        ++cnt;
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.t_empty[tb]);
-            }
-            S.cand_cnt[cb][row] = cnt;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.c_full[cb]);          // mbarrier arrive has release semantics (cta scope)
-        }
-    } else {
-        // ===== tail: exact fp32 re-score, top-k, softmax, readout — one warp per row ===================================
-        const int tw = warp - 8;
-        float *scratch = slow_scratch + ((size_t)blockIdx.x * kTcTailWarps + tw) * kTcSlowScratch;
         uint32_t ti = 0;
+        TCP_DECL;
+#ifdef HVPR_TC_PROFILE
+        long long tcp_row_acc[4] = {0, 0, 0, 0};
+#endif
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
             const int cb = ti & 1;
+            TCP_BEGIN();
             mbar_wait<true>(&S.c_full[cb], (ti >> 1) & 1);
+            TCP_END(0);
+            TCP_BEGIN();
+            // tile t's MMAs are complete (its candidates exist), so its A buffer is free: stage tile t + 2 into it
+            if (t + 2 * (int)gridDim.x < ntiles) load_a_tile(t + 2 * gridDim.x, ti + 2);
             for (int r = tw; r < kTcTileM; r += kTcTailWarps) {
                 const int64_t grow = (int64_t)t * kTcTileM + r;
                 if (grow >= nP) break;
@@ -554,7 +660,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
                 const float *prow = pillars + grow * kTcK;
                 int32_t *idx_row = topk_idx_out ? topk_idx_out + grow * k : nullptr;
                 if (cnt >= k && cnt <= 32)
-                    tail_fast_row(prow, W, k, cnt, &S.cand[cb][0][r], readout + grow * kTcK, idx_row, lane);
+                    tail_fast_row(prow, W, k, cnt, &S.cand[cb][0][r], readout + grow * kTcK, idx_row, lane TCP_ROW_PASS);
                 else if (cnt > 32 && cnt <= kTcCandCap)
                     tail_medium_row(prow, W, k, cnt, &S.cand[cb][0][r], readout + grow * kTcK, idx_row, lane);
                 else
@@ -562,8 +668,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.c_empty[cb]);
+            TCP_END(1);
         }
+        if (tw == 0) { TCP_DUMP(8); }
+#ifdef HVPR_TC_PROFILE
+        if (tw == 0 && lane == 0 && dbg_logits) for (int i_ = 0; i_ < 4; ++i_) reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 16 + 10 + i_] = tcp_row_acc[i_];
+#endif
     }
+#ifdef HVPR_TC_PROFILE
+    if (tid == 0 && dbg_logits) reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 16 + 15] = clock64();
+#endif
 
     tc_fence_before();
     __syncthreads();

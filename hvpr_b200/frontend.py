@@ -22,7 +22,7 @@ from .voxelizer import Voxelizer
 
 class HybridFrontEnd(torch.nn.Module):
     def __init__(self, geom: Geometry, vfe_cfg: Cfg = HVPR_VFE_CFG, bev_cfg: Cfg = HVPR_BEV_CFG,
-                 overflow: str = "continue", mem_precision: str = "fp32", device="cuda"):
+                 overflow: str = "continue", mem_precision: str = "bf16_rescore", device="cuda"):
         super().__init__()
         self.geom = geom
         self.dev = torch.device(device)

@@ -22,7 +22,7 @@ class MemoryUnit_Agg(nn.Module):
         self.weight = Parameter(torch.Tensor(self.mem_dim, self.fea_dim))
         self.bias = None
         self.shrink_thres = shrink_thres
-        self.precision = "fp32"      # "fp32" | "bf16_rescore"
+        self.precision = "bf16_rescore"   # "bf16_rescore" (tcgen05 candidates + exact fp32 re-score) | "fp32" (SIMT)
         self._bf16 = None
         self._bf16_key = None
         self._ws = None

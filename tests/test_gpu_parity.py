@@ -23,7 +23,7 @@ from helpers import GOLDEN, TOL_BF16, TOL_FP32, load_small, rel_err, sha, tie_aw
 pytestmark = pytest.mark.gpu
 
 
-def _frontend(geom, w, overflow="continue", mem_precision="fp32"):
+def _frontend(geom, w, overflow="continue", mem_precision="bf16_rescore"):
     from hvpr_b200.frontend import HybridFrontEnd
     fe = HybridFrontEnd(geom, overflow=overflow, mem_precision=mem_precision)
     fe.load_reference_weights(w)
@@ -372,15 +372,16 @@ def test_frontend_golden_small(name):
         assert tuple(bd[k].shape) == z[k].shape
 
 
+@pytest.mark.parametrize("mem_precision", ["bf16_rescore", "fp32"])
 @pytest.mark.parametrize("gname,dist", [("G1", "L"), ("G2", "L"), ("G2", "U")])
-def test_frontend_planned_graph_vs_oracle(gname, dist):
+def test_frontend_planned_graph_vs_oracle(gname, dist, mem_precision):
     """cfg 1/2 shape: 120k-point frames through the planned, CUDA-graph-replayed path vs the oracle."""
     g = {"G1": G1, "G2": G2}[gname]
     B, N = 2, 120000
     frames = synth.make_batch(dist, N, g.point_cloud_range, B)
     w = hybrid.random_weights(31)
     o = hybrid.frontend(frames, g, w)
-    fe = _frontend(g, w)
+    fe = _frontend(g, w, mem_precision=mem_precision)
     p = fe.plan(B, B * N, N)
     pts, off = to_dev(frames)
     p.points.copy_(pts); p.frame_offsets.copy_(off)
