@@ -13,8 +13,9 @@
 namespace hvpr {
 
 constexpr int kPfnThreads = 128;
-constexpr int kPfnG = 32;        // pillars per block
-constexpr int kPfnStride = 84;   // floats per staged point row: 64 layer-1 pre-activations + 16 layer-0 activations (+pad)
+constexpr int kPfnG = 32;        // pillars per group (one group per block iteration)
+constexpr int kPfnXS = 20;       // row stride (floats) of the layer-0 activation staging: conflict-free fragment loads
+constexpr int kPfnYS = 72;       // row stride of the per-warp accumulator staging: conflict-free 64-bit fragment stores
 
 struct PfnParams {
     HvprPfnWeights w;
@@ -29,9 +30,13 @@ struct PfnSmem {
     float ctr[kPfnG][4];
     float part[4][kPfnG][3];
     float h[kPfnG][17];
-    alignas(16) float xmax[kPfnG][20];   // running max of the layer-0 activations (16 used; float4 rows)
-    alignas(16) float m1[kPfnG][68];     // running max of W1a.x (64 used; padded: lane = pillar access is conflict-free)
-    alignas(16) float buf[kPfnThreads * kPfnStride];
+    alignas(16) uint32_t xmax[kPfnG][kPfnXS];   // running max of the layer-0 activations (>= 0: float bits order as uints)
+    alignas(16) uint32_t m1[kPfnG][68];         // running max of W1a.x as order-preserving keys
+    alignas(16) uint32_t bfrag[2][8][2][2][2][32];  // [W1a|W1b][n-tile][k-step][reg][hi|lo][lane] tf32 B fragments
+    alignas(16) float xs[4][32][kPfnXS];        // per-warp layer-0 activations, one row per point
+    int pid[4][32];                             // per-warp pillar of each staged point (-1: none)
+    float b1s[64];                              // layer-1 BN shift, lane-indexed in the epilogue
+    alignas(16) float ys[4][16][kPfnYS];        // per-warp W1a.x tile (16 points x 64 channels)
 };
 
 __device__ __forceinline__ int find_pillar(const int *poff, int q) {
@@ -41,16 +46,38 @@ __device__ __forceinline__ int find_pillar(const int *poff, int q) {
         if (poff[lo + s] <= q) lo += s;
     return lo;
 }
-
+__device__ __forceinline__ uint32_t pfn_key(float f) {   // order-preserving float -> uint
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float pfn_unkey(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+// D += A(16x8, row) * B(8x8, col), tf32 inputs, fp32 accumulate (legacy warp-level tensor-core path, HMMA in SASS)
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// 3xTF32: x = hi + lo with hi = tf32(x), lo = tf32(x - hi); A.B ~= Alo.Bhi + Ahi.Blo + Ahi.Bhi (error ~2^-21 relative)
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
+    hi = to_tf32(x);
+    lo = to_tf32(x - __uint_as_float(hi));
+}
 
 // Per-pillar phases run with lane = pillar and the channel range split over the 4 warps.  The warp index is folded
 // into a template parameter so every weight index is a compile-time constant (uniform-register operands, no LDC).
 template <int Q>
 __device__ __forceinline__ void pfn_seed(const PfnParams &P, PfnSmem &S, int pl, bool padded) {
 #pragma unroll
-    for (int cc = 0; cc < 16; ++cc) S.m1[pl][Q * 16 + cc] = padded ? P.v1[Q * 16 + cc] : -INFINITY;
+    for (int cc = 0; cc < 16; ++cc) S.m1[pl][Q * 16 + cc] = pfn_key(padded ? P.v1[Q * 16 + cc] : -INFINITY);
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) S.xmax[pl][Q * 4 + kk] = padded ? P.rb0[Q * 4 + kk] : 0.0f;
+    for (int kk = 0; kk < 4; ++kk) S.xmax[pl][Q * 4 + kk] = __float_as_uint(padded ? P.rb0[Q * 4 + kk] : 0.0f);
 }
 template <int Q>
 __device__ __forceinline__ void pfn_scale_hidden(const PfnParams &P, PfnSmem &S, int pl, const float (&in)[5]) {
@@ -75,19 +102,6 @@ __device__ __forceinline__ void pfn_scale_out(const PfnParams &P, PfnSmem &S, in
         o[oo] = fmaxf(a, 0.0f);
     }
 }
-template <int Q>
-__device__ __forceinline__ void pfn_finish(const PfnParams &P, PfnSmem &S, int pl, float (&o)[16]) {
-    float xm[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) xm[k] = S.xmax[pl][k];
-#pragma unroll
-    for (int cc = 0; cc < 16; ++cc) {
-        float a = P.w.b1[Q * 16 + cc];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) a = fmaf(P.w.w1b[Q * 16 + cc][k], xm[k], a);
-        o[cc] = fmaxf(S.m1[pl][Q * 16 + cc] + a, 0.0f);
-    }
-}
 #define PFN_DISPATCH_Q(q, CALL)            \
     switch (q) {                           \
         case 0: { constexpr int Q = 0; CALL; } break; \
@@ -99,8 +113,9 @@ __device__ __forceinline__ void pfn_finish(const PfnParams &P, PfnSmem &S, int p
 // max over a pillar's points commutes with the per-pillar constant and the ReLU:
 //     max_p ReLU(W1a.x_p + c) = ReLU(max_p(W1a.x_p) + c),      c = b1 + W1b.x_max
 // so ONE pass over the real points produces both x_max (layer 0) and max_p(W1a.x_p); c is applied per pillar afterwards.
+// Both 16->64 contractions (W1a.x per point, W1b.x_max per pillar) run on the tensor cores as 3xTF32 m16n8k8 MMAs.
 template <bool kScale>
-__global__ void __launch_bounds__(kPfnThreads) pfn_kernel(const __grid_constant__ PfnParams P,
+__global__ void __launch_bounds__(kPfnThreads, 3) pfn_kernel(const __grid_constant__ PfnParams P,
                                                           const float *__restrict__ voxels,
                                                           const int32_t *__restrict__ num_points,
                                                           const int32_t *__restrict__ coords,
@@ -112,151 +127,235 @@ __global__ void __launch_bounds__(kPfnThreads) pfn_kernel(const __grid_constant_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PfnSmem &S = *reinterpret_cast<PfnSmem *>(smem_raw);
     const int t = threadIdx.x, lane = t & 31, q4 = t >> 5;
+    const int gid = lane >> 2, tig = lane & 3;          // mma fragment coordinates
     int64_t nP = n_pillars_dev ? (int64_t)*n_pillars_dev : n_rows_max;
     if (nP > n_rows_max) nP = n_rows_max;
-    const int64_t g0 = (int64_t)blockIdx.x * kPfnG;
-    if (g0 >= nP) return;
+    const int64_t ngroups = (nP + kPfnG - 1) / kPfnG;
     const float4 *vox4 = reinterpret_cast<const float4 *>(voxels);
 
-    // ---- phase 0: counts, exclusive scan (one warp), pillar centres ------------------------------------------
-    if (t < kPfnG) {
-        const int64_t p = g0 + t;
-        int n = 0;
-        if (p < nP) {
-            n = num_points[p];
-            n = n < 0 ? 0 : (n > T ? T : n);
-            const int4 c = __ldg(reinterpret_cast<const int4 *>(coords) + p);   // [b, z, y, x]
-            // coords*voxel + offset: mul then add, separately rounded (pillar_vfe.py:191-193)
-            S.ctr[t][0] = __fadd_rn(__fmul_rn((float)c.w, vx), x_off);
-            S.ctr[t][1] = __fadd_rn(__fmul_rn((float)c.z, vy), y_off);
-            S.ctr[t][2] = __fadd_rn(__fmul_rn((float)c.y, vz), z_off);
-        }
-        S.n[t] = n;
-        int inc = n;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        S.poff[t] = inc - n;
-        if (t == kPfnG - 1) S.poff[kPfnG] = inc;
+    // ---- once per (persistent) block: tf32 hi/lo B fragments of W1a and W1b ------------------------------------------
+    // B(k, n) = W[n][k];  b0: k = 8*ks + tig, b1: k = 8*ks + tig + 4;  n = 8*nt + gid
+    for (int e = t; e < 2 * 8 * 2 * 2 * 32; e += kPfnThreads) {
+        const int ln = e & 31, reg = (e >> 5) & 1, ks = (e >> 6) & 1, nt = (e >> 7) & 7, mat = e >> 10;
+        const int nn = 8 * nt + (ln >> 2), kk = 8 * ks + (ln & 3) + 4 * reg;
+        const float wv = mat ? P.w.w1b[nn][kk] : P.w.w1a[nn][kk];
+        uint32_t hi, lo;
+        split_tf32(wv, hi, lo);
+        S.bfrag[mat][nt][ks][reg][0][ln] = hi;
+        S.bfrag[mat][nt][ks][reg][1][ln] = lo;
     }
-    __syncthreads();
-    const int total = S.poff[kPfnG];
 
-    // ---- phase 1: per-pillar mean (4 threads per pillar, fixed combination order -> deterministic) ------------
-    {
-        const int pl = lane, n = S.n[pl];
-        const int64_t p = g0 + pl;
-        float sx = 0.f, sy = 0.f, sz = 0.f;
-        for (int j = q4; j < n; j += 4) {
-            float4 v = __ldg(vox4 + p * T + j);
-            sx += v.x; sy += v.y; sz += v.z;
-        }
-        S.part[q4][pl][0] = sx; S.part[q4][pl][1] = sy; S.part[q4][pl][2] = sz;
-        if (mask_out && p < nP)
-            for (int j = q4; j < T; j += 4) mask_out[p * T + j] = (j < n) ? 1.0f : 0.0f;
-        // seeds of the running maxima: the virtual zero-padded row when the pillar has padding, else the identity
-        const bool padded = n < T;
-        PFN_DISPATCH_Q(q4, pfn_seed<Q>(P, S, pl, padded));
-    }
-    __syncthreads();
-    if (t < kPfnG) {
-        const float nf = (float)S.n[t];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            float s = ((S.part[0][t][a] + S.part[1][t][a]) + S.part[2][t][a]) + S.part[3][t][a];
-            S.mean[t][a] = __fdiv_rn(s, nf);                    // pillar_vfe.py:187 (no guard, as the reference)
-        }
-    }
-    __syncthreads();
+    if (t < 64) S.b1s[t] = P.w.b1[t];
 
-    // ---- phase 1b: scale MLP on [n, |mean|, mean_xyz]  (pillar_vfe.py:213-216) --------------------------------
-    if (kScale) {
-        const int pl = lane;
-        const float mx = S.mean[pl][0], my = S.mean[pl][1], mz = S.mean[pl][2];
-        const float in[5] = {(float)S.n[pl], sqrtf(mx * mx + my * my + mz * mz), mx, my, mz};
-        PFN_DISPATCH_Q(q4, pfn_scale_hidden<Q>(P, S, pl, in));
+    for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const int64_t g0 = grp * kPfnG;
+        __syncthreads();      // previous group's readers are done (and the fragments above are visible)
+
+        // ---- phase 0: counts, exclusive scan (one warp), pillar centres --------------------------------------
+        if (t < kPfnG) {
+            const int64_t p = g0 + t;
+            int n = 0;
+            if (p < nP) {
+                n = num_points[p];
+                n = n < 0 ? 0 : (n > T ? T : n);
+                const int4 c = __ldg(reinterpret_cast<const int4 *>(coords) + p);   // [b, z, y, x]
+                // coords*voxel + offset: mul then add, separately rounded (pillar_vfe.py:191-193)
+                S.ctr[t][0] = __fadd_rn(__fmul_rn((float)c.w, vx), x_off);
+                S.ctr[t][1] = __fadd_rn(__fmul_rn((float)c.z, vy), y_off);
+                S.ctr[t][2] = __fadd_rn(__fmul_rn((float)c.y, vz), z_off);
+            }
+            S.n[t] = n;
+            int inc = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            S.poff[t] = inc - n;
+            if (t == kPfnG - 1) S.poff[kPfnG] = inc;
+        }
         __syncthreads();
-        float o[8];
-        PFN_DISPATCH_Q(q4, pfn_scale_out<Q>(P, S, pl, o));
-        const int64_t p = g0 + pl;
-        if (p < nP) {
-            float4 *dst = reinterpret_cast<float4 *>(scale_out + p * 32 + q4 * 8);
-            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-        }
-    }
+        const int total = S.poff[kPfnG];
 
-    // ---- single pass over the real points: layer 0 (10->16, ReLU) and W1a.x (16->64), staged for the pillar max -----
-    for (int c0 = 0; c0 < total; c0 += kPfnThreads) {
-        const int qpt = c0 + t;
-        if (qpt < total) {
-            const int pl = find_pillar(S.poff, qpt);
-            const int j = qpt - S.poff[pl];
-            const float4 v = __ldg(vox4 + (g0 + pl) * T + j);
-            float f[10];
-            f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
-            f[4] = v.x - S.mean[pl][0]; f[5] = v.y - S.mean[pl][1]; f[6] = v.z - S.mean[pl][2];
-            f[7] = v.x - S.ctr[pl][0];  f[8] = v.y - S.ctr[pl][1];  f[9] = v.z - S.ctr[pl][2];
+        // ---- phase 1: per-pillar mean (4 threads per pillar, fixed combination order -> deterministic) --------
+        {
+            const int pl = lane, n = S.n[pl];
+            const int64_t p = g0 + pl;
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+            for (int j = q4; j < n; j += 4) {
+                float4 v = __ldg(vox4 + p * T + j);
+                sx += v.x; sy += v.y; sz += v.z;
+            }
+            S.part[q4][pl][0] = sx; S.part[q4][pl][1] = sy; S.part[q4][pl][2] = sz;
+            if (mask_out && p < nP)
+                for (int j = q4; j < T; j += 4) mask_out[p * T + j] = (j < n) ? 1.0f : 0.0f;
+            // seeds of the running maxima: the virtual zero-padded row when the pillar has padding, else the identity
+            const bool padded = n < T;
+            PFN_DISPATCH_Q(q4, pfn_seed<Q>(P, S, pl, padded));
+        }
+        __syncthreads();
+        if (t < kPfnG) {
+            const float nf = (float)S.n[t];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float s = ((S.part[0][t][a] + S.part[1][t][a]) + S.part[2][t][a]) + S.part[3][t][a];
+                S.mean[t][a] = __fdiv_rn(s, nf);                    // pillar_vfe.py:187 (no guard, as the reference)
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 1b: scale MLP on [n, |mean|, mean_xyz]  (pillar_vfe.py:213-216) ----------------------------
+        if (kScale) {
+            const int pl = lane;
+            const float mx = S.mean[pl][0], my = S.mean[pl][1], mz = S.mean[pl][2];
+            const float in[5] = {(float)S.n[pl], sqrtf(mx * mx + my * my + mz * mz), mx, my, mz};
+            PFN_DISPATCH_Q(q4, pfn_scale_hidden<Q>(P, S, pl, in));
+            __syncthreads();
+            float o[8];
+            PFN_DISPATCH_Q(q4, pfn_scale_out<Q>(P, S, pl, o));
+            const int64_t p = g0 + pl;
+            if (p < nP) {
+                float4 *dst = reinterpret_cast<float4 *>(scale_out + p * 32 + q4 * 8);
+                dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+            }
+        }
+
+        // ---- single pass over the real points; every warp works on its own 32 points, no block-wide barriers ---
+        float (*xs)[kPfnXS] = S.xs[q4];
+        float (*ys)[kPfnYS] = S.ys[q4];
+        int *pid = S.pid[q4];
+        for (int c0 = q4 * 32; c0 < total; c0 += kPfnThreads) {
+            const int qpt = c0 + lane;
+            // layer 0 (10 -> 16, ReLU) on CUDA cores, one point per lane
             float x0[16];
+            int pl = -1;
+            if (qpt < total) {
+                pl = find_pillar(S.poff, qpt);
+                const int j = qpt - S.poff[pl];
+                const float4 v = __ldg(vox4 + (g0 + pl) * T + j);
+                float f[10];
+                f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+                f[4] = v.x - S.mean[pl][0]; f[5] = v.y - S.mean[pl][1]; f[6] = v.z - S.mean[pl][2];
+                f[7] = v.x - S.ctr[pl][0];  f[8] = v.y - S.ctr[pl][1];  f[9] = v.z - S.ctr[pl][2];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                float a = P.w.b0[k];
+                for (int k = 0; k < 16; ++k) {
+                    float a = P.w.b0[k];
 #pragma unroll
-                for (int i = 0; i < 10; ++i) a = fmaf(P.w.w0[k][i], f[i], a);
-                x0[k] = fmaxf(a, 0.0f);
-            }
-            float4 *row = reinterpret_cast<float4 *>(S.buf + t * kPfnStride);
-#pragma unroll
-            for (int c4 = 0; c4 < 16; ++c4) {
-                float y[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float a = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) a = fmaf(P.w.w1a[c4 * 4 + e][k], x0[k], a);
-                    y[e] = a;
+                    for (int i = 0; i < 10; ++i) a = fmaf(P.w.w0[k][i], f[i], a);
+                    x0[k] = fmaxf(a, 0.0f);
                 }
-                row[c4] = make_float4(y[0], y[1], y[2], y[3]);
-            }
+            } else {
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) row[16 + k4] = make_float4(x0[4 * k4], x0[4 * k4 + 1], x0[4 * k4 + 2], x0[4 * k4 + 3]);
-        }
-        __syncthreads();
-        const int c1e = min(c0 + kPfnThreads, total);
-        const int p_lo = find_pillar(S.poff, c0), p_hi = find_pillar(S.poff, c1e - 1);
-        // pillar maxima: 20 float4 columns (16 x layer-1 pre-activations, 4 x layer-0 activations) x 6 pillar slices
-        if (t < 120) {
-            const int col4 = t % 20, slice = t / 20;
-            const int np = p_hi - p_lo + 1, pps = (np + 5) / 6;
-            const int pa = p_lo + slice * pps, pb = min(pa + pps, p_hi + 1);
-            for (int pl = pa; pl < pb; ++pl) {
-                const int a = max(S.poff[pl], c0), b = min(S.poff[pl + 1], c1e);
-                float4 *dst = (col4 < 16) ? reinterpret_cast<float4 *>(&S.m1[pl][col4 * 4])
-                                          : reinterpret_cast<float4 *>(&S.xmax[pl][(col4 - 16) * 4]);
-                float4 m = *dst;
-                const float4 *src = reinterpret_cast<const float4 *>(S.buf + (a - c0) * kPfnStride) + col4;
-                for (int j = a; j < b; ++j, src += kPfnStride / 4) {
-                    const float4 v = *src;
-                    m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
-                }
-                *dst = m;
+                for (int k = 0; k < 16; ++k) x0[k] = 0.0f;
             }
-        }
-        __syncthreads();
-    }
+            __syncwarp();                                   // previous iteration's readers of xs / pid / ys are done
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+                *reinterpret_cast<float4 *>(&xs[lane][4 * k4]) = make_float4(x0[4 * k4], x0[4 * k4 + 1], x0[4 * k4 + 2], x0[4 * k4 + 3]);
+            pid[lane] = pl;
+            __syncwarp();
 
-    // ---- per pillar: c = b1 + W1b.x_max ; pillar_features = ReLU(max + c) -------------------------------------------
-    {
-        const int pl = lane;
-        float o[16];
-        PFN_DISPATCH_Q(q4, pfn_finish<Q>(P, S, pl, o));
-        const int64_t p = g0 + pl;
-        if (p < nP) {
-            float4 *dst = reinterpret_cast<float4 *>(feats + p * 64 + q4 * 16);
+            // pillar max of the layer-0 activations: lane = (half, column); 16 rows each
+            {
+                const int k = lane & 15, r0 = (lane >> 4) * 16;
+                int cur = pid[r0];
+                float acc = 0.0f;
+#pragma unroll 4
+                for (int r = 0; r < 16; ++r) {
+                    const int pr = pid[r0 + r];
+                    const float v = xs[r0 + r][k];
+                    if (pr != cur) {
+                        if (cur >= 0) atomicMax(&S.xmax[cur][k], __float_as_uint(acc));
+                        cur = pr; acc = v;
+                    } else acc = fmaxf(acc, v);
+                }
+                if (cur >= 0) atomicMax(&S.xmax[cur][k], __float_as_uint(acc));
+            }
+
+            // W1a . x on the tensor cores, one 16-point m-tile at a time
+#pragma unroll 1
+            for (int mt = 0; mt < 2; ++mt) {
+                uint32_t ahi[2][4], alo[2][4];
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) dst[c4] = make_float4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
+                for (int ks = 0; ks < 2; ++ks) {
+                    split_tf32(xs[16 * mt + gid][8 * ks + tig], ahi[ks][0], alo[ks][0]);
+                    split_tf32(xs[16 * mt + gid + 8][8 * ks + tig], ahi[ks][1], alo[ks][1]);
+                    split_tf32(xs[16 * mt + gid][8 * ks + tig + 4], ahi[ks][2], alo[ks][2]);
+                    split_tf32(xs[16 * mt + gid + 8][8 * ks + tig + 4], ahi[ks][3], alo[ks][3]);
+                }
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint32_t bh0 = S.bfrag[0][nt][ks][0][0][lane], bl0 = S.bfrag[0][nt][ks][0][1][lane];
+                        const uint32_t bh1 = S.bfrag[0][nt][ks][1][0][lane], bl1 = S.bfrag[0][nt][ks][1][1][lane];
+                        mma_tf32(c, alo[ks], bh0, bh1);
+                        mma_tf32(c, ahi[ks], bl0, bl1);
+                        mma_tf32(c, ahi[ks], bh0, bh1);
+                    }
+                    *reinterpret_cast<float2 *>(&ys[gid][8 * nt + 2 * tig]) = make_float2(c[0], c[1]);
+                    *reinterpret_cast<float2 *>(&ys[gid + 8][8 * nt + 2 * tig]) = make_float2(c[2], c[3]);
+                }
+                __syncwarp();
+                // pillar max over the 16 staged points: lane owns channels (2*lane, 2*lane+1)
+                {
+                    int cur = pid[16 * mt];
+                    float2 acc = make_float2(-INFINITY, -INFINITY);
+#pragma unroll 4
+                    for (int r = 0; r < 16; ++r) {
+                        const int pr = pid[16 * mt + r];
+                        const float2 v = *reinterpret_cast<const float2 *>(&ys[r][2 * lane]);
+                        if (pr != cur) {
+                            if (cur >= 0) { atomicMax(&S.m1[cur][2 * lane], pfn_key(acc.x)); atomicMax(&S.m1[cur][2 * lane + 1], pfn_key(acc.y)); }
+                            cur = pr; acc = v;
+                        } else { acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); }
+                    }
+                    if (cur >= 0) { atomicMax(&S.m1[cur][2 * lane], pfn_key(acc.x)); atomicMax(&S.m1[cur][2 * lane + 1], pfn_key(acc.y)); }
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+
+        // ---- per pillar: c = b1 + W1b.x_max (tensor cores) ; pillar_features = ReLU(max + c) --------------------
+        // warp q4 produces channels [16*q4, 16*q4 + 16) of all 32 pillars: 2 m-tiles x 2 n-tiles
+        {
+            const float (*xm)[kPfnXS] = reinterpret_cast<const float (*)[kPfnXS]>(S.xmax);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    split_tf32(xm[16 * mt + gid][8 * ks + tig], ahi[ks][0], alo[ks][0]);
+                    split_tf32(xm[16 * mt + gid + 8][8 * ks + tig], ahi[ks][1], alo[ks][1]);
+                    split_tf32(xm[16 * mt + gid][8 * ks + tig + 4], ahi[ks][2], alo[ks][2]);
+                    split_tf32(xm[16 * mt + gid + 8][8 * ks + tig + 4], ahi[ks][3], alo[ks][3]);
+                }
+#pragma unroll
+                for (int nn = 0; nn < 2; ++nn) {
+                    const int nt = 2 * q4 + nn;
+                    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint32_t bh0 = S.bfrag[1][nt][ks][0][0][lane], bl0 = S.bfrag[1][nt][ks][0][1][lane];
+                        const uint32_t bh1 = S.bfrag[1][nt][ks][1][0][lane], bl1 = S.bfrag[1][nt][ks][1][1][lane];
+                        mma_tf32(c, alo[ks], bh0, bh1);
+                        mma_tf32(c, ahi[ks], bl0, bl1);
+                        mma_tf32(c, ahi[ks], bh0, bh1);
+                    }
+                    const int ch = 8 * nt + 2 * tig;
+#pragma unroll
+                    for (int hrow = 0; hrow < 2; ++hrow) {
+                        const int pl = 16 * mt + gid + 8 * hrow;
+                        const int64_t p = g0 + pl;
+                        const float o0 = fmaxf(pfn_unkey(S.m1[pl][ch]) + (c[2 * hrow] + S.b1s[ch]), 0.0f);
+                        const float o1 = fmaxf(pfn_unkey(S.m1[pl][ch + 1]) + (c[2 * hrow + 1] + S.b1s[ch + 1]), 0.0f);
+                        if (p < nP) *reinterpret_cast<float2 *>(feats + p * 64 + ch) = make_float2(o0, o1);
+                    }
+                }
+            }
         }
     }
 }
@@ -292,7 +391,8 @@ extern "C" int hvpr_pfn(const float *voxels, const int32_t *num_points, const in
         for (int k = 0; k < 16; ++k) a = fmaf(P.w.w1a[c][k], P.rb0[k], a);
         P.v1[c] = a;
     }
-    const int blocks = (int)ceil_div64(n_rows_max, kPfnG);
+    int64_t want = ceil_div64(n_rows_max, kPfnG);
+    const int blocks = (int)(want < (int64_t)kNumSMs * 3 ? want : (int64_t)kNumSMs * 3);   // persistent: 3 blocks / SM (shared memory)
     if (scale_out)
         pfn_kernel<true><<<blocks, kPfnThreads, sizeof(PfnSmem), stream>>>(
             P, voxels, num_points, coords, n_pillars_dev, n_rows_max, max_points, geom->vs[0], geom->vs[1],

@@ -278,7 +278,23 @@ __device__ __forceinline__ int32_t bitonic_merge32_asc(int32_t x, int lane) {
     return x;
 }
 
-// one warp per voxel (grid-stride over B*max_vox slots)
+// ascending bitonic sort of the first K lanes (K = power of two >= number of real entries; the rest hold INT_MAX)
+__device__ __forceinline__ int32_t bitonic_sort_bounded_asc(int32_t x, int lane, int K) {
+    for (int k = 2; k <= K; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+            const bool up = ((lane & k) == 0);
+            const bool lower = ((lane & j) == 0);
+            x = (lower == up) ? min(x, y) : max(x, y);
+        }
+    }
+    return x;
+}
+
+// One warp handles 32 consecutive voxel slots: lane <-> voxel for the metadata (coalesced), then the voxels are
+// materialised four at a time so that the CSR loads, the point gathers and the 512-byte row stores of four voxels are
+// in flight together (the kernel is latency-bound: each voxel needs two dependent loads).
+constexpr int kGatherGroup = 4;
 template <bool kVec4>
 __global__ void __launch_bounds__(256) vox_gather_kernel(const float *__restrict__ pts, int stride, int xyz_col,
                                                          const int32_t *__restrict__ frame_off, int B, HvprGeom g,
@@ -292,12 +308,11 @@ __global__ void __launch_bounds__(256) vox_gather_kernel(const float *__restrict
                                                          int32_t *__restrict__ num_points,
                                                          int32_t *__restrict__ voxel_offsets,
                                                          int32_t *__restrict__ cell_map) {
-    __shared__ int32_t s_base[65];
+    __shared__ int32_t s_base[65], s_nvox[64], s_start[64];
     const int lane = threadIdx.x & 31;
-    // every block recomputes the tiny exclusive prefix of per-frame voxel counts (B <= 64)
     if (threadIdx.x == 0) {
         int acc = 0;
-        for (int f = 0; f < B; ++f) { s_base[f] = acc; acc += frame_nvox[f]; }
+        for (int f = 0; f < B; ++f) { const int nv = frame_nvox[f]; s_base[f] = acc; s_nvox[f] = nv; s_start[f] = frame_off[f]; acc += nv; }
         s_base[B] = acc;
     }
     __syncthreads();
@@ -306,45 +321,87 @@ __global__ void __launch_bounds__(256) vox_gather_kernel(const float *__restrict
     const int64_t total_slots = (int64_t)B * max_vox;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t w = warp0; w < total_slots; w += nwarps) {
-        const int f = (int)(w / max_vox);
-        const int v = (int)(w - (int64_t)f * max_vox);
-        if (v >= frame_nvox[f]) continue;
-        const int32_t start = frame_off[f];
-        const int n = cursor[w];
-        const int32_t *seg = csr + (int64_t)start + seg_off[w];
-        int32_t best = (lane < n) ? seg[lane] : INT_MAX;
-        best = bitonic_sort32_asc(best, lane);
-        for (int c0 = 32; c0 < n; c0 += 32) {           // more than 32 candidates: keep the 32 lowest indices
-            int32_t e = (c0 + lane < n) ? seg[c0 + lane] : INT_MAX;
-            int32_t worst = __shfl_sync(0xffffffffu, best, 31);
-            if (!__any_sync(0xffffffffu, e < worst)) continue;
-            e = bitonic_sort32_asc(e, lane);
-            int32_t er = __shfl_sync(0xffffffffu, e, 31 - lane);   // descending
-            best = bitonic_merge32_asc(min(best, er), lane);
+    float4 *vox4 = reinterpret_cast<float4 *>(voxels);
+    for (int64_t wbase = warp0 * 32; wbase < total_slots; wbase += nwarps * 32) {
+        // ---- lane <-> voxel metadata -------------------------------------------------------------------------
+        const int64_t w = wbase + lane;
+        int f = 0, n = 0, off = 0, cell = 0;
+        int64_t row = 0;
+        if (w < total_slots) {
+            f = (int)(w / max_vox);
+            const int v = (int)(w - (int64_t)f * max_vox);
+            if (v < s_nvox[f]) {
+                n = cursor[w];
+                off = s_start[f] + seg_off[w];
+                cell = vox_cell[w];
+                row = (int64_t)s_base[f] + v;
+            }
         }
-        const int kept = n < max_points ? n : max_points;
-        const int64_t row = (int64_t)s_base[f] + v;
-        if (lane < max_points) {
-            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane < kept) {
-                const int64_t gi = (int64_t)start + best;
-                if (kVec4) p = __ldg(reinterpret_cast<const float4 *>(pts) + gi);
-                else {
-                    const float *q = pts + gi * stride + xyz_col;
-                    p = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+        const uint32_t live = __ballot_sync(0xffffffffu, n > 0);
+        if (live == 0) continue;
+        const int kept_mine = n < max_points ? n : max_points;
+        if (n > 0) {
+            const int32_t cx = cell % g.grid[0];
+            const int32_t cy = (cell / g.grid[0]) % g.grid[1];
+            const int32_t cz = cell / (g.grid[0] * g.grid[1]);
+            reinterpret_cast<int4 *>(coords)[row] = make_int4(f, cz, cy, cx);
+            num_points[row] = kept_mine;
+            if (cell_map) cell_map[(int64_t)f * cells + cell] = (int32_t)row;
+        }
+        // ---- materialise the rows, kGatherGroup voxels at a time -----------------------------------------------
+        // live voxels form a prefix of every frame's slot range, so walking set bits keeps groups dense
+        uint32_t todo = live;
+        while (todo) {
+            int src[kGatherGroup], nn[kGatherGroup], oo[kGatherGroup];
+            int64_t rr[kGatherGroup];
+            int32_t idx[kGatherGroup];
+#pragma unroll
+            for (int u = 0; u < kGatherGroup; ++u) {
+                src[u] = todo ? (__ffs(todo) - 1) : -1;
+                if (todo) todo &= todo - 1;
+                const int sl = src[u] < 0 ? 0 : src[u];
+                nn[u] = src[u] < 0 ? 0 : __shfl_sync(0xffffffffu, n, sl);
+                oo[u] = __shfl_sync(0xffffffffu, off, sl);
+                rr[u] = __shfl_sync(0xffffffffu, row, sl);
+                idx[u] = (lane < nn[u]) ? __ldg(csr + oo[u] + lane) : INT_MAX;          // CSR loads of the group in flight
+            }
+#pragma unroll
+            for (int u = 0; u < kGatherGroup; ++u) {
+                if (nn[u] > 1) {                                                         // warp-uniform
+                    int K = 2;
+                    while (K < nn[u] && K < 32) K <<= 1;
+                    idx[u] = bitonic_sort_bounded_asc(idx[u], lane, K);
+                    for (int c0 = 32; c0 < nn[u]; c0 += 32) {                            // > 32 candidates: keep the 32 lowest
+                        int32_t e = (c0 + lane < nn[u]) ? __ldg(csr + oo[u] + c0 + lane) : INT_MAX;
+                        const int32_t worst = __shfl_sync(0xffffffffu, idx[u], 31);
+                        if (!__any_sync(0xffffffffu, e < worst)) continue;
+                        e = bitonic_sort32_asc(e, lane);
+                        const int32_t er = __shfl_sync(0xffffffffu, e, 31 - lane);
+                        idx[u] = bitonic_merge32_asc(min(idx[u], er), lane);
+                    }
                 }
             }
-            reinterpret_cast<float4 *>(voxels)[row * max_points + lane] = p;
-        }
-        if (lane == 0) {
-            const int32_t c = vox_cell[w];
-            const int32_t cx = c % g.grid[0];
-            const int32_t cy = (c / g.grid[0]) % g.grid[1];
-            const int32_t cz = c / (g.grid[0] * g.grid[1]);
-            reinterpret_cast<int4 *>(coords)[row] = make_int4(f, cz, cy, cx);
-            num_points[row] = kept;
-            if (cell_map) cell_map[(int64_t)f * cells + c] = (int32_t)row;
+            float4 pv[kGatherGroup];
+#pragma unroll
+            for (int u = 0; u < kGatherGroup; ++u) pv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            // point gathers of the group in flight (idx is frame-local)
+#pragma unroll
+            for (int u = 0; u < kGatherGroup; ++u) {
+                const int sl = src[u] < 0 ? 0 : src[u];
+                const int fsrc = __shfl_sync(0xffffffffu, f, sl);
+                const int kept = nn[u] < max_points ? nn[u] : max_points;
+                if (lane < kept) {
+                    const int64_t gi = (int64_t)s_start[fsrc] + idx[u];
+                    if (kVec4) pv[u] = __ldg(reinterpret_cast<const float4 *>(pts) + gi);
+                    else {
+                        const float *q = pts + gi * stride + xyz_col;
+                        pv[u] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kGatherGroup; ++u)
+                if (src[u] >= 0 && lane < max_points) vox4[rr[u] * max_points + lane] = pv[u];
         }
     }
 }
@@ -421,7 +478,7 @@ extern "C" int hvpr_voxelize(const float *points, int64_t n_total, int pts_strid
     }
     {
         int64_t slots = (int64_t)n_frames * max_voxels;
-        int64_t want = ceil_div64(slots, 8);   // 8 warps per block
+        int64_t want = ceil_div64(slots, 8 * 32);   // 8 warps per block, 32 slots per warp
         int blocks = (int)(want < 148 * 16 ? (want > 0 ? want : 1) : 148 * 16);
         if (vec4) vox_gather_kernel<true><<<blocks, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, n_frames, *geom, cells, max_voxels, max_points, w.vox_cell, w.seg_off, w.cursor, w.csr, w.frame_nvox, voxels, coords, num_points, voxel_offsets, cell_map);
         else vox_gather_kernel<false><<<blocks, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, n_frames, *geom, cells, max_voxels, max_points, w.vox_cell, w.seg_off, w.cursor, w.csr, w.frame_nvox, voxels, coords, num_points, voxel_offsets, cell_map);
