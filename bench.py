@@ -76,7 +76,7 @@ class ClockSampler:
                 for bit, nm in names.items():
                     if r & bit:
                         self.reasons.add(nm)
-                time.sleep(0.05)
+                time.sleep(0.002)
         except Exception as e:  # pragma: no cover
             self.reasons.add("sampler_error:%s" % type(e).__name__)
 
@@ -187,7 +187,7 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
-        dist = sharding.init_process_group("nccl")
+        dist = sharding.init_process_group("nccl", device_id=dev)
 
     geom = G2
     nx, ny, _ = geom.grid_size

@@ -146,6 +146,15 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_kernel(const __grid_consta
     }
 
     if (t < 64) S.b1s[t] = P.w.b1[t];
+    __syncthreads();
+    // W1a fragments live in registers for the whole (persistent) block: no shared-memory traffic in the MMA loop
+    uint32_t wah[8][2][2], wal[8][2][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int rg = 0; rg < 2; ++rg) { wah[nt][ks][rg] = S.bfrag[0][nt][ks][rg][0][lane]; wal[nt][ks][rg] = S.bfrag[0][nt][ks][rg][1][lane]; }
 
     for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         const int64_t g0 = grp * kPfnG;
@@ -289,8 +298,8 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_kernel(const __grid_consta
                     float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
-                        const uint32_t bh0 = S.bfrag[0][nt][ks][0][0][lane], bl0 = S.bfrag[0][nt][ks][0][1][lane];
-                        const uint32_t bh1 = S.bfrag[0][nt][ks][1][0][lane], bl1 = S.bfrag[0][nt][ks][1][1][lane];
+                        const uint32_t bh0 = wah[nt][ks][0], bl0 = wal[nt][ks][0];
+                        const uint32_t bh1 = wah[nt][ks][1], bl1 = wal[nt][ks][1];
                         mma_tf32(c, alo[ks], bh0, bh1);
                         mma_tf32(c, ahi[ks], bl0, bl1);
                         mma_tf32(c, ahi[ks], bh0, bh1);

@@ -21,12 +21,13 @@ def weak_scaling_frames(frames_per_rank: int, rank: int):
     return list(range(rank * frames_per_rank, (rank + 1) * frames_per_rank))
 
 
-def init_process_group(backend: str):
+def init_process_group(backend: str, device_id=None):
     import torch.distributed as dist
     if not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
-        dist.init_process_group(backend=backend)
+        kw = {"device_id": device_id} if (device_id is not None and backend == "nccl") else {}
+        dist.init_process_group(backend=backend, **kw)
     return dist
 
 
