@@ -444,3 +444,61 @@ def test_frontend_run_host_end_to_end():
     o = hybrid.frontend(frames, g, w)
     assert int(hc[-1]) == o["voxel_coords"].shape[0]
     assert rel_err(p.spatial, o["spatial_features"])[0] <= TOL_FP32
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE configs 3 / 4
+def test_config4_dense_frames_extended_range():
+    """BASELINE.json configs[3]: 300k-point frames, 640x640 grid, 80k max pillars (SURVEY §8d cfg 4) — voxelization
+    bit-exact vs the oracle, features within tolerance, canvases consistent with the rows."""
+    g = G3
+    B, N = 2, 300000
+    frames = synth.make_batch("L", N, g.point_cloud_range, B, first_frame=40)
+    w = hybrid.random_weights(5)
+    fe = _frontend(g, w)
+    p = fe.plan(B, B * N, N)
+    pts, off = to_dev(frames)
+    p.points.copy_(pts); p.frame_offsets.copy_(off)
+    fe.run(); torch.cuda.synchronize()
+    P = int(p.vox.voxel_offsets[-1])
+    rv, rc, rn = ov.voxelize_batch(frames, g.range_f32, g.voxel_f32, 32, g.max_voxels)
+    assert P == len(rn)
+    assert np.array_equal(p.vox.coords[:P].cpu().numpy(), rc) and np.array_equal(p.vox.num_points[:P].cpu().numpy(), rn)
+    assert np.array_equal(p.vox.voxels[:P].cpu().numpy().view(np.int32), rv.view(np.int32))
+    with torch.no_grad():
+        pf, psf, _ = hybrid.pillar_vfe(torch.from_numpy(rv), torch.from_numpy(rn), torch.from_numpy(rc), w,
+                                       list(g.voxel_size), g.range_f32)
+        ro = hybrid.memory_attention(pf, w["map_to_bev_module.memory.weight"], 20)
+    assert rel_err(p.pillar_features[:P], pf)[0] <= TOL_FP32 and rel_err(p.pillar_scale[:P], psf)[0] <= TOL_FP32
+    tie_aware_readout_check(p.readout[:P], ro, pf, w["map_to_bev_module.memory.weight"], TOL_FP32)
+    nx, ny, _ = g.grid_size
+    c = p.vox.coords[:P].long()
+    cols = p.spatial.view(B, 128, -1)[c[:, 0], :, c[:, 2] * nx + c[:, 3]]
+    assert torch.equal(cols[:, :64], p.pillar_features[:P]) and torch.equal(cols[:, 64:], p.readout[:P])
+    assert int((p.spatial.view(B, 128, -1).abs().sum(1) != 0).sum()) <= P
+    assert tuple(p.spatial.shape) == (B, 128, 640, 640) and tuple(p.spatial_scale.shape) == (B, 32, 640, 640)
+
+
+def test_config3_many_frames_equals_per_frame_runs():
+    """BASELINE.json configs[2]: a big batch sharded frame-wise gives the same bits as running its frames alone —
+    the property the multi-GPU partition (frame i -> rank i mod W) relies on."""
+    g = G2
+    N = 30000
+    frames = synth.make_batch("L", N, g.point_cloud_range, 16, first_frame=60)
+    w = hybrid.random_weights(6)
+    fe = _frontend(g, w)
+    p = fe.plan(16, 16 * N, N)
+    pts, off = to_dev(frames)
+    p.points.copy_(pts); p.frame_offsets.copy_(off)
+    fe.run(); torch.cuda.synchronize()
+    whole = p.spatial.clone(); whole_s = p.spatial_scale.clone()
+    vo = p.vox.voxel_offsets.cpu().numpy()
+    fe2 = _frontend(g, w)
+    p2 = fe2.plan(4, 4 * N, N)
+    for r in range(4):                                   # "rank" r owns frames r, r+4, r+8, r+12
+        mine = frames[r::4]
+        pts, off = to_dev(mine)
+        p2.points.copy_(pts); p2.frame_offsets.copy_(off)
+        fe2.run(); torch.cuda.synchronize()
+        assert torch.equal(p2.spatial, whole[r::4]) and torch.equal(p2.spatial_scale, whole_s[r::4])
+        vo2 = p2.vox.voxel_offsets.cpu().numpy()
+        assert list(np.diff(vo2)) == list(np.diff(vo)[r::4])
