@@ -81,15 +81,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *b) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *b, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
-template <bool kBackoff = false>
+// kSleepNs == 0: spin (critical path: MMA issuer, filter).  kSleepNs > 0: sleep between polls — a waiter off the critical
+// path must not burn issue slots that the working warps of its SM sub-partition need (measured: 31 % of all issued
+// instructions were polls before this).
+template <int kSleepNs = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
     const uint32_t a = smem_u32(b);
-    const uint32_t hint_ns = kBackoff ? 20000u : 2000u;       // the thread sleeps in hardware until the phase completes
     uint32_t done = 0;
     for (uint32_t spin = 0; !done; ++spin) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(a), "r"(parity), "r"(hint_ns) : "memory");
-        if (!done && spin > (1u << 24)) __trap();             // watchdog: a protocol bug must not hang the GPU
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (!done) {
+            if (kSleepNs > 0) __nanosleep(kSleepNs);
+            if (spin > (1u << 26)) __trap();                  // watchdog: a protocol bug must not hang the GPU
+        }
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -279,16 +284,15 @@ __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, co
     }
     const float logit = s[0];                                  // exact fp32 logit of candidate `lane`
     TCP_ROW_T(1);
-    const uint32_t key = (lane < cnt) ? float_key(logit) : 0u;
-    // rank among the candidates (32 independent shuffles; ties -> lower lane first); keep rank < k
-    int rank = 0;
-#pragma unroll
-    for (int m = 0; m < 32; ++m) {
-        const uint32_t km = __shfl_sync(0xffffffffu, key, m);
-        rank += (km > key || (km == key && m < lane)) ? 1 : 0;
+    bool valid = lane < cnt;
+    uint32_t key = valid ? float_key(logit) : 0xFFFFFFFFu;
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, valid ? key : 0u);
+    // drop the (cnt - k) smallest exact logits, one warp-min each (ties: lowest lane first)
+    for (int e = cnt; e > k; --e) {
+        const uint32_t mn = __reduce_min_sync(0xffffffffu, key);
+        const int victim = __ffs(__ballot_sync(0xffffffffu, key == mn)) - 1;
+        if (lane == victim) { valid = false; key = 0xFFFFFFFFu; }
     }
-    const bool valid = (lane < cnt) && rank < k;
-    const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
     const float mx = key_float(kmax);
     const float ex = valid ? expf(logit - mx) : 0.0f;
     float sum = ex;
@@ -304,7 +308,10 @@ __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, co
     }
     reinterpret_cast<float2 *>(out_row)[lane] = make_float2(o0, o1);
     TCP_ROW_T(3);
-    if (idx_row && valid) idx_row[rank] = my_j;
+    if (idx_row) {
+        const uint32_t kept = __ballot_sync(0xffffffffu, valid);
+        if (valid) idx_row[__popc(kept & ((1u << lane) - 1u))] = my_j;
+    }
 }
 
 // exact fp32 logits of up to 32 candidates: lane c <- logit of candidate c (0 <= c < n), rows are not retained
@@ -422,7 +429,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
                 for (int sweep = 0; sweep < 2; ++sweep)
                     for (int c = 0; c < nchunks; ++c, ++it) {
                         const int s = it % kTcWStages;
-                        mbar_wait<true>(&S.w_empty[s], ((it / kTcWStages) & 1) ^ 1);
+                        mbar_wait<400>(&S.w_empty[s], ((it / kTcWStages) & 1) ^ 1);
                         mbar_arrive_expect_tx(&S.w_full[s], kTcChunkBytes);
                         bulk_g2s(S.w[s], Wpk + (size_t)c * kTcChunkBytes, kTcChunkBytes, &S.w_full[s]);
                     }
@@ -438,7 +445,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
                 const int ab = ti & 1;
                 TCP_BEGIN();
-                mbar_wait(&S.a_full[ab], (ti >> 1) & 1);
+                mbar_wait<64>(&S.a_full[ab], (ti >> 1) & 1);
                 TCP_END(0);
                 tc_fence_after();
                 const uint64_t adesc = umma_desc_sw128(smem_u32(S.a[ab]));
@@ -446,10 +453,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
                     for (int c = 0; c < nchunks; ++c, ++it) {
                         const int s = it % kTcWStages, tb = it & 1;
                         TCP_BEGIN();
-                        mbar_wait(&S.w_full[s], (it / kTcWStages) & 1);
+                        mbar_wait<32>(&S.w_full[s], (it / kTcWStages) & 1);
                         TCP_END(1);
                         TCP_BEGIN();
-                        mbar_wait(&S.t_empty[tb], ((it >> 1) & 1) ^ 1);
+                        mbar_wait<64>(&S.t_empty[tb], ((it >> 1) & 1) ^ 1);    // the issuer has ~50 % slack: do not spin
                         TCP_END(2);
                         tc_fence_after();
                         const uint64_t bdesc = umma_desc_sw128(smem_u32(S.w[s]));
@@ -548,7 +555,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
             const float tau = top[kTcKPrime - 1];
             // ---- sweep 2: candidates = { j : logit_j >= tau } ----
             TCP_BEGIN();
-            mbar_wait<true>(&S.c_empty[cb], ((ti >> 1) & 1) ^ 1);
+            mbar_wait<200>(&S.c_empty[cb], ((ti >> 1) & 1) ^ 1);
             TCP_END(2);
             int cnt = 0;
             for (int c = 0; c < nchunks; ++c, ++it) {
@@ -613,7 +620,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
         // fp32 pillar rows -> bf16, 128-B-swizzled K-major tile; this warp converts rows tw, tw+10, ...
         auto load_a_tile = [&](int t_load, uint32_t ti_load) {
             const int ab = ti_load & 1;
-            mbar_wait<true>(&S.a_empty[ab], ((ti_load >> 1) & 1) ^ 1);
+            mbar_wait<400>(&S.a_empty[ab], ((ti_load >> 1) & 1) ^ 1);
             const int64_t row0 = (int64_t)t_load * kTcTileM;
             const int j = lane & 7, rsub = lane >> 3;               // 4 rows x 8 sixteen-byte pieces per pass
             for (int r = tw * 4 + rsub; r < kTcTileM; r += kTcTailWarps * 4) {
@@ -648,7 +655,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
             const int cb = ti & 1;
             TCP_BEGIN();
-            mbar_wait<true>(&S.c_full[cb], (ti >> 1) & 1);
+            mbar_wait<400>(&S.c_full[cb], (ti >> 1) & 1);
             TCP_END(0);
             TCP_BEGIN();
             // tile t's MMAs are complete (its candidates exist), so its A buffer is free: stage tile t + 2 into it
