@@ -65,8 +65,7 @@ struct TcSmem {
     float gm[16][kTcTileM];                   // group maxima of the current chunk, one column per filter thread
     uint64_t w_full[kTcWStages], w_empty[kTcWStages];
     uint64_t a_full[2], a_empty[2];
-    uint64_t t_full[2], t_empty[2];
-    uint64_t c_full[2], c_empty[2];
+    uint64_t t_full[2];
     uint32_t tmem_base;
 };
 
@@ -97,6 +96,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
         }
     }
 }
+// Hardware named barriers: a waiting warp is descheduled (no polling), unlike an mbarrier try_wait loop.  Used for the long
+// thread-to-thread handoffs; mbarriers remain where the async proxy (TMA, tcgen05.commit) is the signaller.
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+constexpr int kBarCFull = 1;    // +cb : filter (128 arrive) -> tail (320 sync)
+constexpr int kBarCEmpty = 3;   // +cb : tail (320 arrive)  -> filter (128 sync)
+constexpr int kBarTEmpty = 5;   // +tb : filter (128 arrive) -> MMA warp (32 sync)
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -407,8 +413,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
         for (int s = 0; s < kTcWStages; ++s) { mbar_init(&S.w_full[s], 1); mbar_init(&S.w_empty[s], 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&S.a_full[b], kTcTailWarps); mbar_init(&S.a_empty[b], 1);
-            mbar_init(&S.t_full[b], 1); mbar_init(&S.t_empty[b], 4);
-            mbar_init(&S.c_full[b], 4); mbar_init(&S.c_empty[b], kTcTailWarps);
+            mbar_init(&S.t_full[b], 1);
         }
         fence_barrier_init();
     }
@@ -422,43 +427,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
     const uint32_t tmem_base = S.tmem_base;
 
     if (warp == 0) {
-        // ===== W producer: bulk-copy pre-swizzled bf16 chunks (two sweeps per tile) ================================
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
-                for (int sweep = 0; sweep < 2; ++sweep)
-                    for (int c = 0; c < nchunks; ++c, ++it) {
-                        const int s = it % kTcWStages;
-                        mbar_wait<400>(&S.w_empty[s], ((it / kTcWStages) & 1) ^ 1);
-                        mbar_arrive_expect_tx(&S.w_full[s], kTcChunkBytes);
-                        bulk_g2s(S.w[s], Wpk + (size_t)c * kTcChunkBytes, kTcChunkBytes, &S.w_full[s]);
-                    }
-        }
+        // (warp 0 only owns the TMEM allocation; its lanes wait at the final barrier)
     } else if (warp == 1) {
-        // ===== MMA issuer ==========================================================================================
-        if (lane == 0) {
-            // idesc: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcChunkN >> 3) << 17) |
-                                   ((uint32_t)(kTcTileM >> 4) << 24);
-            uint32_t it = 0, ti = 0;
-            TCP_DECL;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
-                const int ab = ti & 1;
-                TCP_BEGIN();
-                mbar_wait<64>(&S.a_full[ab], (ti >> 1) & 1);
-                TCP_END(0);
-                tc_fence_after();
-                const uint64_t adesc = umma_desc_sw128(smem_u32(S.a[ab]));
-                for (int sweep = 0; sweep < 2; ++sweep)
-                    for (int c = 0; c < nchunks; ++c, ++it) {
-                        const int s = it % kTcWStages, tb = it & 1;
-                        TCP_BEGIN();
-                        mbar_wait<32>(&S.w_full[s], (it / kTcWStages) & 1);
-                        TCP_END(1);
-                        TCP_BEGIN();
-                        mbar_wait<64>(&S.t_empty[tb], ((it >> 1) & 1) ^ 1);    // the issuer has ~50 % slack: do not spin
-                        TCP_END(2);
-                        tc_fence_after();
+        // ===== W producer + MMA issuer: the whole warp stays converged (it blocks on named barriers), lane 0 issues ==========
+        // idesc: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcChunkN >> 3) << 17) |
+                               ((uint32_t)(kTcTileM >> 4) << 24);
+        const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        const uint32_t total_it = (uint32_t)my_tiles * 2u * (uint32_t)nchunks;
+        auto issue_load = [&](uint32_t itl) {                 // chunk sequence: tile-major, two sweeps, nchunks each
+            const int s = itl % kTcWStages;
+            const int c = (int)(itl % (uint32_t)nchunks);
+            mbar_wait(&S.w_empty[s], ((itl / kTcWStages) & 1) ^ 1);      // freed by the commit of chunk itl - kTcWStages
+            mbar_arrive_expect_tx(&S.w_full[s], kTcChunkBytes);
+            bulk_g2s(S.w[s], Wpk + (size_t)c * kTcChunkBytes, kTcChunkBytes, &S.w_full[s]);
+        };
+        if (lane == 0)
+            for (uint32_t p = 0; p < (uint32_t)(kTcWStages - 1) && p < total_it; ++p) issue_load(p);
+        uint32_t it = 0, ti = 0;
+        TCP_DECL;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+            const int ab = ti & 1;
+            TCP_BEGIN();
+            mbar_wait(&S.a_full[ab], (ti >> 1) & 1);
+            TCP_END(0);
+            const uint64_t adesc = umma_desc_sw128(smem_u32(S.a[ab]));
+            for (int sweep = 0; sweep < 2; ++sweep)
+                for (int c = 0; c < nchunks; ++c, ++it) {
+                    const int s = it % kTcWStages, tb = it & 1;
+                    if (lane == 0 && it + kTcWStages - 1 < total_it) issue_load(it + kTcWStages - 1);
+                    TCP_BEGIN();
+                    mbar_wait(&S.w_full[s], (it / kTcWStages) & 1);
+                    TCP_END(1);
+                    TCP_BEGIN();
+                    if (it >= 2) named_bar_sync(kBarTEmpty + tb, 128 + 32);     // filter drained this accumulator buffer
+                    TCP_END(2);
+                    tc_fence_after();
+                    if (lane == 0) {
                         const uint64_t bdesc = umma_desc_sw128(smem_u32(S.w[s]));
                         const uint32_t d = tmem_base + (uint32_t)tb * kTcChunkN;
 #pragma unroll
@@ -467,10 +472,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
                         umma_commit(&S.w_empty[s]);
                         umma_commit(&S.t_full[tb]);
                     }
-                umma_commit(&S.a_empty[ab]);
-            }
-            TCP_DUMP(0);
+                    __syncwarp();
+                }
+            if (lane == 0) umma_commit(&S.a_empty[ab]);
+            __syncwarp();
         }
+        TCP_DUMP(0);
     } else if (warp >= 4 && warp < 8) {
         // ===== filter: one accumulator row per thread ===============================================================
         const int q = warp & 3;                 // TMEM lane quadrant of this warp
@@ -539,8 +546,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
                 }
                 FL_E(0);
                 tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.t_empty[tb]);
+                named_bar_arrive(kBarTEmpty + tb, 128 + 32);
                 FL_B();
                 // merge the 16 new group maxima into the running top-32 (descending)
                 float g[16];
@@ -555,7 +561,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
             const float tau = top[kTcKPrime - 1];
             // ---- sweep 2: candidates = { j : logit_j >= tau } ----
             TCP_BEGIN();
-            mbar_wait<200>(&S.c_empty[cb], ((ti >> 1) & 1) ^ 1);
+            if (ti >= 2) named_bar_sync(kBarCEmpty + cb, 128 + 32 * kTcTailWarps);   // tail finished with this candidate buffer
             TCP_END(2);
             int cnt = 0;
             for (int c = 0; c < nchunks; ++c, ++it) {
@@ -602,12 +608,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
                 }
                 FL_E(2);
                 tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.t_empty[tb]);
+                named_bar_arrive(kBarTEmpty + tb, 128 + 32);
             }
             S.cand_cnt[cb][row] = cnt;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.c_full[cb]);          // mbarrier arrive has release semantics (cta scope)
+            named_bar_arrive(kBarCFull + cb, 128 + 32 * kTcTailWarps);   // orders the candidate stores before the tail's reads
         }
         if (q == 0) { TCP_DUMP(4); }
 #ifdef HVPR_TC_PROFILE
@@ -655,7 +659,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
             const int cb = ti & 1;
             TCP_BEGIN();
-            mbar_wait<400>(&S.c_full[cb], (ti >> 1) & 1);
+            named_bar_sync(kBarCFull + cb, 128 + 32 * kTcTailWarps);
             TCP_END(0);
             TCP_BEGIN();
             // tile t's MMAs are complete (its candidates exist), so its A buffer is free: stage tile t + 2 into it
@@ -673,8 +677,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
                 else
                     tail_slow_row(prow, W, M, k, scratch, readout + grow * kTcK, idx_row, lane);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.c_empty[cb]);
+            named_bar_arrive(kBarCEmpty + cb, 128 + 32 * kTcTailWarps);
             TCP_END(1);
         }
         if (tw == 0) { TCP_DUMP(8); }
