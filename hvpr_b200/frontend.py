@@ -115,103 +115,119 @@ class HybridFrontEnd(torch.nn.Module):
 
 
     # ---------------------------------------------------------------------------------------------------------
-    # Streaming mode: consecutive batches are software-pipelined across CUDA streams.
-    #   step k (one CUDA graph):   main stream   K2 PFN -> K3 memory attention -> K4 BEV fill      of batch k
-    #                              side stream   K1 voxelize                                        of batch k+1
-    #   copy stream (eager):       H2D of batch k+1's points while batch k-1's graph is still running
-    # K1 is latency-bound (six small launches, ~40 % of the warps active) and K4 is HBM-write-bound with spare SM
-    # resources, so the voxelization of the next batch hides under the canvas fill of the current one; K2/K3 occupy
-    # whole SMs (registers / shared memory), so nothing co-runs with them.  Every batch still gets exactly the same
-    # kernels on the same data: results are bit-identical to `run()`.
+    # Streaming mode: consecutive batches are software-pipelined, three stages deep, across CUDA streams.
+    #   step k (one CUDA graph):   main stream    K3 memory attention -> K4 BEV fill      of batch k
+    #                              side stream 1  K2 PFN                                   of batch k+1
+    #                              side stream 2  K1 voxelize                              of batch k+2
+    #   copy stream (eager):       H2D of batch k+2's points while the previous graph is still running
+    # K1 is latency-bound (six small launches), K2 is latency/issue-bound and K4 is HBM-write-bound with spare SM resources,
+    # so once the persistent K3 (which occupies whole SMs) retires, the three run concurrently.  Every batch still gets
+    # exactly the same kernels on the same data: results are bit-identical to `run()`; they appear two steps after the
+    # batch was submitted.
+    _NS = 3
+
     def plan_stream(self, n_frames: int, n_total_points: int, max_frame_points: int = 0):
         g, dev = self.geom, self.dev
         nx, ny, _ = g.grid_size
+        NS = self._NS
         p = self._Plan()
         p.B, p.n_total, p.max_frame_points = n_frames, n_total_points, max_frame_points
-        p.in_points = [torch.empty((n_total_points, 4), dtype=torch.float32, device=dev) for _ in range(2)]
-        p.in_offsets = [torch.zeros((n_frames + 1,), dtype=torch.int32, device=dev) for _ in range(2)]
-        p.voxs = [self.voxelizer.alloc_output(n_frames) for _ in range(2)]
+        p.in_points = [torch.empty((n_total_points, 4), dtype=torch.float32, device=dev) for _ in range(NS)]
+        p.in_offsets = [torch.zeros((n_frames + 1,), dtype=torch.int32, device=dev) for _ in range(NS)]
+        p.voxs = [self.voxelizer.alloc_output(n_frames) for _ in range(NS)]
         rows = p.voxs[0].max_rows
-        p.pillar_features = torch.empty((rows, 64), dtype=torch.float32, device=dev)
-        p.pillar_scale = torch.empty((rows, 32), dtype=torch.float32, device=dev)
+        p.pfs = [torch.empty((rows, 64), dtype=torch.float32, device=dev) for _ in range(NS)]
+        p.pss = [torch.empty((rows, 32), dtype=torch.float32, device=dev) for _ in range(NS)]
         p.readout = torch.empty((rows, 64), dtype=torch.float32, device=dev)
         p.spatial = torch.empty((n_frames, 128, ny, nx), dtype=torch.float32, device=dev)
         p.spatial_scale = torch.empty((n_frames, 32, ny, nx), dtype=torch.float32, device=dev)
-        p.side, p.copy = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        p.ev_copied = [torch.cuda.Event() for _ in range(2)]
-        p.ev_input_free = [torch.cuda.Event() for _ in range(2)]
-        p.graphs = [None, None]
-        p.cur = 0            # slot whose voxelization is done and whose PFN/attention/fill run in the next step
+        p.side1, p.side2, p.copy = (torch.cuda.Stream(device=dev) for _ in range(3))
+        p.ev_copied = [torch.cuda.Event() for _ in range(NS)]
+        p.ev_input_free = [torch.cuda.Event() for _ in range(NS)]
+        p.graphs = [None] * NS
+        p.k = 0              # slot of the batch finished by the next step
         p.primed = False
-        p.vox = p.voxs[0]
+        p.vox, p.pillar_features, p.pillar_scale = p.voxs[0], p.pfs[0], p.pss[0]
         self._splan = p
         return p
 
-    def _vox_into(self, p, slot):
+    def _stage_vox(self, p, slot):      # K1
         self.voxelizer.run(p.in_points[slot], p.in_offsets[slot], p.B, p.max_frame_points, out=p.voxs[slot])
 
-    def _tail_of(self, p, slot):
+    def _stage_pfn(self, p, slot):      # K2
         vox = p.voxs[slot]
-        nP = vox.n_pillars_dev
-        self.vfe.run(vox.voxels, vox.num_points, vox.coords, nP, out=p.pillar_features, scale_out=p.pillar_scale)
-        self.map_to_bev_module.run(p.pillar_features, p.pillar_scale, vox.cell_map, p.B, nP, readout=p.readout,
+        self.vfe.run(vox.voxels, vox.num_points, vox.coords, vox.n_pillars_dev, out=p.pfs[slot], scale_out=p.pss[slot])
+
+    def _stage_bev(self, p, slot):      # K3 + K4
+        vox = p.voxs[slot]
+        self.map_to_bev_module.run(p.pfs[slot], p.pss[slot], vox.cell_map, p.B, vox.n_pillars_dev, readout=p.readout,
                                    spatial=p.spatial, spatial_scale=p.spatial_scale)
 
     @torch.no_grad()
-    def stream_prime(self, points=None, frame_offsets=None):
-        """Voxelize the first batch (slot 0).  `points` / `frame_offsets`: device or pinned-host tensors, or None when the
-        caller already filled `in_points[0]` / `in_offsets[0]`."""
+    def stream_prime(self, batch0=None, batch1=None):
+        """Fill the pipeline: batch0 -> voxelized + PFN (slot 0), batch1 -> voxelized (slot 1).  Each batch is a
+        (points, frame_offsets) pair of device or pinned-host tensors, or None when the caller already filled
+        `in_points[slot]` / `in_offsets[slot]`."""
         p = self._splan
+        NS = self._NS
         _lib.init_device()
-        if points is not None:
-            p.in_points[0].copy_(points, non_blocking=True)
-            p.in_offsets[0].copy_(frame_offsets, non_blocking=True)
+        for slot, b in ((0, batch0), (1, batch1)):
+            if b is not None:
+                p.in_points[slot].copy_(b[0], non_blocking=True)
+                p.in_offsets[slot].copy_(b[1], non_blocking=True)
         self.vfe._weights()
         if self.map_to_bev_module.memory.precision == "bf16_rescore":
             self.map_to_bev_module.memory._packed_bf16()
-        self._vox_into(p, 0)
-        if p.graphs[0] is None:                         # warm-up of every kernel outside capture, then capture both phases
-            self._tail_of(p, 0)
-            self._vox_into(p, 1)
+        if p.graphs[0] is None:                         # warm every kernel up outside capture, then capture the NS phases
+            for slot in range(NS):
+                self._stage_vox(p, slot); self._stage_pfn(p, slot)
+            self._stage_bev(p, 0)
             torch.cuda.synchronize()
-            for cur in (0, 1):
-                nxt = cur ^ 1
+            for k in range(NS):
                 gr = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gr):
                     main = torch.cuda.current_stream()
-                    p.side.wait_stream(main)            # fork
-                    with torch.cuda.stream(p.side):
-                        self._vox_into(p, nxt)
-                    self._tail_of(p, cur)
-                    main.wait_stream(p.side)            # join
-                p.graphs[cur] = gr
-            self._vox_into(p, 0)
-        p.cur, p.primed = 0, True
-        p.vox = p.voxs[0]
+                    p.side1.wait_stream(main)           # fork
+                    p.side2.wait_stream(main)
+                    with torch.cuda.stream(p.side2):
+                        self._stage_vox(p, (k + 2) % NS)
+                    with torch.cuda.stream(p.side1):
+                        self._stage_pfn(p, (k + 1) % NS)
+                    self._stage_bev(p, k)
+                    main.wait_stream(p.side1)           # join
+                    main.wait_stream(p.side2)
+                p.graphs[k] = gr
+        self._stage_vox(p, 0); self._stage_pfn(p, 0)
+        self._stage_vox(p, 1)
+        p.k, p.primed = 0, True
+        p.vox, p.pillar_features, p.pillar_scale = p.voxs[0], p.pfs[0], p.pss[0]
         return p
 
     @torch.no_grad()
     def stream_step(self, next_points=None, next_offsets=None, counts_out=None):
-        """Finish the batch voxelized last (its canvases are valid once this step completes) while voxelizing the next
-        one.  next_points / next_offsets: the NEXT batch (pinned host or device tensors); None = already resident in
-        `in_points[cur ^ 1]`.  counts_out: optional pinned (B+1,) int32 receiving the finished batch's pillar offsets."""
+        """One pipeline step: finish the oldest batch in flight (its canvases are valid once this step completes), run the
+        PFN of the next one and voxelize the batch given here (it is finished two steps later).
+        next_points / next_offsets: pinned host or device tensors; None = already resident in `in_points[(k + 2) % 3]`.
+        counts_out: optional pinned (B+1,) int32 receiving the finished batch's per-frame pillar offsets."""
         p = self._splan
+        NS = self._NS
         assert p.primed, "call stream_prime() first"
-        cur, nxt = p.cur, p.cur ^ 1
+        k = p.k
+        vs = (k + 2) % NS                                        # slot voxelized by this step
         main = torch.cuda.current_stream()
         if next_points is not None:
             with torch.cuda.stream(p.copy):
-                p.copy.wait_event(p.ev_input_free[nxt])         # K1 that last read this slot has finished
-                p.in_points[nxt].copy_(next_points, non_blocking=True)
-                p.in_offsets[nxt].copy_(next_offsets, non_blocking=True)
-                p.ev_copied[nxt].record(p.copy)
-            main.wait_event(p.ev_copied[nxt])
-        p.graphs[cur].replay()
-        p.ev_input_free[nxt].record(main)
+                p.copy.wait_event(p.ev_input_free[vs])          # the K1 that last read this slot has finished
+                p.in_points[vs].copy_(next_points, non_blocking=True)
+                p.in_offsets[vs].copy_(next_offsets, non_blocking=True)
+                p.ev_copied[vs].record(p.copy)
+            main.wait_event(p.ev_copied[vs])
+        p.graphs[k].replay()
+        p.ev_input_free[vs].record(main)
         if counts_out is not None:
-            counts_out.copy_(p.voxs[cur].voxel_offsets, non_blocking=True)
-        p.vox = p.voxs[cur]                              # the batch whose results are (being) produced by this step
-        p.cur = nxt
+            counts_out.copy_(p.voxs[k].voxel_offsets, non_blocking=True)
+        p.vox, p.pillar_features, p.pillar_scale = p.voxs[k], p.pfs[k], p.pss[k]   # the batch finished by this step
+        p.k = (k + 1) % NS
         return p
 
     @torch.no_grad()

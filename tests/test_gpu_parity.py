@@ -523,10 +523,10 @@ def test_streaming_mode_is_bit_identical_to_single_stream():
     host = [(torch.from_numpy(np.concatenate(fr, 0)).pin_memory(),
              torch.tensor(np.r_[0, np.cumsum([len(f) for f in fr])], dtype=torch.int32).pin_memory()) for fr in batches]
     cnt = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
-    fe.stream_prime(*host[0])
-    order = [0, 1, 2, 0, 2, 1, 1, 0]
+    order = [0, 1, 2, 0, 2, 1, 1, 0, 2, 2]
+    fe.stream_prime(host[order[0]], host[order[1]])
     for i, b in enumerate(order):
-        nb = order[i + 1] if i + 1 < len(order) else 0
+        nb = order[i + 2] if i + 2 < len(order) else 0            # the batch voxelized by this step finishes 2 steps later
         fe.stream_step(host[nb][0], host[nb][1], cnt)
         torch.cuda.synchronize()
         assert torch.equal(sp.spatial, ref[b][0]) and torch.equal(sp.spatial_scale, ref[b][1]), (i, b)
