@@ -53,15 +53,16 @@ constexpr int kTcChunkBytes = kTcChunkN * kTcK * 2;      // 32 KB
 constexpr int kTcATileBytes = kTcTileM * kTcK * 2;       // 16 KB
 constexpr int kTcCandCap = 64;         // candidate slots per row (<= 32: fast tail, <= 64: two-round tail)
 constexpr int kTcKPrime = 24;          // tau = kTcKPrime-th largest group maximum
-constexpr int kTcThreads = 512;        // warp 0 TMA, warp 1 MMA, warps 4-7 filter, warps 2-3 + 8-15 tail (+ A-tile loads)
-constexpr int kTcTailWarps = 10;
+constexpr int kTcThreads = 512;        // warp 0 TMEM alloc + TMA + MMA, warps 4-7 filter, warps 1-3 + 8-15 tail (+ A-tile loads)
+constexpr int kTcTailWarps = 11;
+constexpr int kTcCandBufs = 3;         // candidate-list ring between the filter and the tail
 constexpr int kTcSlowScratch = 2048;   // floats per tail warp (global workspace) for the overflow path
 
 struct TcSmem {
     uint8_t w[kTcWStages][kTcChunkBytes];     // 1024-aligned
     uint8_t a[2][kTcATileBytes];
-    uint16_t cand[2][kTcCandCap][kTcTileM];
-    int32_t cand_cnt[2][kTcTileM];
+    uint16_t cand[kTcCandBufs][kTcCandCap][kTcTileM];
+    int32_t cand_cnt[kTcCandBufs][kTcTileM];
     float gm[16][kTcTileM];                   // group maxima of the current chunk, one column per filter thread
     uint64_t w_full[kTcWStages], w_empty[kTcWStages];
     uint64_t a_full[2], a_empty[2];
@@ -100,9 +101,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
 // thread-to-thread handoffs; mbarriers remain where the async proxy (TMA, tcgen05.commit) is the signaller.
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-constexpr int kBarCFull = 1;    // +cb : filter (128 arrive) -> tail (320 sync)
-constexpr int kBarCEmpty = 3;   // +cb : tail (320 arrive)  -> filter (128 sync)
-constexpr int kBarTEmpty = 5;   // +tb : filter (128 arrive) -> MMA warp (32 sync)
+constexpr int kBarCFull = 1;    // +cb (3 ids): filter (128 arrive) -> tail warps (sync)
+constexpr int kBarCEmpty = 4;   // +cb (3 ids): tail warps (arrive)  -> filter (128 sync)
+constexpr int kBarTEmpty = 7;   // +tb (2 ids): filter (128 arrive) -> MMA warp (32 sync)
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -427,8 +428,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
     const uint32_t tmem_base = S.tmem_base;
 
     if (warp == 0) {
-        // (warp 0 only owns the TMEM allocation; its lanes wait at the final barrier)
-    } else if (warp == 1) {
         // ===== W producer + MMA issuer: the whole warp stays converged (it blocks on named barriers), lane 0 issues ==========
         // idesc: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcChunkN >> 3) << 17) |
@@ -494,7 +493,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
 #define FL_E(i)
 #endif
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
-            const int cb = ti & 1;
+            const int cb = ti % kTcCandBufs;
             // ---- sweep 1: group maxima -> tau ----
             float top[32];
 #pragma unroll
@@ -561,7 +560,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
             const float tau = top[kTcKPrime - 1];
             // ---- sweep 2: candidates = { j : logit_j >= tau } ----
             TCP_BEGIN();
-            if (ti >= 2) named_bar_sync(kBarCEmpty + cb, 128 + 32 * kTcTailWarps);   // tail finished with this candidate buffer
+            if (ti >= (uint32_t)kTcCandBufs) named_bar_sync(kBarCEmpty + cb, 128 + 32 * kTcTailWarps);   // tail finished with this candidate buffer
             TCP_END(2);
             int cnt = 0;
             for (int c = 0; c < nchunks; ++c, ++it) {
@@ -619,7 +618,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
 #endif
     } else {
         // ===== tail: A-tile loads + exact fp32 re-score, top-k, softmax, readout — one warp per row =================
-        const int tw = (warp < 4) ? (warp - 2) : (warp - 6);    // 0..9
+        const int tw = (warp < 4) ? (warp - 1) : (warp - 5);    // 0..10
         float *scratch = slow_scratch + ((size_t)blockIdx.x * kTcTailWarps + tw) * kTcSlowScratch;
         // fp32 pillar rows -> bf16, 128-B-swizzled K-major tile; this warp converts rows tw, tw+10, ...
         auto load_a_tile = [&](int t_load, uint32_t ti_load) {
@@ -657,7 +656,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
         long long tcp_row_acc[4] = {0, 0, 0, 0};
 #endif
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
-            const int cb = ti & 1;
+            const int cb = ti % kTcCandBufs;
             TCP_BEGIN();
             named_bar_sync(kBarCFull + cb, 128 + 32 * kTcTailWarps);
             TCP_END(0);
