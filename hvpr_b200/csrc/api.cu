@@ -67,3 +67,13 @@ extern "C" int hvpr_mem_attn(const float *pillars, const int32_t *n_pillars_dev,
     }
     return HVPR_ERR_ARG;
 }
+
+// ---- debug helpers (not part of the public header): raw runtime memset / D2D copy, used to probe copy-engine overlap
+extern "C" int hvpr_dbg_memset_async(void *dst, int value, size_t bytes, void *stream) {
+    HVPR_CHECK_CUDA(cudaMemsetAsync(dst, value, bytes, (cudaStream_t)stream));
+    return HVPR_OK;
+}
+extern "C" int hvpr_dbg_memcpy_d2d_async(void *dst, const void *src, size_t bytes, void *stream) {
+    HVPR_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return HVPR_OK;
+}
