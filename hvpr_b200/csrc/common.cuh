@@ -26,6 +26,17 @@ __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // streaming (evict-first) 128-bit store: canvases are written once and not re-read by this path
-__device__ __forceinline__ void st_stream_f4(float4 *p, float4 v) { __stcs(p, v); }
+#ifndef HVPR_BEV_STORE
+#define HVPR_BEV_STORE 0
+#endif
+__device__ __forceinline__ void st_stream_f4(float4 *p, float4 v) {
+#if HVPR_BEV_STORE == 0
+    __stcs(p, v);          // evict-first
+#elif HVPR_BEV_STORE == 1
+    *p = v;                // default write-back
+#else
+    __stwt(p, v);          // write-through
+#endif
+}
 
 }  // namespace hvpr
