@@ -24,9 +24,10 @@ struct BevArgs {
     int chunk_nc[16];    // channels in the chunk (multiple of 4)
 };
 constexpr int kBevChunk = 32;
+constexpr int kBevThreads = 128;   // small blocks: they slot in beside the register-heavy PFN blocks of the next batch
 
 // grid (ceil(cells/4/256), B, n_chunks)
-__global__ void __launch_bounds__(256) bev_fill_kernel(const __grid_constant__ BevArgs A,
+__global__ void __launch_bounds__(kBevThreads) bev_fill_kernel(const __grid_constant__ BevArgs A,
                                                        const int32_t *__restrict__ cell_map, int64_t cells) {
     const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // group of 4 consecutive cells
     const int64_t groups = cells >> 2;
@@ -116,8 +117,8 @@ extern "C" int hvpr_bev_fill(const float *feat_a, int ca, const float *feat_b, i
                 ++n;
             }
         for (int i = n; i < 16; ++i) { A.chunk_src[i] = 0; A.chunk_c0[i] = 0; A.chunk_nc[i] = 0; }
-        dim3 grid((unsigned)ceil_div64(cells / 4, 256), (unsigned)n_frames, (unsigned)n);
-        bev_fill_kernel<<<grid, 256, 0, stream>>>(A, cell_map, cells);
+        dim3 grid((unsigned)ceil_div64(cells / 4, kBevThreads), (unsigned)n_frames, (unsigned)n);
+        bev_fill_kernel<<<grid, kBevThreads, 0, stream>>>(A, cell_map, cells);
         HVPR_CHECK_LAUNCH();
     } else {
         dim3 grid((unsigned)ceil_div64(cells, 256), (unsigned)n_frames);

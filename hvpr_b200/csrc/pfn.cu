@@ -373,6 +373,10 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_kernel(const __grid_consta
 
 using namespace hvpr;
 
+static int g_pfn_blocks_per_sm = 3;
+// tuning knob (include/hvpr_b200.h): persistent PFN blocks per SM (1..3), read at launch time
+extern "C" int hvpr_tune_pfn_blocks_per_sm(int n) { if (n < 1 || n > 3) return HVPR_ERR_ARG; g_pfn_blocks_per_sm = n; return HVPR_OK; }
+
 int hvpr_pfn_init() {
     cudaError_t e;
     e = cudaFuncSetAttribute(pfn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PfnSmem));
@@ -401,7 +405,8 @@ extern "C" int hvpr_pfn(const float *voxels, const int32_t *num_points, const in
         P.v1[c] = a;
     }
     int64_t want = ceil_div64(n_rows_max, kPfnG);
-    const int blocks = (int)(want < (int64_t)kNumSMs * 3 ? want : (int64_t)kNumSMs * 3);   // persistent: 3 blocks / SM (shared memory)
+    const int64_t cap = (int64_t)kNumSMs * g_pfn_blocks_per_sm;                              // persistent blocks
+    const int blocks = (int)(want < cap ? want : cap);
     if (scale_out)
         pfn_kernel<true><<<blocks, kPfnThreads, sizeof(PfnSmem), stream>>>(
             P, voxels, num_points, coords, n_pillars_dev, n_rows_max, max_points, geom->vs[0], geom->vs[1],

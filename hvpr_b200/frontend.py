@@ -141,7 +141,9 @@ class HybridFrontEnd(torch.nn.Module):
         p.readout = torch.empty((rows, 64), dtype=torch.float32, device=dev)
         p.spatial = torch.empty((n_frames, 128, ny, nx), dtype=torch.float32, device=dev)
         p.spatial_scale = torch.empty((n_frames, 32, ny, nx), dtype=torch.float32, device=dev)
-        p.side1, p.side2, p.copy = (torch.cuda.Stream(device=dev) for _ in range(3))
+        # side1 (PFN of the next batch) gets dispatch priority over the canvas fill it shares the SMs with
+        p.side1 = torch.cuda.Stream(device=dev, priority=-1)
+        p.side2, p.copy = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         p.ev_copied = [torch.cuda.Event() for _ in range(NS)]
         p.ev_input_free = [torch.cuda.Event() for _ in range(NS)]
         p.graphs = [None] * NS
@@ -158,10 +160,16 @@ class HybridFrontEnd(torch.nn.Module):
         vox = p.voxs[slot]
         self.vfe.run(vox.voxels, vox.num_points, vox.coords, vox.n_pillars_dev, out=p.pfs[slot], scale_out=p.pss[slot])
 
-    def _stage_bev(self, p, slot):      # K3 + K4
+    def _stage_bev(self, p, slot, after_k3=None):      # K3 + K4
         vox = p.voxs[slot]
-        self.map_to_bev_module.run(p.pfs[slot], p.pss[slot], vox.cell_map, p.B, vox.n_pillars_dev, readout=p.readout,
-                                   spatial=p.spatial, spatial_scale=p.spatial_scale)
+        m = self.map_to_bev_module
+        m.memory.run(p.pfs[slot], m.k, vox.n_pillars_dev, out=p.readout)
+        if after_k3 is not None:
+            after_k3()
+        st = _lib.lib().hvpr_bev_fill(_lib.ptr(p.pfs[slot]), 64, _lib.ptr(p.readout), 64, _lib.ptr(p.pss[slot]), 32,
+                                      _lib.ptr(vox.cell_map), p.B, m.nx, m.ny, _lib.ptr(p.spatial),
+                                      _lib.ptr(p.spatial_scale), _lib.cur_stream())
+        _lib.check(st, "hvpr_bev_fill")
 
     @torch.no_grad()
     def stream_prime(self, batch0=None, batch1=None):
@@ -183,20 +191,26 @@ class HybridFrontEnd(torch.nn.Module):
                 self._stage_vox(p, slot); self._stage_pfn(p, slot)
             self._stage_bev(p, 0)
             torch.cuda.synchronize()
+            # 2 persistent PFN blocks per SM leave registers for the canvas-fill blocks it runs beside (+4 % measured)
+            _lib.check(_lib.lib().hvpr_tune_pfn_blocks_per_sm(2))
             for k in range(NS):
                 gr = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gr):
                     main = torch.cuda.current_stream()
-                    p.side1.wait_stream(main)           # fork
-                    p.side2.wait_stream(main)
+                    p.side2.wait_stream(main)           # fork
                     with torch.cuda.stream(p.side2):
                         self._stage_vox(p, (k + 2) % NS)
-                    with torch.cuda.stream(p.side1):
-                        self._stage_pfn(p, (k + 1) % NS)
-                    self._stage_bev(p, k)
+
+                    def _fork_pfn(k=k):
+                        # K3 holds whole SMs; the PFN of the next batch starts when it retires and shares the SMs with K4
+                        p.side1.wait_stream(main)
+                        with torch.cuda.stream(p.side1):
+                            self._stage_pfn(p, (k + 1) % NS)
+                    self._stage_bev(p, k, after_k3=_fork_pfn)
                     main.wait_stream(p.side1)           # join
                     main.wait_stream(p.side2)
                 p.graphs[k] = gr
+            _lib.check(_lib.lib().hvpr_tune_pfn_blocks_per_sm(3))
         self._stage_vox(p, 0); self._stage_pfn(p, 0)
         self._stage_vox(p, 1)
         p.k, p.primed = 0, True

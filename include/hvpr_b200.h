@@ -5,8 +5,9 @@
  * Every entry point
  *   - takes DEVICE pointers unless a parameter says "host";
  *   - enqueues all its work on `stream` (a cudaStream_t passed as void*), never synchronises the device,
- *     never allocates device memory, keeps no global state -> safe inside CUDA-graph capture and re-entrant
- *     across streams / devices (one process per GPU);
+ *     never allocates device memory, keeps no data state (the only process-wide setting is the launch-shape knob
+ *     hvpr_tune_pfn_blocks_per_sm) -> safe inside CUDA-graph capture and re-entrant across streams / devices
+ *     (one process per GPU);
  *   - returns HVPR_OK (0) or a negative HvprStatus; it never throws.
  * The caller (hvpr_b200/*.py through ctypes, or any C/C++ host) owns every buffer.
  *
@@ -102,6 +103,10 @@ int hvpr_pfn(const float *voxels, const int32_t *num_points, const int32_t *coor
              const int32_t *n_pillars_dev, int64_t n_rows_max, int max_points,
              const HvprPfnWeights *weights_host, const HvprGeom *geom, float x_off, float y_off, float z_off,
              float *pillar_features, float *scale_out, float *mask_out, void *stream);
+
+/* Launch-shape knob: persistent PFN blocks per SM (1..3, default 3).  2 leaves room for the small canvas-fill blocks when
+ * hvpr_pfn of the next batch is run concurrently with hvpr_bev_fill of the current one (streaming mode).  Read at launch. */
+int hvpr_tune_pfn_blocks_per_sm(int blocks_per_sm);
 
 /* ---- K3 memory attention -----------------------------------------------------------------------------------------
  * pillars (rows,64) fp32; mem_weight (M,64) fp32; readout (rows,64) fp32.

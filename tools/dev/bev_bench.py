@@ -1,8 +1,9 @@
 import ctypes, sys, torch
 sys.path.insert(0, '.')
 from hvpr_b200 import _lib
-variant = sys.argv[1]
-_lib.LIB_PATH = _lib.LIB_PATH.replace("libhvpr_b200.so", "libhvpr_b200_bev%s.so" % variant)
+variant = sys.argv[1] if len(sys.argv) > 1 else ""
+if variant:
+    _lib.LIB_PATH = _lib.LIB_PATH.replace("libhvpr_b200.so", "libhvpr_b200_bev%s.so" % variant)
 _lib.init_device(); L = _lib.lib()
 B, nx, ny, P = 8, 432, 496, 25229 * 8
 g = torch.Generator(device="cuda").manual_seed(0)
