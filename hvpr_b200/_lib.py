@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libhvpr_b200.so")
 SYMBOLS = [
     "hvpr_strerror", "hvpr_last_cuda_error", "hvpr_version", "hvpr_init",
     "hvpr_voxelize_workspace_bytes", "hvpr_voxelize", "hvpr_frame_offsets",
-    "hvpr_pfn", "hvpr_tune_pfn_blocks_per_sm",
+    "hvpr_pfn", "hvpr_tune_pfn",
     "hvpr_mem_attn_workspace_bytes", "hvpr_mem_pack_bf16", "hvpr_mem_attn",
     "hvpr_bev_fill", "hvpr_build_cell_map",
 ]
@@ -76,8 +76,8 @@ def lib():
     L.hvpr_pfn.restype = c_int
     L.hvpr_pfn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p,
                            c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]
-    L.hvpr_tune_pfn_blocks_per_sm.restype = c_int
-    L.hvpr_tune_pfn_blocks_per_sm.argtypes = [c_int]
+    L.hvpr_tune_pfn.restype = c_int
+    L.hvpr_tune_pfn.argtypes = [c_int, c_int]
     L.hvpr_mem_attn_workspace_bytes.restype = c_size_t
     L.hvpr_mem_attn_workspace_bytes.argtypes = [c_int64, c_int, c_int]
     L.hvpr_mem_pack_bf16.restype = c_int

@@ -114,7 +114,7 @@ __device__ __forceinline__ void pfn_scale_out(const PfnParams &P, PfnSmem &S, in
 //     max_p ReLU(W1a.x_p + c) = ReLU(max_p(W1a.x_p) + c),      c = b1 + W1b.x_max
 // so ONE pass over the real points produces both x_max (layer 0) and max_p(W1a.x_p); c is applied per pillar afterwards.
 // Both 16->64 contractions (W1a.x per point, W1b.x_max per pillar) run on the tensor cores as 3xTF32 m16n8k8 MMAs.
-template <bool kScale>
+template <bool kScale, bool kFragRegs>
 __global__ void __launch_bounds__(kPfnThreads, 3) pfn_kernel(const __grid_constant__ PfnParams P,
                                                           const float *__restrict__ voxels,
                                                           const int32_t *__restrict__ num_points,
@@ -148,13 +148,15 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_kernel(const __grid_consta
     if (t < 64) S.b1s[t] = P.w.b1[t];
     __syncthreads();
     // W1a fragments live in registers for the whole (persistent) block: no shared-memory traffic in the MMA loop
-    uint32_t wah[8][2][2], wal[8][2][2];
+    uint32_t wah[kFragRegs ? 8 : 1][2][2], wal[kFragRegs ? 8 : 1][2][2];
+    if (kFragRegs) {
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+        for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
+            for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-            for (int rg = 0; rg < 2; ++rg) { wah[nt][ks][rg] = S.bfrag[0][nt][ks][rg][0][lane]; wal[nt][ks][rg] = S.bfrag[0][nt][ks][rg][1][lane]; }
+                for (int rg = 0; rg < 2; ++rg) { wah[nt][ks][rg] = S.bfrag[0][nt][ks][rg][0][lane]; wal[nt][ks][rg] = S.bfrag[0][nt][ks][rg][1][lane]; }
+    }
 
     for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         const int64_t g0 = grp * kPfnG;
@@ -298,8 +300,10 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_kernel(const __grid_consta
                     float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
-                        const uint32_t bh0 = wah[nt][ks][0], bl0 = wal[nt][ks][0];
-                        const uint32_t bh1 = wah[nt][ks][1], bl1 = wal[nt][ks][1];
+                        const uint32_t bh0 = kFragRegs ? wah[kFragRegs ? nt : 0][ks][0] : S.bfrag[0][nt][ks][0][0][lane];
+                        const uint32_t bl0 = kFragRegs ? wal[kFragRegs ? nt : 0][ks][0] : S.bfrag[0][nt][ks][0][1][lane];
+                        const uint32_t bh1 = kFragRegs ? wah[kFragRegs ? nt : 0][ks][1] : S.bfrag[0][nt][ks][1][0][lane];
+                        const uint32_t bl1 = kFragRegs ? wal[kFragRegs ? nt : 0][ks][1] : S.bfrag[0][nt][ks][1][1][lane];
                         mma_tf32(c, alo[ks], bh0, bh1);
                         mma_tf32(c, ahi[ks], bl0, bl1);
                         mma_tf32(c, ahi[ks], bh0, bh1);
@@ -374,14 +378,24 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_kernel(const __grid_consta
 using namespace hvpr;
 
 static int g_pfn_blocks_per_sm = 3;
-// tuning knob (include/hvpr_b200.h): persistent PFN blocks per SM (1..3), read at launch time
-extern "C" int hvpr_tune_pfn_blocks_per_sm(int n) { if (n < 1 || n > 3) return HVPR_ERR_ARG; g_pfn_blocks_per_sm = n; return HVPR_OK; }
+static int g_pfn_frag_regs = 1;
+// launch-shape knob (include/hvpr_b200.h), read at launch time
+extern "C" int hvpr_tune_pfn(int blocks_per_sm, int low_register_variant) {
+    if (blocks_per_sm < 1 || blocks_per_sm > 3) return HVPR_ERR_ARG;
+    g_pfn_blocks_per_sm = blocks_per_sm;
+    g_pfn_frag_regs = low_register_variant ? 0 : 1;
+    return HVPR_OK;
+}
 
 int hvpr_pfn_init() {
     cudaError_t e;
-    e = cudaFuncSetAttribute(pfn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PfnSmem));
+    e = cudaFuncSetAttribute(pfn_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PfnSmem));
     if (e != cudaSuccess) { set_cuda_error(e); return HVPR_ERR_CUDA; }
-    e = cudaFuncSetAttribute(pfn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PfnSmem));
+    e = cudaFuncSetAttribute(pfn_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PfnSmem));
+    if (e != cudaSuccess) { set_cuda_error(e); return HVPR_ERR_CUDA; }
+    e = cudaFuncSetAttribute(pfn_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PfnSmem));
+    if (e != cudaSuccess) { set_cuda_error(e); return HVPR_ERR_CUDA; }
+    e = cudaFuncSetAttribute(pfn_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PfnSmem));
     if (e != cudaSuccess) { set_cuda_error(e); return HVPR_ERR_CUDA; }
     return HVPR_OK;
 }
@@ -407,14 +421,12 @@ extern "C" int hvpr_pfn(const float *voxels, const int32_t *num_points, const in
     int64_t want = ceil_div64(n_rows_max, kPfnG);
     const int64_t cap = (int64_t)kNumSMs * g_pfn_blocks_per_sm;                              // persistent blocks
     const int blocks = (int)(want < cap ? want : cap);
-    if (scale_out)
-        pfn_kernel<true><<<blocks, kPfnThreads, sizeof(PfnSmem), stream>>>(
-            P, voxels, num_points, coords, n_pillars_dev, n_rows_max, max_points, geom->vs[0], geom->vs[1],
-            geom->vs[2], x_off, y_off, z_off, pillar_features, scale_out, mask_out);
-    else
-        pfn_kernel<false><<<blocks, kPfnThreads, sizeof(PfnSmem), stream>>>(
-            P, voxels, num_points, coords, n_pillars_dev, n_rows_max, max_points, geom->vs[0], geom->vs[1],
-            geom->vs[2], x_off, y_off, z_off, pillar_features, scale_out, mask_out);
+#define HVPR_PFN_LAUNCH(SC, FR)                                                                                  \
+    pfn_kernel<SC, FR><<<blocks, kPfnThreads, sizeof(PfnSmem), stream>>>(                                         \
+        P, voxels, num_points, coords, n_pillars_dev, n_rows_max, max_points, geom->vs[0], geom->vs[1], geom->vs[2], \
+        x_off, y_off, z_off, pillar_features, scale_out, mask_out)
+    if (scale_out) { if (g_pfn_frag_regs) HVPR_PFN_LAUNCH(true, true); else HVPR_PFN_LAUNCH(true, false); }
+    else { if (g_pfn_frag_regs) HVPR_PFN_LAUNCH(false, true); else HVPR_PFN_LAUNCH(false, false); }
     HVPR_CHECK_LAUNCH();
     return HVPR_OK;
 }

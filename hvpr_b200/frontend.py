@@ -191,8 +191,8 @@ class HybridFrontEnd(torch.nn.Module):
                 self._stage_vox(p, slot); self._stage_pfn(p, slot)
             self._stage_bev(p, 0)
             torch.cuda.synchronize()
-            # 2 persistent PFN blocks per SM leave registers for the canvas-fill blocks it runs beside (+4 % measured)
-            _lib.check(_lib.lib().hvpr_tune_pfn_blocks_per_sm(2))
+            # the low-register PFN variant leaves room for the canvas-fill blocks it runs beside (+10 % measured)
+            _lib.check(_lib.lib().hvpr_tune_pfn(3, 1))
             for k in range(NS):
                 gr = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gr):
@@ -210,7 +210,7 @@ class HybridFrontEnd(torch.nn.Module):
                     main.wait_stream(p.side1)           # join
                     main.wait_stream(p.side2)
                 p.graphs[k] = gr
-            _lib.check(_lib.lib().hvpr_tune_pfn_blocks_per_sm(3))
+            _lib.check(_lib.lib().hvpr_tune_pfn(3, 0))
         self._stage_vox(p, 0); self._stage_pfn(p, 0)
         self._stage_vox(p, 1)
         p.k, p.primed = 0, True

@@ -6,7 +6,7 @@
  *   - takes DEVICE pointers unless a parameter says "host";
  *   - enqueues all its work on `stream` (a cudaStream_t passed as void*), never synchronises the device,
  *     never allocates device memory, keeps no data state (the only process-wide setting is the launch-shape knob
- *     hvpr_tune_pfn_blocks_per_sm) -> safe inside CUDA-graph capture and re-entrant across streams / devices
+ *     hvpr_tune_pfn) -> safe inside CUDA-graph capture and re-entrant across streams / devices
  *     (one process per GPU);
  *   - returns HVPR_OK (0) or a negative HvprStatus; it never throws.
  * The caller (hvpr_b200/*.py through ctypes, or any C/C++ host) owns every buffer.
@@ -104,9 +104,11 @@ int hvpr_pfn(const float *voxels, const int32_t *num_points, const int32_t *coor
              const HvprPfnWeights *weights_host, const HvprGeom *geom, float x_off, float y_off, float z_off,
              float *pillar_features, float *scale_out, float *mask_out, void *stream);
 
-/* Launch-shape knob: persistent PFN blocks per SM (1..3, default 3).  2 leaves room for the small canvas-fill blocks when
- * hvpr_pfn of the next batch is run concurrently with hvpr_bev_fill of the current one (streaming mode).  Read at launch. */
-int hvpr_tune_pfn_blocks_per_sm(int blocks_per_sm);
+/* Launch-shape knob, read at launch.  blocks_per_sm: persistent PFN blocks per SM (1..3, default 3).
+ * low_register_variant: 0 (default) keeps the W1a tensor-core fragments in registers (168 regs/thread, fastest alone);
+ * 1 reads them from shared memory (106 regs/thread) so that the small canvas-fill blocks of hvpr_bev_fill fit beside the PFN
+ * blocks when the PFN of the next batch runs concurrently with the fill of the current one (streaming mode).          */
+int hvpr_tune_pfn(int blocks_per_sm, int low_register_variant);
 
 /* ---- K3 memory attention -----------------------------------------------------------------------------------------
  * pillars (rows,64) fp32; mem_weight (M,64) fp32; readout (rows,64) fp32.
