@@ -12,7 +12,7 @@ __version__ = "0.1.0"
 def __getattr__(name):
     # torch-dependent modules are imported lazily so `import hvpr_b200` stays cheap
     import importlib
-    if name in ("vfe", "map_to_bev", "voxelizer", "frontend", "_lib"):
+    if name in ("vfe", "map_to_bev", "voxelizer", "frontend", "backbone", "_lib"):
         return importlib.import_module("." + name, __name__)
     if name in ("Voxelizer", "VoxelGenerator", "VoxelGeneratorV2"):
         return getattr(importlib.import_module(".voxelizer", __name__), name)
@@ -20,6 +20,8 @@ def __getattr__(name):
         return getattr(importlib.import_module(".vfe", __name__), name)
     if name in ("PointPillarScatter", "PointPillarScatter_Agg_Memory_1_scale", "MemoryUnit_Agg"):
         return getattr(importlib.import_module(".map_to_bev", __name__), name)
+    if name == "BaseBEVBackbone_Scale":
+        return importlib.import_module(".backbone", __name__).BaseBEVBackbone_Scale
     if name == "HybridFrontEnd":
         return importlib.import_module(".frontend", __name__).HybridFrontEnd
     raise AttributeError(name)

@@ -18,6 +18,7 @@ SYMBOLS = [
     "hvpr_pfn", "hvpr_tune_pfn",
     "hvpr_mem_attn_workspace_bytes", "hvpr_mem_pack_bf16", "hvpr_mem_attn",
     "hvpr_bev_fill", "hvpr_build_cell_map",
+    "hvpr_conv_packed_bytes", "hvpr_conv_pack_weights", "hvpr_conv2d", "hvpr_nchw_to_nhwc_bf16", "hvpr_attention_gate",
 ]
 
 OVERFLOW = {"continue": 0, "break": 1}
@@ -32,6 +33,14 @@ class HvprPfnWeights(ctypes.Structure):
     _fields_ = [("w0", c_float * 160), ("b0", c_float * 16), ("w1a", c_float * 1024), ("w1b", c_float * 1024),
                 ("b1", c_float * 64), ("ws0", c_float * 80), ("bs0", c_float * 16), ("ws1", c_float * 512),
                 ("bs1", c_float * 32)]
+
+
+class HvprConvArgs(ctypes.Structure):
+    _fields_ = [("in_", c_void_p), ("n", c_int32), ("h_in", c_int32), ("w_in", c_int32), ("in_cs", c_int32),
+                ("c_in", c_int32), ("ksize", c_int32), ("stride", c_int32), ("w_packed", c_void_p),
+                ("n_total", c_int32), ("bn", c_int32), ("bias", c_void_p), ("relu", c_int32), ("gate", c_void_p),
+                ("residual", c_void_p), ("res_cs", c_int32), ("out_mode", c_int32), ("out", c_void_p),
+                ("out_cs", c_int32), ("out_c_off", c_int32), ("up", c_int32), ("c_out", c_int32), ("out_ctot", c_int32)]
 
 
 class HvprError(RuntimeError):
@@ -90,6 +99,17 @@ def lib():
                                 c_void_p, c_void_p, c_void_p]
     L.hvpr_build_cell_map.restype = c_int
     L.hvpr_build_cell_map.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]
+    L.hvpr_conv_packed_bytes.restype = c_size_t
+    L.hvpr_conv_packed_bytes.argtypes = [c_int, c_int, c_int]
+    L.hvpr_conv_pack_weights.restype = c_int
+    L.hvpr_conv_pack_weights.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+    L.hvpr_conv2d.restype = c_int
+    L.hvpr_conv2d.argtypes = [ctypes.POINTER(HvprConvArgs), c_void_p]
+    L.hvpr_nchw_to_nhwc_bf16.restype = c_int
+    L.hvpr_nchw_to_nhwc_bf16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]
+    L.hvpr_attention_gate.restype = c_int
+    L.hvpr_attention_gate.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_float), c_float,
+                                      c_void_p, c_void_p, c_void_p]
     _lib = L
     return L
 

@@ -1,0 +1,432 @@
+// N1 — the convolutions of BaseBEVBackbone_Scale (pcdet/models/backbones_2d/base_bev_backbone.py:150-213,
+// eval forward :280-315) as ONE persistent, warp-specialised tcgen05 implicit-GEMM kernel:
+//
+//   3x3 stride-1 / stride-2 Conv2d (+ZeroPad2d(1)) + folded BN + ReLU            blocks[i], sfmblocks_down[i], scale_layers[i]
+//   ... with the SpatialAttention gate and the residual fused in the epilogue     x_att = gate * sfm(x_att) + x_att   (:286-290)
+//   ConvTranspose2d(k = s, stride = s) + folded BN + ReLU as a 1x1 GEMM with      deblocks[i] (:180-188), written straight into
+//   N = s*s*C_out and a pixel-shuffle store                                       its channel slice of the fp32 NCHW concat (:298)
+//
+// GEMM view: M = 128 output pixels (a bx x by patch of one image), N = bn output channels, K = taps x C_in.
+// Activations are NHWC bf16.  The A operand of tap (dy,dx) is the SAME patch shifted by (dy-1, dx-1): a 4-D TMA tensor-map
+// load {64 ch, bx, by, 1} with signed coordinates, out-of-bounds pixels zero-filled by the TMA unit (= the zero padding),
+// landing as the 128-B-swizzled K-major tile tcgen05.mma wants.  Stride 2 uses four "parity" tensor maps over the same
+// buffer (pixel strides doubled, base shifted by the parity), so a tap is again a plain shifted box — no im2col buffer, no
+// wasted MACs.  Weights are pre-packed (bf16, swizzled, BN scale folded in) and streamed with cp.async.bulk.
+// Accumulators live in TMEM, double-buffered: the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warp 0: TMA producer     warp 1: TMEM alloc + MMA issuer     warps 4-7: epilogue (one accumulator row per thread)
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <string.h>
+
+namespace hvpr {
+
+constexpr int kCvThreads = 256;
+constexpr int kCvABytes = 128 * 128;         // 128 pixels x 64 channels bf16
+constexpr int kCvPipeBytes = 192 * 1024;     // operand ring
+constexpr int kCvMaxStages = 8;
+constexpr int kCvMaxN = 2048;                // GEMM columns (bias staged in shared memory)
+
+struct ConvParams {
+    alignas(64) CUtensorMap tmap[4];
+    const uint8_t *wpk;
+    const float *bias;
+    const float *gate;
+    const __nv_bfloat16 *residual;
+    void *out;
+    int n_img, h_out, w_out;
+    int log2_bx, tiles_x, tiles_y;
+    int ntaps, kblocks, bn, n_tiles, nstages, n_total;
+    int relu, res_cs;
+    int out_mode, out_cs, out_c_off;
+    int up, cout, out_h, out_w, out_ctot;
+    int8_t tap_map[16], tap_ox[16], tap_oy[16];
+};
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t cv_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cv_mbar_init(uint64_t *b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cv_smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void cv_mbar_arrive(uint64_t *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cv_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void cv_mbar_expect_tx(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cv_smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cv_mbar_wait(uint64_t *b, uint32_t parity) {
+    const uint32_t a = cv_smem_u32(b);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (!done && spin > (1u << 26)) __trap();             // watchdog: a protocol bug must not hang the GPU
+    }
+}
+__device__ __forceinline__ void cv_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cv_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cv_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(cv_smem_u32(dst)), "l"(src), "r"(bytes), "r"(cv_smem_u32(bar)) : "memory");
+}
+// 4-D tiled TMA load: coordinates (channel, x, y, image), signed; out-of-bounds elements arrive as zeros
+__device__ __forceinline__ void cv_tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(cv_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(cv_smem_u32(bar)),
+                   "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void cv_umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(cv_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cv_umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, 128-byte swizzle, rows of 128 B, 8-row atoms 1024 B apart (same encoding as mem_attn_tc.cu)
+__device__ __forceinline__ uint64_t cv_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void cv_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                      "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                      "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                      "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+}
+__device__ __forceinline__ uint32_t cv_pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+__device__ __forceinline__ float cv_bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float cv_bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+struct CvTile { int nt, img, x0, y0; };
+__device__ __forceinline__ CvTile cv_decode(const ConvParams &P, int tile) {
+    CvTile t;
+    t.nt = tile % P.n_tiles;                 // N tiles fastest: CTAs running together share the A patch through L2
+    int m = tile / P.n_tiles;
+    const int tx = m % P.tiles_x; m /= P.tiles_x;
+    const int ty = m % P.tiles_y;
+    t.img = m / P.tiles_y;
+    t.x0 = tx << P.log2_bx;
+    t.y0 = ty * (128 >> P.log2_bx);
+    return t;
+}
+
+__global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams P) {
+    extern __shared__ uint8_t cv_smem_raw[];
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(cv_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *pipe = base;
+    float *bias_s = reinterpret_cast<float *>(base + kCvPipeBytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(base + kCvPipeBytes + kCvMaxN * 4);
+    uint64_t *empty = full + kCvMaxStages;
+    uint64_t *tfull = empty + kCvMaxStages;
+    uint64_t *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int stage_bytes = kCvABytes + P.bn * 128;
+    const int nst = P.nstages;
+    const int kiters = P.ntaps * P.kblocks;
+    const int total_tiles = P.n_img * P.tiles_y * P.tiles_x * P.n_tiles;
+
+    if (tid == 0) {
+        for (int s = 0; s < kCvMaxStages; ++s) { cv_mbar_init(&full[s], 1); cv_mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { cv_mbar_init(&tfull[a], 1); cv_mbar_init(&tempty[a], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < P.n_total; i += kCvThreads) bias_s[i] = P.bias ? P.bias[i] : 0.0f;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(cv_smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    cv_fence_before();
+    __syncthreads();
+    cv_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== producer: per k-iteration one shifted activation box (TMA tensor map) + one packed weight block (bulk copy)
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const CvTile t = cv_decode(P, tile);
+                const uint8_t *wtile = P.wpk + (size_t)t.nt * kiters * (size_t)(P.bn * 128);
+                for (int tap = 0; tap < P.ntaps; ++tap) {
+                    const CUtensorMap *map = &P.tmap[P.tap_map[tap]];
+                    const int x = t.x0 + P.tap_ox[tap], y = t.y0 + P.tap_oy[tap];
+                    for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
+                        const int s = it % nst;
+                        cv_mbar_wait(&empty[s], ((it / nst) & 1) ^ 1);
+                        uint8_t *dst = pipe + (size_t)s * stage_bytes;
+                        cv_mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+                        cv_tma_load_4d(dst, map, &full[s], kb * 64, x, y, t.img);
+                        cv_bulk_g2s(dst + kCvABytes, wtile + (size_t)(tap * P.kblocks + kb) * (size_t)(P.bn * 128),
+                                    (uint32_t)(P.bn * 128), &full[s]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer ==============================================================================================
+        if (lane == 0) {
+            // idesc: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            uint32_t it = 0, ti = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+                const uint32_t acc = ti & 1;
+                cv_mbar_wait(&tempty[acc], ((ti >> 1) & 1) ^ 1);        // epilogue drained this accumulator
+                cv_fence_after();
+                const uint32_t d = tmem_base + acc * 256u;
+                for (int ki = 0; ki < kiters; ++ki, ++it) {
+                    const int s = it % nst;
+                    cv_mbar_wait(&full[s], (it / nst) & 1);
+                    cv_fence_after();
+                    const uint32_t sa = cv_smem_u32(pipe + (size_t)s * stage_bytes);
+                    const uint64_t adesc = cv_desc_sw128(sa), bdesc = cv_desc_sw128(sa + kCvABytes);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)          // +32 B along K inside the 128-B swizzle atom
+                        cv_umma_bf16(d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (ki | kk) != 0);
+                    cv_umma_commit(&empty[s]);
+                }
+                cv_umma_commit(&tfull[acc]);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===== epilogue: bias (folded BN shift), ReLU, gate * v + residual, store ======================================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int px = row & ((1 << P.log2_bx) - 1), py = row >> P.log2_bx;
+        uint32_t ti = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+            const CvTile t = cv_decode(P, tile);
+            const uint32_t acc = ti & 1;
+            const int x = t.x0 + px, y = t.y0 + py;
+            const bool valid = (x < P.w_out) && (y < P.h_out);
+            const int64_t pix = ((int64_t)t.img * P.h_out + y) * P.w_out + x;
+            const float g = (P.gate && valid) ? __ldg(P.gate + pix) : 1.0f;
+            cv_mbar_wait(&tfull[acc], (ti >> 1) & 1);
+            cv_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
+            for (int ch = 0; ch < P.bn; ch += 32) {
+                uint32_t r[32];
+                __syncwarp();                                   // tcgen05.ld is warp-collective: re-converge after the guarded stores
+                cv_tmem_ld32(taddr + (uint32_t)ch, r);
+                const int col0 = t.nt * P.bn + ch;
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    v[i] = __uint_as_float(r[i]) + bias_s[col0 + i];
+                    if (P.relu) v[i] = fmaxf(v[i], 0.0f);
+                }
+                if (valid && P.out_mode == 0) {
+                    if (P.residual) {
+                        const uint4 *rp = reinterpret_cast<const uint4 *>(P.residual + pix * P.res_cs + col0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 u = __ldg(rp + j);
+                            v[8 * j + 0] = fmaf(g, v[8 * j + 0], cv_bf16_lo(u.x)); v[8 * j + 1] = fmaf(g, v[8 * j + 1], cv_bf16_hi(u.x));
+                            v[8 * j + 2] = fmaf(g, v[8 * j + 2], cv_bf16_lo(u.y)); v[8 * j + 3] = fmaf(g, v[8 * j + 3], cv_bf16_hi(u.y));
+                            v[8 * j + 4] = fmaf(g, v[8 * j + 4], cv_bf16_lo(u.z)); v[8 * j + 5] = fmaf(g, v[8 * j + 5], cv_bf16_hi(u.z));
+                            v[8 * j + 6] = fmaf(g, v[8 * j + 6], cv_bf16_lo(u.w)); v[8 * j + 7] = fmaf(g, v[8 * j + 7], cv_bf16_hi(u.w));
+                        }
+                    } else if (P.gate) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] *= g;
+                    }
+                    uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(P.out) + pix * P.out_cs + P.out_c_off + col0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        op[j] = make_uint4(cv_pack_bf16(v[8 * j], v[8 * j + 1]), cv_pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                           cv_pack_bf16(v[8 * j + 4], v[8 * j + 5]), cv_pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                } else if (valid) {
+                    // pixel shuffle of the transposed conv: GEMM column = (dy*up + dx)*cout + co  ->  fp32 NCHW slice
+                    const int sub = col0 / P.cout, co0 = col0 % P.cout;
+                    const int oy = y * P.up + sub / P.up, ox = x * P.up + sub % P.up;
+                    float *op = reinterpret_cast<float *>(P.out) +
+                                (((int64_t)t.img * P.out_ctot + P.out_c_off + co0) * P.out_h + oy) * P.out_w + ox;
+                    const int64_t cstride = (int64_t)P.out_h * P.out_w;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) __stcs(op + i * cstride, v[i]);
+                }
+            }
+            cv_fence_before();
+            cv_mbar_arrive(&tempty[acc]);
+        }
+    }
+
+    cv_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        cv_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// folded fp32 weights (n_total, taps, cin) -> bf16 image [n-tile][tap][k-block][bn rows x 128 B], 128-B swizzled
+__global__ void conv_pack_kernel(const float *__restrict__ w, int n_total, int taps, int cin, int bn, uint8_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // one 16-byte piece (8 input channels) per thread
+    const int kblocks = cin / 64;
+    const int64_t total = (int64_t)n_total * taps * kblocks * 8;
+    if (i >= total) return;
+    const int j = (int)(i & 7);
+    int64_t rest = i >> 3;
+    const int kb = (int)(rest % kblocks); rest /= kblocks;
+    const int tap = (int)(rest % taps);
+    const int n = (int)(rest / taps);
+    const float *src = w + ((int64_t)n * taps + tap) * cin + kb * 64 + j * 8;
+    uint4 pk;
+    pk.x = cv_pack_bf16(src[0], src[1]); pk.y = cv_pack_bf16(src[2], src[3]);
+    pk.z = cv_pack_bf16(src[4], src[5]); pk.w = cv_pack_bf16(src[6], src[7]);
+    const int nt = n / bn, r = n % bn;
+    const size_t off = ((size_t)(nt * taps + tap) * kblocks + kb) * (size_t)(bn * 128) + (size_t)(r >> 3) * 1024 +
+                       (size_t)(r & 7) * 128 + (size_t)((j ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4 *>(out + off) = pk;
+}
+
+}  // namespace hvpr
+using namespace hvpr;
+
+typedef CUresult (*CvEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static CvEncodeFn cv_encode_fn() {
+    static CvEncodeFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (CvEncodeFn)p;
+    }
+    return fn;
+}
+
+static size_t cv_smem_bytes() { return 1024 + kCvPipeBytes + kCvMaxN * 4 + (2 * kCvMaxStages + 4) * 8 + 16; }
+
+int hvpr_conv_init() {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv_smem_bytes());
+    if (e != cudaSuccess) { set_cuda_error(e); return HVPR_ERR_CUDA; }
+    return HVPR_OK;
+}
+
+extern "C" size_t hvpr_conv_packed_bytes(int n_total, int taps, int c_in) { return (size_t)n_total * taps * c_in * 2; }
+
+extern "C" int hvpr_conv_pack_weights(const float *w_ntc, int n_total, int taps, int c_in, int bn, void *out_packed, void *stream) {
+    if (!w_ntc || !out_packed || n_total <= 0 || taps <= 0 || c_in <= 0) return HVPR_ERR_ARG;
+    if (c_in % 64 || bn < 32 || bn > 256 || (bn & (bn - 1)) || n_total % bn || n_total > kCvMaxN) return HVPR_ERR_UNSUPPORTED;
+    if ((uintptr_t)out_packed % 16 || (uintptr_t)w_ntc % 4) return HVPR_ERR_ARG;
+    const int64_t total = (int64_t)n_total * taps * (c_in / 64) * 8;
+    conv_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w_ntc, n_total, taps, c_in, bn,
+                                                                                      (uint8_t *)out_packed);
+    HVPR_CHECK_LAUNCH();
+    return HVPR_OK;
+}
+
+extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
+    if (!a || !a->in || !a->w_packed || !a->out) return HVPR_ERR_ARG;
+    if (a->n <= 0 || a->h_in <= 0 || a->w_in <= 0) return HVPR_ERR_ARG;
+    if (a->c_in <= 0 || a->c_in % 64 || a->in_cs < a->c_in || a->in_cs % 8) return HVPR_ERR_UNSUPPORTED;
+    if (a->bn < 32 || a->bn > 256 || (a->bn & (a->bn - 1)) || a->n_total % a->bn || a->n_total > kCvMaxN) return HVPR_ERR_UNSUPPORTED;
+    if (!((a->ksize == 3 && (a->stride == 1 || a->stride == 2)) || (a->ksize == 1 && a->stride == 1))) return HVPR_ERR_UNSUPPORTED;
+    if (a->stride == 2 && ((a->h_in | a->w_in) & 1)) return HVPR_ERR_UNSUPPORTED;
+    if (((uintptr_t)a->in | (uintptr_t)a->w_packed | (uintptr_t)a->out | (uintptr_t)a->residual) % 16) return HVPR_ERR_ARG;
+    CvEncodeFn enc = cv_encode_fn();
+    if (!enc) return HVPR_ERR_UNSUPPORTED;
+
+    ConvParams P;
+    memset(&P, 0, sizeof(P));
+    P.n_img = a->n;
+    P.h_out = a->h_in / a->stride;
+    P.w_out = a->w_in / a->stride;
+    // patch shape: the power-of-two split of 128 pixels that wastes the fewest out-of-image pixels (ties: wider rows)
+    int best = -1; int64_t best_cost = 0;
+    for (int l = 0; l <= 7; ++l) {
+        const int bx = 1 << l, by = 128 >> l;
+        const int64_t cost = ceil_div64(P.w_out, bx) * bx * (ceil_div64(P.h_out, by) * by);
+        if (best < 0 || cost < best_cost || (cost == best_cost && l <= 4)) { best = l; best_cost = cost; }
+    }
+    P.log2_bx = best;
+    const int bx = 1 << best, by = 128 >> best;
+    P.tiles_x = (int)ceil_div64(P.w_out, bx);
+    P.tiles_y = (int)ceil_div64(P.h_out, by);
+    P.kblocks = a->c_in / 64;
+    P.bn = a->bn;
+    P.n_total = a->n_total;
+    P.n_tiles = a->n_total / a->bn;
+    const int stage_bytes = kCvABytes + a->bn * 128;
+    P.nstages = kCvPipeBytes / stage_bytes;
+    if (P.nstages > kCvMaxStages) P.nstages = kCvMaxStages;
+    P.wpk = (const uint8_t *)a->w_packed;
+    P.bias = a->bias;
+    P.gate = a->gate;
+    P.residual = (const __nv_bfloat16 *)a->residual;
+    P.res_cs = a->res_cs;
+    P.relu = a->relu;
+    P.out = a->out;
+    P.out_mode = a->out_mode;
+    P.out_cs = a->out_cs;
+    P.out_c_off = a->out_c_off;
+    if (a->out_mode == 0) {
+        if (a->out_cs % 8 || a->out_c_off % 8 || a->out_c_off + a->n_total > a->out_cs) return HVPR_ERR_ARG;
+        if (a->residual && (a->res_cs % 8 || a->res_cs < a->n_total)) return HVPR_ERR_ARG;
+    } else if (a->out_mode == 1) {
+        if (a->up < 1 || a->c_out <= 0 || a->c_out % 32 || a->n_total != a->up * a->up * a->c_out) return HVPR_ERR_ARG;
+        if (a->out_c_off + a->c_out > a->out_ctot || a->residual || a->gate) return HVPR_ERR_ARG;
+        P.up = a->up; P.cout = a->c_out; P.out_ctot = a->out_ctot;
+        P.out_h = P.h_out * a->up; P.out_w = P.w_out * a->up;
+    } else return HVPR_ERR_ARG;
+
+    // tensor maps over the NHWC bf16 input: dims (channel, x, y, image)
+    const cuuint32_t box[4] = {64u, (cuuint32_t)bx, (cuuint32_t)by, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    const uint64_t pix_b = (uint64_t)a->in_cs * 2u;
+    const int nmaps = (a->stride == 2) ? 4 : 1;
+    for (int m = 0; m < nmaps; ++m) {
+        const int pyy = m >> 1, pxx = m & 1;
+        void *gbase = (uint8_t *)a->in + ((uint64_t)pyy * a->w_in + pxx) * pix_b;
+        const cuuint64_t dims[4] = {(cuuint64_t)a->c_in, (cuuint64_t)(a->w_in / a->stride), (cuuint64_t)(a->h_in / a->stride),
+                                    (cuuint64_t)a->n};
+        const cuuint64_t strides[3] = {pix_b * a->stride, pix_b * a->w_in * a->stride, pix_b * a->w_in * a->h_in};
+        CUresult r = enc(&P.tmap[m], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, gbase, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return HVPR_ERR_ARG;
+    }
+    P.ntaps = a->ksize * a->ksize;
+    for (int dy = 0; dy < a->ksize; ++dy)
+        for (int dx = 0; dx < a->ksize; ++dx) {
+            const int tpi = dy * a->ksize + dx;
+            const int oy = (a->ksize == 3) ? dy - 1 : 0, ox = (a->ksize == 3) ? dx - 1 : 0;
+            if (a->stride == 2) {      // input pixel 2*o + off  ->  parity (off & 1), half-resolution offset (off - parity) / 2
+                const int ppy = oy & 1, ppx = ox & 1;
+                P.tap_map[tpi] = (int8_t)(ppy * 2 + ppx);
+                P.tap_oy[tpi] = (int8_t)((oy - ppy) / 2);
+                P.tap_ox[tpi] = (int8_t)((ox - ppx) / 2);
+            } else {
+                P.tap_map[tpi] = 0; P.tap_oy[tpi] = (int8_t)oy; P.tap_ox[tpi] = (int8_t)ox;
+            }
+        }
+    const int64_t total_tiles = (int64_t)P.n_img * P.tiles_x * P.tiles_y * P.n_tiles;
+    const int grid = (int)(total_tiles < kNumSMs ? total_tiles : kNumSMs);
+    conv_tc_kernel<<<grid, kCvThreads, cv_smem_bytes(), (cudaStream_t)stream>>>(P);
+    HVPR_CHECK_LAUNCH();
+    return HVPR_OK;
+}

@@ -134,6 +134,46 @@ int hvpr_bev_fill(const float *feat_a, int ca, const float *feat_b, int cb, cons
 int hvpr_build_cell_map(const int32_t *coords, const int32_t *n_pillars_dev, int64_t n_rows_max,
                         int n_frames, int nx, int ny, int32_t *cell_map, void *stream);
 
+/* ==== N1 (first "next" row): BaseBEVBackbone_Scale convolutions ======================================
+ * Replaces the nn.Conv2d / nn.ConvTranspose2d + BatchNorm2d + ReLU stacks built at
+ * pcdet/models/backbones_2d/base_bev_backbone.py:150-213 and run by the eval forward at :280-315, and the
+ * SpatialAttention gate of pcdet/models/backbones_2d/spatial_attention.py:47-63.
+ * Activations are NHWC bf16 with a channel stride (in_cs / out_cs elements per pixel); eval-mode BN is folded into the
+ * weights (scale) and the bias (shift) by the caller.                                                               */
+typedef struct HvprConvArgs {
+    const void *in;          /* (n, h_in, w_in, in_cs) bf16 */
+    int32_t n, h_in, w_in, in_cs;
+    int32_t c_in;            /* channels contracted: multiple of 64 (pad with zero channels / zero weights) */
+    int32_t ksize, stride;   /* 3 (zero padding 1) with stride 1 | 2 (even h_in, w_in), or 1 with stride 1 */
+    const void *w_packed;    /* hvpr_conv_pack_weights image */
+    int32_t n_total;         /* GEMM columns: c_out (out_mode 0) or up*up*c_out (out_mode 1), <= 2048 */
+    int32_t bn;              /* column tile: 32, 64, 128 or 256, dividing n_total (same value as at pack time) */
+    const float *bias;       /* (n_total) fp32 or NULL */
+    int32_t relu;
+    const float *gate;       /* out_mode 0: optional (n, h_out, w_out) fp32 multiplier applied after the ReLU */
+    const void *residual;    /* out_mode 0: optional (n, h_out, w_out, res_cs) bf16 added after the gate */
+    int32_t res_cs;
+    int32_t out_mode;        /* 0: bf16 NHWC (n, h_out, w_out, out_cs), channels [out_c_off, out_c_off + n_total)
+                                1: ConvTranspose2d(k = up, stride = up) pixel shuffle into fp32 NCHW
+                                   (n, out_ctot, h_out*up, w_out*up), channels [out_c_off, out_c_off + c_out);
+                                   GEMM column = (dy*up + dx)*c_out + co                                          */
+    void *out;
+    int32_t out_cs, out_c_off;
+    int32_t up, c_out, out_ctot;
+} HvprConvArgs;
+
+/* w_ntc: (n_total, taps, c_in) fp32 DEVICE, taps row-major (dy, dx).  out_packed: hvpr_conv_packed_bytes() bytes. */
+size_t hvpr_conv_packed_bytes(int n_total, int taps, int c_in);
+int hvpr_conv_pack_weights(const float *w_ntc, int n_total, int taps, int c_in, int bn, void *out_packed, void *stream);
+/* args is a HOST struct; TMA tensor maps are encoded on the host per call (no device sync, graph-capturable). */
+int hvpr_conv2d(const HvprConvArgs *args, void *stream);
+/* fp32 NCHW (n,c,h,w) -> bf16 NHWC (n,h,w,out_cs), channels [0,c); other channels of out are left untouched. */
+int hvpr_nchw_to_nhwc_bf16(const float *in, int n, int c, int h, int w, void *out, int out_cs, void *stream);
+/* gate = sigmoid(BN(conv3x3_{2->1}([max_c y, mean_c y]) + b)); w18_host = folded weights [(ch*3+dy)*3+dx] (HOST),
+ * bias = folded scalar; pooled_ws: (n*h*w*2) fp32 scratch; gate_out: (n,h,w) fp32.                                 */
+int hvpr_attention_gate(const void *y_nhwc_bf16, int n, int h, int w, int cs, int c, const float *w18_host, float bias,
+                        float *pooled_ws, float *gate_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

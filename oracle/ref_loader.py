@@ -81,3 +81,31 @@ def load():
         PointPillarScatter_Agg_Memory_1_scale=sc.PointPillarScatter_Agg_Memory_1_scale)
     _CACHE["ns"] = ns
     return ns
+
+
+BACKBONE_CFG = Cfg(NAME="BaseBEVBackbone_Scale", LAYER_NUMS=[3, 3, 3], SFM_LAYER_NUMS=[3, 3, 3], LAYER_STRIDES=[1, 2, 2],
+                   NUM_FILTERS=[128, 256, 512], NUM_SCALE_FILTERS=[32, 64, 128], UPSAMPLE_STRIDES=[1, 2, 4],
+                   NUM_UPSAMPLE_FILTERS=[128, 128, 128])                                # hvpr.yaml:87-95
+
+
+def load_backbone():
+    """-> namespace with BaseBEVBackbone, BaseBEVBackbone_Scale, SpatialAttention (row N1 of SURVEY.md §8f).
+
+    One in-memory patch (breakage B4): base_bev_backbone.py:220 instantiates `SpatialAttention` without
+    importing it; the class lives next door in spatial_attention.py:47-63 and is injected into the module namespace.
+    """
+    if "bb" in _CACHE:
+        return _CACHE["bb"]
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REF)
+    sys.dont_write_bytecode = True
+    d = os.path.join(REF, "pcdet/models/backbones_2d")
+    sa = types.ModuleType("_hvpr_ref_spatial_attention")
+    exec(compile(open(os.path.join(d, "spatial_attention.py")).read(), "spatial_attention.py", "exec"), sa.__dict__)
+    bb = types.ModuleType("_hvpr_ref_base_bev_backbone")
+    bb.__dict__["SpatialAttention"] = sa.SpatialAttention                               # patch B4
+    exec(compile(open(os.path.join(d, "base_bev_backbone.py")).read(), "base_bev_backbone.py", "exec"), bb.__dict__)
+    ns = types.SimpleNamespace(BaseBEVBackbone=bb.BaseBEVBackbone, BaseBEVBackbone_Scale=bb.BaseBEVBackbone_Scale,
+                               SpatialAttention=sa.SpatialAttention)
+    _CACHE["bb"] = ns
+    return ns

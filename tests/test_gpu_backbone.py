@@ -1,0 +1,181 @@
+"""GPU parity of row N1 (BaseBEVBackbone_Scale on tcgen05) against the oracle / golden fixture, through the C ABI.
+
+Tolerances (stated here because north_star gives none for this row): activations and weights are bf16 with fp32
+accumulation, so a single layer must match an fp32 convolution of the SAME bf16-rounded operands to bf16 output rounding
+(2^-8 relative to the tensor maximum), and the whole 24-convolution backbone must match the fp32 reference within
+TOL_BACKBONE = 2e-2 (max-norm, relative to max|ref|) and 1e-2 in relative L2.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_LAYER = 2.0 ** -8
+TOL_BACKBONE = 2e-2
+TOL_BACKBONE_L2 = 1e-2
+
+
+def _lib():
+    from hvpr_b200 import _lib
+    _lib.init_device()
+    return _lib
+
+
+def _pack(w_ntc, bn):
+    L = _lib()
+    n_total, taps, cin = w_ntc.shape
+    out = torch.empty(L.lib().hvpr_conv_packed_bytes(n_total, taps, cin), dtype=torch.uint8, device="cuda")
+    L.check(L.lib().hvpr_conv_pack_weights(L.ptr(w_ntc.contiguous()), n_total, taps, cin, bn, L.ptr(out), L.cur_stream()))
+    return out
+
+
+def _conv_call(x_nhwc, wpk, n_total, bn, bias, ksize, stride, c_in, out, *, relu=True, gate=None, residual=None,
+               out_mode=0, out_c_off=0, up=1, c_out=0, out_ctot=0):
+    L = _lib()
+    a = L.HvprConvArgs()
+    n, h, w, cs = x_nhwc.shape
+    a.in_, a.n, a.h_in, a.w_in, a.in_cs, a.c_in = x_nhwc.data_ptr(), n, h, w, cs, c_in
+    a.ksize, a.stride, a.w_packed, a.n_total, a.bn = ksize, stride, wpk.data_ptr(), n_total, bn
+    a.bias, a.relu = (bias.data_ptr() if bias is not None else None), int(relu)
+    a.gate = gate.data_ptr() if gate is not None else None
+    a.residual = residual.data_ptr() if residual is not None else None
+    a.res_cs = residual.shape[-1] if residual is not None else 0
+    a.out_mode, a.out = out_mode, out.data_ptr()
+    a.out_cs = out.shape[-1] if out_mode == 0 else 0
+    a.out_c_off, a.up, a.c_out, a.out_ctot = out_c_off, up, c_out or n_total, out_ctot
+    L.check(L.lib().hvpr_conv2d(ctypes.byref(a), L.cur_stream()), "hvpr_conv2d")
+    torch.cuda.synchronize()
+
+
+def _rand_case(seed, n, h, w, cin, cout, k):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(n, cin, h, w, generator=g).cuda().bfloat16()
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda().bfloat16()
+    b = torch.randn(cout, generator=g).cuda() * 0.1
+    return x, wt, b
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,stride,bn", [
+    (1, 16, 8, 64, 32, 1, 32),          # exactly one 128-pixel patch
+    (2, 20, 28, 128, 128, 1, 128),      # ragged patches: TMA zero fill on every side + masked stores
+    (1, 24, 40, 128, 256, 2, 256),      # stride 2 through the four parity tensor maps
+    (2, 12, 12, 256, 256, 1, 256),
+    (1, 10, 36, 64, 64, 2, 64),
+    (1, 9, 130, 128, 128, 1, 128),      # wider than one patch row, odd height
+])
+def test_conv3x3_layer_matches_fp32_conv_of_same_bf16_operands(n, h, w, cin, cout, stride, bn):
+    x, wt, b = _rand_case(n * 1000 + h, n, h, w, cin, cout, 3)
+    ref = F.relu(F.conv2d(x.float(), wt.float(), b, stride=stride, padding=1))
+    w_ntc = wt.float().permute(0, 2, 3, 1).reshape(cout, 9, cin)
+    wpk = _pack(w_ntc, bn)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    out = torch.full((n, h // stride, w // stride, cout + 8), 7.0, dtype=torch.bfloat16, device="cuda")   # +8: channel stride > C
+    _conv_call(x_nhwc, wpk, cout, bn, b, 3, stride, cin, out)
+    got = out[..., :cout].permute(0, 3, 1, 2).float()
+    assert rel_err(got, ref)[0] <= TOL_LAYER, rel_err(got, ref)
+    assert torch.all(out[..., cout:] == 7.0)            # pad channels untouched
+
+
+def test_conv_gate_and_residual_epilogue():
+    n, h, w, c = 2, 12, 20, 128
+    x, wt, b = _rand_case(5, n, h, w, c, c, 3)
+    gate = torch.rand(n, h, w, device="cuda")
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    ref = gate[:, None] * F.relu(F.conv2d(x.float(), wt.float(), b, padding=1)) + x.float()
+    wpk = _pack(wt.float().permute(0, 2, 3, 1).reshape(c, 9, c), 128)
+    out = torch.empty(n, h, w, c, dtype=torch.bfloat16, device="cuda")
+    _conv_call(x_nhwc, wpk, c, 128, b, 3, 1, c, out, gate=gate, residual=x_nhwc)
+    assert rel_err(out.permute(0, 3, 1, 2).float(), ref)[0] <= TOL_LAYER
+
+
+@pytest.mark.parametrize("up,cin", [(1, 128), (2, 256), (4, 512)])
+def test_transposed_conv_pixel_shuffle_into_nchw_slice(up, cin):
+    n, h, w, cout, ctot, coff = 2, 6, 10, 128, 384, 128
+    g = torch.Generator(device="cpu").manual_seed(up)
+    x = torch.randn(n, cin, h, w, generator=g).cuda().bfloat16()
+    wt = (torch.randn(cin, cout, up, up, generator=g) / cin ** 0.5).cuda().bfloat16()
+    b = torch.randn(cout, generator=g).cuda() * 0.1
+    ref = F.relu(F.conv_transpose2d(x.float(), wt.float(), b, stride=up))
+    w_ntc = wt.float().permute(2, 3, 1, 0).reshape(up * up * cout, 1, cin)
+    bn = 256 if (up * up * cout) % 256 == 0 else 128
+    wpk = _pack(w_ntc, bn)
+    out = torch.full((n, ctot, h * up, w * up), -3.0, device="cuda")
+    _conv_call(x.permute(0, 2, 3, 1).contiguous(), wpk, up * up * cout, bn, b.repeat(up * up), 1, 1, cin, out,
+               out_mode=1, out_c_off=coff, up=up, c_out=cout, out_ctot=ctot)
+    assert rel_err(out[:, coff:coff + cout], ref)[0] <= 1e-5         # fp32 output: only the summation order differs
+    assert torch.all(out[:, :coff] == -3.0) and torch.all(out[:, coff + cout:] == -3.0)
+
+
+def test_attention_gate_matches_oracle():
+    from oracle import backbone as ob
+    L = _lib()
+    w = ob.random_backbone_weights(3)
+    n, h, wd, c = 2, 10, 14, 32
+    y = torch.rand(n, c, h, wd).bfloat16()
+    ref = ob.attention_gate(y.float(), w)[:, 0]
+    cw, s = torch.from_numpy(w["attention.spatial.conv.weight"]).double(), None
+    s = torch.from_numpy(w["attention.spatial.norm.weight"]).double() / torch.sqrt(
+        torch.from_numpy(w["attention.spatial.norm.running_var"]).double() + 1e-3)
+    shift = torch.from_numpy(w["attention.spatial.norm.bias"]).double() + (
+        torch.from_numpy(w["attention.spatial.conv.bias"]).double() - torch.from_numpy(w["attention.spatial.norm.running_mean"]).double()) * s
+    w18 = (ctypes.c_float * 18)(*[float(v) for v in (cw * s).reshape(-1)])
+    y_nhwc = torch.zeros(n, h, wd, 64, dtype=torch.bfloat16, device="cuda")
+    y_nhwc[..., :c] = y.permute(0, 2, 3, 1).cuda()
+    pooled = torch.empty(n, h, wd, 2, device="cuda")
+    gate = torch.empty(n, h, wd, device="cuda")
+    L.check(L.lib().hvpr_attention_gate(L.ptr(y_nhwc), n, h, wd, 64, c, w18, float(shift[0]), L.ptr(pooled), L.ptr(gate),
+                                        L.cur_stream()))
+    assert rel_err(gate, ref)[0] <= 1e-5
+
+
+def test_nchw_to_nhwc_bf16_is_exact_rounding():
+    L = _lib()
+    x = torch.randn(2, 32, 7, 45, device="cuda")
+    out = torch.zeros(2, 7, 45, 64, dtype=torch.bfloat16, device="cuda")
+    L.check(L.lib().hvpr_nchw_to_nhwc_bf16(L.ptr(x), 2, 32, 7, 45, L.ptr(out), 64, L.cur_stream()))
+    assert torch.equal(out[..., :32], x.permute(0, 2, 3, 1).bfloat16()) and torch.all(out[..., 32:] == 0)
+
+
+def _backbone(wseed):
+    from hvpr_b200.backbone import BaseBEVBackbone_Scale
+    from hvpr_b200.config import Cfg
+    from oracle import backbone as ob
+    m = BaseBEVBackbone_Scale(Cfg(NAME="BaseBEVBackbone_Scale", **ob.CFG), 128).cuda().eval()
+    w = ob.random_backbone_weights(wseed)
+    missing = m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=False)
+    assert not missing.unexpected_keys and all(k.endswith("num_batches_tracked") for k in missing.missing_keys)
+    return m, w
+
+
+def test_backbone_matches_reference_golden():
+    """tests/golden/backbone_tiny.npz = output of the reference's own module (oracle/make_golden_backbone.py)."""
+    from oracle import backbone as ob
+    z = np.load(os.path.join(GOLDEN, "backbone_tiny.npz"))
+    B, H, W = (int(v) for v in z["shape"])
+    m, _ = _backbone(int(z["wseed"]))
+    spatial, scale = ob.random_canvases(int(z["xseed"]), B, H, W)
+    with torch.no_grad():
+        out = m({"spatial_features": torch.from_numpy(spatial).cuda(), "spatial_scale_features": torch.from_numpy(scale).cuda()})
+    got, ref = out["spatial_features_2d"], torch.from_numpy(z["spatial_features_2d"])
+    assert got.shape == ref.shape and got.dtype == torch.float32
+    e = rel_err(got, ref)
+    assert e[0] <= TOL_BACKBONE and e[1] <= TOL_BACKBONE_L2, e
+
+
+def test_backbone_matches_oracle_on_a_ragged_batch():
+    """batch of 2, 40 x 72 canvas: patches straddle image borders at every level (40/4 = 10 rows, 72/4 = 18 columns)."""
+    from oracle import backbone as ob
+    m, w = _backbone(11)
+    spatial, scale = ob.random_canvases(12, 2, 40, 72)
+    ref = torch.from_numpy(ob.backbone_forward(w, spatial, scale))
+    with torch.no_grad():
+        out = m({"spatial_features": torch.from_numpy(spatial).cuda(), "spatial_scale_features": torch.from_numpy(scale).cuda()})
+    e = rel_err(out["spatial_features_2d"], ref)
+    assert e[0] <= TOL_BACKBONE and e[1] <= TOL_BACKBONE_L2, e

@@ -150,3 +150,38 @@ def test_padded_row_term_is_not_optional():
         only, _, _ = hybrid.pillar_vfe(vox[p:p + 1, :k], n[p:p + 1], c[p:p + 1], w, list(geom.voxel_size), geom.range_f32)
         diff += int(not torch.allclose(only, full[p:p + 1], rtol=1e-5, atol=1e-6))
     assert diff > 0
+
+
+# ---- row N1: BaseBEVBackbone_Scale restatement ------------------------------------------------------------------------
+def test_backbone_oracle_matches_reference_golden():
+    """oracle/backbone.py vs the output of the reference's own module stored by oracle/make_golden_backbone.py."""
+    import hashlib
+    from oracle import backbone as ob
+    z = np.load(os.path.join(GOLDEN, "backbone_tiny.npz"))
+    w = ob.random_backbone_weights(int(z["wseed"]))
+    h = hashlib.sha256()
+    for k in sorted(w):
+        h.update(k.encode() + np.ascontiguousarray(w[k]).tobytes())
+    assert h.hexdigest() == str(z["weights_sha256"]), "seeded weights drifted: regenerate the fixture"
+    B, H, W = (int(v) for v in z["shape"])
+    spatial, scale = ob.random_canvases(int(z["xseed"]), B, H, W)
+    out = ob.backbone_forward(w, spatial, scale)
+    ref = z["spatial_features_2d"]
+    assert out.shape == ref.shape
+    assert np.abs(out - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+def test_backbone_oracle_matches_reference_module_when_tree_present():
+    from oracle import backbone as ob, ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present")
+    import torch
+    ns = ref_loader.load_backbone()
+    w = ob.random_backbone_weights(5)
+    m = ns.BaseBEVBackbone_Scale(ref_loader.BACKBONE_CFG, 128).eval()
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=False)
+    spatial, scale = ob.random_canvases(6, 2, 8, 12)
+    with torch.no_grad():
+        ref = m({"spatial_features": torch.from_numpy(spatial), "spatial_scale_features": torch.from_numpy(scale)})
+    out = ob.backbone_forward(w, spatial, scale)
+    assert np.abs(out - ref["spatial_features_2d"].numpy()).max() <= 1e-5 * np.abs(out).max()
