@@ -143,11 +143,11 @@ class BaseBEVBackbone_Scale(nn.Module):
             sl = self._pack_conv(*_fold(self.scale_layers[i][1].weight, self.scale_layers[i][2]), dev)
             sl.stride = self.scale_layers[i][1].stride[0]
             P["scale"].append(sl)
-            # ConvTranspose2d(k = s, stride = s): GEMM column (dy*s + dx)*Cout + co  <-  W[ci, co, dy, dx]
+            # ConvTranspose2d(k = s, stride = s): GEMM column (dy*Cout + co)*s + dx  <-  W[ci, co, dy, dx]
             w, s, shift = _fold(self.deblocks[i][0].weight, self.deblocks[i][1])
             ci, co, u, _ = w.shape
-            wn = (w * s[None, :, None, None]).permute(2, 3, 1, 0).reshape(u * u * co, 1, ci).float().to(dev)
-            de = self._pack(wn, shift.float().repeat(u * u).to(dev), u * u * co, 1, ci, 1, dev)
+            wn = (w * s[None, :, None, None]).permute(2, 1, 3, 0).reshape(u * u * co, 1, ci).float().to(dev)
+            de = self._pack(wn, shift.float().repeat_interleave(u).repeat(u).to(dev), u * u * co, 1, ci, 1, dev)
             de.up, de.c_out = u, co
             P["de"].append(de)
         a = self.attention.spatial

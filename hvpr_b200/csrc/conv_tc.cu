@@ -23,8 +23,9 @@ namespace hvpr {
 
 constexpr int kCvThreads = 256;
 constexpr int kCvABytes = 128 * 128;         // 128 pixels x 64 channels bf16
-constexpr int kCvPipeBytes = 192 * 1024;     // operand ring
+constexpr int kCvPipeBytes = 216 * 1024;     // operand ring(s)
 constexpr int kCvMaxStages = 8;
+constexpr int kCvHaloW = 10;                 // halo patch row: 8 output pixels + 1 on each side
 constexpr int kCvMaxN = 2048;                // GEMM columns (bias staged in shared memory)
 
 struct ConvParams {
@@ -37,6 +38,8 @@ struct ConvParams {
     int n_img, h_out, w_out;
     int log2_bx, tiles_x, tiles_y;
     int ntaps, kblocks, bn, n_tiles, nstages, n_total;
+    int halo;                 // 3x3 stride-1: one halo patch per k-block feeds all 9 taps (see the MMA issuer)
+    int msub;                 // 128-pixel sub-tiles per tile (2 when bn <= 128: two A patches share every weight block)
     int relu, res_cs;
     int out_mode, out_cs, out_c_off;
     int up, cout, out_h, out_w, out_ctot;
@@ -93,6 +96,20 @@ __device__ __forceinline__ uint64_t cv_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// A tile read out of a halo patch of kCvHaloW-pixel rows: 8-row groups (8 pixels of one image row) one halo row apart, the
+// start shifted by whole 128-B rows (dy*kCvHaloW + dx pixels).  The MMA unit applies the 128-B swizzle XOR to the ABSOLUTE
+// shared-memory address bits [7,10) — exactly what TMA did when it wrote the patch — so any 128-B-aligned start and any
+// group stride read back consistently with base_offset = 0 (measured with tools/dev/halo_diag.py: a non-zero base_offset
+// permutes the 16-B chunks).
+__device__ __forceinline__ uint64_t cv_desc_halo(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((kCvHaloW * 128) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 __device__ __forceinline__ void cv_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -124,7 +141,7 @@ __device__ __forceinline__ CvTile cv_decode(const ConvParams &P, int tile) {
     const int ty = m % P.tiles_y;
     t.img = m / P.tiles_y;
     t.x0 = tx << P.log2_bx;
-    t.y0 = ty * (128 >> P.log2_bx);
+    t.y0 = ty * (128 >> P.log2_bx) * P.msub;
     return t;
 }
 
@@ -137,17 +154,23 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
     uint64_t *empty = full + kCvMaxStages;
     uint64_t *tfull = empty + kCvMaxStages;
     uint64_t *tempty = tfull + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    uint64_t *hfull = tempty + 2;
+    uint64_t *hempty = hfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(hempty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int stage_bytes = kCvABytes + P.bn * 128;
+    const int halo_box = kCvHaloW * (16 * P.msub + 2) * 128;                 // halo pixels x 64 ch bf16
+    const int halo_bytes = P.halo ? (halo_box + 1023) & ~1023 : 0;
+    const int a_bytes = P.halo ? 0 : P.msub * kCvABytes;
+    const int stage_bytes = a_bytes + P.bn * 128;
+    uint8_t *ring = pipe + 2 * halo_bytes;                                   // [halo slot 0][halo slot 1][operand ring]
     const int nst = P.nstages;
     const int kiters = P.ntaps * P.kblocks;
     const int total_tiles = P.n_img * P.tiles_y * P.tiles_x * P.n_tiles;
 
     if (tid == 0) {
         for (int s = 0; s < kCvMaxStages; ++s) { cv_mbar_init(&full[s], 1); cv_mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { cv_mbar_init(&tfull[a], 1); cv_mbar_init(&tempty[a], 128); }
+        for (int a = 0; a < 2; ++a) { cv_mbar_init(&tfull[a], 1); cv_mbar_init(&tempty[a], 128); cv_mbar_init(&hfull[a], 1); cv_mbar_init(&hempty[a], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < P.n_total; i += kCvThreads) bias_s[i] = P.bias ? P.bias[i] : 0.0f;
@@ -163,20 +186,36 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
     if (warp == 0) {
         // ===== producer: per k-iteration one shifted activation box (TMA tensor map) + one packed weight block (bulk copy)
         if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t it = 0, hit = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const CvTile t = cv_decode(P, tile);
                 const uint8_t *wtile = P.wpk + (size_t)t.nt * kiters * (size_t)(P.bn * 128);
+                if (P.halo) {
+                    for (int kb = 0; kb < P.kblocks; ++kb, ++hit) {
+                        const int hs = hit & 1;
+                        cv_mbar_wait(&hempty[hs], ((hit >> 1) & 1) ^ 1);
+                        cv_mbar_expect_tx(&hfull[hs], (uint32_t)halo_box);
+                        cv_tma_load_4d(pipe + (size_t)hs * halo_bytes, &P.tmap[0], &hfull[hs], kb * 64, t.x0 - 1, t.y0 - 1, t.img);
+                        for (int tap = 0; tap < 9; ++tap, ++it) {
+                            const int s = it % nst;
+                            cv_mbar_wait(&empty[s], ((it / nst) & 1) ^ 1);
+                            cv_mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+                            cv_bulk_g2s(ring + (size_t)s * stage_bytes, wtile + (size_t)(tap * P.kblocks + kb) * (size_t)(P.bn * 128),
+                                        (uint32_t)(P.bn * 128), &full[s]);
+                        }
+                    }
+                    continue;
+                }
                 for (int tap = 0; tap < P.ntaps; ++tap) {
                     const CUtensorMap *map = &P.tmap[P.tap_map[tap]];
                     const int x = t.x0 + P.tap_ox[tap], y = t.y0 + P.tap_oy[tap];
                     for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
                         const int s = it % nst;
                         cv_mbar_wait(&empty[s], ((it / nst) & 1) ^ 1);
-                        uint8_t *dst = pipe + (size_t)s * stage_bytes;
+                        uint8_t *dst = ring + (size_t)s * stage_bytes;
                         cv_mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
                         cv_tma_load_4d(dst, map, &full[s], kb * 64, x, y, t.img);
-                        cv_bulk_g2s(dst + kCvABytes, wtile + (size_t)(tap * P.kblocks + kb) * (size_t)(P.bn * 128),
+                        cv_bulk_g2s(dst + a_bytes, wtile + (size_t)(tap * P.kblocks + kb) * (size_t)(P.bn * 128),
                                     (uint32_t)(P.bn * 128), &full[s]);
                     }
                 }
@@ -188,21 +227,50 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
         if (lane == 0) {
             // idesc: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            uint32_t it = 0, ti = 0;
+            uint32_t it = 0, ti = 0, hit = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
                 const uint32_t acc = ti & 1;
                 cv_mbar_wait(&tempty[acc], ((ti >> 1) & 1) ^ 1);        // epilogue drained this accumulator
                 cv_fence_after();
                 const uint32_t d = tmem_base + acc * 256u;
+                if (P.halo) {
+                    // one halo patch (10 x (rows+2) pixels x 64 ch) per k-block; tap (dy,dx) = the same patch read from a
+                    // start address shifted by dy*kCvHaloW + dx pixel rows — 9x less activation traffic than one box per tap
+                    for (int kb = 0; kb < P.kblocks; ++kb, ++hit) {
+                        const int hs = hit & 1;
+                        cv_mbar_wait(&hfull[hs], (hit >> 1) & 1);
+                        const uint32_t ha = cv_smem_u32(pipe + (size_t)hs * halo_bytes);
+                        for (int tap = 0; tap < 9; ++tap, ++it) {
+                            const int s = it % nst;
+                            cv_mbar_wait(&full[s], (it / nst) & 1);
+                            cv_fence_after();
+                            const uint64_t bdesc = cv_desc_sw128(cv_smem_u32(ring + (size_t)s * stage_bytes));
+                            const int dy = tap / 3, dx = tap - 3 * dy;
+                            for (int m = 0; m < P.msub; ++m) {
+                                const uint64_t adesc = cv_desc_halo(ha + (uint32_t)(((m * 16 + dy) * kCvHaloW + dx) * 128));
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+                                    cv_umma_bf16(d + (uint32_t)(m * P.bn), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                                                 (kb | tap | kk) != 0);
+                            }
+                            cv_umma_commit(&empty[s]);
+                        }
+                        cv_umma_commit(&hempty[hs]);
+                    }
+                } else
                 for (int ki = 0; ki < kiters; ++ki, ++it) {
                     const int s = it % nst;
                     cv_mbar_wait(&full[s], (it / nst) & 1);
                     cv_fence_after();
-                    const uint32_t sa = cv_smem_u32(pipe + (size_t)s * stage_bytes);
-                    const uint64_t adesc = cv_desc_sw128(sa), bdesc = cv_desc_sw128(sa + kCvABytes);
+                    const uint32_t sa = cv_smem_u32(ring + (size_t)s * stage_bytes);
+                    const uint64_t bdesc = cv_desc_sw128(sa + a_bytes);
+                    for (int m = 0; m < P.msub; ++m) {
+                        const uint64_t adesc = cv_desc_sw128(sa + m * kCvABytes);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)          // +32 B along K inside the 128-B swizzle atom
-                        cv_umma_bf16(d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (ki | kk) != 0);
+                        for (int kk = 0; kk < 4; ++kk)      // +32 B along K inside the 128-B swizzle atom
+                            cv_umma_bf16(d + (uint32_t)(m * P.bn), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                                         (ki | kk) != 0);
+                    }
                     cv_umma_commit(&empty[s]);
                 }
                 cv_umma_commit(&tfull[acc]);
@@ -218,13 +286,14 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
             const CvTile t = cv_decode(P, tile);
             const uint32_t acc = ti & 1;
-            const int x = t.x0 + px, y = t.y0 + py;
+            cv_mbar_wait(&tfull[acc], (ti >> 1) & 1);
+            cv_fence_after();
+            for (int m = 0; m < P.msub; ++m) {
+            const int x = t.x0 + px, y = t.y0 + m * (128 >> P.log2_bx) + py;
             const bool valid = (x < P.w_out) && (y < P.h_out);
             const int64_t pix = ((int64_t)t.img * P.h_out + y) * P.w_out + x;
             const float g = (P.gate && valid) ? __ldg(P.gate + pix) : 1.0f;
-            cv_mbar_wait(&tfull[acc], (ti >> 1) & 1);
-            cv_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)(m * P.bn);
             for (int ch = 0; ch < P.bn; ch += 32) {
                 uint32_t r[32];
                 __syncwarp();                                   // tcgen05.ld is warp-collective: re-converge after the guarded stores
@@ -257,15 +326,28 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                         op[j] = make_uint4(cv_pack_bf16(v[8 * j], v[8 * j + 1]), cv_pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                                            cv_pack_bf16(v[8 * j + 4], v[8 * j + 5]), cv_pack_bf16(v[8 * j + 6], v[8 * j + 7]));
                 } else if (valid) {
-                    // pixel shuffle of the transposed conv: GEMM column = (dy*up + dx)*cout + co  ->  fp32 NCHW slice
-                    const int sub = col0 / P.cout, co0 = col0 % P.cout;
-                    const int oy = y * P.up + sub / P.up, ox = x * P.up + sub % P.up;
+                    // pixel shuffle of the transposed conv: GEMM column = (dy*cout + co)*up + dx  ->  fp32 NCHW slice.
+                    // dx is the fastest column index, so a thread owns `up` horizontally adjacent output pixels of each
+                    // channel and neighbouring lanes (x, x+1, ...) extend the run: full 32-B sectors for every up.
+                    const int per_dy = P.cout * P.up;
+                    const int dy = col0 / per_dy, co0 = (col0 % per_dy) / P.up;
                     float *op = reinterpret_cast<float *>(P.out) +
-                                (((int64_t)t.img * P.out_ctot + P.out_c_off + co0) * P.out_h + oy) * P.out_w + ox;
+                                (((int64_t)t.img * P.out_ctot + P.out_c_off + co0) * P.out_h + (y * P.up + dy)) * P.out_w + x * P.up;
                     const int64_t cstride = (int64_t)P.out_h * P.out_w;
+                    if (P.up == 4) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) __stcs(op + i * cstride, v[i]);
+                        for (int c = 0; c < 8; ++c)
+                            __stcs(reinterpret_cast<float4 *>(op + c * cstride), make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+                    } else if (P.up == 2) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c)
+                            __stcs(reinterpret_cast<float2 *>(op + c * cstride), make_float2(v[2 * c], v[2 * c + 1]));
+                    } else if (P.up == 1) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) __stcs(op + c * cstride, v[c]);
+                    }
                 }
+            }
             }
             cv_fence_before();
             cv_mbar_arrive(&tempty[acc]);
@@ -319,13 +401,24 @@ static CvEncodeFn cv_encode_fn() {
     return fn;
 }
 
-static size_t cv_smem_bytes() { return 1024 + kCvPipeBytes + kCvMaxN * 4 + (2 * kCvMaxStages + 4) * 8 + 16; }
+static size_t cv_smem_bytes() { return 1024 + kCvPipeBytes + kCvMaxN * 4 + (2 * kCvMaxStages + 8) * 8 + 16; }
 
 int hvpr_conv_init() {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv_smem_bytes());
     if (e != cudaSuccess) { set_cuda_error(e); return HVPR_ERR_CUDA; }
     return HVPR_OK;
 }
+
+// debug knob (not part of the public header): 0 = automatic tile policy, 1 / 2 = force the number of 128-pixel sub-tiles
+static int g_cv_force_msub = 0;
+static int g_cv_halo_off = 1;   // measured (tools/dev/backbone_bench.py A/B): the halo path halves L2->SM traffic but is 5-15 % slower
+extern "C" int hvpr_dbg_conv_force_msub(int msub) {
+    if (msub < 0 || msub > 2) return HVPR_ERR_ARG;
+    g_cv_force_msub = msub;
+    return HVPR_OK;
+}
+// knob: 1 (default) = one TMA box per tap; 0 = 3x3 stride-1 layers read all nine taps out of one halo patch
+extern "C" int hvpr_dbg_conv_halo_off(int off) { g_cv_halo_off = off ? 1 : 0; return HVPR_OK; }
 
 extern "C" size_t hvpr_conv_packed_bytes(int n_total, int taps, int c_in) { return (size_t)n_total * taps * c_in * 2; }
 
@@ -357,22 +450,27 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
     P.h_out = a->h_in / a->stride;
     P.w_out = a->w_in / a->stride;
     // patch shape: the power-of-two split of 128 pixels that wastes the fewest out-of-image pixels (ties: wider rows)
+    // two 128-pixel sub-tiles per tile when the column tile is narrow: halves the weight traffic per MAC
+    P.msub = (a->bn <= 128 && (int64_t)a->n * P.h_out * P.w_out >= 2 * 128 * (int64_t)kNumSMs) ? 2 : 1;
+    if (g_cv_force_msub == 1 || (g_cv_force_msub == 2 && a->bn <= 128)) P.msub = g_cv_force_msub;
+    P.halo = (a->ksize == 3 && a->stride == 1 && !g_cv_halo_off) ? 1 : 0;
     int best = -1; int64_t best_cost = 0;
-    for (int l = 0; l <= 7; ++l) {
-        const int bx = 1 << l, by = 128 >> l;
+    for (int l = P.halo ? 3 : 0; l <= (P.halo ? 3 : 7); ++l) {      // halo path: patches are 8 pixels wide
+        const int bx = 1 << l, by = (128 >> l) * P.msub;
         const int64_t cost = ceil_div64(P.w_out, bx) * bx * (ceil_div64(P.h_out, by) * by);
         if (best < 0 || cost < best_cost || (cost == best_cost && l <= 4)) { best = l; best_cost = cost; }
     }
     P.log2_bx = best;
-    const int bx = 1 << best, by = 128 >> best;
+    const int bx = 1 << best, by = (128 >> best) * P.msub;
     P.tiles_x = (int)ceil_div64(P.w_out, bx);
     P.tiles_y = (int)ceil_div64(P.h_out, by);
     P.kblocks = a->c_in / 64;
     P.bn = a->bn;
     P.n_total = a->n_total;
     P.n_tiles = a->n_total / a->bn;
-    const int stage_bytes = kCvABytes + a->bn * 128;
-    P.nstages = kCvPipeBytes / stage_bytes;
+    const int halo_bytes = P.halo ? (kCvHaloW * (16 * P.msub + 2) * 128 + 1023) & ~1023 : 0;
+    const int stage_bytes = (P.halo ? 0 : P.msub * kCvABytes) + a->bn * 128;
+    P.nstages = (kCvPipeBytes - 2 * halo_bytes) / stage_bytes;
     if (P.nstages > kCvMaxStages) P.nstages = kCvMaxStages;
     P.wpk = (const uint8_t *)a->w_packed;
     P.bias = a->bias;
@@ -388,14 +486,15 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
         if (a->out_cs % 8 || a->out_c_off % 8 || a->out_c_off + a->n_total > a->out_cs) return HVPR_ERR_ARG;
         if (a->residual && (a->res_cs % 8 || a->res_cs < a->n_total)) return HVPR_ERR_ARG;
     } else if (a->out_mode == 1) {
-        if (a->up < 1 || a->c_out <= 0 || a->c_out % 32 || a->n_total != a->up * a->up * a->c_out) return HVPR_ERR_ARG;
+        if (a->up != 1 && a->up != 2 && a->up != 4) return HVPR_ERR_UNSUPPORTED;
+        if (a->c_out <= 0 || a->c_out % 32 || a->n_total != a->up * a->up * a->c_out) return HVPR_ERR_ARG;
         if (a->out_c_off + a->c_out > a->out_ctot || a->residual || a->gate) return HVPR_ERR_ARG;
         P.up = a->up; P.cout = a->c_out; P.out_ctot = a->out_ctot;
         P.out_h = P.h_out * a->up; P.out_w = P.w_out * a->up;
     } else return HVPR_ERR_ARG;
 
     // tensor maps over the NHWC bf16 input: dims (channel, x, y, image)
-    const cuuint32_t box[4] = {64u, (cuuint32_t)bx, (cuuint32_t)by, 1u};
+    const cuuint32_t box[4] = {64u, (cuuint32_t)(P.halo ? kCvHaloW : bx), (cuuint32_t)(P.halo ? by + 2 : by), 1u};
     const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
     const uint64_t pix_b = (uint64_t)a->in_cs * 2u;
     const int nmaps = (a->stride == 2) ? 4 : 1;

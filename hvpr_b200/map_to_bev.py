@@ -151,6 +151,18 @@ class PointPillarScatter_Agg_Memory_1_scale(nn.Module):
         _lib.check(st, "hvpr_bev_fill")
         return spatial, spatial_scale, readout
 
+    def run_nhwc(self, pillar_features, pillar_scale_features, cell_map, B, n_pillars_dev, readout, spatial_nhwc, scale_nhwc):
+        """Same as run(), but the canvases come out channels-last bf16 — (B,ny,nx,>=128) and (B,ny,nx,>=32), pad channels
+        zero — the layout hvpr_b200.backbone consumes without a transposition pass."""
+        C, Cs = pillar_features.shape[1], pillar_scale_features.shape[1]
+        readout = self.memory.run(pillar_features, self.k, n_pillars_dev, out=readout)
+        st = _lib.lib().hvpr_bev_fill_nhwc_bf16(_lib.ptr(pillar_features), C, _lib.ptr(readout), C,
+                                                _lib.ptr(pillar_scale_features), Cs, _lib.ptr(cell_map), B, self.nx, self.ny,
+                                                _lib.ptr(spatial_nhwc), spatial_nhwc.shape[-1], _lib.ptr(scale_nhwc),
+                                                scale_nhwc.shape[-1], _lib.cur_stream())
+        _lib.check(st, "hvpr_bev_fill_nhwc_bf16")
+        return spatial_nhwc, scale_nhwc, readout
+
     def forward(self, batch_dict, **kwargs):
         if self.training:
             raise NotImplementedError("hvpr_b200 implements the eval branch (pointpillar_scatter.py:169-220) only")

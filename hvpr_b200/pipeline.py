@@ -1,0 +1,97 @@
+"""Front end + 2-D backbone as one object: raw points -> spatial_features_2d.
+
+Rows (a)-(e) of SURVEY.md §8 (K1 voxelize, K2 PFN, K3 memory attention, K4 canvas fill) followed by row N1
+(BaseBEVBackbone_Scale on the tcgen05 convolution kernel).  Between the two the canvases stay channels-last bf16
+(K4 writes them in that layout directly), so the fp32 NCHW canvases of the module API (1.1 GB per 8-frame batch at
+432 x 496) are never materialised and no transposition pass runs.  The whole chain is captured in one CUDA graph.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .backbone import BaseBEVBackbone_Scale
+from .config import Cfg
+from .frontend import HybridFrontEnd
+
+# tools/cfgs/kitti_models/hvpr.yaml:87-95
+HVPR_BACKBONE_CFG = Cfg(NAME="BaseBEVBackbone_Scale", LAYER_NUMS=[3, 3, 3], SFM_LAYER_NUMS=[3, 3, 3], LAYER_STRIDES=[1, 2, 2],
+                        NUM_FILTERS=[128, 256, 512], NUM_SCALE_FILTERS=[32, 64, 128], UPSAMPLE_STRIDES=[1, 2, 4],
+                        NUM_UPSAMPLE_FILTERS=[128, 128, 128])
+
+
+class FrontEndWithBackbone(torch.nn.Module):
+    def __init__(self, geom, backbone_cfg=HVPR_BACKBONE_CFG, device="cuda", **frontend_kwargs):
+        super().__init__()
+        self.frontend = HybridFrontEnd(geom, device=device, **frontend_kwargs) if frontend_kwargs else HybridFrontEnd(geom, device=device)
+        self.backbone_2d = BaseBEVBackbone_Scale(backbone_cfg, self.frontend.map_to_bev_module.num_bev_features).to(device).eval()
+        self._p = None
+
+    def plan(self, n_frames: int, n_total_points: int, max_frame_points: int = 0):
+        fe = self.frontend
+        p = fe.plan(n_frames, n_total_points, max_frame_points, use_graph=False)
+        nx, ny, _ = fe.geom.grid_size
+        # the fp32 NCHW canvases of the module API are not needed on this path
+        p.spatial = p.spatial_scale = None
+        bf = dict(dtype=torch.bfloat16, device=p.points.device)
+        p.x_nhwc = torch.zeros((n_frames, ny, nx, 128), **bf)
+        p.y_nhwc = torch.zeros((n_frames, ny, nx, 64), **bf)
+        p.graph = None
+        self._p = p
+        return p
+
+    def _enqueue(self, p):
+        fe = self.frontend
+        nx, ny, _ = fe.geom.grid_size
+        vox = fe.voxelizer.run(p.points, p.frame_offsets, p.B, p.max_frame_points, out=p.vox)
+        nP = vox.n_pillars_dev
+        fe.vfe.run(vox.voxels, vox.num_points, vox.coords, nP, out=p.pillar_features, scale_out=p.pillar_scale)
+        fe.map_to_bev_module.run_nhwc(p.pillar_features, p.pillar_scale, vox.cell_map, p.B, nP, p.readout, p.x_nhwc, p.y_nhwc)
+        p.out = self.backbone_2d.run_nhwc(p.x_nhwc, p.y_nhwc, p.B, ny, nx)
+
+    def kernel_launches_per_run(self) -> int:
+        bb = self.backbone_2d
+        convs = sum(1 + n for n in bb.layer_nums) + sum(bb.sfm_layer_nums) + 2 * len(bb.num_filters)     # blocks + sfm + scale + deblock
+        return 6 + 1 + 1 + 2 + convs + 2 * len(bb.num_filters)                                            # K1 x6, K2, K3, K4 x2, convs, gate x2/level
+
+    @torch.no_grad()
+    def run(self):
+        """points / frame_offsets already resident in plan.points -> plan.out = spatial_features_2d (B,384,ny,nx) fp32."""
+        p = self._p
+        _lib.init_device()
+        if p.graph is None:
+            fe = self.frontend
+            fe.vfe._weights()
+            if fe.map_to_bev_module.memory.precision == "bf16_rescore":
+                fe.map_to_bev_module.memory._packed_bf16()
+            self.backbone_2d._ensure_packed(p.points.device)
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._enqueue(p)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                self._enqueue(p)
+            p.graph = gr
+        p.graph.replay()
+        return p
+
+    @torch.no_grad()
+    def forward(self, batch_dict: dict) -> dict:
+        """batch_dict['points'] (sum N, 5) [b,x,y,z,r] on the GPU + 'batch_size'  ->  adds 'spatial_features_2d'."""
+        pts = batch_dict["points"]
+        if not pts.is_cuda:
+            raise _lib.HvprError("FrontEndWithBackbone needs CUDA tensors; there is no CPU path")
+        B = int(batch_dict["batch_size"])
+        n = pts.shape[0]
+        if self._p is None or self._p.B != B or self._p.n_total != n:
+            self.plan(B, n)
+        p = self._p
+        p.points.copy_(pts[:, 1:5])
+        st = _lib.lib().hvpr_frame_offsets(_lib.ptr(pts.contiguous()), n, 5, B, _lib.ptr(p.frame_offsets), _lib.cur_stream())
+        _lib.check(st, "hvpr_frame_offsets")
+        self.run()
+        batch_dict["spatial_features_2d"] = p.out
+        return batch_dict

@@ -156,7 +156,7 @@ typedef struct HvprConvArgs {
     int32_t out_mode;        /* 0: bf16 NHWC (n, h_out, w_out, out_cs), channels [out_c_off, out_c_off + n_total)
                                 1: ConvTranspose2d(k = up, stride = up) pixel shuffle into fp32 NCHW
                                    (n, out_ctot, h_out*up, w_out*up), channels [out_c_off, out_c_off + c_out);
-                                   GEMM column = (dy*up + dx)*c_out + co                                          */
+                                   GEMM column = (dy*c_out + co)*up + dx                                          */
     void *out;
     int32_t out_cs, out_c_off;
     int32_t up, c_out, out_ctot;
@@ -167,6 +167,12 @@ size_t hvpr_conv_packed_bytes(int n_total, int taps, int c_in);
 int hvpr_conv_pack_weights(const float *w_ntc, int n_total, int taps, int c_in, int bn, void *out_packed, void *stream);
 /* args is a HOST struct; TMA tensor maps are encoded on the host per call (no device sync, graph-capturable). */
 int hvpr_conv2d(const HvprConvArgs *args, void *stream);
+/* K4 in the layout the backbone consumes: channels-last bf16 canvases, every element written once (feature or 0).
+ *   spatial_nhwc (n_frames, ny, nx, spatial_cs) bf16: channels [feat_a | feat_b | 0...]
+ *   scale_nhwc   (n_frames, ny, nx, scale_cs)   bf16: channels [feat_s | 0...]      (pointpillar_scatter.py:204-218)   */
+int hvpr_bev_fill_nhwc_bf16(const float *feat_a, int ca, const float *feat_b, int cb, const float *feat_s, int cs,
+                            const int32_t *cell_map, int n_frames, int nx, int ny,
+                            void *spatial_nhwc, int spatial_cs, void *scale_nhwc, int scale_cs, void *stream);
 /* fp32 NCHW (n,c,h,w) -> bf16 NHWC (n,h,w,out_cs), channels [0,c); other channels of out are left untouched. */
 int hvpr_nchw_to_nhwc_bf16(const float *in, int n, int c, int h, int w, void *out, int out_cs, void *stream);
 /* gate = sigmoid(BN(conv3x3_{2->1}([max_c y, mean_c y]) + b)); w18_host = folded weights [(ch*3+dy)*3+dx] (HOST),

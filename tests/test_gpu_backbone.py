@@ -83,6 +83,64 @@ def test_conv3x3_layer_matches_fp32_conv_of_same_bf16_operands(n, h, w, cin, cou
     assert torch.all(out[..., cout:] == 7.0)            # pad channels untouched
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,stride,bn", [(2, 20, 28, 128, 128, 1, 128), (1, 24, 40, 64, 64, 2, 64), (1, 37, 50, 64, 32, 1, 32)])
+def test_conv3x3_two_subtile_mode(n, h, w, cin, cout, stride, bn):
+    """bn <= 128 layers on large canvases process two 128-pixel patches per weight block; force that policy on a small case."""
+    L = _lib()
+    if stride == 2 and (h % 2 or w % 2):
+        h, w = h + h % 2, w + w % 2
+    x, wt, b = _rand_case(99 + h, n, h, w, cin, cout, 3)
+    ref = F.relu(F.conv2d(x.float(), wt.float(), b, stride=stride, padding=1))
+    wpk = _pack(wt.float().permute(0, 2, 3, 1).reshape(cout, 9, cin), bn)
+    out = torch.empty(n, h // stride, w // stride, cout, dtype=torch.bfloat16, device="cuda")
+    assert L.lib().hvpr_dbg_conv_force_msub(2) == 0
+    try:
+        _conv_call(x.permute(0, 2, 3, 1).contiguous(), wpk, cout, bn, b, 3, stride, cin, out)
+    finally:
+        L.lib().hvpr_dbg_conv_force_msub(0)
+    assert rel_err(out.permute(0, 3, 1, 2).float(), ref)[0] <= TOL_LAYER
+
+
+@pytest.mark.parametrize("msub", [1, 2])
+@pytest.mark.parametrize("n,h,w,cin,cout,bn", [(2, 20, 28, 128, 128, 128), (1, 33, 19, 256, 256, 256), (1, 16, 8, 64, 32, 32)])
+def test_conv3x3_halo_operand_path(msub, n, h, w, cin, cout, bn):
+    """Optional operand path for stride-1 3x3 layers: ONE (8+2) x (rows+2) halo patch per k-block feeds all nine taps
+    through shifted UMMA descriptors (9x less activation traffic; off by default because it measured slower)."""
+    L = _lib()
+    x, wt, b = _rand_case(7 + h, n, h, w, cin, cout, 3)
+    ref = F.relu(F.conv2d(x.float(), wt.float(), b, padding=1))
+    wpk = _pack(wt.float().permute(0, 2, 3, 1).reshape(cout, 9, cin), bn)
+    out = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device="cuda")
+    L.lib().hvpr_dbg_conv_halo_off(0)
+    L.lib().hvpr_dbg_conv_force_msub(msub)
+    try:
+        _conv_call(x.permute(0, 2, 3, 1).contiguous(), wpk, cout, bn, b, 3, 1, cin, out)
+    finally:
+        L.lib().hvpr_dbg_conv_halo_off(1)
+        L.lib().hvpr_dbg_conv_force_msub(0)
+    assert rel_err(out.permute(0, 3, 1, 2).float(), ref)[0] <= TOL_LAYER
+
+
+def test_bev_fill_nhwc_bf16_matches_the_nchw_fill():
+    """K4 in channels-last bf16 (what the backbone consumes) == bf16 rounding of the fp32 NCHW canvases."""
+    L = _lib()
+    torch.manual_seed(3)
+    B, nx, ny, P = 2, 24, 20, 150
+    cells = torch.randperm(B * nx * ny)[:P]
+    cmap = torch.full((B * nx * ny,), -1, dtype=torch.int32)
+    cmap[cells] = torch.arange(P, dtype=torch.int32)
+    cmap = cmap.cuda()
+    fa, fb, fs = torch.randn(P, 64).cuda(), torch.randn(P, 64).cuda(), torch.randn(P, 32).cuda()
+    sp = torch.empty(B, 128, ny, nx, device="cuda"); sc = torch.empty(B, 32, ny, nx, device="cuda")
+    L.check(L.lib().hvpr_bev_fill(L.ptr(fa), 64, L.ptr(fb), 64, L.ptr(fs), 32, L.ptr(cmap), B, nx, ny, L.ptr(sp), L.ptr(sc), L.cur_stream()))
+    xo = torch.full((B, ny, nx, 128), 9.0, dtype=torch.bfloat16, device="cuda")
+    yo = torch.full((B, ny, nx, 64), 9.0, dtype=torch.bfloat16, device="cuda")
+    L.check(L.lib().hvpr_bev_fill_nhwc_bf16(L.ptr(fa), 64, L.ptr(fb), 64, L.ptr(fs), 32, L.ptr(cmap), B, nx, ny,
+                                            L.ptr(xo), 128, L.ptr(yo), 64, L.cur_stream()))
+    assert torch.equal(xo, sp.permute(0, 2, 3, 1).bfloat16())
+    assert torch.equal(yo[..., :32], sc.permute(0, 2, 3, 1).bfloat16()) and torch.all(yo[..., 32:] == 0)
+
+
 def test_conv_gate_and_residual_epilogue():
     n, h, w, c = 2, 12, 20, 128
     x, wt, b = _rand_case(5, n, h, w, c, c, 3)
@@ -103,11 +161,11 @@ def test_transposed_conv_pixel_shuffle_into_nchw_slice(up, cin):
     wt = (torch.randn(cin, cout, up, up, generator=g) / cin ** 0.5).cuda().bfloat16()
     b = torch.randn(cout, generator=g).cuda() * 0.1
     ref = F.relu(F.conv_transpose2d(x.float(), wt.float(), b, stride=up))
-    w_ntc = wt.float().permute(2, 3, 1, 0).reshape(up * up * cout, 1, cin)
+    w_ntc = wt.float().permute(2, 1, 3, 0).reshape(up * up * cout, 1, cin)      # column (dy*cout + co)*up + dx
     bn = 256 if (up * up * cout) % 256 == 0 else 128
     wpk = _pack(w_ntc, bn)
     out = torch.full((n, ctot, h * up, w * up), -3.0, device="cuda")
-    _conv_call(x.permute(0, 2, 3, 1).contiguous(), wpk, up * up * cout, bn, b.repeat(up * up), 1, 1, cin, out,
+    _conv_call(x.permute(0, 2, 3, 1).contiguous(), wpk, up * up * cout, bn, b.repeat_interleave(up).repeat(up), 1, 1, cin, out,
                out_mode=1, out_c_off=coff, up=up, c_out=cout, out_ctot=ctot)
     assert rel_err(out[:, coff:coff + cout], ref)[0] <= 1e-5         # fp32 output: only the summation order differs
     assert torch.all(out[:, :coff] == -3.0) and torch.all(out[:, coff + cout:] == -3.0)
@@ -179,3 +237,31 @@ def test_backbone_matches_oracle_on_a_ragged_batch():
         out = m({"spatial_features": torch.from_numpy(spatial).cuda(), "spatial_scale_features": torch.from_numpy(scale).cuda()})
     e = rel_err(out["spatial_features_2d"], ref)
     assert e[0] <= TOL_BACKBONE and e[1] <= TOL_BACKBONE_L2, e
+
+
+def test_points_to_spatial_features_2d_pipeline_vs_oracle_chain():
+    """raw points -> K1..K4 (channels-last bf16 canvases) -> backbone, one CUDA graph, vs oracle front end + oracle backbone."""
+    from helpers import load_small, to_dev
+    from hvpr_b200.pipeline import FrontEndWithBackbone
+    from oracle import backbone as ob, hybrid
+    z, geom, frames, overflow, wseed = load_small("tiny_continue")
+    w_fe, w_bb = hybrid.random_weights(wseed), ob.random_backbone_weights(21)
+    o = hybrid.frontend(frames, geom, w_fe, overflow)
+    ref = torch.from_numpy(ob.backbone_forward(w_bb, o["spatial_features"].numpy(), o["spatial_scale_features"].numpy()))
+    pipe = FrontEndWithBackbone(geom, overflow=overflow)
+    pipe.frontend.load_reference_weights({k: torch.from_numpy(np.asarray(v)) if not torch.is_tensor(v) else v for k, v in w_fe.items()})
+    pipe.backbone_2d.load_state_dict({k: torch.from_numpy(v) for k, v in w_bb.items()}, strict=False)
+    pts, off = to_dev(frames)
+    p = pipe.plan(len(frames), pts.shape[0])
+    p.points.copy_(pts); p.frame_offsets.copy_(off)
+    for _ in range(2):                      # graph replay must be idempotent
+        pipe.run()
+    torch.cuda.synchronize()
+    e = rel_err(p.out, ref)
+    assert tuple(p.out.shape) == tuple(ref.shape)
+    assert e[0] <= TOL_BACKBONE and e[1] <= TOL_BACKBONE_L2, e
+    # module-style entry point gives the same tensor
+    from hvpr_b200 import synth
+    bd = pipe({"points": torch.from_numpy(synth.collate_points(frames)).cuda(), "batch_size": len(frames)})
+    torch.cuda.synchronize()
+    assert torch.equal(bd["spatial_features_2d"], p.out)
