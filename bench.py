@@ -174,6 +174,65 @@ def workload_config(geom):
 
 
 # --------------------------------------------------------------------------------------------------- GPU arm
+def backbone_flops(bb, B, H, W):
+    tot, h, w, cin, cs = 0, H, W, bb.input_channels, bb.input_channels // 4
+    for i, nf in enumerate(bb.num_filters):
+        h, w = h // bb.layer_strides[i], w // bb.layer_strides[i]
+        px = B * h * w
+        tot += 2 * 9 * cin * nf * px + (bb.layer_nums[i] + bb.sfm_layer_nums[i]) * 2 * 9 * nf * nf * px
+        tot += 2 * 9 * cs * bb.num_scale_filters[i] * px
+        tot += 2 * nf * bb.num_upsample_filters[i] * bb.upsample_strides[i] ** 2 * px
+        cin, cs = nf, bb.num_scale_filters[i]
+    return tot
+
+
+def bench_backbone(geom, w, host_pts, host_off, B, N, dev, mem_precision, steps=10, warmup=3):
+    """points -> spatial_features_2d (front end + backbone in one CUDA graph) and the backbone alone, same batch as the headline."""
+    import torch
+    from hvpr_b200.pipeline import FrontEndWithBackbone
+    nx, ny, _ = geom.grid_size
+    torch.manual_seed(0)
+    pipe = FrontEndWithBackbone(geom, device=dev, mem_precision=mem_precision)
+    pipe.frontend.load_reference_weights(w)
+    p = pipe.plan(B, B * N, N)
+    p.points.copy_(host_pts)
+    p.frame_offsets.copy_(host_off)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(warmup):
+        pipe.run()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        pipe.run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_pipe = e0.elapsed_time(e1) / steps
+    bb = pipe.backbone_2d
+    t = 0.0
+    for i in range(steps + warmup):
+        flush.zero_()                       # activations (>= 439 MB per layer) already exceed L2; flush anyway
+        e0.record()
+        bb.run_nhwc(p.x_nhwc, p.y_nhwc, B, ny, nx)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= warmup:
+            t += e0.elapsed_time(e1) / steps
+    fl = backbone_flops(bb, B, ny, nx)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak = peaks.get("bf16_tflops_sustained", 1376.4)
+    out = {"component": "BaseBEVBackbone_Scale (hvpr.yaml:87-95), bf16 tcgen05 implicit GEMM, fp32 accumulate",
+           "ms_per_batch": t, "frames_per_sec": B / (t * 1e-3), "gflop_per_batch": fl / 1e9,
+           "roofline": {"bound": "tensor", "achieved": fl / (t * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                        "frac": fl / (t * 1e-3) / 1e12 / peak, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"},
+           "gpu_launches_per_batch": pipe.kernel_launches_per_run() - 10,
+           "points_to_spatial_features_2d": {"ms_per_batch": ms_pipe, "frames_per_sec": B / (ms_pipe * 1e-3),
+                                             "gpu_launches_per_batch": pipe.kernel_launches_per_run()}}
+    del pipe, p, flush
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     from hvpr_b200 import sharding
@@ -330,6 +389,12 @@ def run_gpu_arm(args):
         total_alg = sum(alg.values()) * B
         line["path_roofline"] = {"alg_bytes_per_step": int(total_alg), "achieved_gbs": total_alg / (ms_step * 1e-3) / 1e9,
                                  "frac_hbm": total_alg / (ms_step * 1e-3) / 1e9 / peak}
+        # ---- next row N1: BaseBEVBackbone_Scale on the tcgen05 conv kernel, reported beside the headline ----
+        if world == 1 and not args.no_backbone:
+            try:
+                line["next_rows"] = {"bev_backbone": bench_backbone(geom, w, host_pts, host_off, B, N, dev, args.mem_precision)}
+            except Exception as e:   # the headline line must survive a failure of the widened row
+                line["next_rows"] = {"bev_backbone": {"error": repr(e)[:300]}}
         # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ---------------------------
         if world == 1 and not args.no_cpu_baseline:
             fps, ms, ncores = cpu_reference_run(geom, frames, w, steps=3, warmup=1, frames_per_step=2)
@@ -352,6 +417,7 @@ def main():
     ap.add_argument("--mem-precision", default=os.environ.get("HVPR_MEM_PRECISION", "bf16_rescore"), choices=["fp32", "bf16_rescore"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-backbone", action="store_true", help="skip the next-row (N1) backbone measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
