@@ -28,13 +28,29 @@ constexpr int kCvMaxStages = 8;
 constexpr int kCvHaloW = 10;                 // halo patch row: 8 output pixels + 1 on each side
 constexpr int kCvMaxN = 2048;                // GEMM columns (bias staged in shared memory)
 
+// Optional cycle accounting (compile with -DHVPR_CV_PROFILE, `make prof`): per CTA and role, cycles spent at each wait site,
+// accumulated into P.prof[blockIdx.x][16].  Never enabled in the shipped library.
+#ifdef HVPR_CV_PROFILE
+#define CVP_DECL long long cvp_t = 0, cvp_acc[4] = {0, 0, 0, 0}
+#define CVP_B() cvp_t = clock64()
+#define CVP_E(i) cvp_acc[i] += clock64() - cvp_t
+#define CVP_DUMP(base) do { if (P.prof) for (int i_ = 0; i_ < 4; ++i_) atomicAdd(reinterpret_cast<unsigned long long *>(P.prof) + (size_t)blockIdx.x * 16 + (base) + i_, (unsigned long long)cvp_acc[i_]); } while (0)
+#else
+#define CVP_DECL
+#define CVP_B()
+#define CVP_E(i)
+#define CVP_DUMP(base)
+#endif
+
 struct ConvParams {
     alignas(64) CUtensorMap tmap[4];
+    alignas(64) CUtensorMap tmap_w;       // CTA-pair kernel: the packed weight image viewed as [rows][64] bf16 (no TMA swizzle)
     const uint8_t *wpk;
     const float *bias;
     const float *gate;
     const __nv_bfloat16 *residual;
     void *out;
+    long long *prof;          // cycle-accounting sink (profile build only), else null
     int n_img, h_out, w_out;
     int log2_bx, tiles_x, tiles_y;
     int ntaps, kblocks, bn, n_tiles, nstages, n_total;
@@ -145,155 +161,14 @@ __device__ __forceinline__ CvTile cv_decode(const ConvParams &P, int tile) {
     return t;
 }
 
-__global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams P) {
-    extern __shared__ uint8_t cv_smem_raw[];
-    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(cv_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *pipe = base;
-    float *bias_s = reinterpret_cast<float *>(base + kCvPipeBytes);
-    uint64_t *full = reinterpret_cast<uint64_t *>(base + kCvPipeBytes + kCvMaxN * 4);
-    uint64_t *empty = full + kCvMaxStages;
-    uint64_t *tfull = empty + kCvMaxStages;
-    uint64_t *tempty = tfull + 2;
-    uint64_t *hfull = tempty + 2;
-    uint64_t *hempty = hfull + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(hempty + 2);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int halo_box = kCvHaloW * (16 * P.msub + 2) * 128;                 // halo pixels x 64 ch bf16
-    const int halo_bytes = P.halo ? (halo_box + 1023) & ~1023 : 0;
-    const int a_bytes = P.halo ? 0 : P.msub * kCvABytes;
-    const int stage_bytes = a_bytes + P.bn * 128;
-    uint8_t *ring = pipe + 2 * halo_bytes;                                   // [halo slot 0][halo slot 1][operand ring]
-    const int nst = P.nstages;
-    const int kiters = P.ntaps * P.kblocks;
-    const int total_tiles = P.n_img * P.tiles_y * P.tiles_x * P.n_tiles;
-
-    if (tid == 0) {
-        for (int s = 0; s < kCvMaxStages; ++s) { cv_mbar_init(&full[s], 1); cv_mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { cv_mbar_init(&tfull[a], 1); cv_mbar_init(&tempty[a], 128); cv_mbar_init(&hfull[a], 1); cv_mbar_init(&hempty[a], 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = tid; i < P.n_total; i += kCvThreads) bias_s[i] = P.bias ? P.bias[i] : 0.0f;
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(cv_smem_u32(tmem_slot)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    cv_fence_before();
-    __syncthreads();
-    cv_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ===== producer: per k-iteration one shifted activation box (TMA tensor map) + one packed weight block (bulk copy)
-        if (lane == 0) {
-            uint32_t it = 0, hit = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const CvTile t = cv_decode(P, tile);
-                const uint8_t *wtile = P.wpk + (size_t)t.nt * kiters * (size_t)(P.bn * 128);
-                if (P.halo) {
-                    for (int kb = 0; kb < P.kblocks; ++kb, ++hit) {
-                        const int hs = hit & 1;
-                        cv_mbar_wait(&hempty[hs], ((hit >> 1) & 1) ^ 1);
-                        cv_mbar_expect_tx(&hfull[hs], (uint32_t)halo_box);
-                        cv_tma_load_4d(pipe + (size_t)hs * halo_bytes, &P.tmap[0], &hfull[hs], kb * 64, t.x0 - 1, t.y0 - 1, t.img);
-                        for (int tap = 0; tap < 9; ++tap, ++it) {
-                            const int s = it % nst;
-                            cv_mbar_wait(&empty[s], ((it / nst) & 1) ^ 1);
-                            cv_mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
-                            cv_bulk_g2s(ring + (size_t)s * stage_bytes, wtile + (size_t)(tap * P.kblocks + kb) * (size_t)(P.bn * 128),
-                                        (uint32_t)(P.bn * 128), &full[s]);
-                        }
-                    }
-                    continue;
-                }
-                for (int tap = 0; tap < P.ntaps; ++tap) {
-                    const CUtensorMap *map = &P.tmap[P.tap_map[tap]];
-                    const int x = t.x0 + P.tap_ox[tap], y = t.y0 + P.tap_oy[tap];
-                    for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
-                        const int s = it % nst;
-                        cv_mbar_wait(&empty[s], ((it / nst) & 1) ^ 1);
-                        uint8_t *dst = ring + (size_t)s * stage_bytes;
-                        cv_mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
-                        cv_tma_load_4d(dst, map, &full[s], kb * 64, x, y, t.img);
-                        cv_bulk_g2s(dst + a_bytes, wtile + (size_t)(tap * P.kblocks + kb) * (size_t)(P.bn * 128),
-                                    (uint32_t)(P.bn * 128), &full[s]);
-                    }
-                }
-            }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        // ===== MMA issuer ==============================================================================================
-        if (lane == 0) {
-            // idesc: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            uint32_t it = 0, ti = 0, hit = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-                const uint32_t acc = ti & 1;
-                cv_mbar_wait(&tempty[acc], ((ti >> 1) & 1) ^ 1);        // epilogue drained this accumulator
-                cv_fence_after();
-                const uint32_t d = tmem_base + acc * 256u;
-                if (P.halo) {
-                    // one halo patch (10 x (rows+2) pixels x 64 ch) per k-block; tap (dy,dx) = the same patch read from a
-                    // start address shifted by dy*kCvHaloW + dx pixel rows — 9x less activation traffic than one box per tap
-                    for (int kb = 0; kb < P.kblocks; ++kb, ++hit) {
-                        const int hs = hit & 1;
-                        cv_mbar_wait(&hfull[hs], (hit >> 1) & 1);
-                        const uint32_t ha = cv_smem_u32(pipe + (size_t)hs * halo_bytes);
-                        for (int tap = 0; tap < 9; ++tap, ++it) {
-                            const int s = it % nst;
-                            cv_mbar_wait(&full[s], (it / nst) & 1);
-                            cv_fence_after();
-                            const uint64_t bdesc = cv_desc_sw128(cv_smem_u32(ring + (size_t)s * stage_bytes));
-                            const int dy = tap / 3, dx = tap - 3 * dy;
-                            for (int m = 0; m < P.msub; ++m) {
-                                const uint64_t adesc = cv_desc_halo(ha + (uint32_t)(((m * 16 + dy) * kCvHaloW + dx) * 128));
-#pragma unroll
-                                for (int kk = 0; kk < 4; ++kk)
-                                    cv_umma_bf16(d + (uint32_t)(m * P.bn), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
-                                                 (kb | tap | kk) != 0);
-                            }
-                            cv_umma_commit(&empty[s]);
-                        }
-                        cv_umma_commit(&hempty[hs]);
-                    }
-                } else
-                for (int ki = 0; ki < kiters; ++ki, ++it) {
-                    const int s = it % nst;
-                    cv_mbar_wait(&full[s], (it / nst) & 1);
-                    cv_fence_after();
-                    const uint32_t sa = cv_smem_u32(ring + (size_t)s * stage_bytes);
-                    const uint64_t bdesc = cv_desc_sw128(sa + a_bytes);
-                    for (int m = 0; m < P.msub; ++m) {
-                        const uint64_t adesc = cv_desc_sw128(sa + m * kCvABytes);
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)      // +32 B along K inside the 128-B swizzle atom
-                            cv_umma_bf16(d + (uint32_t)(m * P.bn), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
-                                         (ki | kk) != 0);
-                    }
-                    cv_umma_commit(&empty[s]);
-                }
-                cv_umma_commit(&tfull[acc]);
-            }
-        }
-        __syncwarp();
-    } else if (warp >= 4) {
-        // ===== epilogue: bias (folded BN shift), ReLU, gate * v + residual, store ======================================
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const int px = row & ((1 << P.log2_bx) - 1), py = row >> P.log2_bx;
-        uint32_t ti = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-            const CvTile t = cv_decode(P, tile);
-            const uint32_t acc = ti & 1;
-            cv_mbar_wait(&tfull[acc], (ti >> 1) & 1);
-            cv_fence_after();
-            for (int m = 0; m < P.msub; ++m) {
-            const int x = t.x0 + px, y = t.y0 + m * (128 >> P.log2_bx) + py;
+// Epilogue of one accumulator row (one output pixel) over the bn columns of the tile: bias (folded BN shift), ReLU,
+// gate * v + residual, then either the bf16 NHWC store or the pixel-shuffle store of the transposed convolution.
+// Warp-collective (tcgen05.ld): every lane of the warp must call it.
+__device__ __forceinline__ void cv_epilogue_rows(const ConvParams &P, const CvTile &t, const float *bias_s, int x, int y,
+                                                 uint32_t taddr) {
             const bool valid = (x < P.w_out) && (y < P.h_out);
             const int64_t pix = ((int64_t)t.img * P.h_out + y) * P.w_out + x;
             const float g = (P.gate && valid) ? __ldg(P.gate + pix) : 1.0f;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)(m * P.bn);
             for (int ch = 0; ch < P.bn; ch += 32) {
                 uint32_t r[32];
                 __syncwarp();                                   // tcgen05.ld is warp-collective: re-converge after the guarded stores
@@ -348,10 +223,175 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                     }
                 }
             }
+}
+
+__global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams P) {
+    extern __shared__ uint8_t cv_smem_raw[];
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(cv_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *pipe = base;
+    float *bias_s = reinterpret_cast<float *>(base + kCvPipeBytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(base + kCvPipeBytes + kCvMaxN * 4);
+    uint64_t *empty = full + kCvMaxStages;
+    uint64_t *tfull = empty + kCvMaxStages;
+    uint64_t *tempty = tfull + 2;
+    uint64_t *hfull = tempty + 2;
+    uint64_t *hempty = hfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(hempty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int halo_box = kCvHaloW * (16 * P.msub + 2) * 128;                 // halo pixels x 64 ch bf16
+    const int halo_bytes = P.halo ? (halo_box + 1023) & ~1023 : 0;
+    const int a_bytes = P.halo ? 0 : P.msub * kCvABytes;
+    const int stage_bytes = a_bytes + P.bn * 128;
+    uint8_t *ring = pipe + 2 * halo_bytes;                                   // [halo slot 0][halo slot 1][operand ring]
+    const int nst = P.nstages;
+    const int kiters = P.ntaps * P.kblocks;
+    const int total_tiles = P.n_img * P.tiles_y * P.tiles_x * P.n_tiles;
+
+    if (tid == 0) {
+        for (int s = 0; s < kCvMaxStages; ++s) { cv_mbar_init(&full[s], 1); cv_mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { cv_mbar_init(&tfull[a], 1); cv_mbar_init(&tempty[a], 128); cv_mbar_init(&hfull[a], 1); cv_mbar_init(&hempty[a], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < P.n_total; i += kCvThreads) bias_s[i] = P.bias ? P.bias[i] : 0.0f;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(cv_smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    cv_fence_before();
+    __syncthreads();
+    cv_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== producer: per k-iteration one shifted activation box (TMA tensor map) + one packed weight block (bulk copy)
+        if (lane == 0) {
+            uint32_t it = 0, hit = 0;
+            CVP_DECL;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const CvTile t = cv_decode(P, tile);
+                const uint8_t *wtile = P.wpk + (size_t)t.nt * kiters * (size_t)(P.bn * 128);
+                if (P.halo) {
+                    for (int kb = 0; kb < P.kblocks; ++kb, ++hit) {
+                        const int hs = hit & 1;
+                        cv_mbar_wait(&hempty[hs], ((hit >> 1) & 1) ^ 1);
+                        cv_mbar_expect_tx(&hfull[hs], (uint32_t)halo_box);
+                        cv_tma_load_4d(pipe + (size_t)hs * halo_bytes, &P.tmap[0], &hfull[hs], kb * 64, t.x0 - 1, t.y0 - 1, t.img);
+                        for (int tap = 0; tap < 9; ++tap, ++it) {
+                            const int s = it % nst;
+                            cv_mbar_wait(&empty[s], ((it / nst) & 1) ^ 1);
+                            cv_mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+                            cv_bulk_g2s(ring + (size_t)s * stage_bytes, wtile + (size_t)(tap * P.kblocks + kb) * (size_t)(P.bn * 128),
+                                        (uint32_t)(P.bn * 128), &full[s]);
+                        }
+                    }
+                    continue;
+                }
+                for (int tap = 0; tap < P.ntaps; ++tap) {
+                    const CUtensorMap *map = &P.tmap[P.tap_map[tap]];
+                    const int x = t.x0 + P.tap_ox[tap], y = t.y0 + P.tap_oy[tap];
+                    for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
+                        const int s = it % nst;
+                        CVP_B();
+                        cv_mbar_wait(&empty[s], ((it / nst) & 1) ^ 1);
+                        CVP_E(0);
+                        uint8_t *dst = ring + (size_t)s * stage_bytes;
+                        cv_mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+                        cv_tma_load_4d(dst, map, &full[s], kb * 64, x, y, t.img);
+                        cv_bulk_g2s(dst + a_bytes, wtile + (size_t)(tap * P.kblocks + kb) * (size_t)(P.bn * 128),
+                                    (uint32_t)(P.bn * 128), &full[s]);
+                    }
+                }
             }
+            CVP_DUMP(0);
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer ==============================================================================================
+        if (lane == 0) {
+            // idesc: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            uint32_t it = 0, ti = 0, hit = 0;
+            CVP_DECL;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+                const uint32_t acc = ti & 1;
+                CVP_B();
+                cv_mbar_wait(&tempty[acc], ((ti >> 1) & 1) ^ 1);
+                CVP_E(0);        // epilogue drained this accumulator
+                cv_fence_after();
+                const uint32_t d = tmem_base + acc * 256u;
+                if (P.halo) {
+                    // one halo patch (10 x (rows+2) pixels x 64 ch) per k-block; tap (dy,dx) = the same patch read from a
+                    // start address shifted by dy*kCvHaloW + dx pixel rows — 9x less activation traffic than one box per tap
+                    for (int kb = 0; kb < P.kblocks; ++kb, ++hit) {
+                        const int hs = hit & 1;
+                        cv_mbar_wait(&hfull[hs], (hit >> 1) & 1);
+                        const uint32_t ha = cv_smem_u32(pipe + (size_t)hs * halo_bytes);
+                        for (int tap = 0; tap < 9; ++tap, ++it) {
+                            const int s = it % nst;
+                            cv_mbar_wait(&full[s], (it / nst) & 1);
+                            cv_fence_after();
+                            const uint64_t bdesc = cv_desc_sw128(cv_smem_u32(ring + (size_t)s * stage_bytes));
+                            const int dy = tap / 3, dx = tap - 3 * dy;
+                            for (int m = 0; m < P.msub; ++m) {
+                                const uint64_t adesc = cv_desc_halo(ha + (uint32_t)(((m * 16 + dy) * kCvHaloW + dx) * 128));
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+                                    cv_umma_bf16(d + (uint32_t)(m * P.bn), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                                                 (kb | tap | kk) != 0);
+                            }
+                            cv_umma_commit(&empty[s]);
+                        }
+                        cv_umma_commit(&hempty[hs]);
+                    }
+                } else
+                for (int ki = 0; ki < kiters; ++ki, ++it) {
+                    const int s = it % nst;
+                    CVP_B();
+                    cv_mbar_wait(&full[s], (it / nst) & 1);
+                    CVP_E(1);
+                    CVP_B();
+                    cv_fence_after();
+                    const uint32_t sa = cv_smem_u32(ring + (size_t)s * stage_bytes);
+                    const uint64_t bdesc = cv_desc_sw128(sa + a_bytes);
+                    for (int m = 0; m < P.msub; ++m) {
+                        const uint64_t adesc = cv_desc_sw128(sa + m * kCvABytes);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)      // +32 B along K inside the 128-B swizzle atom
+                            cv_umma_bf16(d + (uint32_t)(m * P.bn), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                                         (ki | kk) != 0);
+                    }
+                    cv_umma_commit(&empty[s]);
+                    CVP_E(2);
+                }
+                cv_umma_commit(&tfull[acc]);
+            }
+            CVP_DUMP(4);
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===== epilogue: bias (folded BN shift), ReLU, gate * v + residual, store ======================================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int px = row & ((1 << P.log2_bx) - 1), py = row >> P.log2_bx;
+        uint32_t ti = 0;
+        CVP_DECL;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+            const CvTile t = cv_decode(P, tile);
+            const uint32_t acc = ti & 1;
+            CVP_B();
+            cv_mbar_wait(&tfull[acc], (ti >> 1) & 1);
+            CVP_E(0);
+            CVP_B();
+            cv_fence_after();
+            for (int m = 0; m < P.msub; ++m)
+                cv_epilogue_rows(P, t, bias_s, t.x0 + px, t.y0 + m * (128 >> P.log2_bx) + py,
+                                 tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)(m * P.bn));
             cv_fence_before();
             cv_mbar_arrive(&tempty[acc]);
+            CVP_E(1);
         }
+        if (warp == 4 && lane == 0) { CVP_DUMP(8); }
     }
 
     cv_fence_before();
@@ -359,6 +399,185 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
     if (warp == 1) {
         cv_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------- CTA-pair variant
+// Same GEMM on a CTA pair (cluster of 2, tcgen05 cta_group::2): UMMA M = 256 — each CTA owns one 128-pixel patch (its rows of
+// the accumulator stay in its own TMEM) and loads only HALF of every weight block; the tensor core of each SM reads the
+// peer's half through the pair's shared-memory window.  Per SM that halves both the weight bytes pulled from L2 and the
+// operand bytes the MMA reads from shared memory — the single-CTA kernel above spends 96 B/clk on operand reads plus 96 B/clk
+// on TMA fills against a 128 B/clk shared-memory port and plateaus near 60 % tensor-pipe activity.
+//   rank 0 (leader): TMA producer, MMA issuer, epilogue          rank 1: TMA producer, epilogue
+// Barriers: full[s] lives in the leader (its producer posts the bytes of both CTAs, both CTAs' TMA complete_tx on it);
+// empty[s] / tfull[acc] are signalled in BOTH CTAs by a multicast tcgen05.commit; tempty[acc] lives in the leader and counts
+// the 8 epilogue warps of the pair.
+__device__ __forceinline__ uint32_t cv_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cv_mapa(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cv_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cv_mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cv_mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cv_tma2_load_4d(void *dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(cv_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr),
+                   "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void cv_tma2_load_2d(void *dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(cv_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void cv_umma2_commit_mc(uint64_t *bar) {       // arrive on `bar` in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(cv_smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void cv_umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1) conv_tc2_kernel(const __grid_constant__ ConvParams P) {
+    extern __shared__ uint8_t cv_smem_raw[];
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(cv_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *pipe = base;
+    float *bias_s = reinterpret_cast<float *>(base + kCvPipeBytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(base + kCvPipeBytes + kCvMaxN * 4);
+    uint64_t *empty = full + kCvMaxStages;
+    uint64_t *tfull = empty + kCvMaxStages;
+    uint64_t *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 6);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cv_cluster_rank();
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int b_half = P.bn * 64;                              // bytes of half a weight block: (bn/2 rows) x 128 B
+    const int stage_bytes = kCvABytes + b_half;                // per CTA
+    const int nst = P.nstages;
+    const int kiters = P.ntaps * P.kblocks;
+    const int total_tiles = P.n_img * P.tiles_y * P.tiles_x * P.n_tiles;   // tiles_y counts 256-pixel super-tiles (msub = 2)
+    const int by = 128 >> P.log2_bx;
+
+    if (tid == 0) {
+        for (int s = 0; s < kCvMaxStages; ++s) { cv_mbar_init(&full[s], 1); cv_mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { cv_mbar_init(&tfull[a], 1); cv_mbar_init(&tempty[a], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < P.n_total; i += kCvThreads) bias_s[i] = P.bias ? P.bias[i] : 0.0f;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(cv_smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    cv_fence_before();
+    __syncthreads();
+    cv_cluster_sync();
+    cv_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== producer (both CTAs): my 128-pixel patch + my half of the weight block, signalled on the LEADER's full[s] ====
+        if (lane == 0) {
+            uint32_t it = 0;
+            CVP_DECL;
+            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+                const CvTile t = cv_decode(P, tile);
+                const int y0 = t.y0 + (int)rank * by;
+                const int wrow0 = t.nt * kiters * P.bn + (int)rank * (P.bn >> 1);     // row of the packed image viewed as [rows][64]
+                for (int tap = 0; tap < P.ntaps; ++tap) {
+                    const CUtensorMap *map = &P.tmap[P.tap_map[tap]];
+                    const int x = t.x0 + P.tap_ox[tap], y = y0 + P.tap_oy[tap];
+                    for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
+                        const int s = it % nst;
+                        CVP_B();
+                        cv_mbar_wait(&empty[s], ((it / nst) & 1) ^ 1);
+                        CVP_E(0);
+                        uint8_t *dst = pipe + (size_t)s * stage_bytes;
+                        const uint32_t lfull = cv_mapa(cv_smem_u32(&full[s]), 0);
+                        // the leader posts the byte count of BOTH CTAs with one local arrive; the peer only issues its loads
+                        // (a remote arrive per stage costs a cluster round trip on the producer's critical path).  The peer's
+                        // complete_tx may land first: the phase still cannot complete before the leader's arrive.
+                        if (rank == 0) cv_mbar_expect_tx(&full[s], 2u * (uint32_t)stage_bytes);
+                        cv_tma2_load_4d(dst, map, lfull, kb * 64, x, y, t.img);
+                        cv_tma2_load_2d(dst + kCvABytes, &P.tmap_w, lfull, 0, wrow0 + (tap * P.kblocks + kb) * P.bn);
+                    }
+                }
+            }
+            CVP_DUMP(0);
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader only): M = 256 across the pair ======================================================
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            uint32_t it = 0, ti = 0;
+            CVP_DECL;
+            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++ti) {
+                const uint32_t acc = ti & 1;
+                CVP_B();
+                cv_mbar_wait(&tempty[acc], ((ti >> 1) & 1) ^ 1);
+                CVP_E(0);        // both CTAs' epilogues drained this accumulator
+                cv_fence_after();
+                const uint32_t d = tmem_base + acc * 256u;
+                for (int ki = 0; ki < kiters; ++ki, ++it) {
+                    const int s = it % nst;
+                    CVP_B();
+                    cv_mbar_wait(&full[s], (it / nst) & 1);
+                    CVP_E(1);
+                    CVP_B();
+                    cv_fence_after();
+                    const uint32_t sa = cv_smem_u32(pipe + (size_t)s * stage_bytes);
+                    const uint64_t adesc = cv_desc_sw128(sa), bdesc = cv_desc_sw128(sa + kCvABytes);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        cv_umma2_bf16(d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (ki | kk) != 0);
+                    cv_umma2_commit_mc(&empty[s]);
+                    CVP_E(2);
+                }
+                cv_umma2_commit_mc(&tfull[acc]);
+            }
+            CVP_DUMP(4);
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===== epilogue (both CTAs): my 128 accumulator rows ==========================================================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int px = row & ((1 << P.log2_bx) - 1), py = row >> P.log2_bx;
+        uint32_t ti = 0;
+        CVP_DECL;
+        for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++ti) {
+            const CvTile t = cv_decode(P, tile);
+            const uint32_t acc = ti & 1;
+            CVP_B();
+            cv_mbar_wait(&tfull[acc], (ti >> 1) & 1);
+            CVP_E(0);
+            CVP_B();
+            cv_fence_after();
+            cv_epilogue_rows(P, t, bias_s, t.x0 + px, t.y0 + (int)rank * by + py, tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u);
+            cv_fence_before();
+            __syncwarp();
+            if (lane == 0) cv_mbar_arrive_cluster(cv_mapa(cv_smem_u32(&tempty[acc]), 0));
+            CVP_E(1);
+        }
+        if (warp == 4 && lane == 0) { CVP_DUMP(8); }
+    }
+
+    cv_fence_before();
+    __syncthreads();
+    cv_cluster_sync();                      // the peer may still multicast into my barriers / read my shared memory until here
+    if (warp == 1) {
+        cv_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -406,6 +625,8 @@ static size_t cv_smem_bytes() { return 1024 + kCvPipeBytes + kCvMaxN * 4 + (2 * 
 int hvpr_conv_init() {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv_smem_bytes());
     if (e != cudaSuccess) { set_cuda_error(e); return HVPR_ERR_CUDA; }
+    e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv_smem_bytes());
+    if (e != cudaSuccess) { set_cuda_error(e); return HVPR_ERR_CUDA; }
     return HVPR_OK;
 }
 
@@ -415,6 +636,15 @@ static int g_cv_halo_off = 1;   // measured (tools/dev/backbone_bench.py A/B): t
 extern "C" int hvpr_dbg_conv_force_msub(int msub) {
     if (msub < 0 || msub > 2) return HVPR_ERR_ARG;
     g_cv_force_msub = msub;
+    return HVPR_OK;
+}
+// knob: 0 = automatic choice between the single-CTA and the CTA-pair (cta_group::2) kernel, 1 = never pair, 2 = always pair
+static long long *g_cv_prof = nullptr;
+extern "C" int hvpr_dbg_conv_prof(void *buf) { g_cv_prof = (long long *)buf; return HVPR_OK; }   // (grid, 16) int64, profile build
+static int g_cv_pair_mode = 1;
+extern "C" int hvpr_dbg_conv_pair(int mode) {
+    if (mode < 0 || mode > 2) return HVPR_ERR_ARG;
+    g_cv_pair_mode = mode;
     return HVPR_OK;
 }
 // knob: 1 (default) = one TMA box per tap; 0 = 3x3 stride-1 layers read all nine taps out of one halo patch
@@ -447,13 +677,17 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
     ConvParams P;
     memset(&P, 0, sizeof(P));
     P.n_img = a->n;
+    P.prof = g_cv_prof;
     P.h_out = a->h_in / a->stride;
     P.w_out = a->w_in / a->stride;
     // patch shape: the power-of-two split of 128 pixels that wastes the fewest out-of-image pixels (ties: wider rows)
     // two 128-pixel sub-tiles per tile when the column tile is narrow: halves the weight traffic per MAC
     P.msub = (a->bn <= 128 && (int64_t)a->n * P.h_out * P.w_out >= 2 * 128 * (int64_t)kNumSMs) ? 2 : 1;
     if (g_cv_force_msub == 1 || (g_cv_force_msub == 2 && a->bn <= 128)) P.msub = g_cv_force_msub;
-    P.halo = (a->ksize == 3 && a->stride == 1 && !g_cv_halo_off) ? 1 : 0;
+    const bool pair = g_cv_pair_mode == 2 ||
+                      (g_cv_pair_mode == 0 && (int64_t)a->n * P.h_out * P.w_out >= 256 * (int64_t)(kNumSMs / 2));
+    if (pair) P.msub = 2;        // a tile is a 256-pixel super-tile: one 128-pixel patch per CTA of the pair
+    P.halo = (!pair && a->ksize == 3 && a->stride == 1 && !g_cv_halo_off) ? 1 : 0;
     int best = -1; int64_t best_cost = 0;
     for (int l = P.halo ? 3 : 0; l <= (P.halo ? 3 : 7); ++l) {      // halo path: patches are 8 pixels wide
         const int bx = 1 << l, by = (128 >> l) * P.msub;
@@ -469,7 +703,7 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
     P.n_total = a->n_total;
     P.n_tiles = a->n_total / a->bn;
     const int halo_bytes = P.halo ? (kCvHaloW * (16 * P.msub + 2) * 128 + 1023) & ~1023 : 0;
-    const int stage_bytes = (P.halo ? 0 : P.msub * kCvABytes) + a->bn * 128;
+    const int stage_bytes = pair ? kCvABytes + a->bn * 64 : (P.halo ? 0 : P.msub * kCvABytes) + a->bn * 128;
     P.nstages = (kCvPipeBytes - 2 * halo_bytes) / stage_bytes;
     if (P.nstages > kCvMaxStages) P.nstages = kCvMaxStages;
     P.wpk = (const uint8_t *)a->w_packed;
@@ -494,7 +728,7 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
     } else return HVPR_ERR_ARG;
 
     // tensor maps over the NHWC bf16 input: dims (channel, x, y, image)
-    const cuuint32_t box[4] = {64u, (cuuint32_t)(P.halo ? kCvHaloW : bx), (cuuint32_t)(P.halo ? by + 2 : by), 1u};
+    const cuuint32_t box[4] = {64u, (cuuint32_t)(P.halo ? kCvHaloW : bx), (cuuint32_t)(P.halo ? by + 2 : (pair ? by / 2 : by)), 1u};
     const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
     const uint64_t pix_b = (uint64_t)a->in_cs * 2u;
     const int nmaps = (a->stride == 2) ? 4 : 1;
@@ -524,6 +758,21 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
             }
         }
     const int64_t total_tiles = (int64_t)P.n_img * P.tiles_x * P.tiles_y * P.n_tiles;
+    if (pair) {
+        // weights: the pre-swizzled image as a plain [rows][64] bf16 tensor; each CTA pulls bn/2 rows of every block verbatim
+        const cuuint64_t wdims[2] = {64u, (cuuint64_t)a->n_total * (cuuint64_t)(P.ntaps * P.kblocks)};
+        const cuuint64_t wstr[1] = {128u};
+        const cuuint32_t wbox[2] = {64u, (cuuint32_t)(a->bn / 2)};
+        const cuuint32_t wes[2] = {1u, 1u};
+        CUresult r = enc(&P.tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)a->w_packed, wdims, wstr, wbox, wes,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return HVPR_ERR_ARG;
+        const int64_t clusters = total_tiles < kNumSMs / 2 ? total_tiles : kNumSMs / 2;
+        conv_tc2_kernel<<<(unsigned)(2 * clusters), kCvThreads, cv_smem_bytes(), (cudaStream_t)stream>>>(P);
+        HVPR_CHECK_LAUNCH();
+        return HVPR_OK;
+    }
     const int grid = (int)(total_tiles < kNumSMs ? total_tiles : kNumSMs);
     conv_tc_kernel<<<grid, kCvThreads, cv_smem_bytes(), (cudaStream_t)stream>>>(P);
     HVPR_CHECK_LAUNCH();

@@ -121,6 +121,28 @@ def test_conv3x3_halo_operand_path(msub, n, h, w, cin, cout, bn):
     assert rel_err(out.permute(0, 3, 1, 2).float(), ref)[0] <= TOL_LAYER
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,stride,bn,ksize", [
+    (1, 16, 16, 64, 64, 1, 64, 3),         # one super-tile, one CTA pair
+    (2, 20, 28, 128, 128, 1, 128, 3),
+    (1, 40, 24, 256, 256, 1, 256, 3),
+    (1, 24, 40, 128, 256, 2, 256, 3),
+    (3, 9, 70, 64, 32, 1, 32, 3),
+])
+def test_conv_cta_pair_kernel(n, h, w, cin, cout, stride, bn, ksize):
+    """cta_group::2 variant: UMMA M = 256 across a CTA pair, each CTA loading half of every weight block."""
+    L = _lib()
+    x, wt, b = _rand_case(17 + h, n, h, w, cin, cout, ksize)
+    ref = F.relu(F.conv2d(x.float(), wt.float(), b, stride=stride, padding=1))
+    wpk = _pack(wt.float().permute(0, 2, 3, 1).reshape(cout, 9, cin), bn)
+    out = torch.empty(n, h // stride, w // stride, cout, dtype=torch.bfloat16, device="cuda")
+    assert L.lib().hvpr_dbg_conv_pair(2) == 0
+    try:
+        _conv_call(x.permute(0, 2, 3, 1).contiguous(), wpk, cout, bn, b, 3, stride, cin, out)
+    finally:
+        L.lib().hvpr_dbg_conv_pair(1)
+    assert rel_err(out.permute(0, 3, 1, 2).float(), ref)[0] <= TOL_LAYER
+
+
 def test_bev_fill_nhwc_bf16_matches_the_nchw_fill():
     """K4 in channels-last bf16 (what the backbone consumes) == bf16 rounding of the fp32 NCHW canvases."""
     L = _lib()

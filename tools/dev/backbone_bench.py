@@ -15,6 +15,7 @@ from hvpr_b200 import G1, G2, G3, _lib                      # noqa: E402
 from hvpr_b200.backbone import BaseBEVBackbone_Scale        # noqa: E402
 from hvpr_b200.config import Cfg                            # noqa: E402
 
+PAIR_DEFAULT = int(os.environ.get("HVPR_CONV_PAIR", "1"))      # hvpr_dbg_conv_pair mode used for the whole-network timing
 CFG = dict(LAYER_NUMS=[3, 3, 3], SFM_LAYER_NUMS=[3, 3, 3], LAYER_STRIDES=[1, 2, 2], NUM_FILTERS=[128, 256, 512],
            NUM_SCALE_FILTERS=[32, 64, 128], UPSAMPLE_STRIDES=[1, 2, 4], NUM_UPSAMPLE_FILTERS=[128, 128, 128])
 
@@ -63,6 +64,7 @@ def main():
         if p.dim() == 4:
             torch.nn.init.uniform_(p, -(3.0 / (p.shape[1] * p.shape[2] * p.shape[3])) ** 0.5, (3.0 / (p.shape[1] * p.shape[2] * p.shape[3])) ** 0.5)
     _lib.init_device()
+    _lib.lib().hvpr_dbg_conv_pair(PAIR_DEFAULT)
     occ = (torch.rand(B, H, W, 1, device="cuda") < 0.12)
     x_in = (torch.randn(B, H, W, 128, device="cuda").abs() * occ).bfloat16()
     y_in = torch.zeros(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
@@ -93,8 +95,9 @@ def main():
                 kw = dict(gate=lv["gate"], residual=s) if name == "sfm" else {}
                 dst = lv["b"]
                 ts = {}
-                for mode in ("halo", "per_tap"):          # A/B inside one run: boxes and thermal state differ between runs
-                    _lib.lib().hvpr_dbg_conv_halo_off(int(mode == "per_tap"))
+                for mode in ("single", "halo", "pair"):   # A/B inside one run: boxes and thermal state differ between runs
+                    _lib.lib().hvpr_dbg_conv_halo_off(int(mode != "halo"))
+                    _lib.lib().hvpr_dbg_conv_pair(2 if mode == "pair" else 1)
                     for _ in range(2):
                         m._conv(lay, s, B, hi, wi, dst, **kw)
                     e0.record()
@@ -103,13 +106,26 @@ def main():
                     e1.record()
                     torch.cuda.synchronize()
                     ts[mode] = e0.elapsed_time(e1) / a.iters
-                _lib.lib().hvpr_dbg_conv_halo_off(0)
-                t = ts["halo"]
+                _lib.lib().hvpr_dbg_conv_halo_off(1)
+                _lib.lib().hvpr_dbg_conv_pair(PAIR_DEFAULT)
+                t = ts["single"]
                 f = 2 * 9 * lay.c_in * lay.n_total * B * lv["h"] * lv["w"]
                 layers.append({"level": i, "layer": name, "cin": lay.c_in, "cout": lay.n_total, "stride": lay.stride,
                                "hw": [lv["h"], lv["w"]], "ms": round(t, 4), "tflops": round(f / t / 1e9, 1),
-                               "ms_per_tap_path": round(ts["per_tap"], 4)})
+                               "ms_halo": round(ts["halo"], 4), "ms_pair": round(ts["pair"], 4)})
             de = P["de"][i]
+            tde = {}
+            for mode in ("single", "pair"):
+                _lib.lib().hvpr_dbg_conv_pair(2 if mode == "pair" else 1)
+                for _ in range(2):
+                    m._conv(de, lv["a"], B, lv["h"], lv["w"], pl["out"], out_mode=1, out_c_off=128 * i, out_ctot=384)
+                e0.record()
+                for _ in range(a.iters):
+                    m._conv(de, lv["a"], B, lv["h"], lv["w"], pl["out"], out_mode=1, out_c_off=128 * i, out_ctot=384)
+                e1.record()
+                torch.cuda.synchronize()
+                tde[mode] = e0.elapsed_time(e1) / a.iters
+            _lib.lib().hvpr_dbg_conv_pair(PAIR_DEFAULT)
             for _ in range(2):
                 m._conv(de, lv["a"], B, lv["h"], lv["w"], pl["out"], out_mode=1, out_c_off=128 * i, out_ctot=384)
             e0.record()
@@ -120,7 +136,7 @@ def main():
             t = e0.elapsed_time(e1) / a.iters
             layers.append({"level": i, "layer": "deblock", "cin": de.c_in, "cout": de.n_total, "ms": round(t, 4),
                            "tflops": round(2 * de.c_in * de.n_total * B * lv["h"] * lv["w"] / t / 1e9, 1),
-                           "out_gbps": round(B * 128 * H * W * 4 / t / 1e6, 1)})
+                           "out_gbps": round(B * 128 * H * W * 4 / t / 1e6, 1), "ms_single": round(tde["single"], 4), "ms_pair": round(tde["pair"], 4)})
             h, w, src = lv["h"], lv["w"], lv["a"]
     res["layers"] = layers
     if not a.no_cudnn:
