@@ -55,7 +55,8 @@ struct ConvParams {
     int log2_bx, tiles_x, tiles_y;
     int ntaps, kblocks, bn, n_tiles, nstages, n_total;
     int halo;                 // 3x3 stride-1: one halo patch per k-block feeds all 9 taps (see the MMA issuer)
-    int msub;                 // 128-pixel sub-tiles per tile (2 when bn <= 128: two A patches share every weight block)
+    int msub;                 // 128-pixel sub-tiles per CTA and tile (2: two A patches share every weight block)
+    int pair;                 // 1: CTA-pair kernel (a tile spans the patches of both CTAs)
     int relu, res_cs;
     int out_mode, out_cs, out_c_off;
     int up, cout, out_h, out_w, out_ctot;
@@ -157,7 +158,7 @@ __device__ __forceinline__ CvTile cv_decode(const ConvParams &P, int tile) {
     const int ty = m % P.tiles_y;
     t.img = m / P.tiles_y;
     t.x0 = tx << P.log2_bx;
-    t.y0 = ty * (128 >> P.log2_bx) * P.msub;
+    t.y0 = ty * (128 >> P.log2_bx) * P.msub * (P.pair + 1);
     return t;
 }
 
@@ -456,21 +457,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1) conv_
     uint64_t *empty = full + kCvMaxStages;
     uint64_t *tfull = empty + kCvMaxStages;
     uint64_t *tempty = tfull + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 6);
+    uint64_t *hfull = tempty + 2;
+    uint64_t *hempty = hfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(hempty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cv_cluster_rank();
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const int b_half = P.bn * 64;                              // bytes of half a weight block: (bn/2 rows) x 128 B
-    const int stage_bytes = kCvABytes + b_half;                // per CTA
+    const int halo_box = kCvHaloW * (16 * P.msub + 2) * 128;   // halo path: my patch rows + 2, 10 pixels wide, 64 ch
+    const int halo_bytes = P.halo ? (halo_box + 1023) & ~1023 : 0;
+    const int stage_bytes = (P.halo ? 0 : kCvABytes) + b_half; // per CTA
+    uint8_t *ring = pipe + 2 * halo_bytes;
     const int nst = P.nstages;
     const int kiters = P.ntaps * P.kblocks;
-    const int total_tiles = P.n_img * P.tiles_y * P.tiles_x * P.n_tiles;   // tiles_y counts 256-pixel super-tiles (msub = 2)
-    const int by = 128 >> P.log2_bx;
+    const int total_tiles = P.n_img * P.tiles_y * P.tiles_x * P.n_tiles;   // a tile spans the patches of both CTAs
+    const int by = (128 >> P.log2_bx) * P.msub;                // rows of the image this CTA owns per tile
 
     if (tid == 0) {
         for (int s = 0; s < kCvMaxStages; ++s) { cv_mbar_init(&full[s], 1); cv_mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { cv_mbar_init(&tfull[a], 1); cv_mbar_init(&tempty[a], 8); }
+        for (int a = 0; a < 2; ++a) { cv_mbar_init(&tfull[a], 1); cv_mbar_init(&tempty[a], 8); cv_mbar_init(&hfull[a], 1); cv_mbar_init(&hempty[a], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < P.n_total; i += kCvThreads) bias_s[i] = P.bias ? P.bias[i] : 0.0f;
@@ -487,12 +493,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1) conv_
     if (warp == 0) {
         // ===== producer (both CTAs): my 128-pixel patch + my half of the weight block, signalled on the LEADER's full[s] ====
         if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t it = 0, hit = 0;
             CVP_DECL;
             for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
                 const CvTile t = cv_decode(P, tile);
                 const int y0 = t.y0 + (int)rank * by;
                 const int wrow0 = t.nt * kiters * P.bn + (int)rank * (P.bn >> 1);     // row of the packed image viewed as [rows][64]
+                if (P.halo) {
+                    for (int kb = 0; kb < P.kblocks; ++kb, ++hit) {
+                        const int hs = hit & 1;
+                        cv_mbar_wait(&hempty[hs], ((hit >> 1) & 1) ^ 1);
+                        if (rank == 0) cv_mbar_expect_tx(&hfull[hs], 2u * (uint32_t)halo_box);
+                        cv_tma2_load_4d(pipe + (size_t)hs * halo_bytes, &P.tmap[0], cv_mapa(cv_smem_u32(&hfull[hs]), 0), kb * 64,
+                                        t.x0 - 1, y0 - 1, t.img);
+                        for (int tap = 0; tap < 9; ++tap, ++it) {
+                            const int s = it % nst;
+                            CVP_B();
+                            cv_mbar_wait(&empty[s], ((it / nst) & 1) ^ 1);
+                            CVP_E(0);
+                            if (rank == 0) cv_mbar_expect_tx(&full[s], 2u * (uint32_t)stage_bytes);
+                            cv_tma2_load_2d(ring + (size_t)s * stage_bytes, &P.tmap_w, cv_mapa(cv_smem_u32(&full[s]), 0), 0,
+                                            wrow0 + (tap * P.kblocks + kb) * P.bn);
+                        }
+                    }
+                    continue;
+                }
                 for (int tap = 0; tap < P.ntaps; ++tap) {
                     const CUtensorMap *map = &P.tmap[P.tap_map[tap]];
                     const int x = t.x0 + P.tap_ox[tap], y = y0 + P.tap_oy[tap];
@@ -501,7 +526,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1) conv_
                         CVP_B();
                         cv_mbar_wait(&empty[s], ((it / nst) & 1) ^ 1);
                         CVP_E(0);
-                        uint8_t *dst = pipe + (size_t)s * stage_bytes;
+                        uint8_t *dst = ring + (size_t)s * stage_bytes;
                         const uint32_t lfull = cv_mapa(cv_smem_u32(&full[s]), 0);
                         // the leader posts the byte count of BOTH CTAs with one local arrive; the peer only issues its loads
                         // (a remote arrive per stage costs a cluster round trip on the producer's critical path).  The peer's
@@ -519,7 +544,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1) conv_
         // ===== MMA issuer (leader only): M = 256 across the pair ======================================================
         if (lane == 0 && rank == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-            uint32_t it = 0, ti = 0;
+            uint32_t it = 0, ti = 0, hit = 0;
             CVP_DECL;
             for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++ti) {
                 const uint32_t acc = ti & 1;
@@ -528,6 +553,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1) conv_
                 CVP_E(0);        // both CTAs' epilogues drained this accumulator
                 cv_fence_after();
                 const uint32_t d = tmem_base + acc * 256u;
+                if (P.halo) {
+                    for (int kb = 0; kb < P.kblocks; ++kb, ++hit) {
+                        const int hs = hit & 1;
+                        CVP_B();
+                        cv_mbar_wait(&hfull[hs], (hit >> 1) & 1);
+                        CVP_E(3);
+                        const uint32_t ha = cv_smem_u32(pipe + (size_t)hs * halo_bytes);
+                        for (int tap = 0; tap < 9; ++tap, ++it) {
+                            const int s = it % nst;
+                            CVP_B();
+                            cv_mbar_wait(&full[s], (it / nst) & 1);
+                            CVP_E(1);
+                            CVP_B();
+                            cv_fence_after();
+                            const uint64_t bdesc = cv_desc_sw128(cv_smem_u32(ring + (size_t)s * stage_bytes));
+                            const int dy = tap / 3, dx = tap - 3 * dy;
+                            for (int m = 0; m < P.msub; ++m) {
+                                const uint64_t adesc = cv_desc_halo(ha + (uint32_t)(((m * 16 + dy) * kCvHaloW + dx) * 128));
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+                                    cv_umma2_bf16(d + (uint32_t)(m * P.bn), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                                                  (kb | tap | kk) != 0);
+                            }
+                            cv_umma2_commit_mc(&empty[s]);
+                            CVP_E(2);
+                        }
+                        cv_umma2_commit_mc(&hempty[hs]);
+                    }
+                } else
                 for (int ki = 0; ki < kiters; ++ki, ++it) {
                     const int s = it % nst;
                     CVP_B();
@@ -535,7 +589,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1) conv_
                     CVP_E(1);
                     CVP_B();
                     cv_fence_after();
-                    const uint32_t sa = cv_smem_u32(pipe + (size_t)s * stage_bytes);
+                    const uint32_t sa = cv_smem_u32(ring + (size_t)s * stage_bytes);
                     const uint64_t adesc = cv_desc_sw128(sa), bdesc = cv_desc_sw128(sa + kCvABytes);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
@@ -563,7 +617,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1) conv_
             CVP_E(0);
             CVP_B();
             cv_fence_after();
-            cv_epilogue_rows(P, t, bias_s, t.x0 + px, t.y0 + (int)rank * by + py, tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u);
+            for (int m = 0; m < P.msub; ++m)
+                cv_epilogue_rows(P, t, bias_s, t.x0 + px, t.y0 + (int)rank * by + m * (128 >> P.log2_bx) + py,
+                                 tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)(m * P.bn));
             cv_fence_before();
             __syncwarp();
             if (lane == 0) cv_mbar_arrive_cluster(cv_mapa(cv_smem_u32(&tempty[acc]), 0));
@@ -641,7 +697,7 @@ extern "C" int hvpr_dbg_conv_force_msub(int msub) {
 // knob: 0 = automatic choice between the single-CTA and the CTA-pair (cta_group::2) kernel, 1 = never pair, 2 = always pair
 static long long *g_cv_prof = nullptr;
 extern "C" int hvpr_dbg_conv_prof(void *buf) { g_cv_prof = (long long *)buf; return HVPR_OK; }   // (grid, 16) int64, profile build
-static int g_cv_pair_mode = 1;
+static int g_cv_pair_mode = 0;
 extern "C" int hvpr_dbg_conv_pair(int mode) {
     if (mode < 0 || mode > 2) return HVPR_ERR_ARG;
     g_cv_pair_mode = mode;
@@ -684,18 +740,24 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
     // two 128-pixel sub-tiles per tile when the column tile is narrow: halves the weight traffic per MAC
     P.msub = (a->bn <= 128 && (int64_t)a->n * P.h_out * P.w_out >= 2 * 128 * (int64_t)kNumSMs) ? 2 : 1;
     if (g_cv_force_msub == 1 || (g_cv_force_msub == 2 && a->bn <= 128)) P.msub = g_cv_force_msub;
+    // automatic policy (measured per layer with tools/dev/backbone_bench.py, 432 x 496 canvases, batch 8): the pair kernel wins
+    // 6-9 % on the 256-column 3x3 layers (weight traffic and operand reads halved per SM); narrow layers and the transposed
+    // convolutions (short K loops, store-bound epilogue) are faster on the single-CTA kernel
     const bool pair = g_cv_pair_mode == 2 ||
-                      (g_cv_pair_mode == 0 && (int64_t)a->n * P.h_out * P.w_out >= 256 * (int64_t)(kNumSMs / 2));
-    if (pair) P.msub = 2;        // a tile is a 256-pixel super-tile: one 128-pixel patch per CTA of the pair
-    P.halo = (!pair && a->ksize == 3 && a->stride == 1 && !g_cv_halo_off) ? 1 : 0;
+                      (g_cv_pair_mode == 0 && a->bn == 256 && a->ksize == 3 && a->out_mode == 0 &&
+                       (int64_t)a->n * P.h_out * P.w_out >= 256 * (int64_t)(kNumSMs / 2) * 4);
+    P.pair = pair ? 1 : 0;
+    P.halo = (a->ksize == 3 && a->stride == 1 && !g_cv_halo_off) ? 1 : 0;
+    if (pair && !(P.halo && a->bn <= 128 && g_cv_force_msub != 1)) P.msub = 1;   // pair: two sub-tiles per CTA only on the halo path
     int best = -1; int64_t best_cost = 0;
     for (int l = P.halo ? 3 : 0; l <= (P.halo ? 3 : 7); ++l) {      // halo path: patches are 8 pixels wide
-        const int bx = 1 << l, by = (128 >> l) * P.msub;
+        const int bx = 1 << l, by = (128 >> l) * P.msub * (P.pair + 1);
         const int64_t cost = ceil_div64(P.w_out, bx) * bx * (ceil_div64(P.h_out, by) * by);
         if (best < 0 || cost < best_cost || (cost == best_cost && l <= 4)) { best = l; best_cost = cost; }
     }
     P.log2_bx = best;
-    const int bx = 1 << best, by = (128 >> best) * P.msub;
+    const int bx = 1 << best, by = (128 >> best) * P.msub * (P.pair + 1);      // rows of a whole tile
+    const int by_cta = (128 >> best) * P.msub;                                    // rows one CTA loads
     P.tiles_x = (int)ceil_div64(P.w_out, bx);
     P.tiles_y = (int)ceil_div64(P.h_out, by);
     P.kblocks = a->c_in / 64;
@@ -703,7 +765,7 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
     P.n_total = a->n_total;
     P.n_tiles = a->n_total / a->bn;
     const int halo_bytes = P.halo ? (kCvHaloW * (16 * P.msub + 2) * 128 + 1023) & ~1023 : 0;
-    const int stage_bytes = pair ? kCvABytes + a->bn * 64 : (P.halo ? 0 : P.msub * kCvABytes) + a->bn * 128;
+    const int stage_bytes = pair ? (P.halo ? 0 : kCvABytes) + a->bn * 64 : (P.halo ? 0 : P.msub * kCvABytes) + a->bn * 128;
     P.nstages = (kCvPipeBytes - 2 * halo_bytes) / stage_bytes;
     if (P.nstages > kCvMaxStages) P.nstages = kCvMaxStages;
     P.wpk = (const uint8_t *)a->w_packed;
@@ -728,7 +790,7 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
     } else return HVPR_ERR_ARG;
 
     // tensor maps over the NHWC bf16 input: dims (channel, x, y, image)
-    const cuuint32_t box[4] = {64u, (cuuint32_t)(P.halo ? kCvHaloW : bx), (cuuint32_t)(P.halo ? by + 2 : (pair ? by / 2 : by)), 1u};
+    const cuuint32_t box[4] = {64u, (cuuint32_t)(P.halo ? kCvHaloW : bx), (cuuint32_t)(P.halo ? by_cta + 2 : by_cta), 1u};
     const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
     const uint64_t pix_b = (uint64_t)a->in_cs * 2u;
     const int nmaps = (a->stride == 2) ? 4 : 1;

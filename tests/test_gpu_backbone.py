@@ -139,7 +139,24 @@ def test_conv_cta_pair_kernel(n, h, w, cin, cout, stride, bn, ksize):
     try:
         _conv_call(x.permute(0, 2, 3, 1).contiguous(), wpk, cout, bn, b, 3, stride, cin, out)
     finally:
-        L.lib().hvpr_dbg_conv_pair(1)
+        L.lib().hvpr_dbg_conv_pair(0)
+    assert rel_err(out.permute(0, 3, 1, 2).float(), ref)[0] <= TOL_LAYER
+
+
+@pytest.mark.parametrize("msub", [1, 2])
+@pytest.mark.parametrize("n,h,w,cin,cout,bn", [(2, 40, 28, 128, 128, 128), (1, 33, 19, 256, 256, 256), (1, 70, 9, 64, 64, 64)])
+def test_conv_cta_pair_kernel_with_halo_operands(msub, n, h, w, cin, cout, bn):
+    """CTA pair + halo patch: each CTA loads ONE halo patch per k-block and half of every weight block (least L2 traffic)."""
+    L = _lib()
+    x, wt, b = _rand_case(23 + h, n, h, w, cin, cout, 3)
+    ref = F.relu(F.conv2d(x.float(), wt.float(), b, padding=1))
+    wpk = _pack(wt.float().permute(0, 2, 3, 1).reshape(cout, 9, cin), bn)
+    out = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device="cuda")
+    L.lib().hvpr_dbg_conv_pair(2); L.lib().hvpr_dbg_conv_halo_off(0); L.lib().hvpr_dbg_conv_force_msub(msub)
+    try:
+        _conv_call(x.permute(0, 2, 3, 1).contiguous(), wpk, cout, bn, b, 3, 1, cin, out)
+    finally:
+        L.lib().hvpr_dbg_conv_pair(0); L.lib().hvpr_dbg_conv_halo_off(1); L.lib().hvpr_dbg_conv_force_msub(0)
     assert rel_err(out.permute(0, 3, 1, 2).float(), ref)[0] <= TOL_LAYER
 
 

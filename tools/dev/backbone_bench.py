@@ -15,7 +15,7 @@ from hvpr_b200 import G1, G2, G3, _lib                      # noqa: E402
 from hvpr_b200.backbone import BaseBEVBackbone_Scale        # noqa: E402
 from hvpr_b200.config import Cfg                            # noqa: E402
 
-PAIR_DEFAULT = int(os.environ.get("HVPR_CONV_PAIR", "1"))      # hvpr_dbg_conv_pair mode used for the whole-network timing
+PAIR_DEFAULT = int(os.environ.get("HVPR_CONV_PAIR", "0"))      # hvpr_dbg_conv_pair mode used for the whole-network timing
 CFG = dict(LAYER_NUMS=[3, 3, 3], SFM_LAYER_NUMS=[3, 3, 3], LAYER_STRIDES=[1, 2, 2], NUM_FILTERS=[128, 256, 512],
            NUM_SCALE_FILTERS=[32, 64, 128], UPSAMPLE_STRIDES=[1, 2, 4], NUM_UPSAMPLE_FILTERS=[128, 128, 128])
 
@@ -95,9 +95,9 @@ def main():
                 kw = dict(gate=lv["gate"], residual=s) if name == "sfm" else {}
                 dst = lv["b"]
                 ts = {}
-                for mode in ("single", "halo", "pair"):   # A/B inside one run: boxes and thermal state differ between runs
-                    _lib.lib().hvpr_dbg_conv_halo_off(int(mode != "halo"))
-                    _lib.lib().hvpr_dbg_conv_pair(2 if mode == "pair" else 1)
+                for mode in ("single", "halo", "pair", "pair_halo"):   # A/B inside one run: boxes and thermal state differ between runs
+                    _lib.lib().hvpr_dbg_conv_halo_off(int("halo" not in mode))
+                    _lib.lib().hvpr_dbg_conv_pair(2 if "pair" in mode else 1)
                     for _ in range(2):
                         m._conv(lay, s, B, hi, wi, dst, **kw)
                     e0.record()
@@ -112,7 +112,7 @@ def main():
                 f = 2 * 9 * lay.c_in * lay.n_total * B * lv["h"] * lv["w"]
                 layers.append({"level": i, "layer": name, "cin": lay.c_in, "cout": lay.n_total, "stride": lay.stride,
                                "hw": [lv["h"], lv["w"]], "ms": round(t, 4), "tflops": round(f / t / 1e9, 1),
-                               "ms_halo": round(ts["halo"], 4), "ms_pair": round(ts["pair"], 4)})
+                               "ms_halo": round(ts["halo"], 4), "ms_pair": round(ts["pair"], 4), "ms_pair_halo": round(ts["pair_halo"], 4)})
             de = P["de"][i]
             tde = {}
             for mode in ("single", "pair"):

@@ -46,4 +46,4 @@ with torch.no_grad():
             for i, n in enumerate(names):
                 if n != "-":
                     print("    %-18s %9.1f kcycles (all CTAs mean %.1f)" % (n, rows[:, i].mean() / 1e3, pr[:, i].mean() / 1e3))
-    L.hvpr_dbg_conv_pair(1)
+    L.hvpr_dbg_conv_pair(0)
