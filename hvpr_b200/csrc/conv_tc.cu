@@ -11,7 +11,7 @@
 // load {64 ch, bx, by, 1} with signed coordinates, out-of-bounds pixels zero-filled by the TMA unit (= the zero padding),
 // landing as the 128-B-swizzled K-major tile tcgen05.mma wants.  Stride 2 uses four "parity" tensor maps over the same
 // buffer (pixel strides doubled, base shifted by the parity), so a tap is again a plain shifted box — no im2col buffer, no
-// wasted MACs.  Weights are pre-packed (bf16, swizzled, BN scale folded in) and streamed with cp.async.bulk.
+// wasted MACs.  Weights are pre-packed (bf16, pre-swizzled, BN scale folded in) and streamed as verbatim TMA row boxes.
 // Accumulators live in TMEM, double-buffered: the epilogue of tile i overlaps the MMAs of tile i+1.
 //   warp 0: TMA producer     warp 1: TMEM alloc + MMA issuer     warps 4-7: epilogue (one accumulator row per thread)
 #include "common.cuh"
@@ -85,24 +85,6 @@ __device__ __forceinline__ void cv_mbar_wait(uint64_t *b, uint32_t parity) {
 }
 __device__ __forceinline__ void cv_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void cv_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void cv_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(cv_smem_u32(dst)), "l"(src), "r"(bytes), "r"(cv_smem_u32(bar)) : "memory");
-}
-// 4-D tiled TMA load: coordinates (channel, x, y, image), signed; out-of-bounds elements arrive as zeros
-__device__ __forceinline__ void cv_tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(cv_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(cv_smem_u32(bar)),
-                   "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void cv_umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(cv_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void cv_umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
 // K-major, 128-byte swizzle, rows of 128 B, 8-row atoms 1024 B apart (same encoding as mem_attn_tc.cu)
 __device__ __forceinline__ uint64_t cv_desc_sw128(uint32_t saddr) {
     uint64_t d = 0;
@@ -226,194 +208,7 @@ __device__ __forceinline__ void cv_epilogue_rows(const ConvParams &P, const CvTi
             }
 }
 
-__global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams P) {
-    extern __shared__ uint8_t cv_smem_raw[];
-    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(cv_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *pipe = base;
-    float *bias_s = reinterpret_cast<float *>(base + kCvPipeBytes);
-    uint64_t *full = reinterpret_cast<uint64_t *>(base + kCvPipeBytes + kCvMaxN * 4);
-    uint64_t *empty = full + kCvMaxStages;
-    uint64_t *tfull = empty + kCvMaxStages;
-    uint64_t *tempty = tfull + 2;
-    uint64_t *hfull = tempty + 2;
-    uint64_t *hempty = hfull + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(hempty + 2);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int halo_box = kCvHaloW * (16 * P.msub + 2) * 128;                 // halo pixels x 64 ch bf16
-    const int halo_bytes = P.halo ? (halo_box + 1023) & ~1023 : 0;
-    const int a_bytes = P.halo ? 0 : P.msub * kCvABytes;
-    const int stage_bytes = a_bytes + P.bn * 128;
-    uint8_t *ring = pipe + 2 * halo_bytes;                                   // [halo slot 0][halo slot 1][operand ring]
-    const int nst = P.nstages;
-    const int kiters = P.ntaps * P.kblocks;
-    const int total_tiles = P.n_img * P.tiles_y * P.tiles_x * P.n_tiles;
-
-    if (tid == 0) {
-        for (int s = 0; s < kCvMaxStages; ++s) { cv_mbar_init(&full[s], 1); cv_mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { cv_mbar_init(&tfull[a], 1); cv_mbar_init(&tempty[a], 128); cv_mbar_init(&hfull[a], 1); cv_mbar_init(&hempty[a], 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = tid; i < P.n_total; i += kCvThreads) bias_s[i] = P.bias ? P.bias[i] : 0.0f;
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(cv_smem_u32(tmem_slot)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    cv_fence_before();
-    __syncthreads();
-    cv_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ===== producer: per k-iteration one shifted activation box (TMA tensor map) + one packed weight block (bulk copy)
-        if (lane == 0) {
-            uint32_t it = 0, hit = 0;
-            CVP_DECL;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const CvTile t = cv_decode(P, tile);
-                const uint8_t *wtile = P.wpk + (size_t)t.nt * kiters * (size_t)(P.bn * 128);
-                if (P.halo) {
-                    for (int kb = 0; kb < P.kblocks; ++kb, ++hit) {
-                        const int hs = hit & 1;
-                        cv_mbar_wait(&hempty[hs], ((hit >> 1) & 1) ^ 1);
-                        cv_mbar_expect_tx(&hfull[hs], (uint32_t)halo_box);
-                        cv_tma_load_4d(pipe + (size_t)hs * halo_bytes, &P.tmap[0], &hfull[hs], kb * 64, t.x0 - 1, t.y0 - 1, t.img);
-                        for (int tap = 0; tap < 9; ++tap, ++it) {
-                            const int s = it % nst;
-                            cv_mbar_wait(&empty[s], ((it / nst) & 1) ^ 1);
-                            cv_mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
-                            cv_bulk_g2s(ring + (size_t)s * stage_bytes, wtile + (size_t)(tap * P.kblocks + kb) * (size_t)(P.bn * 128),
-                                        (uint32_t)(P.bn * 128), &full[s]);
-                        }
-                    }
-                    continue;
-                }
-                for (int tap = 0; tap < P.ntaps; ++tap) {
-                    const CUtensorMap *map = &P.tmap[P.tap_map[tap]];
-                    const int x = t.x0 + P.tap_ox[tap], y = t.y0 + P.tap_oy[tap];
-                    for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
-                        const int s = it % nst;
-                        CVP_B();
-                        cv_mbar_wait(&empty[s], ((it / nst) & 1) ^ 1);
-                        CVP_E(0);
-                        uint8_t *dst = ring + (size_t)s * stage_bytes;
-                        cv_mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
-                        cv_tma_load_4d(dst, map, &full[s], kb * 64, x, y, t.img);
-                        cv_bulk_g2s(dst + a_bytes, wtile + (size_t)(tap * P.kblocks + kb) * (size_t)(P.bn * 128),
-                                    (uint32_t)(P.bn * 128), &full[s]);
-                    }
-                }
-            }
-            CVP_DUMP(0);
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        // ===== MMA issuer ==============================================================================================
-        if (lane == 0) {
-            // idesc: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            uint32_t it = 0, ti = 0, hit = 0;
-            CVP_DECL;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-                const uint32_t acc = ti & 1;
-                CVP_B();
-                cv_mbar_wait(&tempty[acc], ((ti >> 1) & 1) ^ 1);
-                CVP_E(0);        // epilogue drained this accumulator
-                cv_fence_after();
-                const uint32_t d = tmem_base + acc * 256u;
-                if (P.halo) {
-                    // one halo patch (10 x (rows+2) pixels x 64 ch) per k-block; tap (dy,dx) = the same patch read from a
-                    // start address shifted by dy*kCvHaloW + dx pixel rows — 9x less activation traffic than one box per tap
-                    for (int kb = 0; kb < P.kblocks; ++kb, ++hit) {
-                        const int hs = hit & 1;
-                        cv_mbar_wait(&hfull[hs], (hit >> 1) & 1);
-                        const uint32_t ha = cv_smem_u32(pipe + (size_t)hs * halo_bytes);
-                        for (int tap = 0; tap < 9; ++tap, ++it) {
-                            const int s = it % nst;
-                            cv_mbar_wait(&full[s], (it / nst) & 1);
-                            cv_fence_after();
-                            const uint64_t bdesc = cv_desc_sw128(cv_smem_u32(ring + (size_t)s * stage_bytes));
-                            const int dy = tap / 3, dx = tap - 3 * dy;
-                            for (int m = 0; m < P.msub; ++m) {
-                                const uint64_t adesc = cv_desc_halo(ha + (uint32_t)(((m * 16 + dy) * kCvHaloW + dx) * 128));
-#pragma unroll
-                                for (int kk = 0; kk < 4; ++kk)
-                                    cv_umma_bf16(d + (uint32_t)(m * P.bn), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
-                                                 (kb | tap | kk) != 0);
-                            }
-                            cv_umma_commit(&empty[s]);
-                        }
-                        cv_umma_commit(&hempty[hs]);
-                    }
-                } else
-                for (int ki = 0; ki < kiters; ++ki, ++it) {
-                    const int s = it % nst;
-                    CVP_B();
-                    cv_mbar_wait(&full[s], (it / nst) & 1);
-                    CVP_E(1);
-                    CVP_B();
-                    cv_fence_after();
-                    const uint32_t sa = cv_smem_u32(ring + (size_t)s * stage_bytes);
-                    const uint64_t bdesc = cv_desc_sw128(sa + a_bytes);
-                    for (int m = 0; m < P.msub; ++m) {
-                        const uint64_t adesc = cv_desc_sw128(sa + m * kCvABytes);
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)      // +32 B along K inside the 128-B swizzle atom
-                            cv_umma_bf16(d + (uint32_t)(m * P.bn), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
-                                         (ki | kk) != 0);
-                    }
-                    cv_umma_commit(&empty[s]);
-                    CVP_E(2);
-                }
-                cv_umma_commit(&tfull[acc]);
-            }
-            CVP_DUMP(4);
-        }
-        __syncwarp();
-    } else if (warp >= 4) {
-        // ===== epilogue: bias (folded BN shift), ReLU, gate * v + residual, store ======================================
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const int px = row & ((1 << P.log2_bx) - 1), py = row >> P.log2_bx;
-        uint32_t ti = 0;
-        CVP_DECL;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-            const CvTile t = cv_decode(P, tile);
-            const uint32_t acc = ti & 1;
-            CVP_B();
-            cv_mbar_wait(&tfull[acc], (ti >> 1) & 1);
-            CVP_E(0);
-            CVP_B();
-            cv_fence_after();
-            for (int m = 0; m < P.msub; ++m)
-                cv_epilogue_rows(P, t, bias_s, t.x0 + px, t.y0 + m * (128 >> P.log2_bx) + py,
-                                 tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)(m * P.bn));
-            cv_fence_before();
-            cv_mbar_arrive(&tempty[acc]);
-            CVP_E(1);
-        }
-        if (warp == 4 && lane == 0) { CVP_DUMP(8); }
-    }
-
-    cv_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        cv_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------------- CTA-pair variant
-// Same GEMM on a CTA pair (cluster of 2, tcgen05 cta_group::2): UMMA M = 256 — each CTA owns one 128-pixel patch (its rows of
-// the accumulator stay in its own TMEM) and loads only HALF of every weight block; the tensor core of each SM reads the
-// peer's half through the pair's shared-memory window.  Per SM that halves both the weight bytes pulled from L2 and the
-// operand bytes the MMA reads from shared memory — the single-CTA kernel above spends 96 B/clk on operand reads plus 96 B/clk
-// on TMA fills against a 128 B/clk shared-memory port and plateaus near 60 % tensor-pipe activity.
-//   rank 0 (leader): TMA producer, MMA issuer, epilogue          rank 1: TMA producer, epilogue
-// Barriers: full[s] lives in the leader (its producer posts the bytes of both CTAs, both CTAs' TMA complete_tx on it);
-// empty[s] / tfull[acc] are signalled in BOTH CTAs by a multicast tcgen05.commit; tempty[acc] lives in the leader and counts
-// the 8 epilogue warps of the pair.
+// ---------------------------------------------------------------------------------------------- cluster / CTA-pair helpers
 __device__ __forceinline__ uint32_t cv_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cv_mapa(uint32_t saddr, uint32_t rank) {
     uint32_t r;
@@ -426,29 +221,58 @@ __device__ __forceinline__ void cv_cluster_sync() {
 __device__ __forceinline__ void cv_mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void cv_mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+// TMA tensor-map loads.  kPair: the cta_group::2 form, whose mbarrier operand may live in the peer CTA (the pair's leader).
+template <bool kPair>
+__device__ __forceinline__ void cv_tma_4d(void *dst, const CUtensorMap *map, uint32_t bar_addr, int c0, int c1, int c2, int c3) {
+    if (kPair)
+        asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(cv_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(cv_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
-__device__ __forceinline__ void cv_tma2_load_4d(void *dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(cv_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr),
-                   "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+template <bool kPair>
+__device__ __forceinline__ void cv_tma_2d(void *dst, const CUtensorMap *map, uint32_t bar_addr, int c0, int c1) {
+    if (kPair)
+        asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(cv_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_addr), "r"(c0), "r"(c1) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(cv_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_addr), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void cv_tma2_load_2d(void *dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(cv_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+template <bool kPair>
+__device__ __forceinline__ void cv_commit(uint64_t *bar) {       // kPair: arrive on `bar` in BOTH CTAs of the pair
+    if (kPair)
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(cv_smem_u32(bar)), "h"((uint16_t)3) : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(cv_smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void cv_umma2_commit_mc(uint64_t *bar) {       // arrive on `bar` in both CTAs of the pair
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(cv_smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void cv_umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+template <bool kPair>
+__device__ __forceinline__ void cv_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (kPair)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1) conv_tc2_kernel(const __grid_constant__ ConvParams P) {
+// ---------------------------------------------------------------------------------------------- the kernel body
+// kMsub  128-pixel sub-tiles per CTA and tile (2: two A patches share every weight block; needs bn <= 128)
+// kHalo  3x3 stride-1 only: ONE (8+2) x (rows+2) halo patch per k-block feeds all nine taps through shifted UMMA descriptors
+// kPair  CTA pair (cluster of 2, tcgen05 cta_group::2): UMMA M = 256 — each CTA owns the patches of its half of the tile (its
+//        accumulator rows stay in its own TMEM) and loads only HALF of every weight block; the pair's tensor cores share the
+//        halves.  Per SM that halves the weight bytes pulled from L2 and the B-operand bytes read from shared memory.
+//        rank 0 (leader): TMA producer, MMA issuer, epilogue      rank 1: TMA producer, epilogue
+//        full[s] / hfull[s] live in the leader: its producer posts the byte count of BOTH CTAs with one local arrive and both
+//        CTAs' TMA loads complete_tx on it (a remote arrive per stage would put a cluster round trip on the producer's
+//        critical path — measured: 2x slower); empty[s] / hempty / tfull[acc] are signalled in both CTAs by a multicast
+//        tcgen05.commit; tempty[acc] lives in the leader and counts the epilogue warps of the pair.
+// The single MMA-issuing thread is the critical path of the whole CTA: its loop carries no divisions, no runtime inner loops and
+// precomputed descriptors (measured: a runtime sub-tile loop and it % nstages in this loop cost 12 %).
+template <int kMsub, bool kHalo, bool kPair>
+__device__ __forceinline__ void cv_body(const ConvParams &P) {
     extern __shared__ uint8_t cv_smem_raw[];
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(cv_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *pipe = base;
@@ -462,78 +286,87 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1) conv_
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(hempty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t rank = cv_cluster_rank();
-    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-    const int b_half = P.bn * 64;                              // bytes of half a weight block: (bn/2 rows) x 128 B
-    const int halo_box = kCvHaloW * (16 * P.msub + 2) * 128;   // halo path: my patch rows + 2, 10 pixels wide, 64 ch
-    const int halo_bytes = P.halo ? (halo_box + 1023) & ~1023 : 0;
-    const int stage_bytes = (P.halo ? 0 : kCvABytes) + b_half; // per CTA
-    uint8_t *ring = pipe + 2 * halo_bytes;
+    const uint32_t rank = kPair ? cv_cluster_rank() : 0u;
+    const int tile0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    constexpr uint32_t kCtas = kPair ? 2u : 1u;
+    constexpr int kHaloBox = kCvHaloW * (16 * kMsub + 2) * 128;          // halo pixels x 64 ch bf16
+    constexpr int kHaloBytes = kHalo ? (kHaloBox + 1023) & ~1023 : 0;
+    constexpr int kABytes = kHalo ? 0 : kMsub * kCvABytes;
+    const int b_rows = kPair ? P.bn >> 1 : P.bn;                          // weight rows this CTA loads per block
+    const int stage_bytes = kABytes + b_rows * 128;
+    uint8_t *ring = pipe + 2 * kHaloBytes;                                // [halo slot 0][halo slot 1][operand ring]
     const int nst = P.nstages;
     const int kiters = P.ntaps * P.kblocks;
-    const int total_tiles = P.n_img * P.tiles_y * P.tiles_x * P.n_tiles;   // a tile spans the patches of both CTAs
-    const int by = (128 >> P.log2_bx) * P.msub;                // rows of the image this CTA owns per tile
+    const int total_tiles = P.n_img * P.tiles_y * P.tiles_x * P.n_tiles;
+    const int by_cta = (128 >> P.log2_bx) * kMsub;                        // image rows this CTA owns per tile
 
     if (tid == 0) {
         for (int s = 0; s < kCvMaxStages; ++s) { cv_mbar_init(&full[s], 1); cv_mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { cv_mbar_init(&tfull[a], 1); cv_mbar_init(&tempty[a], 8); cv_mbar_init(&hfull[a], 1); cv_mbar_init(&hempty[a], 1); }
+        for (int a = 0; a < 2; ++a) {
+            cv_mbar_init(&tfull[a], 1); cv_mbar_init(&tempty[a], 4 * kCtas);
+            cv_mbar_init(&hfull[a], 1); cv_mbar_init(&hempty[a], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < P.n_total; i += kCvThreads) bias_s[i] = P.bias ? P.bias[i] : 0.0f;
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(cv_smem_u32(tmem_slot)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        if (kPair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(cv_smem_u32(tmem_slot)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(cv_smem_u32(tmem_slot)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     cv_fence_before();
     __syncthreads();
-    cv_cluster_sync();
+    if (kPair) cv_cluster_sync();
     cv_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== producer (both CTAs): my 128-pixel patch + my half of the weight block, signalled on the LEADER's full[s] ====
+        // ===== producer: activation boxes (TMA tensor map) + my rows of the packed weight blocks, signalled on the leader =====
         if (lane == 0) {
-            uint32_t it = 0, hit = 0;
+            int s = 0, hs = 0;
+            uint32_t ph = 0, hph = 0;
             CVP_DECL;
-            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+            for (int tile = tile0; tile < total_tiles; tile += tile_step) {
                 const CvTile t = cv_decode(P, tile);
-                const int y0 = t.y0 + (int)rank * by;
-                const int wrow0 = t.nt * kiters * P.bn + (int)rank * (P.bn >> 1);     // row of the packed image viewed as [rows][64]
-                if (P.halo) {
-                    for (int kb = 0; kb < P.kblocks; ++kb, ++hit) {
-                        const int hs = hit & 1;
-                        cv_mbar_wait(&hempty[hs], ((hit >> 1) & 1) ^ 1);
-                        if (rank == 0) cv_mbar_expect_tx(&hfull[hs], 2u * (uint32_t)halo_box);
-                        cv_tma2_load_4d(pipe + (size_t)hs * halo_bytes, &P.tmap[0], cv_mapa(cv_smem_u32(&hfull[hs]), 0), kb * 64,
-                                        t.x0 - 1, y0 - 1, t.img);
-                        for (int tap = 0; tap < 9; ++tap, ++it) {
-                            const int s = it % nst;
+                const int y0 = t.y0 + (int)rank * by_cta;
+                const int wrow0 = t.nt * kiters * P.bn + (int)rank * b_rows;      // row of the packed image viewed as [rows][64]
+                if (kHalo) {
+                    for (int kb = 0; kb < P.kblocks; ++kb) {
+                        cv_mbar_wait(&hempty[hs], hph ^ 1);
+                        if (rank == 0) cv_mbar_expect_tx(&hfull[hs], kCtas * (uint32_t)kHaloBox);
+                        cv_tma_4d<kPair>(pipe + (size_t)hs * kHaloBytes, &P.tmap[0], kPair ? cv_mapa(cv_smem_u32(&hfull[hs]), 0) : cv_smem_u32(&hfull[hs]),
+                                         kb * 64, t.x0 - 1, y0 - 1, t.img);
+                        if (++hs == 2) { hs = 0; hph ^= 1; }
+                        for (int tap = 0; tap < 9; ++tap) {
                             CVP_B();
-                            cv_mbar_wait(&empty[s], ((it / nst) & 1) ^ 1);
+                            cv_mbar_wait(&empty[s], ph ^ 1);
                             CVP_E(0);
-                            if (rank == 0) cv_mbar_expect_tx(&full[s], 2u * (uint32_t)stage_bytes);
-                            cv_tma2_load_2d(ring + (size_t)s * stage_bytes, &P.tmap_w, cv_mapa(cv_smem_u32(&full[s]), 0), 0,
-                                            wrow0 + (tap * P.kblocks + kb) * P.bn);
+                            if (rank == 0) cv_mbar_expect_tx(&full[s], kCtas * (uint32_t)stage_bytes);
+                            cv_tma_2d<kPair>(ring + (size_t)s * stage_bytes, &P.tmap_w, kPair ? cv_mapa(cv_smem_u32(&full[s]), 0) : cv_smem_u32(&full[s]),
+                                             0, wrow0 + (tap * P.kblocks + kb) * P.bn);
+                            if (++s == nst) { s = 0; ph ^= 1; }
                         }
                     }
-                    continue;
-                }
-                for (int tap = 0; tap < P.ntaps; ++tap) {
-                    const CUtensorMap *map = &P.tmap[P.tap_map[tap]];
-                    const int x = t.x0 + P.tap_ox[tap], y = y0 + P.tap_oy[tap];
-                    for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
-                        const int s = it % nst;
-                        CVP_B();
-                        cv_mbar_wait(&empty[s], ((it / nst) & 1) ^ 1);
-                        CVP_E(0);
-                        uint8_t *dst = ring + (size_t)s * stage_bytes;
-                        const uint32_t lfull = cv_mapa(cv_smem_u32(&full[s]), 0);
-                        // the leader posts the byte count of BOTH CTAs with one local arrive; the peer only issues its loads
-                        // (a remote arrive per stage costs a cluster round trip on the producer's critical path).  The peer's
-                        // complete_tx may land first: the phase still cannot complete before the leader's arrive.
-                        if (rank == 0) cv_mbar_expect_tx(&full[s], 2u * (uint32_t)stage_bytes);
-                        cv_tma2_load_4d(dst, map, lfull, kb * 64, x, y, t.img);
-                        cv_tma2_load_2d(dst + kCvABytes, &P.tmap_w, lfull, 0, wrow0 + (tap * P.kblocks + kb) * P.bn);
+                } else {
+                    for (int tap = 0; tap < P.ntaps; ++tap) {
+                        const CUtensorMap *map = &P.tmap[P.tap_map[tap]];
+                        const int x = t.x0 + P.tap_ox[tap], y = y0 + P.tap_oy[tap];
+                        for (int kb = 0; kb < P.kblocks; ++kb) {
+                            CVP_B();
+                            cv_mbar_wait(&empty[s], ph ^ 1);
+                            CVP_E(0);
+                            uint8_t *dst = ring + (size_t)s * stage_bytes;
+                            const uint32_t lfull = kPair ? cv_mapa(cv_smem_u32(&full[s]), 0) : cv_smem_u32(&full[s]);
+                            if (rank == 0) cv_mbar_expect_tx(&full[s], kCtas * (uint32_t)stage_bytes);
+                            cv_tma_4d<kPair>(dst, map, lfull, kb * 64, x, y, t.img);
+                            cv_tma_2d<kPair>(dst + kABytes, &P.tmap_w, lfull, 0, wrow0 + (tap * P.kblocks + kb) * P.bn);
+                            if (++s == nst) { s = 0; ph ^= 1; }
+                        }
                     }
                 }
             }
@@ -541,75 +374,92 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1) conv_
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===== MMA issuer (leader only): M = 256 across the pair ======================================================
+        // ===== MMA issuer (the pair's leader only) ====================================================================
         if (lane == 0 && rank == 0) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-            uint32_t it = 0, ti = 0, hit = 0;
+            // idesc: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) |
+                                   ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);
+            const uint64_t ring_desc = cv_desc_sw128(cv_smem_u32(ring));
+            const uint32_t stage_units = (uint32_t)stage_bytes >> 4;          // descriptor address units (16 B)
+            const uint32_t bn = (uint32_t)P.bn;
+            int s = 0, hs = 0;
+            uint32_t ph = 0, hph = 0, ti = 0, soff = 0;
             CVP_DECL;
-            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++ti) {
+            for (int tile = tile0; tile < total_tiles; tile += tile_step, ++ti) {
                 const uint32_t acc = ti & 1;
                 CVP_B();
-                cv_mbar_wait(&tempty[acc], ((ti >> 1) & 1) ^ 1);
-                CVP_E(0);        // both CTAs' epilogues drained this accumulator
+                cv_mbar_wait(&tempty[acc], ((ti >> 1) & 1) ^ 1);                  // the epilogues drained this accumulator
+                CVP_E(0);
                 cv_fence_after();
                 const uint32_t d = tmem_base + acc * 256u;
-                if (P.halo) {
-                    for (int kb = 0; kb < P.kblocks; ++kb, ++hit) {
-                        const int hs = hit & 1;
+                uint32_t accum = 0;
+                if (kHalo) {
+                    for (int kb = 0; kb < P.kblocks; ++kb) {
                         CVP_B();
-                        cv_mbar_wait(&hfull[hs], (hit >> 1) & 1);
+                        cv_mbar_wait(&hfull[hs], hph);
                         CVP_E(3);
-                        const uint32_t ha = cv_smem_u32(pipe + (size_t)hs * halo_bytes);
-                        for (int tap = 0; tap < 9; ++tap, ++it) {
-                            const int s = it % nst;
-                            CVP_B();
-                            cv_mbar_wait(&full[s], (it / nst) & 1);
-                            CVP_E(1);
-                            CVP_B();
-                            cv_fence_after();
-                            const uint64_t bdesc = cv_desc_sw128(cv_smem_u32(ring + (size_t)s * stage_bytes));
-                            const int dy = tap / 3, dx = tap - 3 * dy;
-                            for (int m = 0; m < P.msub; ++m) {
-                                const uint64_t adesc = cv_desc_halo(ha + (uint32_t)(((m * 16 + dy) * kCvHaloW + dx) * 128));
+                        const uint32_t ha = cv_smem_u32(pipe + (size_t)hs * kHaloBytes);
+                        for (int dy = 0; dy < 3; ++dy)
+                            for (int dx = 0; dx < 3; ++dx) {
+                                CVP_B();
+                                cv_mbar_wait(&full[s], ph);
+                                CVP_E(1);
+                                CVP_B();
+                                cv_fence_after();
+                                const uint64_t bdesc = ring_desc + soff;
 #pragma unroll
-                                for (int kk = 0; kk < 4; ++kk)
-                                    cv_umma2_bf16(d + (uint32_t)(m * P.bn), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
-                                                  (kb | tap | kk) != 0);
+                                for (int m = 0; m < kMsub; ++m) {
+                                    const uint64_t adesc = cv_desc_halo(ha + (uint32_t)(((m * 16 + dy) * kCvHaloW + dx) * 128));
+#pragma unroll
+                                    for (int kk = 0; kk < 4; ++kk)
+                                        cv_mma<kPair>(d + (uint32_t)m * bn, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                                                      accum | (uint32_t)(kk > 0));
+                                }
+                                accum = 1;
+                                cv_commit<kPair>(&empty[s]);
+                                CVP_E(2);
+                                soff += stage_units;
+                                if (++s == nst) { s = 0; ph ^= 1; soff = 0; }
                             }
-                            cv_umma2_commit_mc(&empty[s]);
-                            CVP_E(2);
-                        }
-                        cv_umma2_commit_mc(&hempty[hs]);
+                        cv_commit<kPair>(&hempty[hs]);
+                        if (++hs == 2) { hs = 0; hph ^= 1; }
                     }
-                } else
-                for (int ki = 0; ki < kiters; ++ki, ++it) {
-                    const int s = it % nst;
-                    CVP_B();
-                    cv_mbar_wait(&full[s], (it / nst) & 1);
-                    CVP_E(1);
-                    CVP_B();
-                    cv_fence_after();
-                    const uint32_t sa = cv_smem_u32(ring + (size_t)s * stage_bytes);
-                    const uint64_t adesc = cv_desc_sw128(sa), bdesc = cv_desc_sw128(sa + kCvABytes);
+                } else {
+                    for (int ki = 0; ki < kiters; ++ki) {
+                        CVP_B();
+                        cv_mbar_wait(&full[s], ph);
+                        CVP_E(1);
+                        CVP_B();
+                        cv_fence_after();
+                        const uint64_t adesc0 = ring_desc + soff, bdesc = adesc0 + (uint64_t)(kABytes >> 4);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        cv_umma2_bf16(d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (ki | kk) != 0);
-                    cv_umma2_commit_mc(&empty[s]);
-                    CVP_E(2);
+                        for (int m = 0; m < kMsub; ++m) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)        // +32 B along K inside the 128-B swizzle atom
+                                cv_mma<kPair>(d + (uint32_t)m * bn, adesc0 + (uint64_t)(m * (kCvABytes >> 4) + kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                                              accum | (uint32_t)(kk > 0));
+                        }
+                        accum = 1;
+                        cv_commit<kPair>(&empty[s]);
+                        CVP_E(2);
+                        soff += stage_units;
+                        if (++s == nst) { s = 0; ph ^= 1; soff = 0; }
+                    }
                 }
-                cv_umma2_commit_mc(&tfull[acc]);
+                cv_commit<kPair>(&tfull[acc]);
             }
             CVP_DUMP(4);
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // ===== epilogue (both CTAs): my 128 accumulator rows ==========================================================
+        // ===== epilogue: my 128 x kMsub accumulator rows =============================================================
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int px = row & ((1 << P.log2_bx) - 1), py = row >> P.log2_bx;
+        const uint32_t tempty_addr = kPair ? cv_mapa(cv_smem_u32(&tempty[0]), 0) : cv_smem_u32(&tempty[0]);
         uint32_t ti = 0;
         CVP_DECL;
-        for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++ti) {
+        for (int tile = tile0; tile < total_tiles; tile += tile_step, ++ti) {
             const CvTile t = cv_decode(P, tile);
             const uint32_t acc = ti & 1;
             CVP_B();
@@ -617,12 +467,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1) conv_
             CVP_E(0);
             CVP_B();
             cv_fence_after();
-            for (int m = 0; m < P.msub; ++m)
-                cv_epilogue_rows(P, t, bias_s, t.x0 + px, t.y0 + (int)rank * by + m * (128 >> P.log2_bx) + py,
+#pragma unroll
+            for (int m = 0; m < kMsub; ++m)
+                cv_epilogue_rows(P, t, bias_s, t.x0 + px, t.y0 + (int)rank * by_cta + m * (128 >> P.log2_bx) + py,
                                  tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)(m * P.bn));
             cv_fence_before();
             __syncwarp();
-            if (lane == 0) cv_mbar_arrive_cluster(cv_mapa(cv_smem_u32(&tempty[acc]), 0));
+            if (lane == 0) cv_mbar_arrive_cluster(tempty_addr + acc * 8u);
             CVP_E(1);
         }
         if (warp == 4 && lane == 0) { CVP_DUMP(8); }
@@ -630,12 +481,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1) conv_
 
     cv_fence_before();
     __syncthreads();
-    cv_cluster_sync();                      // the peer may still multicast into my barriers / read my shared memory until here
+    if (kPair) cv_cluster_sync();           // the peer may still multicast into my barriers / read my shared memory until here
     if (warp == 1) {
         cv_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
+
+template <int kMsub, bool kHalo>
+__global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams P) { cv_body<kMsub, kHalo, false>(P); }
+template <int kMsub, bool kHalo>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1) conv_tc2_kernel(const __grid_constant__ ConvParams P) { cv_body<kMsub, kHalo, true>(P); }
 
 // folded fp32 weights (n_total, taps, cin) -> bf16 image [n-tile][tap][k-block][bn rows x 128 B], 128-B swizzled
 __global__ void conv_pack_kernel(const float *__restrict__ w, int n_total, int taps, int cin, int bn, uint8_t *__restrict__ out) {
@@ -679,10 +536,14 @@ static CvEncodeFn cv_encode_fn() {
 static size_t cv_smem_bytes() { return 1024 + kCvPipeBytes + kCvMaxN * 4 + (2 * kCvMaxStages + 8) * 8 + 16; }
 
 int hvpr_conv_init() {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv_smem_bytes());
-    if (e != cudaSuccess) { set_cuda_error(e); return HVPR_ERR_CUDA; }
-    e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv_smem_bytes());
-    if (e != cudaSuccess) { set_cuda_error(e); return HVPR_ERR_CUDA; }
+    const void *fns[8] = {(const void *)conv_tc_kernel<1, false>, (const void *)conv_tc_kernel<2, false>,
+                          (const void *)conv_tc_kernel<1, true>, (const void *)conv_tc_kernel<2, true>,
+                          (const void *)conv_tc2_kernel<1, false>, (const void *)conv_tc2_kernel<2, false>,
+                          (const void *)conv_tc2_kernel<1, true>, (const void *)conv_tc2_kernel<2, true>};
+    for (int i = 0; i < 8; ++i) {
+        cudaError_t e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv_smem_bytes());
+        if (e != cudaSuccess) { set_cuda_error(e); return HVPR_ERR_CUDA; }
+    }
     return HVPR_OK;
 }
 
@@ -748,7 +609,7 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
                        (int64_t)a->n * P.h_out * P.w_out >= 256 * (int64_t)(kNumSMs / 2) * 4);
     P.pair = pair ? 1 : 0;
     P.halo = (a->ksize == 3 && a->stride == 1 && !g_cv_halo_off) ? 1 : 0;
-    if (pair && !(P.halo && a->bn <= 128 && g_cv_force_msub != 1)) P.msub = 1;   // pair: two sub-tiles per CTA only on the halo path
+    if (pair && (a->bn > 128 || g_cv_force_msub == 1)) P.msub = 1;
     int best = -1; int64_t best_cost = 0;
     for (int l = P.halo ? 3 : 0; l <= (P.halo ? 3 : 7); ++l) {      // halo path: patches are 8 pixels wide
         const int bx = 1 << l, by = (128 >> l) * P.msub * (P.pair + 1);
@@ -765,7 +626,7 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
     P.n_total = a->n_total;
     P.n_tiles = a->n_total / a->bn;
     const int halo_bytes = P.halo ? (kCvHaloW * (16 * P.msub + 2) * 128 + 1023) & ~1023 : 0;
-    const int stage_bytes = pair ? (P.halo ? 0 : kCvABytes) + a->bn * 64 : (P.halo ? 0 : P.msub * kCvABytes) + a->bn * 128;
+    const int stage_bytes = (P.halo ? 0 : P.msub * kCvABytes) + (pair ? a->bn * 64 : a->bn * 128);
     P.nstages = (kCvPipeBytes - 2 * halo_bytes) / stage_bytes;
     if (P.nstages > kCvMaxStages) P.nstages = kCvMaxStages;
     P.wpk = (const uint8_t *)a->w_packed;
@@ -820,23 +681,29 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
             }
         }
     const int64_t total_tiles = (int64_t)P.n_img * P.tiles_x * P.tiles_y * P.n_tiles;
-    if (pair) {
-        // weights: the pre-swizzled image as a plain [rows][64] bf16 tensor; each CTA pulls bn/2 rows of every block verbatim
+    {
+        // weights: the pre-swizzled image as a plain [rows][64] bf16 tensor (no TMA swizzle: rows are copied verbatim); a CTA pulls
+        // bn rows of every block, or bn/2 in the pair kernel
         const cuuint64_t wdims[2] = {64u, (cuuint64_t)a->n_total * (cuuint64_t)(P.ntaps * P.kblocks)};
         const cuuint64_t wstr[1] = {128u};
-        const cuuint32_t wbox[2] = {64u, (cuuint32_t)(a->bn / 2)};
+        const cuuint32_t wbox[2] = {64u, (cuuint32_t)(pair ? a->bn / 2 : a->bn)};
         const cuuint32_t wes[2] = {1u, 1u};
         CUresult r = enc(&P.tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)a->w_packed, wdims, wstr, wbox, wes,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return HVPR_ERR_ARG;
-        const int64_t clusters = total_tiles < kNumSMs / 2 ? total_tiles : kNumSMs / 2;
-        conv_tc2_kernel<<<(unsigned)(2 * clusters), kCvThreads, cv_smem_bytes(), (cudaStream_t)stream>>>(P);
-        HVPR_CHECK_LAUNCH();
-        return HVPR_OK;
     }
-    const int grid = (int)(total_tiles < kNumSMs ? total_tiles : kNumSMs);
-    conv_tc_kernel<<<grid, kCvThreads, cv_smem_bytes(), (cudaStream_t)stream>>>(P);
+    const size_t smem = cv_smem_bytes();
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pair) {
+        const unsigned grid = 2u * (unsigned)(total_tiles < kNumSMs / 2 ? total_tiles : kNumSMs / 2);
+        if (P.msub == 2) { if (P.halo) conv_tc2_kernel<2, true><<<grid, kCvThreads, smem, st>>>(P); else conv_tc2_kernel<2, false><<<grid, kCvThreads, smem, st>>>(P); }
+        else { if (P.halo) conv_tc2_kernel<1, true><<<grid, kCvThreads, smem, st>>>(P); else conv_tc2_kernel<1, false><<<grid, kCvThreads, smem, st>>>(P); }
+    } else {
+        const unsigned grid = (unsigned)(total_tiles < kNumSMs ? total_tiles : kNumSMs);
+        if (P.msub == 2) { if (P.halo) conv_tc_kernel<2, true><<<grid, kCvThreads, smem, st>>>(P); else conv_tc_kernel<2, false><<<grid, kCvThreads, smem, st>>>(P); }
+        else { if (P.halo) conv_tc_kernel<1, true><<<grid, kCvThreads, smem, st>>>(P); else conv_tc_kernel<1, false><<<grid, kCvThreads, smem, st>>>(P); }
+    }
     HVPR_CHECK_LAUNCH();
     return HVPR_OK;
 }

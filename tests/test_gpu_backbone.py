@@ -128,7 +128,8 @@ def test_conv3x3_halo_operand_path(msub, n, h, w, cin, cout, bn):
     (1, 24, 40, 128, 256, 2, 256, 3),
     (3, 9, 70, 64, 32, 1, 32, 3),
 ])
-def test_conv_cta_pair_kernel(n, h, w, cin, cout, stride, bn, ksize):
+@pytest.mark.parametrize("msub", [0, 2])
+def test_conv_cta_pair_kernel(n, h, w, cin, cout, stride, bn, ksize, msub):
     """cta_group::2 variant: UMMA M = 256 across a CTA pair, each CTA loading half of every weight block."""
     L = _lib()
     x, wt, b = _rand_case(17 + h, n, h, w, cin, cout, ksize)
@@ -136,10 +137,11 @@ def test_conv_cta_pair_kernel(n, h, w, cin, cout, stride, bn, ksize):
     wpk = _pack(wt.float().permute(0, 2, 3, 1).reshape(cout, 9, cin), bn)
     out = torch.empty(n, h // stride, w // stride, cout, dtype=torch.bfloat16, device="cuda")
     assert L.lib().hvpr_dbg_conv_pair(2) == 0
+    L.lib().hvpr_dbg_conv_force_msub(msub)          # 2: two sub-tiles per CTA when bn <= 128 (M = 512 per pair and weight block)
     try:
         _conv_call(x.permute(0, 2, 3, 1).contiguous(), wpk, cout, bn, b, 3, stride, cin, out)
     finally:
-        L.lib().hvpr_dbg_conv_pair(0)
+        L.lib().hvpr_dbg_conv_pair(0); L.lib().hvpr_dbg_conv_force_msub(0)
     assert rel_err(out.permute(0, 3, 1, 2).float(), ref)[0] <= TOL_LAYER
 
 
