@@ -13,7 +13,8 @@
 // buffer (pixel strides doubled, base shifted by the parity), so a tap is again a plain shifted box — no im2col buffer, no
 // wasted MACs.  Weights are pre-packed (bf16, pre-swizzled, BN scale folded in) and streamed as verbatim TMA row boxes.
 // Accumulators live in TMEM, double-buffered: the epilogue of tile i overlaps the MMAs of tile i+1.
-//   warp 0: TMA producer     warp 1: TMEM alloc + MMA issuer     warps 4-7: epilogue (one accumulator row per thread)
+//   warp 0: TMA producer     warp 1: TMEM alloc + MMA issuer     warps 4-11: epilogue (one accumulator row per thread, two
+//   warps per TMEM lane quadrant interleaving the 32-column chunks)
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -21,7 +22,7 @@
 
 namespace hvpr {
 
-constexpr int kCvThreads = 256;
+constexpr int kCvThreads = 384;         // warp 0 producer, warp 1 MMA issuer, warps 4-11 epilogue (two warps per TMEM lane quadrant)
 constexpr int kCvABytes = 128 * 128;         // 128 pixels x 64 channels bf16
 constexpr int kCvPipeBytes = 216 * 1024;     // operand ring(s)
 constexpr int kCvMaxStages = 8;
@@ -109,7 +110,7 @@ __device__ __forceinline__ uint64_t cv_desc_halo(uint32_t saddr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-__device__ __forceinline__ void cv_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void cv_tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                  "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -118,11 +119,20 @@ __device__ __forceinline__ void cv_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) 
                    "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr));
+}
+__device__ __forceinline__ void cv_tmem_ld32_wait(uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
                       "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
                       "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
                       "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+}
+// explicit shared-space vector load: the bias table sits behind a rounded-up dynamic-shared pointer, which the compiler can only
+// address generically (32 generic LD.E per chunk were 40 % of the epilogue's stall samples)
+__device__ __forceinline__ float4 cv_lds_f4(uint32_t saddr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
 }
 __device__ __forceinline__ uint32_t cv_pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -144,24 +154,21 @@ __device__ __forceinline__ CvTile cv_decode(const ConvParams &P, int tile) {
     return t;
 }
 
-// Epilogue of one accumulator row (one output pixel) over the bn columns of the tile: bias (folded BN shift), ReLU,
-// gate * v + residual, then either the bf16 NHWC store or the pixel-shuffle store of the transposed convolution.
-// Warp-collective (tcgen05.ld): every lane of the warp must call it.
-__device__ __forceinline__ void cv_epilogue_rows(const ConvParams &P, const CvTile &t, const float *bias_s, int x, int y,
-                                                 uint32_t taddr) {
-            const bool valid = (x < P.w_out) && (y < P.h_out);
-            const int64_t pix = ((int64_t)t.img * P.h_out + y) * P.w_out + x;
-            const float g = (P.gate && valid) ? __ldg(P.gate + pix) : 1.0f;
-            for (int ch = 0; ch < P.bn; ch += 32) {
-                uint32_t r[32];
-                __syncwarp();                                   // tcgen05.ld is warp-collective: re-converge after the guarded stores
-                cv_tmem_ld32(taddr + (uint32_t)ch, r);
+// Epilogue of 32 accumulator columns of one row (one output pixel): bias (folded BN shift), ReLU, gate * v + residual, then
+// either the bf16 NHWC store or the pixel-shuffle store of the transposed convolution.
+__device__ __forceinline__ void cv_epilogue_chunk(const ConvParams &P, const CvTile &t, uint32_t bias_s, bool valid, int64_t pix,
+                                                  float g, int x, int y, const uint32_t (&r)[32], int ch) {
                 const int col0 = t.nt * P.bn + ch;
                 float v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    v[i] = __uint_as_float(r[i]) + bias_s[col0 + i];
-                    if (P.relu) v[i] = fmaxf(v[i], 0.0f);
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 b4 = cv_lds_f4(bias_s + (uint32_t)(col0 + 4 * i4) * 4u);
+                    v[4 * i4 + 0] = __uint_as_float(r[4 * i4 + 0]) + b4.x; v[4 * i4 + 1] = __uint_as_float(r[4 * i4 + 1]) + b4.y;
+                    v[4 * i4 + 2] = __uint_as_float(r[4 * i4 + 2]) + b4.z; v[4 * i4 + 3] = __uint_as_float(r[4 * i4 + 3]) + b4.w;
+                }
+                if (P.relu) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
                 }
                 if (valid && P.out_mode == 0) {
                     if (P.residual) {
@@ -205,7 +212,34 @@ __device__ __forceinline__ void cv_epilogue_rows(const ConvParams &P, const CvTi
                         for (int c = 0; c < 32; ++c) __stcs(op + c * cstride, v[c]);
                     }
                 }
-            }
+}
+
+// One accumulator row over the bn columns of the tile.  The TMEM loads are software-pipelined: chunk c+1 is in flight while
+// chunk c is converted and stored.  Warp-collective (tcgen05.ld): every lane of the warp must call it.
+__device__ __forceinline__ void cv_epilogue_rows(const ConvParams &P, const CvTile &t, uint32_t bias_s, int x, int y,
+                                                 uint32_t taddr, int half) {
+    const bool valid = (x < P.w_out) && (y < P.h_out);
+    const int64_t pix = ((int64_t)t.img * P.h_out + y) * P.w_out + x;
+    const float g = (P.gate && valid) ? __ldg(P.gate + pix) : 1.0f;
+    // the two warps of a lane quadrant interleave the 32-column chunks: this warp owns chunks half, half + 2, half + 4, ...
+    const int c0 = half * 32;
+    if (c0 >= P.bn) return;                               // warp-uniform (bn == 32: the second warp has nothing to do)
+    uint32_t ra[32], rb[32];
+    __syncwarp();
+    cv_tmem_ld32_issue(taddr + (uint32_t)c0, ra);
+    for (int ch = c0; ch < P.bn; ch += 128) {
+        cv_tmem_ld32_wait(ra);
+        const bool more = ch + 64 < P.bn;                 // warp-uniform
+        if (more) cv_tmem_ld32_issue(taddr + (uint32_t)(ch + 64), rb);
+        cv_epilogue_chunk(P, t, bias_s, valid, pix, g, x, y, ra, ch);
+        __syncwarp();                                     // re-converge after the guarded stores before the next collective op
+        if (more) {
+            cv_tmem_ld32_wait(rb);
+            if (ch + 128 < P.bn) cv_tmem_ld32_issue(taddr + (uint32_t)(ch + 128), ra);
+            cv_epilogue_chunk(P, t, bias_s, valid, pix, g, x, y, rb, ch + 64);
+            __syncwarp();
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- cluster / CTA-pair helpers
@@ -218,8 +252,11 @@ __device__ __forceinline__ uint32_t cv_mapa(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void cv_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Accumulator hand-back to the MMA issuer (possibly in the peer CTA).  RELAXED on purpose: the only accesses that must be ordered
+// before it are the tcgen05.ld reads, which tcgen05.fence::before_thread_sync already orders; a .release here would also wait for
+// the epilogue's global stores to drain (measured: 20 % of all stall samples of the kernel sat on this one instruction).
 __device__ __forceinline__ void cv_mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA tensor-map loads.  kPair: the cta_group::2 form, whose mbarrier operand may live in the peer CTA (the pair's leader).
 template <bool kPair>
@@ -304,7 +341,7 @@ __device__ __forceinline__ void cv_body(const ConvParams &P) {
     if (tid == 0) {
         for (int s = 0; s < kCvMaxStages; ++s) { cv_mbar_init(&full[s], 1); cv_mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) {
-            cv_mbar_init(&tfull[a], 1); cv_mbar_init(&tempty[a], 4 * kCtas);
+            cv_mbar_init(&tfull[a], 1); cv_mbar_init(&tempty[a], 8 * kCtas);
             cv_mbar_init(&hfull[a], 1); cv_mbar_init(&hempty[a], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -453,7 +490,7 @@ __device__ __forceinline__ void cv_body(const ConvParams &P) {
         __syncwarp();
     } else if (warp >= 4) {
         // ===== epilogue: my 128 x kMsub accumulator rows =============================================================
-        const int q = warp & 3;
+        const int q = warp & 3, half = (warp - 4) >> 2;
         const int row = q * 32 + lane;
         const int px = row & ((1 << P.log2_bx) - 1), py = row >> P.log2_bx;
         const uint32_t tempty_addr = kPair ? cv_mapa(cv_smem_u32(&tempty[0]), 0) : cv_smem_u32(&tempty[0]);
@@ -469,8 +506,8 @@ __device__ __forceinline__ void cv_body(const ConvParams &P) {
             cv_fence_after();
 #pragma unroll
             for (int m = 0; m < kMsub; ++m)
-                cv_epilogue_rows(P, t, bias_s, t.x0 + px, t.y0 + (int)rank * by_cta + m * (128 >> P.log2_bx) + py,
-                                 tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)(m * P.bn));
+                cv_epilogue_rows(P, t, cv_smem_u32(bias_s), t.x0 + px, t.y0 + (int)rank * by_cta + m * (128 >> P.log2_bx) + py,
+                                 tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)(m * P.bn), half);
             cv_fence_before();
             __syncwarp();
             if (lane == 0) cv_mbar_arrive_cluster(tempty_addr + acc * 8u);
@@ -611,7 +648,9 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
     P.halo = (a->ksize == 3 && a->stride == 1 && !g_cv_halo_off) ? 1 : 0;
     if (pair && (a->bn > 128 || g_cv_force_msub == 1)) P.msub = 1;
     int best = -1; int64_t best_cost = 0;
-    for (int l = P.halo ? 3 : 0; l <= (P.halo ? 3 : 7); ++l) {      // halo path: patches are 8 pixels wide
+    // transposed-conv epilogue: a warp's store covers bx*up consecutive floats per output row -> keep patches >= 16 pixels wide
+    const int l_min = P.halo ? 3 : ((a->out_mode == 1 && P.w_out >= 16) ? 4 : 0);
+    for (int l = l_min; l <= (P.halo ? 3 : 7); ++l) {      // halo path: patches are 8 pixels wide
         const int bx = 1 << l, by = (128 >> l) * P.msub * (P.pair + 1);
         const int64_t cost = ceil_div64(P.w_out, bx) * bx * (ceil_div64(P.h_out, by) * by);
         if (best < 0 || cost < best_cost || (cost == best_cost && l <= 4)) { best = l; best_cost = cost; }

@@ -19,7 +19,7 @@ _lib.init_device()
 L = _lib.lib()
 x_in = torch.randn(B, H, W, 128, device="cuda").abs().bfloat16()
 y_in = torch.zeros(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
-names = ["prod.wait_empty", "-", "-", "-", "mma.wait_tempty", "mma.wait_full", "mma.issue+commit", "-",
+names = ["prod.wait_empty", "-", "-", "-", "mma.wait_tempty", "mma.wait_full", "mma.issue+commit", "mma.wait_hfull",
          "epi.wait_tfull", "epi.work", "-", "-"]
 with torch.no_grad():
     m.run_nhwc(x_in, y_in, B, H, W)
@@ -28,6 +28,8 @@ with torch.no_grad():
     lv0, lv1, lv2 = pl["lv"]
     cases = [("L0 body 128->128", P["blocks"][0][1], lv0["a"], H, W, lv0["b"]),
              ("L1 body 256->256", P["blocks"][1][1], lv1["a"], lv1["h"], lv1["w"], lv1["b"])]
+    cases.append(("L2 deblock 512->2048 (up 4)", P["de"][2], lv2["a"], lv2["h"], lv2["w"], None))
+    cases.append(("L0 deblock 128->128 (up 1)", P["de"][0], lv0["a"], H, W, None))
     for label, lay, src, h, w, dst in cases:
         for pair in (1, 2):
             L.hvpr_dbg_conv_pair(pair)
@@ -35,7 +37,10 @@ with torch.no_grad():
             L.hvpr_dbg_conv_prof(_lib.ptr(prof))
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            m._conv(lay, src, B, h, w, dst)
+            if dst is None:
+                m._conv(lay, src, B, h, w, pl["out"], out_mode=1, out_c_off=0, out_ctot=384)
+            else:
+                m._conv(lay, src, B, h, w, dst)
             e1.record()
             torch.cuda.synchronize()
             L.hvpr_dbg_conv_prof(None)
