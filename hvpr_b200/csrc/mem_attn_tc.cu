@@ -403,8 +403,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
                                                                     int32_t *__restrict__ topk_idx_out,
                                                                     float *__restrict__ slow_scratch,
                                                                     float *__restrict__ dbg_logits) {
-    extern __shared__ uint8_t smem_raw[];
-    TcSmem &S = *reinterpret_cast<TcSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // __align__(1024) (128-B swizzle atoms) instead of rounding the pointer up by hand: integer arithmetic on the address makes
+    // the compiler lose the shared address space and emit generic LD.E / ST.E for every access to S (group maxima, candidate
+    // ring, A-tile stores) in this latency-bound kernel
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    TcSmem &S = *reinterpret_cast<TcSmem *>(smem_raw);
+    if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int64_t nP = n_pillars_dev ? (int64_t)*n_pillars_dev : n_rows_max;
     if (nP > n_rows_max) nP = n_rows_max;
