@@ -171,3 +171,62 @@ def test_synth_generators_are_deterministic():
     assert a.dtype == np.float32 and a.shape == (5000, 4) and np.array_equal(a, b)
     c = synth.collate_points([a, b])
     assert c.shape == (10000, 5) and c[4999, 0] == 0 and c[5000, 0] == 1
+
+
+# ---- row N1: backbone host side and conv C ABI (no GPU needed) -------------------------------------------------------
+def test_conv_args_struct_layout_and_validation_without_gpu():
+    assert ctypes.sizeof(_lib.HvprConvArgs) == 128
+    assert _lib.HvprConvArgs.w_packed.offset == 40 and _lib.HvprConvArgs.out.offset == 96 and _lib.HvprConvArgs.out_ctot.offset == 120
+    L = _lib.lib()
+    assert L.hvpr_conv_packed_bytes(128, 9, 128) == 128 * 9 * 128 * 2
+    assert L.hvpr_conv2d(None, None) == -1
+    a = _lib.HvprConvArgs()                                    # all-null arguments are rejected before any CUDA call
+    assert L.hvpr_conv2d(ctypes.byref(a), None) == -1
+    assert L.hvpr_conv_pack_weights(None, 128, 9, 128, 128, None, None) == -1
+    buf = ctypes.create_string_buffer(64)
+    assert L.hvpr_conv_pack_weights(buf, 128, 9, 100, 128, buf, None) == -2     # c_in must be a multiple of 64
+    assert L.hvpr_conv_pack_weights(buf, 96, 9, 128, 128, buf, None) == -2      # n_total must be a multiple of bn
+    assert L.hvpr_attention_gate(None, 1, 8, 8, 64, 32, None, 0.0, None, None, None) == -1
+    assert L.hvpr_nchw_to_nhwc_bf16(None, 1, 32, 8, 8, None, 64, None) == -1
+    assert L.hvpr_bev_fill_nhwc_bf16(None, 64, None, 64, None, 32, None, 1, 8, 8, None, 128, None, 64, None) == -1
+
+
+def test_backbone_registry_state_dict_names_and_loud_failures():
+    from hvpr_b200.backbone import BaseBEVBackbone_Scale
+    from hvpr_b200.pipeline import HVPR_BACKBONE_CFG
+    from oracle import backbone as ob
+    m = BaseBEVBackbone_Scale(HVPR_BACKBONE_CFG, 128)
+    assert m.num_bev_features == 384
+    w = ob.random_backbone_weights(0)
+    sd = m.state_dict()
+    assert {k for k in sd if not k.endswith("num_batches_tracked")} == set(w)
+    assert all(tuple(sd[k].shape) == w[k].shape for k in w)
+    r = m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=False)
+    assert not r.unexpected_keys
+    with pytest.raises(_lib.HvprError):                        # CPU tensors: no fallback
+        m.eval()({"spatial_features": torch.zeros(1, 128, 8, 8), "spatial_scale_features": torch.zeros(1, 32, 8, 8)})
+    with pytest.raises(NotImplementedError):                   # training branch is out of scope
+        m.train()({"spatial_features": torch.zeros(1, 128, 8, 8), "spatial_scale_features": torch.zeros(1, 32, 8, 8)})
+    with pytest.raises(NotImplementedError):                   # unsupported layouts are refused at construction
+        BaseBEVBackbone_Scale(config.Cfg(HVPR_BACKBONE_CFG, LAYER_STRIDES=[1, 3, 2]), 128)
+    if ob is not None:                                         # same names as the reference's own module when the tree is present
+        from oracle import ref_loader
+        if ref_loader.available():
+            ref = ref_loader.load_backbone().BaseBEVBackbone_Scale(ref_loader.BACKBONE_CFG, 128)
+            assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+
+
+def test_backbone_bn_folding_matches_oracle_layer():
+    """float64 BN folding of one conv block reproduces conv -> BN(eval) of the oracle (CPU, fp32 tolerance)."""
+    import torch.nn.functional as F
+    from hvpr_b200.backbone import BaseBEVBackbone_Scale, _fold
+    from hvpr_b200.pipeline import HVPR_BACKBONE_CFG
+    from oracle import backbone as ob
+    w = ob.random_backbone_weights(4)
+    m = BaseBEVBackbone_Scale(HVPR_BACKBONE_CFG, 128).eval()
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=False)
+    cw, s, shift = _fold(m.blocks[1][1].weight, m.blocks[1][2])
+    x = torch.randn(1, 128, 6, 8)
+    got = F.conv2d(x.double(), cw * s[:, None, None, None], shift, stride=2, padding=1)
+    ref = ob._conv_bn_relu(x, w, "blocks.1.1.weight", "blocks.1.2", 2, relu=False)
+    assert float((got - ref.double()).abs().max()) <= 1e-5 * float(ref.abs().max())
