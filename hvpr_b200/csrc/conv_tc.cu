@@ -26,7 +26,6 @@ constexpr int kCvThreads = 384;         // warp 0 producer, warp 1 MMA issuer, w
 constexpr int kCvABytes = 128 * 128;         // 128 pixels x 64 channels bf16
 constexpr int kCvPipeBytes = 216 * 1024;     // operand ring(s)
 constexpr int kCvMaxStages = 8;
-constexpr int kCvHaloW = 10;                 // halo patch row: 8 output pixels + 1 on each side
 constexpr int kCvMaxN = 2048;                // GEMM columns (bias staged in shared memory)
 
 // Optional cycle accounting (compile with -DHVPR_CV_PROFILE, `make prof`): per CTA and role, cycles spent at each wait site,
@@ -55,7 +54,7 @@ struct ConvParams {
     int n_img, h_out, w_out;
     int log2_bx, tiles_x, tiles_y;
     int ntaps, kblocks, bn, n_tiles, nstages, n_total;
-    int halo;                 // 3x3 stride-1: one halo patch per k-block feeds all 9 taps (see the MMA issuer)
+    int halo;                 // 3x3 stride-1: three column-shifted patches per k-block feed all 9 taps (see cv_body)
     int msub;                 // 128-pixel sub-tiles per CTA and tile (2: two A patches share every weight block)
     int pair;                 // 1: CTA-pair kernel (a tile spans the patches of both CTAs)
     int relu, res_cs;
@@ -92,20 +91,6 @@ __device__ __forceinline__ uint64_t cv_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)1 << 16;
     d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// A tile read out of a halo patch of kCvHaloW-pixel rows: 8-row groups (8 pixels of one image row) one halo row apart, the
-// start shifted by whole 128-B rows (dy*kCvHaloW + dx pixels).  The MMA unit applies the 128-B swizzle XOR to the ABSOLUTE
-// shared-memory address bits [7,10) — exactly what TMA did when it wrote the patch — so any 128-B-aligned start and any
-// group stride read back consistently with base_offset = 0 (measured with tools/dev/halo_diag.py: a non-zero base_offset
-// permutes the 16-B chunks).
-__device__ __forceinline__ uint64_t cv_desc_halo(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)((kCvHaloW * 128) >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
@@ -297,7 +282,11 @@ __device__ __forceinline__ void cv_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
 
 // ---------------------------------------------------------------------------------------------- the kernel body
 // kMsub  128-pixel sub-tiles per CTA and tile (2: two A patches share every weight block; needs bn <= 128)
-// kHalo  3x3 stride-1 only: ONE (8+2) x (rows+2) halo patch per k-block feeds all nine taps through shifted UMMA descriptors
+// kHalo  3x3 stride-1 only: three column-shifted 8 x (rows+2) patches per k-block (dx = -1, 0, +1) feed all nine taps: tap (dy,dx)
+//        is patch dx read from a start address dy image rows (dy x 1024 B) further down — every 8-row UMMA group stays one aligned
+//        1024-B swizzle atom.  3.4x instead of 9x the activation bytes.  (A single (8+2)-wide halo patch with starts shifted by
+//        128-B rows also reads back correctly — the tensor core applies the swizzle XOR to ABSOLUTE shared-memory address bits, so
+//        base_offset stays 0, measured with tools/dev/halo_diag.py — but those unaligned groups run 5-25 % slower.)
 // kPair  CTA pair (cluster of 2, tcgen05 cta_group::2): UMMA M = 256 — each CTA owns the patches of its half of the tile (its
 //        accumulator rows stay in its own TMEM) and loads only HALF of every weight block; the pair's tensor cores share the
 //        halves.  Per SM that halves the weight bytes pulled from L2 and the B-operand bytes read from shared memory.
@@ -327,8 +316,9 @@ __device__ __forceinline__ void cv_body(const ConvParams &P) {
     const int tile0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tile_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     constexpr uint32_t kCtas = kPair ? 2u : 1u;
-    constexpr int kHaloBox = kCvHaloW * (16 * kMsub + 2) * 128;          // halo pixels x 64 ch bf16
-    constexpr int kHaloBytes = kHalo ? (kHaloBox + 1023) & ~1023 : 0;
+    constexpr int kHaloPatch = 8 * (16 * kMsub + 2) * 128;               // one column-shifted patch: 8 px x (rows + 2) x 64 ch bf16
+    constexpr int kHaloBox = 3 * kHaloPatch;                              // patches for dx = -1, 0, +1
+    constexpr int kHaloBytes = kHalo ? kHaloBox : 0;                      // multiple of 1024 (8 px x 128 B per image row)
     constexpr int kABytes = kHalo ? 0 : kMsub * kCvABytes;
     const int b_rows = kPair ? P.bn >> 1 : P.bn;                          // weight rows this CTA loads per block
     const int stage_bytes = kABytes + b_rows * 128;
@@ -376,8 +366,10 @@ __device__ __forceinline__ void cv_body(const ConvParams &P) {
                     for (int kb = 0; kb < P.kblocks; ++kb) {
                         cv_mbar_wait(&hempty[hs], hph ^ 1);
                         if (rank == 0) cv_mbar_expect_tx(&hfull[hs], kCtas * (uint32_t)kHaloBox);
-                        cv_tma_4d<kPair>(pipe + (size_t)hs * kHaloBytes, &P.tmap[0], kPair ? cv_mapa(cv_smem_u32(&hfull[hs]), 0) : cv_smem_u32(&hfull[hs]),
-                                         kb * 64, t.x0 - 1, y0 - 1, t.img);
+                        const uint32_t hbar = kPair ? cv_mapa(cv_smem_u32(&hfull[hs]), 0) : cv_smem_u32(&hfull[hs]);
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx)
+                            cv_tma_4d<kPair>(pipe + (size_t)hs * kHaloBytes + dx * kHaloPatch, &P.tmap[0], hbar, kb * 64, t.x0 - 1 + dx, y0 - 1, t.img);
                         if (++hs == 2) { hs = 0; hph ^= 1; }
                         for (int tap = 0; tap < 9; ++tap) {
                             CVP_B();
@@ -446,7 +438,7 @@ __device__ __forceinline__ void cv_body(const ConvParams &P) {
                                 const uint64_t bdesc = ring_desc + soff;
 #pragma unroll
                                 for (int m = 0; m < kMsub; ++m) {
-                                    const uint64_t adesc = cv_desc_halo(ha + (uint32_t)(((m * 16 + dy) * kCvHaloW + dx) * 128));
+                                    const uint64_t adesc = cv_desc_sw128(ha + (uint32_t)(dx * kHaloPatch + (m * 16 + dy) * 1024));
 #pragma unroll
                                     for (int kk = 0; kk < 4; ++kk)
                                         cv_mma<kPair>(d + (uint32_t)m * bn, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
@@ -586,7 +578,7 @@ int hvpr_conv_init() {
 
 // debug knob (not part of the public header): 0 = automatic tile policy, 1 / 2 = force the number of 128-pixel sub-tiles
 static int g_cv_force_msub = 0;
-static int g_cv_halo_off = 1;   // measured (tools/dev/backbone_bench.py A/B): the halo path halves L2->SM traffic but is 5-15 % slower
+static int g_cv_halo_off = 1;
 extern "C" int hvpr_dbg_conv_force_msub(int msub) {
     if (msub < 0 || msub > 2) return HVPR_ERR_ARG;
     g_cv_force_msub = msub;
@@ -601,7 +593,7 @@ extern "C" int hvpr_dbg_conv_pair(int mode) {
     g_cv_pair_mode = mode;
     return HVPR_OK;
 }
-// knob: 1 (default) = one TMA box per tap; 0 = 3x3 stride-1 layers read all nine taps out of one halo patch
+// knob: 1 (default) = one TMA box per tap; 0 = 3x3 stride-1 layers read all nine taps out of three column-shifted patches
 extern "C" int hvpr_dbg_conv_halo_off(int off) { g_cv_halo_off = off ? 1 : 0; return HVPR_OK; }
 
 extern "C" size_t hvpr_conv_packed_bytes(int n_total, int taps, int c_in) { return (size_t)n_total * taps * c_in * 2; }
@@ -646,6 +638,7 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
                        (int64_t)a->n * P.h_out * P.w_out >= 256 * (int64_t)(kNumSMs / 2) * 4);
     P.pair = pair ? 1 : 0;
     P.halo = (a->ksize == 3 && a->stride == 1 && !g_cv_halo_off) ? 1 : 0;
+    if (P.halo) P.msub = 1;      // two double-buffered patch triples of a 256-pixel tile (2 x 102 KB) do not fit beside the weight ring
     if (pair && (a->bn > 128 || g_cv_force_msub == 1)) P.msub = 1;
     int best = -1; int64_t best_cost = 0;
     // transposed-conv epilogue: a warp's store covers bx*up consecutive floats per output row -> keep patches >= 16 pixels wide
@@ -664,7 +657,7 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
     P.bn = a->bn;
     P.n_total = a->n_total;
     P.n_tiles = a->n_total / a->bn;
-    const int halo_bytes = P.halo ? (kCvHaloW * (16 * P.msub + 2) * 128 + 1023) & ~1023 : 0;
+    const int halo_bytes = P.halo ? 3 * 8 * (16 * P.msub + 2) * 128 : 0;
     const int stage_bytes = (P.halo ? 0 : P.msub * kCvABytes) + (pair ? a->bn * 64 : a->bn * 128);
     P.nstages = (kCvPipeBytes - 2 * halo_bytes) / stage_bytes;
     if (P.nstages > kCvMaxStages) P.nstages = kCvMaxStages;
@@ -690,7 +683,7 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
     } else return HVPR_ERR_ARG;
 
     // tensor maps over the NHWC bf16 input: dims (channel, x, y, image)
-    const cuuint32_t box[4] = {64u, (cuuint32_t)(P.halo ? kCvHaloW : bx), (cuuint32_t)(P.halo ? by_cta + 2 : by_cta), 1u};
+    const cuuint32_t box[4] = {64u, (cuuint32_t)(P.halo ? 8 : bx), (cuuint32_t)(P.halo ? by_cta + 2 : by_cta), 1u};
     const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
     const uint64_t pix_b = (uint64_t)a->in_cs * 2u;
     const int nmaps = (a->stride == 2) ? 4 : 1;

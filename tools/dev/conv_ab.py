@@ -18,7 +18,7 @@ _lib.init_device()
 L = _lib.lib()
 x_in = torch.randn(B, H, W, 128, device="cuda").abs().bfloat16()
 y_in = torch.zeros(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
-MODES = {"single": (1, 1, 0), "single_msub1": (1, 1, 1), "pair": (2, 1, 0), "pair_msub1": (2, 1, 1), "halo": (1, 0, 0), "pair_halo": (2, 0, 0)}
+MODES = {"single": (1, 1, 0), "pair": (2, 1, 0), "halo": (1, 0, 0), "pair_halo": (2, 0, 0)}
 with torch.no_grad():
     m.run_nhwc(x_in, y_in, B, H, W)
     torch.cuda.synchronize()
