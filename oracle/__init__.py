@@ -14,4 +14,7 @@ Pinning status:
   * VFE / memory / BEV — pinned against the reference's OWN Python modules imported from /root/reference in the
                          build container (oracle/ref_loader.py, 3 in-memory patches) — see oracle/make_golden.py and
                          tests/golden/*.npz, and tests/test_oracle_vs_reference.py (runs wherever /root/reference exists).
+  * 2-D backbone (N1)  — oracle/backbone.py, pinned against the reference's OWN BaseBEVBackbone_Scale
+                         (oracle/ref_loader.load_backbone, one in-memory patch: breakage B4) — oracle/make_golden_backbone.py,
+                         tests/golden/backbone_tiny.npz.
 """

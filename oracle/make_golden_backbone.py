@@ -35,8 +35,6 @@ def main():
     missing = m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=False)
     assert not missing.unexpected_keys and all(k.endswith("num_batches_tracked") for k in missing.missing_keys), missing
     spatial, scale = ob.random_canvases(XSEED, B, H, W)
-    levels = {}
-    hooks = []
     with torch.no_grad():
         out = m({"spatial_features": torch.from_numpy(spatial), "spatial_scale_features": torch.from_numpy(scale)})
     ref = out["spatial_features_2d"].numpy()
