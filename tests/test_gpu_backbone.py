@@ -306,3 +306,27 @@ def test_points_to_spatial_features_2d_pipeline_vs_oracle_chain():
     bd = pipe({"points": torch.from_numpy(synth.collate_points(frames)).cuda(), "batch_size": len(frames)})
     torch.cuda.synchronize()
     assert torch.equal(bd["spatial_features_2d"], p.out)
+
+
+def test_full_size_backbone_is_invariant_to_the_kernel_policy():
+    """BASELINE-size canvases (296 x 248, batch 2): the automatic policy (CTA-pair kernel on the 256-column layers, two sub-tiles
+    on the 128-column level) must agree with the plain single-CTA / one-sub-tile kernels — same operands, same K order — and
+    the result must be a sane feature map (size-independent property check; the oracle comparison runs on small canvases)."""
+    from oracle import backbone as ob
+    L = _lib()
+    m, _ = _backbone(5)
+    B, H, W = 2, 248, 296
+    spatial, scale = ob.random_canvases(9, B, H, W, occupancy=0.12)
+    bd = {"spatial_features": torch.from_numpy(spatial).cuda(), "spatial_scale_features": torch.from_numpy(scale).cuda()}
+    with torch.no_grad():
+        auto = m(dict(bd))["spatial_features_2d"].clone()
+        L.lib().hvpr_dbg_conv_pair(1); L.lib().hvpr_dbg_conv_force_msub(1)
+        try:
+            plain = m(dict(bd))["spatial_features_2d"].clone()
+        finally:
+            L.lib().hvpr_dbg_conv_pair(0); L.lib().hvpr_dbg_conv_force_msub(0)
+    torch.cuda.synchronize()
+    assert auto.shape == (B, 384, H, W) and torch.isfinite(auto).all() and float(auto.min()) >= 0.0      # ReLU outputs
+    assert float(auto.abs().max()) > 0.1
+    e = rel_err(auto, plain)
+    assert e[0] <= 2.0 ** -7 and e[1] <= 1e-3, e
