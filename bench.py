@@ -238,7 +238,7 @@ def run_gpu_arm(args):
     from hvpr_b200 import sharding
     from hvpr_b200.frontend import HybridFrontEnd
     from hvpr_b200.geometry import G2
-    from oracle import hybrid   # random-init weights (reference state_dict names) + the cpu_baseline leg only
+    from hvpr_b200 import synth
 
     rank, local_rank, world = sharding.dist_env()
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
@@ -254,7 +254,7 @@ def run_gpu_arm(args):
     nx, ny, _ = geom.grid_size
     B, N = FRAMES_PER_GPU, POINTS_PER_FRAME
     frames = make_frames(geom, rank)
-    w = hybrid.random_weights(0)
+    w = synth.random_frontend_weights(0)     # synthetic weights under the reference's state_dict names
     fe = HybridFrontEnd(geom, mem_precision=args.mem_precision, device=dev).load_reference_weights(w)
     p = fe.plan(B, B * N, N, use_graph=not args.no_graph)
     host_pts = torch.from_numpy(np.ascontiguousarray(np.concatenate(frames, 0))).pin_memory()

@@ -20,43 +20,10 @@ BN_EPS = 1e-3          # pillar_vfe.py:23, :162
 
 def random_weights(seed: int = 0, num_filters=(32, 64), num_scale=(16, 32), in_feat=10, mem=(2000, 64),
                    randomize_bn: bool = True, vfe_scale: bool = True):
-    """Random-init weights as the reference modules would have (nn.Linear Kaiming-uniform; memory U(+-1/sqrt(C)),
-    memory_module.py:23-25) with BN affine + running stats randomised (default BN hides the padded-row term,
-    SURVEY.md §8c)."""
-    g = torch.Generator().manual_seed(seed)
-    w = {}
-
-    def lin(o, i):
-        b = 1.0 / math.sqrt(i)            # kaiming_uniform_(a=sqrt(5)) bound == 1/sqrt(fan_in)
-        return (torch.rand(o, i, generator=g) * 2 - 1) * b
-
-    def bn(prefix, c):
-        if randomize_bn:
-            w[prefix + ".weight"] = torch.rand(c, generator=g) * 1.0 + 0.5
-            w[prefix + ".bias"] = torch.randn(c, generator=g) * 0.5
-            w[prefix + ".running_mean"] = torch.randn(c, generator=g) * 0.5
-            w[prefix + ".running_var"] = torch.rand(c, generator=g) * 1.5 + 0.25
-        else:
-            w[prefix + ".weight"] = torch.ones(c)
-            w[prefix + ".bias"] = torch.zeros(c)
-            w[prefix + ".running_mean"] = torch.zeros(c)
-            w[prefix + ".running_var"] = torch.ones(c)
-
-    filt = [in_feat] + list(num_filters)
-    for i in range(len(filt) - 1):
-        last = i >= len(filt) - 2
-        o = filt[i + 1] if last else filt[i + 1] // 2            # pillar_vfe.py:18-19
-        w["vfe.pfn_layers.%d.linear.weight" % i] = lin(o, filt[i])
-        bn("vfe.pfn_layers.%d.norm" % i, o)
-    if vfe_scale:
-        sc = [5] + list(num_scale)
-        for i in range(len(sc) - 1):
-            w["vfe.pfn_scale_layers.%d.0.weight" % i] = lin(sc[i + 1], sc[i])
-            bn("vfe.pfn_scale_layers.%d.1" % i, sc[i + 1])
-    if mem is not None:
-        stdv = 1.0 / math.sqrt(mem[1])
-        w["map_to_bev_module.memory.weight"] = (torch.rand(mem[0], mem[1], generator=g) * 2 - 1) * stdv
-    return w
+    """Seeded random-init weights under the reference's state_dict names (the generator lives with the other synthetic
+    inputs in hvpr_b200/synth.py so that bench.py's GPU arm does not have to import this package)."""
+    from hvpr_b200 import synth
+    return synth.random_frontend_weights(seed, num_filters, num_scale, in_feat, mem, randomize_bn, vfe_scale)
 
 
 def _bn_eval(x, w, prefix):
