@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_kernel(const __grid_consta
             // W1a . x on the tensor cores, one 16-point m-tile at a time
 #pragma unroll 1
             for (int mt = 0; mt < 2; ++mt) {
+                if (c0 + 16 * mt >= total) break;           // warp-uniform: this 16-point m-tile holds no real point
                 uint32_t ahi[2][4], alo[2][4];
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
