@@ -20,8 +20,8 @@ def __getattr__(name):
         return getattr(importlib.import_module(".vfe", __name__), name)
     if name in ("PointPillarScatter", "PointPillarScatter_Agg_Memory_1_scale", "MemoryUnit_Agg"):
         return getattr(importlib.import_module(".map_to_bev", __name__), name)
-    if name == "BaseBEVBackbone_Scale":
-        return importlib.import_module(".backbone", __name__).BaseBEVBackbone_Scale
+    if name in ("BaseBEVBackbone", "BaseBEVBackbone_Scale"):
+        return getattr(importlib.import_module(".backbone", __name__), name)
     if name == "HybridFrontEnd":
         return importlib.import_module(".frontend", __name__).HybridFrontEnd
     raise AttributeError(name)

@@ -58,6 +58,10 @@ class _ConvLayer:
 
 
 class BaseBEVBackbone_Scale(nn.Module):
+    """Eval forward of base_bev_backbone.py:280-315; the plain BaseBEVBackbone (:62-102, no scale branch / SFM loop) is the
+    subclass below with _WITH_SCALE = False."""
+    _WITH_SCALE = True
+
     def __init__(self, model_cfg, input_channels):
         super().__init__()
         self.model_cfg = model_cfg
@@ -67,8 +71,10 @@ class BaseBEVBackbone_Scale(nn.Module):
         self.sfm_layer_nums = list(g("SFM_LAYER_NUMS") or [])
         up_strides, up_filters = list(g("UPSAMPLE_STRIDES") or []), list(g("NUM_UPSAMPLE_FILTERS") or [])
         scale_filters = list(g("NUM_SCALE_FILTERS") or [])
+        if not self._WITH_SCALE:
+            scale_filters, self.sfm_layer_nums = [0] * len(filters), [0] * len(filters)
         if not (len(up_strides) == len(up_filters) == len(scale_filters) == len(self.sfm_layer_nums) == len(filters)):
-            raise NotImplementedError("BaseBEVBackbone_Scale (B200): one deblock, scale layer and SFM count per level "
+            raise NotImplementedError("BaseBEVBackbone[_Scale] (B200): one deblock (and scale layer / SFM count) per level "
                                       "(hvpr.yaml:87-95 layout) is what the kernels are wired for")
         if any(s not in (1, 2) for s in strides) or any((not float(u).is_integer()) or u < 1 for u in up_strides):
             raise NotImplementedError("LAYER_STRIDES in {1,2} and integer UPSAMPLE_STRIDES >= 1 only")
@@ -86,13 +92,17 @@ class BaseBEVBackbone_Scale(nn.Module):
             for _ in range(layer_nums[i]):
                 mods += [nn.Conv2d(nf, nf, 3, padding=1, bias=False), _bn(nf), nn.ReLU()]
             self.blocks.append(_slots(*mods))
-            self.sfmblocks_down.append(_slots(nn.Conv2d(nf, nf, 3, padding=1, bias=False), _bn(nf), nn.ReLU()))
             u = self.upsample_strides[i]
             self.deblocks.append(_slots(nn.ConvTranspose2d(nf, up_filters[i], u, stride=u, bias=False), _bn(up_filters[i]), nn.ReLU()))
-            self.scale_layers.append(_slots(nn.ZeroPad2d(1), nn.Conv2d(c_in_s[i], scale_filters[i], 3, stride=strides[i],
-                                                                       padding=0, bias=False), _bn(scale_filters[i]), nn.ReLU()))
+            if self._WITH_SCALE:
+                self.sfmblocks_down.append(_slots(nn.Conv2d(nf, nf, 3, padding=1, bias=False), _bn(nf), nn.ReLU()))
+                self.scale_layers.append(_slots(nn.ZeroPad2d(1), nn.Conv2d(c_in_s[i], scale_filters[i], 3, stride=strides[i],
+                                                                           padding=0, bias=False), _bn(scale_filters[i]), nn.ReLU()))
         self.num_bev_features = sum(up_filters)
-        self.attention = _SpatialGateParams()
+        if self._WITH_SCALE:
+            self.attention = _SpatialGateParams()
+        else:
+            del self.sfmblocks_down, self.sfmblocks_up, self.scale_layers      # the plain backbone has no such sub-modules
         self._packed = None
         self._packed_key = None
         self._plans = {}
@@ -139,10 +149,11 @@ class BaseBEVBackbone_Scale(nn.Module):
                 lay.stride = seq[j].stride[0]
                 convs.append(lay)
             P["blocks"].append(convs)
-            P["sfm"].append(self._pack_conv(*_fold(self.sfmblocks_down[i][0].weight, self.sfmblocks_down[i][1]), dev))
-            sl = self._pack_conv(*_fold(self.scale_layers[i][1].weight, self.scale_layers[i][2]), dev)
-            sl.stride = self.scale_layers[i][1].stride[0]
-            P["scale"].append(sl)
+            if self._WITH_SCALE:
+                P["sfm"].append(self._pack_conv(*_fold(self.sfmblocks_down[i][0].weight, self.sfmblocks_down[i][1]), dev))
+                sl = self._pack_conv(*_fold(self.scale_layers[i][1].weight, self.scale_layers[i][2]), dev)
+                sl.stride = self.scale_layers[i][1].stride[0]
+                P["scale"].append(sl)
             # ConvTranspose2d(k = s, stride = s): GEMM column (dy*Cout + co)*s + dx  <-  W[ci, co, dy, dx]
             w, s, shift = _fold(self.deblocks[i][0].weight, self.deblocks[i][1])
             ci, co, u, _ = w.shape
@@ -150,10 +161,11 @@ class BaseBEVBackbone_Scale(nn.Module):
             de = self._pack(wn, shift.float().repeat_interleave(u).repeat(u).to(dev), u * u * co, 1, ci, 1, dev)
             de.up, de.c_out = u, co
             P["de"].append(de)
-        a = self.attention.spatial
-        w, s, shift = _fold(a.conv.weight, a.norm, a.conv.bias)
-        P["gate_w"] = (ctypes.c_float * 18)(*[float(v) for v in (w * s[:, None, None, None]).reshape(-1).cpu()])
-        P["gate_b"] = float(shift.reshape(-1)[0].cpu())
+        if self._WITH_SCALE:
+            a = self.attention.spatial
+            w, s, shift = _fold(a.conv.weight, a.norm, a.conv.bias)
+            P["gate_w"] = (ctypes.c_float * 18)(*[float(v) for v in (w * s[:, None, None, None]).reshape(-1).cpu()])
+            P["gate_b"] = float(shift.reshape(-1)[0].cpu())
         self._packed, self._packed_key = P, key
         return P
 
@@ -168,20 +180,25 @@ class BaseBEVBackbone_Scale(nn.Module):
         if H % tot or W % tot:
             raise NotImplementedError("canvas %dx%d is not divisible by the total stride %d" % (H, W, tot))
         bf = dict(dtype=torch.bfloat16, device=dev)
-        pl = {"x_in": torch.zeros(B, H, W, (self.input_channels + 63) // 64 * 64, **bf),
-              "y_in": torch.zeros(B, H, W, (self.input_channels // 4 + 63) // 64 * 64, **bf), "lv": []}
+        pl = {"x_in": torch.zeros(B, H, W, (self.input_channels + 63) // 64 * 64, **bf), "lv": []}
+        if self._WITH_SCALE:
+            pl["y_in"] = torch.zeros(B, H, W, (self.input_channels // 4 + 63) // 64 * 64, **bf)
         h, w = H, W
         for i, nf in enumerate(self.num_filters):
             h, w = h // self.layer_strides[i], w // self.layer_strides[i]
-            ycs = (self.num_scale_filters[i] + 63) // 64 * 64
-            pl["lv"].append({"h": h, "w": w, "a": torch.empty(B, h, w, nf, **bf), "b": torch.empty(B, h, w, nf, **bf),
-                             "c": torch.empty(B, h, w, nf, **bf),
-                             "y": torch.zeros(B, h, w, ycs, **bf),             # pad channels stay zero
-                             "pooled": torch.empty(B, h, w, 2, dtype=torch.float32, device=dev),
-                             "gate": torch.empty(B, h, w, dtype=torch.float32, device=dev)})
-        pl["out"] = torch.empty(B, self.num_bev_features, H, W, dtype=torch.float32, device=dev)
-        if pl["lv"] and (pl["lv"][0]["h"] * self.upsample_strides[0] != H):
-            raise NotImplementedError("deblock outputs must all land on the input resolution (hvpr.yaml:91-94)")
+            lv = {"h": h, "w": w, "a": torch.empty(B, h, w, nf, **bf), "b": torch.empty(B, h, w, nf, **bf)}
+            if self._WITH_SCALE:
+                ycs = (self.num_scale_filters[i] + 63) // 64 * 64
+                lv.update({"c": torch.empty(B, h, w, nf, **bf),
+                           "y": torch.zeros(B, h, w, ycs, **bf),               # pad channels stay zero
+                           "pooled": torch.empty(B, h, w, 2, dtype=torch.float32, device=dev),
+                           "gate": torch.empty(B, h, w, dtype=torch.float32, device=dev)})
+            pl["lv"].append(lv)
+        # every deblock must land on one common resolution (they are concatenated, :298 / :96)
+        ho, wo = pl["lv"][0]["h"] * self.upsample_strides[0], pl["lv"][0]["w"] * self.upsample_strides[0]
+        if any(lv["h"] * u != ho or lv["w"] * u != wo for lv, u in zip(pl["lv"], self.upsample_strides)):
+            raise NotImplementedError("deblock outputs must share one resolution (UPSAMPLE_STRIDES vs LAYER_STRIDES)")
+        pl["out"] = torch.empty(B, self.num_bev_features, ho, wo, dtype=torch.float32, device=dev)
         self._plans[key] = pl
         return pl
 
@@ -213,32 +230,45 @@ class BaseBEVBackbone_Scale(nn.Module):
             for j, lay in enumerate(P["blocks"][i]):                                   # :283
                 self._conv(lay, x, B, h if j == 0 else lv["h"], w if j == 0 else lv["w"], cur)
                 x, cur, other = cur, other, cur
-            self._conv(P["scale"][i], y, B, h, w, lv["y"])                              # :284
-            h, w, y = lv["h"], lv["w"], lv["y"]
-            _lib.check(L.hvpr_attention_gate(_lib.ptr(y), B, h, w, y.shape[-1], self.num_scale_filters[i], P["gate_w"],
-                                             P["gate_b"], _lib.ptr(lv["pooled"]), _lib.ptr(lv["gate"]), st),
-                       "hvpr_attention_gate")
-            # the SFM chain works on a copy-free side branch: x (the blocks' output) also feeds the next level (:283)
-            xa, ring = x, (cur, lv["c"])
-            for k in range(self.sfm_layer_nums[i]):                                    # :286-290
-                self._conv(P["sfm"][i], xa, B, h, w, ring[k & 1], gate=lv["gate"], residual=xa)
-                xa = ring[k & 1]
+            xa = x
+            if self._WITH_SCALE:
+                self._conv(P["scale"][i], y, B, h, w, lv["y"])                          # :284
+                y = lv["y"]
+                _lib.check(L.hvpr_attention_gate(_lib.ptr(y), B, lv["h"], lv["w"], y.shape[-1], self.num_scale_filters[i],
+                                                 P["gate_w"], P["gate_b"], _lib.ptr(lv["pooled"]), _lib.ptr(lv["gate"]), st),
+                           "hvpr_attention_gate")
+                # the SFM chain works on a copy-free side branch: x (the blocks' output) also feeds the next level (:283)
+                ring = (cur, lv["c"])
+                for k in range(self.sfm_layer_nums[i]):                                # :286-290
+                    self._conv(P["sfm"][i], xa, B, lv["h"], lv["w"], ring[k & 1], gate=lv["gate"], residual=xa)
+                    xa = ring[k & 1]
+            h, w = lv["h"], lv["w"]
             self._conv(P["de"][i], xa, B, h, w, pl["out"], out_mode=1, out_c_off=c_off, out_ctot=self.num_bev_features)  # :293-299
             c_off += self.num_upsample_filters[i]
         return pl["out"]
 
     def forward(self, data_dict):
         if self.training:
-            raise NotImplementedError("hvpr_b200.BaseBEVBackbone_Scale accelerates the eval forward "
-                                      "(base_bev_backbone.py:280-315); training is out of scope")
-        sp, sc = data_dict["spatial_features"], data_dict["spatial_scale_features"]
+            raise NotImplementedError("hvpr_b200 backbones accelerate the eval forward (base_bev_backbone.py:62-102, :280-315); "
+                                      "training is out of scope")
+        sp = data_dict["spatial_features"]
         if not sp.is_cuda:
-            raise _lib.HvprError("BaseBEVBackbone_Scale needs CUDA tensors; there is no CPU path")
+            raise _lib.HvprError("%s needs CUDA tensors; there is no CPU path" % type(self).__name__)
         _lib.init_device()
         B, C, H, W = sp.shape
         pl, L, st = self._plan(B, H, W, sp.device), _lib.lib(), _lib.cur_stream()
-        sp, sc = sp.contiguous().float(), sc.contiguous().float()
+        sp = sp.contiguous().float()
         _lib.check(L.hvpr_nchw_to_nhwc_bf16(_lib.ptr(sp), B, C, H, W, _lib.ptr(pl["x_in"]), pl["x_in"].shape[-1], st), "nchw_to_nhwc")
-        _lib.check(L.hvpr_nchw_to_nhwc_bf16(_lib.ptr(sc), B, sc.shape[1], H, W, _lib.ptr(pl["y_in"]), pl["y_in"].shape[-1], st), "nchw_to_nhwc")
-        data_dict["spatial_features_2d"] = self.run_nhwc(pl["x_in"], pl["y_in"], B, H, W)
+        if self._WITH_SCALE:
+            sc = data_dict["spatial_scale_features"].contiguous().float()
+            _lib.check(L.hvpr_nchw_to_nhwc_bf16(_lib.ptr(sc), B, sc.shape[1], H, W, _lib.ptr(pl["y_in"]), pl["y_in"].shape[-1], st), "nchw_to_nhwc")
+        data_dict["spatial_features_2d"] = self.run_nhwc(pl["x_in"], pl.get("y_in"), B, H, W)
         return data_dict
+
+
+class BaseBEVBackbone(BaseBEVBackbone_Scale):
+    """The plain 2-D backbone (base_bev_backbone.py:6-102): blocks -> deblocks -> concat, same kernels, no scale branch."""
+    _WITH_SCALE = False
+
+
+__all__ = {"BaseBEVBackbone": BaseBEVBackbone, "BaseBEVBackbone_Scale": BaseBEVBackbone_Scale}      # backbones_2d/__init__.py:3-6

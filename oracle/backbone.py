@@ -25,13 +25,19 @@ def _bn(rng, prefix, c, w):
     w[prefix + ".running_var"] = rng.uniform(0.5, 1.5, c).astype(np.float32)
 
 
-def random_backbone_weights(seed: int, cfg=CFG, input_channels: int = 128):
+# the plain backbone as configured for PointPillars (tools/cfgs/kitti_models/pointpillar.yaml BACKBONE_2D)
+PLAIN_CFG = dict(LAYER_NUMS=[3, 5, 5], LAYER_STRIDES=[2, 2, 2], NUM_FILTERS=[64, 128, 256], UPSAMPLE_STRIDES=[1, 2, 4],
+                 NUM_UPSAMPLE_FILTERS=[128, 128, 128])
+
+
+def random_backbone_weights(seed: int, cfg=CFG, input_channels: int = 128, with_scale: bool = True):
     """Reference parameter names/shapes (state_dict of BaseBEVBackbone_Scale).  Conv weights ~ U(+-sqrt(3/fan_in)) keep
     the activation scale ~1 through 7 layers; BN affine and running stats are randomised (default BN is almost identity).
     numpy PCG64 streams are stable across versions, so the GPU box regenerates the same tensors from the seed."""
     rng = np.random.default_rng(seed)
     w = {}
-    nf, nsf = cfg["NUM_FILTERS"], cfg["NUM_SCALE_FILTERS"]
+    nf = cfg["NUM_FILTERS"]
+    nsf = cfg["NUM_SCALE_FILTERS"] if with_scale else [0] * len(nf)
     cin = [input_channels] + nf[:-1]
     cin_s = [input_channels // 4] + nsf[:-1]
 
@@ -45,17 +51,20 @@ def random_backbone_weights(seed: int, cfg=CFG, input_channels: int = 128):
         for k in range(cfg["LAYER_NUMS"][i]):
             conv("blocks.%d.%d.weight" % (i, 4 + 3 * k), nf[i], nf[i], 3, 3)
             _bn(rng, "blocks.%d.%d" % (i, 5 + 3 * k), nf[i], w)
-        conv("sfmblocks_down.%d.0.weight" % i, nf[i], nf[i], 3, 3)
-        _bn(rng, "sfmblocks_down.%d.1" % i, nf[i], w)
+        if with_scale:
+            conv("sfmblocks_down.%d.0.weight" % i, nf[i], nf[i], 3, 3)
+            _bn(rng, "sfmblocks_down.%d.1" % i, nf[i], w)
         s = cfg["UPSAMPLE_STRIDES"][i]
         a = np.sqrt(3.0 / nf[i])
         w["deblocks.%d.0.weight" % i] = rng.uniform(-a, a, (nf[i], cfg["NUM_UPSAMPLE_FILTERS"][i], s, s)).astype(np.float32)
         _bn(rng, "deblocks.%d.1" % i, cfg["NUM_UPSAMPLE_FILTERS"][i], w)
-        conv("scale_layers.%d.1.weight" % i, nsf[i], cin_s[i], 3, 3)
-        _bn(rng, "scale_layers.%d.2" % i, nsf[i], w)
-    w["attention.spatial.conv.weight"] = rng.uniform(-0.5, 0.5, (1, 2, 3, 3)).astype(np.float32)
-    w["attention.spatial.conv.bias"] = rng.uniform(-0.2, 0.2, 1).astype(np.float32)
-    _bn(rng, "attention.spatial.norm", 1, w)
+        if with_scale:
+            conv("scale_layers.%d.1.weight" % i, nsf[i], cin_s[i], 3, 3)
+            _bn(rng, "scale_layers.%d.2" % i, nsf[i], w)
+    if with_scale:
+        w["attention.spatial.conv.weight"] = rng.uniform(-0.5, 0.5, (1, 2, 3, 3)).astype(np.float32)
+        w["attention.spatial.conv.bias"] = rng.uniform(-0.2, 0.2, 1).astype(np.float32)
+        _bn(rng, "attention.spatial.norm", 1, w)
     return w
 
 
@@ -89,9 +98,10 @@ def attention_gate(y, w):
 
 
 def backbone_forward(w, spatial, scale, cfg=CFG, return_levels: bool = False):
-    """base_bev_backbone.py:280-315 (eval branch).  spatial (B,128,H,W), scale (B,32,H,W) fp32 -> (B,384,H,W)."""
+    """base_bev_backbone.py:280-315 (eval branch).  spatial (B,128,H,W), scale (B,32,H,W) fp32 -> (B,384,H,W).
+    scale=None: the plain BaseBEVBackbone.forward (:62-102) — no scale branch, no SFM loop."""
     x = torch.from_numpy(np.asarray(spatial)).float()
-    y = torch.from_numpy(np.asarray(scale)).float()
+    y = torch.from_numpy(np.asarray(scale)).float() if scale is not None else None
     ups, levels = [], []
     with torch.no_grad():
         for i in range(len(cfg["NUM_FILTERS"])):
@@ -99,11 +109,12 @@ def backbone_forward(w, spatial, scale, cfg=CFG, return_levels: bool = False):
             x = _conv_bn_relu(x, w, "blocks.%d.1.weight" % i, "blocks.%d.2" % i, s)               # :283, layers :152-165
             for k in range(cfg["LAYER_NUMS"][i]):
                 x = _conv_bn_relu(x, w, "blocks.%d.%d.weight" % (i, 4 + 3 * k), "blocks.%d.%d" % (i, 5 + 3 * k), 1)
-            y = _conv_bn_relu(y, w, "scale_layers.%d.1.weight" % i, "scale_layers.%d.2" % i, s)   # :284, layers :204-213
-            gate = attention_gate(y, w)
             xa = x
-            for _ in range(cfg["SFM_LAYER_NUMS"][i]):                                            # :286-290
-                xa = gate * _conv_bn_relu(xa, w, "sfmblocks_down.%d.0.weight" % i, "sfmblocks_down.%d.1" % i, 1) + xa
+            if y is not None:
+                y = _conv_bn_relu(y, w, "scale_layers.%d.1.weight" % i, "scale_layers.%d.2" % i, s)   # :284, layers :204-213
+                gate = attention_gate(y, w)
+                for _ in range(cfg["SFM_LAYER_NUMS"][i]):                                            # :286-290
+                    xa = gate * _conv_bn_relu(xa, w, "sfmblocks_down.%d.0.weight" % i, "sfmblocks_down.%d.1" % i, 1) + xa
             levels.append(xa)
             us = cfg["UPSAMPLE_STRIDES"][i]
             u = F.conv_transpose2d(xa, _t(w, "deblocks.%d.0.weight" % i), stride=us)             # :293-294, layers :180-188

@@ -330,3 +330,22 @@ def test_full_size_backbone_is_invariant_to_the_kernel_policy():
     assert float(auto.abs().max()) > 0.1
     e = rel_err(auto, plain)
     assert e[0] <= 2.0 ** -7 and e[1] <= 1e-3, e
+
+
+def test_plain_backbone_matches_reference_golden():
+    """The plain BaseBEVBackbone (PointPillars layout: 64 channels in, every level stride 2) on the same kernels vs the
+    reference module's output; exercises a stride-2 first level and deblocks that land on half the input resolution."""
+    from hvpr_b200.backbone import BaseBEVBackbone
+    from hvpr_b200.config import Cfg
+    from oracle import backbone as ob
+    z = np.load(os.path.join(GOLDEN, "backbone_plain_tiny.npz"))
+    w = ob.random_backbone_weights(int(z["wseed"]), ob.PLAIN_CFG, 64, with_scale=False)
+    m = BaseBEVBackbone(Cfg(NAME="BaseBEVBackbone", **ob.PLAIN_CFG), 64).cuda().eval()
+    r = m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=False)
+    assert not r.unexpected_keys and all(k.endswith("num_batches_tracked") for k in r.missing_keys)
+    with torch.no_grad():
+        out = m({"spatial_features": torch.from_numpy(z["spatial_features"]).cuda()})["spatial_features_2d"]
+    ref = torch.from_numpy(z["spatial_features_2d"])
+    assert tuple(out.shape) == tuple(ref.shape)
+    e = rel_err(out, ref)
+    assert e[0] <= TOL_BACKBONE and e[1] <= TOL_BACKBONE_L2, e

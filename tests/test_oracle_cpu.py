@@ -185,3 +185,13 @@ def test_backbone_oracle_matches_reference_module_when_tree_present():
         ref = m({"spatial_features": torch.from_numpy(spatial), "spatial_scale_features": torch.from_numpy(scale)})
     out = ob.backbone_forward(w, spatial, scale)
     assert np.abs(out - ref["spatial_features_2d"].numpy()).max() <= 1e-5 * np.abs(out).max()
+
+
+def test_plain_backbone_oracle_matches_reference_golden():
+    """oracle/backbone.py (scale=None) vs the reference's own BaseBEVBackbone output (tests/golden/backbone_plain_tiny.npz)."""
+    from oracle import backbone as ob
+    z = np.load(os.path.join(GOLDEN, "backbone_plain_tiny.npz"))
+    w = ob.random_backbone_weights(int(z["wseed"]), ob.PLAIN_CFG, 64, with_scale=False)
+    out = ob.backbone_forward(w, z["spatial_features"], None, ob.PLAIN_CFG)
+    ref = z["spatial_features_2d"]
+    assert out.shape == ref.shape and np.abs(out - ref).max() <= 1e-5 * np.abs(ref).max()
