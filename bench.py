@@ -228,6 +228,39 @@ def bench_backbone(geom, w, host_pts, host_off, B, N, dev, mem_precision, steps=
            "gpu_launches_per_batch": pipe.kernel_launches_per_run() - 10,
            "points_to_spatial_features_2d": {"ms_per_batch": ms_pipe, "frames_per_sec": B / (ms_pipe * 1e-3),
                                              "gpu_launches_per_batch": pipe.kernel_launches_per_run()}}
+    # library baseline on the same box: the same network through torch's own layers (cuDNN, bf16 channels_last, eager).
+    # The module's nn.Sequential parameter containers are ordinary torch layers, so they can simply be called.
+    try:
+        torch.backends.cudnn.benchmark = True
+        mb = bb.to(memory_format=torch.channels_last).bfloat16()
+        xc = p.x_nhwc[..., :128].permute(0, 3, 1, 2)
+        yc = p.y_nhwc[..., :32].permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
+
+        def cudnn_forward():
+            x, y, ups, a = xc, yc, [], mb.attention.spatial
+            for i in range(len(mb.blocks)):
+                x = mb.blocks[i](x)
+                y = mb.scale_layers[i](y)
+                gate = torch.sigmoid(a.norm(a.conv(torch.cat((y.max(1, keepdim=True)[0], y.mean(1, keepdim=True)), 1))))
+                xa = x
+                for _ in range(mb.sfm_layer_nums[i]):
+                    xa = gate * mb.sfmblocks_down[i](xa) + xa
+                ups.append(mb.deblocks[i](xa))
+            return torch.cat(ups, 1)
+        with torch.no_grad():
+            for _ in range(2):
+                cudnn_forward()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                cudnn_forward()
+            e1.record()
+            torch.cuda.synchronize()
+        tc = e0.elapsed_time(e1) / 5
+        out["library_baseline"] = {"what": "same network via cuDNN (torch eager, bf16 channels_last, cudnn.benchmark), bf16 output",
+                                   "ms_per_batch": tc, "tflops": fl / (tc * 1e-3) / 1e12, "speedup": tc / t}
+    except Exception as e:
+        out["library_baseline"] = {"error": repr(e)[:200]}
     del pipe, p, flush
     torch.cuda.empty_cache()
     return out

@@ -44,7 +44,7 @@ constexpr int kCvMaxN = 2048;                // GEMM columns (bias staged in sha
 
 struct ConvParams {
     alignas(64) CUtensorMap tmap[4];
-    alignas(64) CUtensorMap tmap_w;       // CTA-pair kernel: the packed weight image viewed as [rows][64] bf16 (no TMA swizzle)
+    alignas(64) CUtensorMap tmap_w;       // the packed (pre-swizzled) weight image viewed as [rows][64] bf16, copied verbatim
     const uint8_t *wpk;
     const float *bias;
     const float *gate;
