@@ -3,11 +3,11 @@ sys.path.insert(0,'.')
 from hvpr_b200 import _lib
 _lib.LIB_PATH = _lib.LIB_PATH.replace("libhvpr_b200.so","libhvpr_b200_prof.so")
 _lib.init_device(); L=_lib.lib()
-from oracle import hybrid
+from hvpr_b200 import synth as hybrid_syn
 from hvpr_b200 import synth
 from hvpr_b200.geometry import G2
 from hvpr_b200.frontend import HybridFrontEnd
-w = hybrid.random_weights(0)
+w = hybrid_syn.random_frontend_weights(0)
 fe = HybridFrontEnd(G2, mem_precision="fp32").load_reference_weights(w)
 B,N=8,120000
 frames = synth.make_batch("L", N, G2.point_cloud_range, B)
