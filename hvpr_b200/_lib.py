@@ -19,7 +19,7 @@ SYMBOLS = [
     "hvpr_mem_attn_workspace_bytes", "hvpr_mem_pack_bf16", "hvpr_mem_attn",
     "hvpr_bev_fill", "hvpr_build_cell_map",
     "hvpr_conv_packed_bytes", "hvpr_conv_pack_weights", "hvpr_conv2d", "hvpr_nchw_to_nhwc_bf16", "hvpr_attention_gate",
-    "hvpr_bev_fill_nhwc_bf16",
+    "hvpr_bev_fill_nhwc_bf16", "hvpr_head_decode",
 ]
 
 OVERFLOW = {"continue": 0, "break": 1}
@@ -109,6 +109,9 @@ def lib():
     L.hvpr_bev_fill_nhwc_bf16.restype = c_int
     L.hvpr_bev_fill_nhwc_bf16.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                           c_void_p, c_int, c_void_p, c_int, c_void_p]
+    L.hvpr_head_decode.restype = c_int
+    L.hvpr_head_decode.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                   c_float, c_float, c_void_p, c_void_p, c_void_p]
     L.hvpr_nchw_to_nhwc_bf16.restype = c_int
     L.hvpr_nchw_to_nhwc_bf16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]
     L.hvpr_attention_gate.restype = c_int

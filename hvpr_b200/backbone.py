@@ -212,7 +212,7 @@ class BaseBEVBackbone_Scale(nn.Module):
         a.residual = residual.data_ptr() if residual is not None else None
         a.res_cs = residual.shape[-1] if residual is not None else 0
         a.out_mode, a.out = out_mode, dst.data_ptr()
-        a.out_cs = dst.shape[-1] if out_mode == 0 else 0
+        a.out_cs = dst.shape[-1] if out_mode in (0, 2) else 0
         a.out_c_off, a.up, a.c_out, a.out_ctot = out_c_off, lay.up, lay.c_out, out_ctot
         _lib.check(_lib.lib().hvpr_conv2d(ctypes.byref(a), _lib.cur_stream()), "hvpr_conv2d")
 

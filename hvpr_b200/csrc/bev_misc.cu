@@ -97,3 +97,61 @@ extern "C" int hvpr_attention_gate(const void *y_nhwc_bf16, int n, int h, int w,
     HVPR_CHECK_LAUNCH();
     return HVPR_OK;
 }
+
+// ---- N2: AnchorHeadSingle eval — generate_predicted_boxes (pcdet/models/dense_heads/anchor_head_template.py:293-340)
+// with ResidualCoder.decode_torch (pcdet/utils/box_coder_utils.py:45-77) and the direction-classifier fix-up
+// (common_utils.limit_period, pcdet/utils/common_utils.py:20-23).  One thread per (frame, pixel, anchor); the three 1x1 head
+// convolutions ran as ONE tcgen05 GEMM whose fp32 NHWC output row holds [cls A*C | box A*7 | dir A*bins | pad].
+// Separately rounded mul/add (no FMA contraction), as the torch expression evaluates them.
+namespace hvpr {
+__global__ void __launch_bounds__(256) head_decode_kernel(const float *__restrict__ head, int cs, const float *__restrict__ anchors,
+                                                          int64_t hw, int n_batch, int A, int C, int cls_off, int box_off, int dir_off,
+                                                          int bins, float dir_offset, float dir_limit_offset, float period,
+                                                          float *__restrict__ cls_out, float *__restrict__ box_out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)n_batch * hw * A;
+    if (i >= total) return;
+    const int a = (int)(i % A);
+    const int64_t bp = i / A;                 // frame * hw + pixel
+    const int64_t pix = bp % hw;
+    const float *src = head + bp * cs;
+    for (int c = 0; c < C; ++c) cls_out[i * C + c] = src[cls_off + a * C + c];
+    const float *t = src + box_off + a * 7;
+    const float *an = anchors + (pix * A + a) * 7;
+    const float xa = an[0], ya = an[1], za = an[2], dxa = an[3], dya = an[4], dza = an[5], ra = an[6];
+    const float diag = sqrtf(__fadd_rn(__fmul_rn(dxa, dxa), __fmul_rn(dya, dya)));
+    float *o = box_out + i * 7;
+    o[0] = __fadd_rn(__fmul_rn(t[0], diag), xa);
+    o[1] = __fadd_rn(__fmul_rn(t[1], diag), ya);
+    o[2] = __fadd_rn(__fmul_rn(t[2], dza), za);
+    o[3] = __fmul_rn(expf(t[3]), dxa);
+    o[4] = __fmul_rn(expf(t[4]), dya);
+    o[5] = __fmul_rn(expf(t[5]), dza);
+    float rg = __fadd_rn(t[6], ra);
+    if (dir_off >= 0) {
+        const float *d = src + dir_off + a * bins;
+        int label = 0;
+        float best = d[0];
+        for (int b = 1; b < bins; ++b) if (d[b] > best) { best = d[b]; label = b; }       // torch.max: first maximum wins
+        const float val = __fsub_rn(rg, dir_offset);
+        const float rot = __fsub_rn(val, __fmul_rn(floorf(__fadd_rn(__fdiv_rn(val, period), dir_limit_offset)), period));
+        rg = __fadd_rn(__fadd_rn(rot, dir_offset), __fmul_rn(period, (float)label));
+    }
+    o[6] = rg;
+}
+}  // namespace hvpr
+
+extern "C" int hvpr_head_decode(const float *head_nhwc, int n, int h, int w, int cs, int A, int C, int cls_off, int box_off,
+                                int dir_off, int num_dir_bins, const float *anchors, float dir_offset, float dir_limit_offset,
+                                float *cls_out, float *box_out, void *stream) {
+    if (!head_nhwc || !anchors || !cls_out || !box_out || n <= 0 || h <= 0 || w <= 0 || A <= 0 || C <= 0) return HVPR_ERR_ARG;
+    if (cls_off < 0 || box_off < 0 || cls_off + A * C > cs || box_off + A * 7 > cs) return HVPR_ERR_ARG;
+    if (dir_off >= 0 && (num_dir_bins < 1 || dir_off + A * num_dir_bins > cs)) return HVPR_ERR_ARG;
+    const int64_t total = (int64_t)n * h * w * A;
+    const float period = (float)(2.0 * 3.14159265358979323846 / (double)(num_dir_bins > 0 ? num_dir_bins : 1));
+    hvpr::head_decode_kernel<<<(unsigned)hvpr::ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        head_nhwc, cs, anchors, (int64_t)h * w, n, A, C, cls_off, box_off, dir_off, num_dir_bins, dir_offset, dir_limit_offset, period,
+        cls_out, box_out);
+    HVPR_CHECK_LAUNCH();
+    return HVPR_OK;
+}

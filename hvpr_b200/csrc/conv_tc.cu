@@ -175,6 +175,11 @@ __device__ __forceinline__ void cv_epilogue_chunk(const ConvParams &P, const CvT
                     for (int j = 0; j < 4; ++j)
                         op[j] = make_uint4(cv_pack_bf16(v[8 * j], v[8 * j + 1]), cv_pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                                            cv_pack_bf16(v[8 * j + 4], v[8 * j + 5]), cv_pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                } else if (valid && P.out_mode == 2) {
+                    // fp32 NHWC (dense-head logits / box deltas must not be rounded to bf16)
+                    float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(P.out) + pix * P.out_cs + P.out_c_off + col0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 } else if (valid) {
                     // pixel shuffle of the transposed conv: GEMM column = (dy*cout + co)*up + dx  ->  fp32 NCHW slice.
                     // dx is the fastest column index, so a thread owns `up` horizontally adjacent output pixels of each
@@ -671,8 +676,9 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
     P.out_mode = a->out_mode;
     P.out_cs = a->out_cs;
     P.out_c_off = a->out_c_off;
-    if (a->out_mode == 0) {
+    if (a->out_mode == 0 || a->out_mode == 2) {
         if (a->out_cs % 8 || a->out_c_off % 8 || a->out_c_off + a->n_total > a->out_cs) return HVPR_ERR_ARG;
+        if (a->out_mode == 2 && (a->residual || a->gate)) return HVPR_ERR_ARG;
         if (a->residual && (a->res_cs % 8 || a->res_cs < a->n_total)) return HVPR_ERR_ARG;
     } else if (a->out_mode == 1) {
         if (a->up != 1 && a->up != 2 && a->up != 4) return HVPR_ERR_UNSUPPORTED;

@@ -156,7 +156,8 @@ typedef struct HvprConvArgs {
     int32_t out_mode;        /* 0: bf16 NHWC (n, h_out, w_out, out_cs), channels [out_c_off, out_c_off + n_total)
                                 1: ConvTranspose2d(k = up, stride = up) pixel shuffle into fp32 NCHW
                                    (n, out_ctot, h_out*up, w_out*up), channels [out_c_off, out_c_off + c_out);
-                                   GEMM column = (dy*c_out + co)*up + dx                                          */
+                                   GEMM column = (dy*c_out + co)*up + dx
+                                2: fp32 NHWC (n, h_out, w_out, out_cs), channels [out_c_off, out_c_off + n_total) (no gate / residual) */
     void *out;
     int32_t out_cs, out_c_off;
     int32_t up, c_out, out_ctot;
@@ -179,6 +180,16 @@ int hvpr_nchw_to_nhwc_bf16(const float *in, int n, int c, int h, int w, void *ou
  * bias = folded scalar; pooled_ws: (n*h*w*2) fp32 scratch; gate_out: (n,h,w) fp32.                                 */
 int hvpr_attention_gate(const void *y_nhwc_bf16, int n, int h, int w, int cs, int c, const float *w18_host, float bias,
                         float *pooled_ws, float *gate_out, void *stream);
+
+/* ==== N2: AnchorHeadSingle eval (anchor_head_single.py:109-145) ======================================================
+ * The three 1x1 head convolutions run as one hvpr_conv2d (out_mode 2) whose fp32 NHWC rows hold
+ * [cls A*C | box A*7 | dir A*bins | pad] at channel offsets cls_off / box_off / dir_off (dir_off < 0: no direction classifier).
+ * hvpr_head_decode = generate_predicted_boxes (anchor_head_template.py:293-340): ResidualCoder.decode_torch against
+ * anchors (h*w*A, 7) [x,y,z,dx,dy,dz,r] and the direction fix-up rg = limit_period(rg - dir_offset, dir_limit_offset,
+ * 2*pi/bins) + dir_offset + 2*pi/bins * argmax(dir).  cls_out (n, h*w*A, C) raw logits; box_out (n, h*w*A, 7).       */
+int hvpr_head_decode(const float *head_nhwc, int n, int h, int w, int cs, int A, int C, int cls_off, int box_off,
+                     int dir_off, int num_dir_bins, const float *anchors, float dir_offset, float dir_limit_offset,
+                     float *cls_out, float *box_out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -230,3 +230,20 @@ def test_backbone_bn_folding_matches_oracle_layer():
     got = F.conv2d(x.double(), cw * s[:, None, None, None], shift, stride=2, padding=1)
     ref = ob._conv_bn_relu(x, w, "blocks.1.1.weight", "blocks.1.2", 2, relu=False)
     assert float((got - ref.double()).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+def test_dense_head_module_names_anchors_and_loud_failures():
+    from hvpr_b200.dense_head import AnchorHeadSingle, build_anchors
+    from oracle import dense_head as od
+    rng = [0, -39.68, -3, 69.12, 39.68, 1]
+    m = AnchorHeadSingle(config.Cfg(**od.HEAD_CFG), 384, 1, ["Car"], [48, 40, 1], rng)
+    w = od.random_head_weights(0)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: v.shape for k, v in w.items()}
+    assert m.num_anchors_per_location == 2 and m._layout() == (0, 2, 16, 32)
+    assert torch.equal(build_anchors(od.HEAD_CFG["ANCHOR_GENERATOR_CONFIG"], [48, 40, 1], rng, "cpu"),
+                       od.generate_anchors(od.HEAD_CFG, (48, 40, 1), rng))
+    with pytest.raises(_lib.HvprError):
+        m.eval()({"spatial_features_2d": torch.zeros(1, 384, 40, 48)})
+    with pytest.raises(NotImplementedError):
+        m.train()({"spatial_features_2d": torch.zeros(1, 384, 40, 48)})
+    assert _lib.lib().hvpr_head_decode(None, 1, 1, 1, 32, 2, 1, 0, 2, 16, 2, None, 0.0, 0.0, None, None, None) == -1

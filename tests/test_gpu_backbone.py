@@ -349,3 +349,55 @@ def test_plain_backbone_matches_reference_golden():
     assert tuple(out.shape) == tuple(ref.shape)
     e = rel_err(out, ref)
     assert e[0] <= TOL_BACKBONE and e[1] <= TOL_BACKBONE_L2, e
+
+
+# ---- row N2: AnchorHeadSingle -------------------------------------------------------------------------------------------------
+def _head(seed, grid, rng):
+    from hvpr_b200.config import Cfg
+    from hvpr_b200.dense_head import AnchorHeadSingle
+    from oracle import dense_head as od
+    m = AnchorHeadSingle(Cfg(**od.HEAD_CFG), 384, 1, ["Car"], list(grid), rng).cuda().eval()
+    w = od.random_head_weights(seed)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+    return m, w
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 20, 24), (1, 37, 50)])
+def test_dense_head_matches_oracle(B, H, W):
+    """conv_cls / conv_box / conv_dir_cls as one tcgen05 GEMM + decode vs the oracle (whose decode / anchors / limit_period are the
+    reference's own functions).  The GEMM operands are bf16 (fp32 accumulate, fp32 output): logits and box deltas carry ~2^-8 of
+    their scale, so boxes are compared with an absolute tolerance of 2e-2 of the anchor diagonal / size, and anchors whose two
+    direction logits are closer than 0.05 are excluded from the heading check (the argmax may legitimately flip there)."""
+    from oracle import dense_head as od
+    rng = [0, -39.68, -3, 69.12, 39.68, 1]
+    m, w = _head(7, (W, H, 1), rng)
+    x = np.abs(np.random.default_rng(8).standard_normal((B, 384, H, W))).astype(np.float32) * (np.random.default_rng(9).random((B, 1, H, W)) < 0.6)
+    x = x.astype(np.float32)
+    cls_ref, box_ref, (_, _, dir_raw) = od.head_forward(w, x, od.HEAD_CFG, (W, H, 1), rng, return_raw=True)
+    with torch.no_grad():
+        out = m({"spatial_features_2d": torch.from_numpy(x).cuda()})
+    torch.cuda.synchronize()
+    cls, box = out["batch_cls_preds"].cpu().numpy(), out["batch_box_preds"].cpu().numpy()
+    assert cls.shape == cls_ref.shape and box.shape == box_ref.shape and out["cls_preds_normalized"] is False
+    assert np.abs(cls - cls_ref).max() <= 2e-2 * max(1.0, np.abs(cls_ref).max())
+    diag = float(np.sqrt(3.9 ** 2 + 1.6 ** 2))
+    assert np.abs(box[..., :2] - box_ref[..., :2]).max() <= 2e-2 * diag
+    assert np.abs(box[..., 2] - box_ref[..., 2]).max() <= 2e-2 * 1.56
+    assert np.abs(box[..., 3:6] / box_ref[..., 3:6] - 1).max() <= 2e-2
+    d = dir_raw.reshape(B, -1, 2)
+    clear = np.abs(d[..., 0] - d[..., 1]) > 0.05
+    dr = np.abs(box[..., 6] - box_ref[..., 6])[clear]
+    dr = np.minimum(dr, np.abs(dr - np.pi))          # a heading within 2e-2 of a period boundary may wrap by one period (pi)
+    assert dr.max() <= 2e-2 and clear.mean() > 0.8
+
+
+def test_dense_head_rejects_the_shipped_anchor_stride_mismatch():
+    """hvpr.yaml puts anchors on a stride-2 map under a full-resolution backbone (B10): fail loudly instead of mis-indexing."""
+    from hvpr_b200 import _lib
+    from hvpr_b200.config import Cfg
+    from hvpr_b200.dense_head import AnchorHeadSingle
+    from oracle import dense_head as od
+    cfg = dict(od.HEAD_CFG, ANCHOR_GENERATOR_CONFIG=[dict(od.HEAD_CFG["ANCHOR_GENERATOR_CONFIG"][0], feature_map_stride=2)])
+    m = AnchorHeadSingle(Cfg(**cfg), 384, 1, ["Car"], [48, 40, 1], [0, -39.68, -3, 69.12, 39.68, 1]).cuda().eval()
+    with pytest.raises(_lib.HvprError):
+        m({"spatial_features_2d": torch.zeros(1, 384, 40, 48, device="cuda")})

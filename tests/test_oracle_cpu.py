@@ -195,3 +195,46 @@ def test_plain_backbone_oracle_matches_reference_golden():
     out = ob.backbone_forward(w, z["spatial_features"], None, ob.PLAIN_CFG)
     ref = z["spatial_features_2d"]
     assert out.shape == ref.shape and np.abs(out - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+# ---- row N2: AnchorHeadSingle restatement pinned piecewise on the reference's own functions ---------------------------------
+def test_dense_head_oracle_pieces_match_the_reference_functions():
+    from oracle import dense_head as od
+    if not ref_loader.available():
+        pytest.skip("reference tree not present")
+    ns = od.load_reference_pieces()
+
+    class C(dict):
+        __getattr__ = dict.__getitem__
+    rng = [0, -39.68, -3, 69.12, 39.68, 1]
+    for stride_cfg, grid in ((od.HEAD_CFG, (48, 40, 1)), (dict(od.HEAD_CFG, ANCHOR_GENERATOR_CONFIG=[dict(
+            od.HEAD_CFG["ANCHOR_GENERATOR_CONFIG"][0], anchor_sizes=[[3.9, 1.6, 1.56], [0.8, 0.6, 1.73]], align_center=True)]), (36, 28, 1))):
+        g = ns.AnchorGenerator(anchor_range=rng, anchor_generator_config=[C(stride_cfg["ANCHOR_GENERATOR_CONFIG"][0])])
+        ref, per_loc = g.generate_anchors([np.array(grid[:2])])
+        mine = od.generate_anchors(stride_cfg, grid, rng)
+        assert per_loc == [mine.shape[2]] and torch.equal(ref[0].reshape(-1, 7), mine.reshape(-1, 7))
+    an = od.generate_anchors(od.HEAD_CFG, (48, 40, 1), rng).reshape(-1, 7)[:500][None].repeat(2, 1, 1)
+    be = torch.randn(2, 500, 7, generator=torch.Generator().manual_seed(1)) * 0.4
+    assert torch.equal(ns.ResidualCoder().decode_torch(be, an), od.decode(be, an))
+    v = torch.randn(4096, generator=torch.Generator().manual_seed(2)) * 6
+    for off, per in ((0.0, np.pi), (0.5, 2 * np.pi), (0.0, 2 * np.pi / 2)):
+        assert torch.equal(ns.limit_period(v, off, per), od.limit_period(v, off, per))
+
+
+def test_dense_head_oracle_assembly_is_self_consistent():
+    """generate_predicted_boxes restated: shapes, anchor ordering (pixel-major, then size, then rotation) and the direction fix-up."""
+    from oracle import dense_head as od
+    rng = [0, -39.68, -3, 69.12, 39.68, 1]
+    w = od.random_head_weights(3)
+    x = np.abs(np.random.default_rng(4).standard_normal((2, 384, 20, 24))).astype(np.float32)
+    cls, box, (cls_raw, box_raw, dir_raw) = od.head_forward(w, x, od.HEAD_CFG, (24, 20, 1), rng, return_raw=True)
+    assert cls.shape == (2, 20 * 24 * 2, 1) and box.shape == (2, 20 * 24 * 2, 7)
+    an = od.generate_anchors(od.HEAD_CFG, (24, 20, 1), rng)
+    # anchor (y=3, x=5, a=1) sits at flat index ((3*24+5)*2+1); its decoded centre moves by delta * diagonal
+    i = (3 * 24 + 5) * 2 + 1
+    diag = float(torch.sqrt(an[3, 5, 1, 3] ** 2 + an[3, 5, 1, 4] ** 2))
+    assert abs(box[0, i, 0] - (box_raw[0, 3, 5, 7 + 0] * diag + float(an[3, 5, 1, 0]))) < 1e-5
+    period = np.pi
+    rot = box[..., 6] - od.HEAD_CFG["DIR_OFFSET"]
+    lab = dir_raw.reshape(2, -1, 2).argmax(-1)
+    assert np.all((rot - period * lab > -1e-4) & (rot - period * lab < period + 1e-4))      # limit_period range + label shift
