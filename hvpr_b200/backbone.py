@@ -140,7 +140,7 @@ class BaseBEVBackbone_Scale(nn.Module):
         if self._packed is not None and self._packed_key == key:
             return self._packed
         _lib.init_device()
-        P = {"blocks": [], "sfm": [], "scale": [], "de": []}
+        P = {"blocks": [], "sfm": [], "scale": [], "de": [], "de_nhwc": []}
         for i in range(len(self.num_filters)):
             seq = self.blocks[i]
             convs = []
@@ -161,6 +161,11 @@ class BaseBEVBackbone_Scale(nn.Module):
             de = self._pack(wn, shift.float().repeat_interleave(u).repeat(u).to(dev), u * u * co, 1, ci, 1, dev)
             de.up, de.c_out = u, co
             P["de"].append(de)
+            # channels-last variant (out_mode 3, for a native consumer of bf16 NHWC features): column (dy*s + dx)*Cout + co
+            wn = (w * s[None, :, None, None]).permute(2, 3, 1, 0).reshape(u * u * co, 1, ci).float().to(dev)
+            de2 = self._pack(wn, shift.float().repeat(u * u).to(dev), u * u * co, 1, ci, 1, dev)
+            de2.up, de2.c_out = u, co
+            P["de_nhwc"].append(de2)
         if self._WITH_SCALE:
             a = self.attention.spatial
             w, s, shift = _fold(a.conv.weight, a.norm, a.conv.bias)
@@ -212,13 +217,14 @@ class BaseBEVBackbone_Scale(nn.Module):
         a.residual = residual.data_ptr() if residual is not None else None
         a.res_cs = residual.shape[-1] if residual is not None else 0
         a.out_mode, a.out = out_mode, dst.data_ptr()
-        a.out_cs = dst.shape[-1] if out_mode in (0, 2) else 0
+        a.out_cs = dst.shape[-1] if out_mode in (0, 2, 3) else 0
         a.out_c_off, a.up, a.c_out, a.out_ctot = out_c_off, lay.up, lay.c_out, out_ctot
         _lib.check(_lib.lib().hvpr_conv2d(ctypes.byref(a), _lib.cur_stream()), "hvpr_conv2d")
 
     # ------------------------------------------------------------------------------------------ forward
-    def run_nhwc(self, x_in, y_in, B, H, W):
-        """x_in (B,H,W,>=C) / y_in (B,H,W,>=C/4) NHWC bf16 (zero pad channels) -> spatial_features_2d (B,384,H,W) fp32."""
+    def run_nhwc(self, x_in, y_in, B, H, W, out_nhwc=None):
+        """x_in (B,H,W,>=C) / y_in (B,H,W,>=C/4) NHWC bf16 (zero pad channels) -> spatial_features_2d (B,384,H,W) fp32, or — when
+        `out_nhwc` (B,Ho,Wo,>=384) bf16 is given — the same features channels-last for a native consumer (the dense head)."""
         dev = x_in.device
         P, pl, L = self._ensure_packed(dev), self._plan(B, H, W, dev), _lib.lib()
         st = _lib.cur_stream()
@@ -243,9 +249,12 @@ class BaseBEVBackbone_Scale(nn.Module):
                     self._conv(P["sfm"][i], xa, B, lv["h"], lv["w"], ring[k & 1], gate=lv["gate"], residual=xa)
                     xa = ring[k & 1]
             h, w = lv["h"], lv["w"]
-            self._conv(P["de"][i], xa, B, h, w, pl["out"], out_mode=1, out_c_off=c_off, out_ctot=self.num_bev_features)  # :293-299
+            if out_nhwc is None:
+                self._conv(P["de"][i], xa, B, h, w, pl["out"], out_mode=1, out_c_off=c_off, out_ctot=self.num_bev_features)  # :293-299
+            else:
+                self._conv(P["de_nhwc"][i], xa, B, h, w, out_nhwc, out_mode=3, out_c_off=c_off)
             c_off += self.num_upsample_filters[i]
-        return pl["out"]
+        return pl["out"] if out_nhwc is None else out_nhwc
 
     def forward(self, data_dict):
         if self.training:

@@ -175,6 +175,16 @@ __device__ __forceinline__ void cv_epilogue_chunk(const ConvParams &P, const CvT
                     for (int j = 0; j < 4; ++j)
                         op[j] = make_uint4(cv_pack_bf16(v[8 * j], v[8 * j + 1]), cv_pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                                            cv_pack_bf16(v[8 * j + 4], v[8 * j + 5]), cv_pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                } else if (valid && P.out_mode == 3) {
+                    // transposed conv, channels-last: GEMM column = (dy*up + dx)*cout + co, so a 32-column chunk is 32 consecutive
+                    // channels of ONE output pixel (y*up + dy, x*up + dx) -> 64 contiguous bytes of the bf16 NHWC tensor
+                    const int sub = col0 / P.cout, co0 = col0 % P.cout;
+                    const int64_t opix = ((int64_t)t.img * P.out_h + (y * P.up + sub / P.up)) * P.out_w + (x * P.up + sub % P.up);
+                    uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(P.out) + opix * P.out_cs + P.out_c_off + co0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        op[j] = make_uint4(cv_pack_bf16(v[8 * j], v[8 * j + 1]), cv_pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                           cv_pack_bf16(v[8 * j + 4], v[8 * j + 5]), cv_pack_bf16(v[8 * j + 6], v[8 * j + 7]));
                 } else if (valid && P.out_mode == 2) {
                     // fp32 NHWC (dense-head logits / box deltas must not be rounded to bf16)
                     float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(P.out) + pix * P.out_cs + P.out_c_off + col0);
@@ -680,10 +690,11 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
         if (a->out_cs % 8 || a->out_c_off % 8 || a->out_c_off + a->n_total > a->out_cs) return HVPR_ERR_ARG;
         if (a->out_mode == 2 && (a->residual || a->gate)) return HVPR_ERR_ARG;
         if (a->residual && (a->res_cs % 8 || a->res_cs < a->n_total)) return HVPR_ERR_ARG;
-    } else if (a->out_mode == 1) {
+    } else if (a->out_mode == 1 || a->out_mode == 3) {
+        if (a->out_mode == 3 && (a->out_cs % 8 || a->out_c_off % 8 || a->out_c_off + a->c_out > a->out_cs)) return HVPR_ERR_ARG;
         if (a->up != 1 && a->up != 2 && a->up != 4) return HVPR_ERR_UNSUPPORTED;
         if (a->c_out <= 0 || a->c_out % 32 || a->n_total != a->up * a->up * a->c_out) return HVPR_ERR_ARG;
-        if (a->out_c_off + a->c_out > a->out_ctot || a->residual || a->gate) return HVPR_ERR_ARG;
+        if ((a->out_mode == 1 && a->out_c_off + a->c_out > a->out_ctot) || a->residual || a->gate) return HVPR_ERR_ARG;
         P.up = a->up; P.cout = a->c_out; P.out_ctot = a->out_ctot;
         P.out_h = P.h_out * a->up; P.out_w = P.w_out * a->up;
     } else return HVPR_ERR_ARG;

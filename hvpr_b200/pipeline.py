@@ -12,6 +12,7 @@ import torch
 from . import _lib
 from .backbone import BaseBEVBackbone_Scale
 from .config import Cfg
+from .dense_head import AnchorHeadSingle
 from .frontend import HybridFrontEnd
 
 # tools/cfgs/kitti_models/hvpr.yaml:87-95
@@ -20,11 +21,25 @@ HVPR_BACKBONE_CFG = Cfg(NAME="BaseBEVBackbone_Scale", LAYER_NUMS=[3, 3, 3], SFM_
                         NUM_UPSAMPLE_FILTERS=[128, 128, 128])
 
 
+# tools/cfgs/kitti_models/hvpr.yaml:96-118, with feature_map_stride 1: the backbone emits full-resolution features and the shipped
+# stride 2 cannot be reshaped onto them (breakage B10)
+HVPR_HEAD_CFG = Cfg(NAME="AnchorHeadSingle", CLASS_AGNOSTIC=False, USE_DIRECTION_CLASSIFIER=True, DIR_OFFSET=0.78539,
+                    DIR_LIMIT_OFFSET=0.0, NUM_DIR_BINS=2,
+                    ANCHOR_GENERATOR_CONFIG=[dict(class_name="Car", anchor_sizes=[[3.9, 1.6, 1.56]], anchor_rotations=[0, 1.57],
+                                                  anchor_bottom_heights=[-1.78], align_center=False, feature_map_stride=1,
+                                                  matched_threshold=0.6, unmatched_threshold=0.45)])
+
+
 class FrontEndWithBackbone(torch.nn.Module):
-    def __init__(self, geom, backbone_cfg=HVPR_BACKBONE_CFG, device="cuda", **frontend_kwargs):
+    def __init__(self, geom, backbone_cfg=HVPR_BACKBONE_CFG, device="cuda", head_cfg=None, **frontend_kwargs):
         super().__init__()
         self.frontend = HybridFrontEnd(geom, device=device, **frontend_kwargs) if frontend_kwargs else HybridFrontEnd(geom, device=device)
         self.backbone_2d = BaseBEVBackbone_Scale(backbone_cfg, self.frontend.map_to_bev_module.num_bev_features).to(device).eval()
+        # optional row N2: the dense head consumes the backbone's features channels-last, the fp32 NCHW tensor is never written
+        self.dense_head = None
+        if head_cfg is not None:
+            self.dense_head = AnchorHeadSingle(head_cfg, self.backbone_2d.num_bev_features, 1, ["Car"], geom.grid_size,
+                                               geom.point_cloud_range).to(device).eval()
         self._p = None
 
     def plan(self, n_frames: int, n_total_points: int, max_frame_points: int = 0):
@@ -36,6 +51,8 @@ class FrontEndWithBackbone(torch.nn.Module):
         bf = dict(dtype=torch.bfloat16, device=p.points.device)
         p.x_nhwc = torch.zeros((n_frames, ny, nx, 128), **bf)
         p.y_nhwc = torch.zeros((n_frames, ny, nx, 64), **bf)
+        if self.dense_head is not None:
+            p.f2d_nhwc = torch.empty((n_frames, ny, nx, self.backbone_2d.num_bev_features), **bf)
         p.graph = None
         self._p = p
         return p
@@ -47,12 +64,17 @@ class FrontEndWithBackbone(torch.nn.Module):
         nP = vox.n_pillars_dev
         fe.vfe.run(vox.voxels, vox.num_points, vox.coords, nP, out=p.pillar_features, scale_out=p.pillar_scale)
         fe.map_to_bev_module.run_nhwc(p.pillar_features, p.pillar_scale, vox.cell_map, p.B, nP, p.readout, p.x_nhwc, p.y_nhwc)
-        p.out = self.backbone_2d.run_nhwc(p.x_nhwc, p.y_nhwc, p.B, ny, nx)
+        if self.dense_head is None:
+            p.out = self.backbone_2d.run_nhwc(p.x_nhwc, p.y_nhwc, p.B, ny, nx)
+        else:
+            self.backbone_2d.run_nhwc(p.x_nhwc, p.y_nhwc, p.B, ny, nx, out_nhwc=p.f2d_nhwc)
+            p.cls_preds, p.box_preds = self.dense_head.run_nhwc(p.f2d_nhwc, p.B, ny, nx)
 
     def kernel_launches_per_run(self) -> int:
         bb = self.backbone_2d
         convs = sum(1 + n for n in bb.layer_nums) + sum(bb.sfm_layer_nums) + 2 * len(bb.num_filters)     # blocks + sfm + scale + deblock
-        return 6 + 1 + 1 + 2 + convs + 2 * len(bb.num_filters)                                            # K1 x6, K2, K3, K4 x2, convs, gate x2/level
+        head = 2 if self.dense_head is not None else 0                                                    # head GEMM + decode
+        return 6 + 1 + 1 + 2 + convs + 2 * len(bb.num_filters) + head                                     # K1 x6, K2, K3, K4 x2, convs, gate x2/level
 
     @torch.no_grad()
     def run(self):
@@ -65,6 +87,9 @@ class FrontEndWithBackbone(torch.nn.Module):
             if fe.map_to_bev_module.memory.precision == "bf16_rescore":
                 fe.map_to_bev_module.memory._packed_bf16()
             self.backbone_2d._ensure_packed(p.points.device)
+            if self.dense_head is not None:
+                self.dense_head._ensure_packed(p.points.device)
+                self.dense_head.anchors(p.points.device)
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
@@ -93,5 +118,9 @@ class FrontEndWithBackbone(torch.nn.Module):
         st = _lib.lib().hvpr_frame_offsets(_lib.ptr(pts.contiguous()), n, 5, B, _lib.ptr(p.frame_offsets), _lib.cur_stream())
         _lib.check(st, "hvpr_frame_offsets")
         self.run()
-        batch_dict["spatial_features_2d"] = p.out
+        if self.dense_head is None:
+            batch_dict["spatial_features_2d"] = p.out
+        else:
+            batch_dict["batch_cls_preds"], batch_dict["batch_box_preds"] = p.cls_preds, p.box_preds
+            batch_dict["cls_preds_normalized"] = False
         return batch_dict

@@ -157,7 +157,10 @@ typedef struct HvprConvArgs {
                                 1: ConvTranspose2d(k = up, stride = up) pixel shuffle into fp32 NCHW
                                    (n, out_ctot, h_out*up, w_out*up), channels [out_c_off, out_c_off + c_out);
                                    GEMM column = (dy*c_out + co)*up + dx
-                                2: fp32 NHWC (n, h_out, w_out, out_cs), channels [out_c_off, out_c_off + n_total) (no gate / residual) */
+                                2: fp32 NHWC (n, h_out, w_out, out_cs), channels [out_c_off, out_c_off + n_total) (no gate / residual)
+                                3: ConvTranspose2d(k = up, stride = up) pixel shuffle into bf16 NHWC
+                                   (n, h_out*up, w_out*up, out_cs), channels [out_c_off, out_c_off + c_out);
+                                   GEMM column = (dy*up + dx)*c_out + co                                          */
     void *out;
     int32_t out_cs, out_c_off;
     int32_t up, c_out, out_ctot;

@@ -401,3 +401,32 @@ def test_dense_head_rejects_the_shipped_anchor_stride_mismatch():
     m = AnchorHeadSingle(Cfg(**cfg), 384, 1, ["Car"], [48, 40, 1], [0, -39.68, -3, 69.12, 39.68, 1]).cuda().eval()
     with pytest.raises(_lib.HvprError):
         m({"spatial_features_2d": torch.zeros(1, 384, 40, 48, device="cuda")})
+
+
+def test_points_to_boxes_pipeline_vs_oracle_chain():
+    """raw points -> front end -> backbone (channels-last features, fp32 NCHW never written) -> dense head, one CUDA graph."""
+    from helpers import load_small, to_dev
+    from hvpr_b200.pipeline import HVPR_HEAD_CFG, FrontEndWithBackbone
+    from oracle import backbone as ob, dense_head as od, hybrid
+    z, geom, frames, overflow, wseed = load_small("tiny_continue")
+    w_fe, w_bb, w_hd = hybrid.random_weights(wseed), ob.random_backbone_weights(21), od.random_head_weights(22)
+    o = hybrid.frontend(frames, geom, w_fe, overflow)
+    f2d = ob.backbone_forward(w_bb, o["spatial_features"].numpy(), o["spatial_scale_features"].numpy())
+    cls_ref, box_ref, (_, _, dir_raw) = od.head_forward(w_hd, f2d, od.HEAD_CFG, geom.grid_size, list(geom.point_cloud_range), return_raw=True)
+    pipe = FrontEndWithBackbone(geom, overflow=overflow, head_cfg=HVPR_HEAD_CFG)
+    pipe.frontend.load_reference_weights(w_fe)
+    pipe.backbone_2d.load_state_dict({k: torch.from_numpy(v) for k, v in w_bb.items()}, strict=False)
+    pipe.dense_head.load_state_dict({k: torch.from_numpy(v) for k, v in w_hd.items()})
+    pts, off = to_dev(frames)
+    p = pipe.plan(len(frames), pts.shape[0])
+    p.points.copy_(pts); p.frame_offsets.copy_(off)
+    for _ in range(2):
+        pipe.run()
+    torch.cuda.synchronize()
+    cls, box = p.cls_preds.cpu().numpy(), p.box_preds.cpu().numpy()
+    assert cls.shape == cls_ref.shape and box.shape == box_ref.shape
+    # the features feeding the head already carry the backbone's bf16 tolerance (2e-2 of their maximum)
+    fscale = float(np.abs(f2d).max())
+    assert np.abs(cls - cls_ref).max() <= 3e-2 * max(1.0, np.abs(cls_ref).max(), fscale)
+    assert np.abs(box[..., :2] - box_ref[..., :2]).max() <= 5e-2 * float(np.sqrt(3.9 ** 2 + 1.6 ** 2))
+    assert np.abs(box[..., 3:6] / box_ref[..., 3:6] - 1).max() <= 5e-2
