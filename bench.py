@@ -228,6 +228,39 @@ def bench_backbone(geom, w, host_pts, host_off, B, N, dev, mem_precision, steps=
            "gpu_launches_per_batch": pipe.kernel_launches_per_run() - 10,
            "points_to_spatial_features_2d": {"ms_per_batch": ms_pipe, "frames_per_sec": B / (ms_pipe * 1e-3),
                                              "gpu_launches_per_batch": pipe.kernel_launches_per_run()}}
+    # row N2 on top: points -> boxes (dense head fed with channels-last features; the fp32 NCHW feature map is never written)
+    try:
+        from hvpr_b200.pipeline import HVPR_HEAD_CFG
+        pipe2 = FrontEndWithBackbone(geom, device=dev, mem_precision=mem_precision, head_cfg=HVPR_HEAD_CFG)
+        pipe2.frontend.load_reference_weights(w)
+        p2 = pipe2.plan(B, B * N, N)
+        p2.points.copy_(host_pts)
+        p2.frame_offsets.copy_(host_off)
+        for _ in range(warmup):
+            pipe2.run()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            pipe2.run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1) / steps
+        th = 0.0
+        for i in range(steps + warmup):
+            e0.record()
+            pipe2.dense_head.run_nhwc(p2.f2d_nhwc, B, ny, nx)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= warmup:
+                th += e0.elapsed_time(e1) / steps
+        out["dense_head"] = {"component": "AnchorHeadSingle eval (one tcgen05 GEMM for conv_cls/box/dir + decode), %d anchors per frame"
+                                          % (ny * nx * pipe2.dense_head.num_anchors_per_location),
+                             "ms_per_batch": th,
+                             "points_to_boxes": {"ms_per_batch": ms2, "frames_per_sec": B / (ms2 * 1e-3),
+                                                 "gpu_launches_per_batch": pipe2.kernel_launches_per_run()}}
+        del pipe2, p2
+    except Exception as e:
+        out["dense_head"] = {"error": repr(e)[:200]}
     # library baseline on the same box: the same network through torch's own layers (cuDNN, bf16 channels_last, eager).
     # The module's nn.Sequential parameter containers are ordinary torch layers, so they can simply be called.
     try:

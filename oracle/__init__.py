@@ -17,4 +17,6 @@ Pinning status:
   * 2-D backbone (N1)  — oracle/backbone.py, pinned against the reference's OWN BaseBEVBackbone_Scale
                          (oracle/ref_loader.load_backbone, one in-memory patch: breakage B4) — oracle/make_golden_backbone.py,
                          tests/golden/backbone_tiny.npz.
+  * dense head (N2)    — oracle/dense_head.py: assembly restated (the head class is not importable: B5/B6), its decode / anchor /
+                         limit_period building blocks pinned bit-exactly on the reference's own functions (tests/test_oracle_cpu.py).
 """
