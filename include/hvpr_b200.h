@@ -194,6 +194,20 @@ int hvpr_head_decode(const float *head_nhwc, int n, int h, int w, int cs, int A,
                      int dir_off, int num_dir_bins, const float *anchors, float dir_offset, float dir_limit_offset,
                      float *cls_out, float *box_out, void *stream);
 
+/* ==== N3: single-stage post-processing ================================================================================
+ * Detector3DTemplate.post_processing, class-agnostic branch (pcdet/models/detectors/detector3d_template.py:168-260) +
+ * class_agnostic_nms (pcdet/models/model_utils/model_nms_utils.py:6-25): sigmoid / max over classes, score threshold,
+ * top nms_pre_max (<= 4096) by score, greedy rotated-BEV-IoU NMS, first nms_post_max survivors per frame.
+ * The reference's IoU/NMS op (`iou3d_nms`, setup.py:53-62) is not in the tree: parity for it is UNPINNED.
+ * cls_preds (n_frames, n_boxes, num_class), box_preds (n_frames, n_boxes, 7) [x,y,z,dx,dy,dz,heading] fp32 device.
+ * outputs (capacity nms_post_max per frame, in descending score order): out_boxes (n_frames, post, 7), out_scores,
+ * out_labels (1-based), out_index (anchor index of each kept box), out_count (n_frames).                             */
+size_t hvpr_post_process_workspace_bytes(int n_frames, int64_t n_boxes);
+int hvpr_post_process(const float *cls_preds, const float *box_preds, int n_frames, int64_t n_boxes, int num_class,
+                      int cls_normalized, float score_thresh, int nms_pre_max, int nms_post_max, float nms_thresh,
+                      float *out_boxes, float *out_scores, int32_t *out_labels, int32_t *out_index, int32_t *out_count,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

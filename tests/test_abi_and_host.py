@@ -247,3 +247,26 @@ def test_dense_head_module_names_anchors_and_loud_failures():
     with pytest.raises(NotImplementedError):
         m.train()({"spatial_features_2d": torch.zeros(1, 384, 40, 48)})
     assert _lib.lib().hvpr_head_decode(None, 1, 1, 1, 32, 2, 1, 0, 2, 16, 2, None, 0.0, 0.0, None, None, None) == -1
+
+
+def test_post_process_abi_and_oracle_geometry_without_gpu():
+    L = _lib.lib()
+    assert L.hvpr_post_process_workspace_bytes(0, 10) == 0
+    n = L.hvpr_post_process_workspace_bytes(8, 428544)
+    assert 8 * 428544 * 8 < n < 64 * 2 ** 20
+    assert L.hvpr_post_process(None, None, 1, 10, 1, 0, 0.1, 4096, 500, 0.1, None, None, None, None, None, None, 0, None) == -1
+    buf = ctypes.create_string_buffer(64)
+    assert L.hvpr_post_process(buf, buf, 1, 10, 1, 0, 0.1, 8192, 500, 0.1, buf, buf, buf, buf, buf, buf, 64, None) == -2   # pre > 4096
+    assert L.hvpr_post_process(buf, buf, 1, 10, 1, 0, 0.1, 4096, 500, 0.1, buf, buf, buf, buf, buf, buf, 64, None) == -3   # workspace
+    from hvpr_b200.post_process import PostProcessor
+    with pytest.raises(NotImplementedError):
+        PostProcessor(config.Cfg(SCORE_THRESH=0.1, NMS_CONFIG=config.Cfg(MULTI_CLASSES_NMS=True, NMS_THRESH=0.1, NMS_PRE_MAXSIZE=4096,
+                                                                         NMS_POST_MAXSIZE=500)))
+    # oracle geometry: known answers of the rotated IoU
+    from oracle import post_process as op
+    b = np.array([0, 0, 0, 4, 2, 1, 0.3])
+    assert abs(op.iou_bev(b, b) - 1.0) < 1e-12 and op.iou_bev(b, b + np.array([10, 0, 0, 0, 0, 0, 0])) == 0.0
+    b1, b2 = np.array([0, 0, 0, 4, 2, 1, 0.0]), np.array([2, 0, 0, 4, 2, 1, 0.0])
+    assert abs(op.iou_bev(b1, b2) - 1.0 / 3.0) < 1e-12
+    sq, rot = np.array([0, 0, 0, 2, 2, 1, 0.0]), np.array([0, 0, 0, 2, 2, 1, np.pi / 4])
+    assert abs(op.iou_bev(sq, rot) - (8 * (np.sqrt(2) - 1)) / (8 - 8 * (np.sqrt(2) - 1))) < 1e-9       # regular octagon of two unit squares

@@ -1,0 +1,79 @@
+"""GPU parity of row N3 (score threshold -> top-k -> rotated-BEV NMS -> first POST_MAXSIZE) against oracle/post_process.py, through
+the C ABI.  The reference's own NMS op is not in the tree (parity unpinned upstream); the oracle is an independent float64 restatement,
+so kept INDEX LISTS must be identical whenever no pair's IoU lies within 1e-4 of the threshold (the oracle reports that margin)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(cls_list, box_list, cfg, normalized=False):
+    from hvpr_b200.config import Cfg
+    from hvpr_b200.post_process import PostProcessor
+    pp = PostProcessor(Cfg(SCORE_THRESH=cfg["SCORE_THRESH"], NMS_CONFIG=Cfg(MULTI_CLASSES_NMS=False, NMS_TYPE="nms_gpu",
+                                                                          NMS_THRESH=cfg["NMS_THRESH"], NMS_PRE_MAXSIZE=cfg["NMS_PRE_MAXSIZE"],
+                                                                          NMS_POST_MAXSIZE=cfg["NMS_POST_MAXSIZE"])))
+    bd = {"batch_cls_preds": torch.from_numpy(np.stack(cls_list)).cuda(), "batch_box_preds": torch.from_numpy(np.stack(box_list)).cuda(),
+          "cls_preds_normalized": normalized}
+    out = pp.post_processing(bd)
+    torch.cuda.synchronize()
+    return out
+
+
+def _good_seed(start, n, cfg, **kw):
+    from oracle import post_process as op
+    for seed in range(start, start + 20):
+        cls, box = op.random_detections(seed, n, **kw)
+        sel, sc, lab, margin = op.post_process_frame(cls, box, cfg, return_margin=True)
+        if margin > 1e-4:
+            return cls, box, sel, sc, lab
+    raise AssertionError("no seed with a clear IoU margin")
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(SCORE_THRESH=0.1, NMS_PRE_MAXSIZE=4096, NMS_POST_MAXSIZE=500, NMS_THRESH=0.1),        # hvpr.yaml:136-148
+    dict(SCORE_THRESH=0.05, NMS_PRE_MAXSIZE=1000, NMS_POST_MAXSIZE=100, NMS_THRESH=0.5),
+    dict(SCORE_THRESH=0.3, NMS_PRE_MAXSIZE=100, NMS_POST_MAXSIZE=10, NMS_THRESH=0.01),
+])
+def test_post_processing_matches_oracle(cfg):
+    frames = [_good_seed(10, 20000, cfg), _good_seed(40, 20000, cfg, n_clusters=40)]
+    out = _run([f[0] for f in frames], [f[1] for f in frames], cfg)
+    for (cls, box, sel, sc, lab), o in zip(frames, out):
+        got = o["pred_anchor_index"].cpu().numpy()
+        assert got.tolist() == sel.tolist()                                        # same boxes, same (descending score) order
+        assert np.allclose(o["pred_scores"].cpu().numpy(), sc, rtol=1e-6, atol=1e-7)
+        assert np.array_equal(o["pred_boxes"].cpu().numpy(), box[sel])
+        assert np.array_equal(o["pred_labels"].cpu().numpy(), lab)
+
+
+def test_post_processing_edge_cases():
+    from oracle import post_process as op
+    cfg = dict(op.POST_CFG)
+    # (1) no candidate at all, (2) fewer than one 64-box block, (3) more candidates than NMS_PRE_MAXSIZE with many equal scores
+    cls0, box0 = op.random_detections(3, 5000)
+    cls0[:] = -9.0
+    cls1, box1 = op.random_detections(4, 5000)
+    cls1[:] = -9.0
+    cls1[[7, 4000, 4999, 123], 0] = [2.0, 1.0, 3.0, 0.5]
+    box1[[7, 4000, 4999, 123], 0] = [5.0, 25.0, 45.0, 65.0]                         # far apart: nothing suppressed
+    cls2, box2 = op.random_detections(5, 5000, n_clusters=5000)
+    cls2[:] = 1.25                                                                  # 5000 identical scores: ties -> lower index first
+    out = _run([cls0, cls1, cls2], [box0, box1, box2], cfg)
+    assert len(out[0]["pred_scores"]) == 0
+    assert out[1]["pred_anchor_index"].cpu().tolist() == [4999, 7, 4000, 123]
+    sel2, sc2, _ = op.post_process_frame(cls2, box2, cfg)
+    assert out[2]["pred_anchor_index"].cpu().tolist() == sel2.tolist() and sel2.max() < 4096
+
+
+def test_post_processing_multi_class_labels_and_normalized_scores():
+    from oracle import post_process as op
+    cfg = dict(op.POST_CFG, NMS_THRESH=0.3)
+    rng = np.random.default_rng(6)
+    _, box = op.random_detections(7, 8000)
+    prob = rng.uniform(0.0, 1.0, (8000, 3)).astype(np.float32) ** 4                 # already-normalised scores, 3 classes
+    sel, sc, lab, margin = op.post_process_frame(prob, box, cfg, normalized=True, return_margin=True)
+    assert margin > 1e-5
+    out = _run([prob], [box], cfg, normalized=True)[0]
+    assert out["pred_anchor_index"].cpu().tolist() == sel.tolist()
+    assert np.array_equal(out["pred_labels"].cpu().numpy(), lab)
