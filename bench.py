@@ -230,12 +230,20 @@ def bench_backbone(geom, w, host_pts, host_off, B, N, dev, mem_precision, steps=
                                              "gpu_launches_per_batch": pipe.kernel_launches_per_run()}}
     # row N2 on top: points -> boxes (dense head fed with channels-last features; the fp32 NCHW feature map is never written)
     try:
-        from hvpr_b200.pipeline import HVPR_HEAD_CFG
-        pipe2 = FrontEndWithBackbone(geom, device=dev, mem_precision=mem_precision, head_cfg=HVPR_HEAD_CFG)
+        from hvpr_b200.pipeline import HVPR_HEAD_CFG, HVPR_POST_CFG
+        pipe2 = FrontEndWithBackbone(geom, device=dev, mem_precision=mem_precision, head_cfg=HVPR_HEAD_CFG, post_cfg=HVPR_POST_CFG)
         pipe2.frontend.load_reference_weights(w)
         p2 = pipe2.plan(B, B * N, N)
         p2.points.copy_(host_pts)
         p2.frame_offsets.copy_(host_off)
+        pipe2.run()
+        torch.cuda.synchronize()
+        # random-init logits never reach the 0.1 threshold (conv_cls.bias = -4.6): shift the bias so that ~1 % of the anchors pass,
+        # i.e. NMS_PRE_MAXSIZE (4096) is saturated in every frame - the worst case for the NMS kernels
+        with torch.no_grad():
+            q99 = torch.quantile(p2.cls_preds.flatten()[:: 16].float(), 0.99)
+            pipe2.dense_head.conv_cls.bias += float(-2.1972246 - q99)        # logit(0.1) = -2.197
+        p2.graph = None
         for _ in range(warmup):
             pipe2.run()
         torch.cuda.synchronize()
@@ -253,11 +261,22 @@ def bench_backbone(geom, w, host_pts, host_off, B, N, dev, mem_precision, steps=
             torch.cuda.synchronize()
             if i >= warmup:
                 th += e0.elapsed_time(e1) / steps
+        tn = 0.0
+        for i in range(steps + warmup):
+            e0.record()
+            pipe2.post.run(p2.cls_preds, p2.box_preds)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= warmup:
+                tn += e0.elapsed_time(e1) / steps
         out["dense_head"] = {"component": "AnchorHeadSingle eval (one tcgen05 GEMM for conv_cls/box/dir + decode), %d anchors per frame"
                                           % (ny * nx * pipe2.dense_head.num_anchors_per_location),
-                             "ms_per_batch": th,
-                             "points_to_boxes": {"ms_per_batch": ms2, "frames_per_sec": B / (ms2 * 1e-3),
-                                                 "gpu_launches_per_batch": pipe2.kernel_launches_per_run()}}
+                             "ms_per_batch": th}
+        out["post_processing"] = {"component": "score threshold 0.1 -> top-4096 -> rotated-BEV NMS 0.1 -> 500; head bias calibrated so that ~1 % of "
+                                               "the 428 544 anchors per frame pass the threshold (NMS_PRE_MAXSIZE saturated)", "ms_per_batch": tn,
+                                  "candidates_after_nms_per_frame": [int(v) for v in p2.det["count"].cpu().tolist()]}
+        out["points_to_detections"] = {"ms_per_batch": ms2, "frames_per_sec": B / (ms2 * 1e-3),
+                                       "gpu_launches_per_batch": pipe2.kernel_launches_per_run()}
         del pipe2, p2
     except Exception as e:
         out["dense_head"] = {"error": repr(e)[:200]}

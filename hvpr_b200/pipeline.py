@@ -13,6 +13,7 @@ from . import _lib
 from .backbone import BaseBEVBackbone_Scale
 from .config import Cfg
 from .dense_head import AnchorHeadSingle
+from .post_process import PostProcessor
 from .frontend import HybridFrontEnd
 
 # tools/cfgs/kitti_models/hvpr.yaml:87-95
@@ -30,8 +31,13 @@ HVPR_HEAD_CFG = Cfg(NAME="AnchorHeadSingle", CLASS_AGNOSTIC=False, USE_DIRECTION
                                                   matched_threshold=0.6, unmatched_threshold=0.45)])
 
 
+# tools/cfgs/kitti_models/hvpr.yaml:136-148
+HVPR_POST_CFG = Cfg(RECALL_THRESH_LIST=[0.3, 0.5, 0.7], SCORE_THRESH=0.1, OUTPUT_RAW_SCORE=False, EVAL_METRIC="kitti",
+                    NMS_CONFIG=Cfg(MULTI_CLASSES_NMS=False, NMS_TYPE="nms_gpu", NMS_THRESH=0.1, NMS_PRE_MAXSIZE=4096, NMS_POST_MAXSIZE=500))
+
+
 class FrontEndWithBackbone(torch.nn.Module):
-    def __init__(self, geom, backbone_cfg=HVPR_BACKBONE_CFG, device="cuda", head_cfg=None, **frontend_kwargs):
+    def __init__(self, geom, backbone_cfg=HVPR_BACKBONE_CFG, device="cuda", head_cfg=None, post_cfg=None, **frontend_kwargs):
         super().__init__()
         self.frontend = HybridFrontEnd(geom, device=device, **frontend_kwargs) if frontend_kwargs else HybridFrontEnd(geom, device=device)
         self.backbone_2d = BaseBEVBackbone_Scale(backbone_cfg, self.frontend.map_to_bev_module.num_bev_features).to(device).eval()
@@ -40,6 +46,8 @@ class FrontEndWithBackbone(torch.nn.Module):
         if head_cfg is not None:
             self.dense_head = AnchorHeadSingle(head_cfg, self.backbone_2d.num_bev_features, 1, ["Car"], geom.grid_size,
                                                geom.point_cloud_range).to(device).eval()
+        # optional row N3: score threshold / top-k / rotated NMS on the head's output (needs head_cfg)
+        self.post = PostProcessor(post_cfg) if (post_cfg is not None and head_cfg is not None) else None
         self._p = None
 
     def plan(self, n_frames: int, n_total_points: int, max_frame_points: int = 0):
@@ -69,11 +77,13 @@ class FrontEndWithBackbone(torch.nn.Module):
         else:
             self.backbone_2d.run_nhwc(p.x_nhwc, p.y_nhwc, p.B, ny, nx, out_nhwc=p.f2d_nhwc)
             p.cls_preds, p.box_preds = self.dense_head.run_nhwc(p.f2d_nhwc, p.B, ny, nx)
+            if self.post is not None:
+                p.det = self.post.run(p.cls_preds, p.box_preds, cls_normalized=False)
 
     def kernel_launches_per_run(self) -> int:
         bb = self.backbone_2d
         convs = sum(1 + n for n in bb.layer_nums) + sum(bb.sfm_layer_nums) + 2 * len(bb.num_filters)     # blocks + sfm + scale + deblock
-        head = 2 if self.dense_head is not None else 0                                                    # head GEMM + decode
+        head = (2 if self.dense_head is not None else 0) + (4 if self.post is not None else 0)            # head GEMM + decode, 4 NMS kernels
         return 6 + 1 + 1 + 2 + convs + 2 * len(bb.num_filters) + head                                     # K1 x6, K2, K3, K4 x2, convs, gate x2/level
 
     @torch.no_grad()
@@ -123,4 +133,8 @@ class FrontEndWithBackbone(torch.nn.Module):
         else:
             batch_dict["batch_cls_preds"], batch_dict["batch_box_preds"] = p.cls_preds, p.box_preds
             batch_dict["cls_preds_normalized"] = False
+            if self.post is not None:                    # pred_dicts as Detector3DTemplate.post_processing returns them (one D2H of the counts)
+                counts = p.det["count"].cpu().tolist()
+                batch_dict["pred_dicts"] = [{"pred_boxes": p.det["boxes"][i, :k], "pred_scores": p.det["scores"][i, :k],
+                                             "pred_labels": p.det["labels"][i, :k].long()} for i, k in enumerate(counts)]
         return batch_dict

@@ -77,3 +77,34 @@ def test_post_processing_multi_class_labels_and_normalized_scores():
     out = _run([prob], [box], cfg, normalized=True)[0]
     assert out["pred_anchor_index"].cpu().tolist() == sel.tolist()
     assert np.array_equal(out["pred_labels"].cpu().numpy(), lab)
+
+
+def test_points_to_detections_pipeline():
+    """cfg 5 (full single-stage inference): raw points -> front end -> backbone -> head -> post-processing in one CUDA graph; the
+    detections must equal the oracle's post-processing of the PIPELINE's own head output (each stage is pinned separately)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import load_small, to_dev
+    from hvpr_b200 import synth
+    from hvpr_b200.pipeline import HVPR_HEAD_CFG, HVPR_POST_CFG, FrontEndWithBackbone
+    from oracle import backbone as ob, dense_head as od, hybrid, post_process as op
+    z, geom, frames, overflow, wseed = load_small("tiny_continue")
+    pipe = FrontEndWithBackbone(geom, overflow=overflow, head_cfg=HVPR_HEAD_CFG, post_cfg=HVPR_POST_CFG)
+    pipe.frontend.load_reference_weights(hybrid.random_weights(wseed))
+    pipe.backbone_2d.load_state_dict({k: torch.from_numpy(v) for k, v in ob.random_backbone_weights(21).items()}, strict=False)
+    wh = od.random_head_weights(22)
+    wh["conv_cls.bias"] = wh["conv_cls.bias"] + 1.0                     # enough candidates above the 0.1 threshold
+    pipe.dense_head.load_state_dict({k: torch.from_numpy(v) for k, v in wh.items()})
+    bd = pipe({"points": torch.from_numpy(synth.collate_points(frames)).cuda(), "batch_size": len(frames)})
+    torch.cuda.synchronize()
+    cls, box = bd["batch_cls_preds"].cpu().numpy(), bd["batch_box_preds"].cpu().numpy()
+    assert len(bd["pred_dicts"]) == len(frames)
+    total = 0
+    for f, pd in enumerate(bd["pred_dicts"]):
+        sel, sc, lab, margin = op.post_process_frame(cls[f], box[f], return_margin=True)
+        if margin <= 1e-5:
+            continue
+        assert np.array_equal(pd["pred_boxes"].cpu().numpy(), box[f][sel])
+        assert np.allclose(pd["pred_scores"].cpu().numpy(), sc, rtol=1e-6, atol=1e-7)
+        total += len(sel)
+    assert total > 0
