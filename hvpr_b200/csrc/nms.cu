@@ -8,8 +8,8 @@
 //   pp_score_kernel    one thread per anchor: score/threshold, append a 64-bit key (score bits : ~index) to the frame's candidate list
 //   pp_topk_kernel     one block per frame: exact radix select of the K largest keys (6 x 11-bit passes), then a bitonic sort in shared
 //                      memory -> candidates in descending score order (ties: lower anchor index first), deterministic
-//   pp_iou_mask_kernel 64 x 64 tiles of the upper triangle: polygon clipping (Sutherland-Hodgman) of rectangle i by rectangle j,
-//                      shoelace area, bit j of mask[i] = IoU > thresh
+//   pp_iou_mask_kernel 64 x 64 tiles of the upper triangle: intersection area of two rotated rectangles as a boundary integral over
+//                      Liang-Barsky-clipped edges (registers only), bit j of mask[i] = IoU > thresh
 //   pp_reduce_kernel   one block per frame: 64 boxes at a time, the diagonal word resolved serially, kept rows OR-ed into the
 //                      suppression words; gathers the kept boxes / scores / labels
 #include "common.cuh"
@@ -148,40 +148,83 @@ __device__ __forceinline__ PpRect pp_rect(const float *b) {
     r.rad2 = r.hx * r.hx + r.hy * r.hy;
     return r;
 }
-// area of (rectangle a) ∩ (rectangle b): a's corners are expressed in b's frame, then clipped by b's four axis-aligned half-planes
-__device__ float pp_intersection(const PpRect &a, const PpRect &b) {
-    float px[8], py[8], qx[8], qy[8];
-    int n = 4;
+// Area of (rectangle a) ∩ (rectangle b) without building the intersection polygon: by Green's theorem the area is the boundary integral
+// 1/2 ∮ (x dy - y dx), and the boundary of the intersection consists of the parts of a's edges inside b plus the parts of b's edges
+// inside a (both counter-clockwise).  Each edge is clipped against the other rectangle's four half-planes (Liang-Barsky) in that
+// rectangle's local frame, where they are axis-aligned — eight segments, fully unrolled, registers only.  Edges of a use CLOSED
+// half-planes and edges of b OPEN ones, so coincident boundaries (e.g. identical boxes) are counted once.
+template <bool kClosed>
+__device__ __forceinline__ float pp_edge_integral(float x0, float y0, float x1, float y1, float hx, float hy) {
+    // segment p(t) = p0 + t (p1 - p0), t in [0,1], clipped to |x| <= hx, |y| <= hy; returns 1/2 (xa*yb - xb*ya) of the clipped piece
+    float t0 = 0.0f, t1 = 1.0f;
+    const float dx = x1 - x0, dy = y1 - y0;
+    const float pd[4] = {dx, -dx, dy, -dy};
+    const float qd[4] = {hx - x0, hx + x0, hy - y0, hy + y0};          // distance to each boundary, >= 0 inside
+    bool ok = true;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        if (pd[e] == 0.0f) {
+            ok = ok && (kClosed ? qd[e] >= 0.0f : qd[e] > 0.0f);
+        } else {
+            const float r = qd[e] / pd[e];
+            if (pd[e] > 0.0f) t1 = fminf(t1, r); else t0 = fmaxf(t0, r);
+        }
+    }
+    if (!ok || t0 >= t1) return 0.0f;
+    const float ax = x0 + t0 * dx, ay = y0 + t0 * dy, bx = x0 + t1 * dx, by = y0 + t1 * dy;
+    return 0.5f * (ax * by - bx * ay);
+}
+// corners of rectangle `a` (counter-clockwise) expressed in the local frame of `b`, then its four edges integrated inside b
+template <bool kClosed>
+__device__ __forceinline__ float pp_boundary_inside(const PpRect &a, const PpRect &b) {
     const float lx[4] = {a.hx, -a.hx, -a.hx, a.hx}, ly[4] = {a.hy, a.hy, -a.hy, -a.hy};
+    float px[4], py[4];
+#pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float wx = a.cx + lx[i] * a.c - ly[i] * a.s - b.cx, wy = a.cy + lx[i] * a.s + ly[i] * a.c - b.cy;   // world, relative to b
-        px[i] = wx * b.c + wy * b.s;                                                                                // into b's frame
+        const float wx = a.cx + lx[i] * a.c - ly[i] * a.s - b.cx, wy = a.cy + lx[i] * a.s + ly[i] * a.c - b.cy;
+        px[i] = wx * b.c + wy * b.s;
         py[i] = -wx * b.s + wy * b.c;
     }
-    // clip against x <= hx, x >= -hx, y <= hy, y >= -hy
-    for (int e = 0; e < 4 && n > 0; ++e) {
-        const float lim = (e < 2) ? b.hx : b.hy;
-        const float sgn = (e & 1) ? -1.0f : 1.0f;
-        int m = 0;
-        for (int i = 0; i < n; ++i) {
-            const int j = (i + 1 == n) ? 0 : i + 1;
-            const float vi = sgn * ((e < 2) ? px[i] : py[i]) - lim, vj = sgn * ((e < 2) ? px[j] : py[j]) - lim;   // <= 0: inside
-            if (vi <= 0.0f) { qx[m] = px[i]; qy[m] = py[i]; ++m; }
-            if ((vi < 0.0f && vj > 0.0f) || (vi > 0.0f && vj < 0.0f)) {
-                const float tpar = vi / (vi - vj);
-                qx[m] = px[i] + tpar * (px[j] - px[i]); qy[m] = py[i] + tpar * (py[j] - py[i]); ++m;
-            }
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc += pp_edge_integral<kClosed>(px[i], py[i], px[(i + 1) & 3], py[(i + 1) & 3], b.hx, b.hy);
+    return acc;
+}
+__device__ __forceinline__ float pp_intersection(const PpRect &a, const PpRect &b) {
+    // Every piece is evaluated in ONE coordinate system (b's local frame): the closed integral is origin-independent, its parts are not.
+    // a's edges: clipped and evaluated in b's frame.  b's edges: clip parameters from a's frame (they are frame-independent), positions
+    // taken in b's frame, where b's corners are simply (+-hx, +-hy).
+    const float part_a = pp_boundary_inside<true>(a, b);
+    // b's edges: corners in b's frame are (±hx, ±hy); clip parameters come from a's frame
+    const float lx[4] = {b.hx, -b.hx, -b.hx, b.hx}, ly[4] = {b.hy, b.hy, -b.hy, -b.hy};
+    float qx[4], qy[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {            // b's corners in a's frame
+        const float wx = b.cx + lx[i] * b.c - ly[i] * b.s - a.cx, wy = b.cy + lx[i] * b.s + ly[i] * b.c - a.cy;
+        qx[i] = wx * a.c + wy * a.s;
+        qy[i] = -wx * a.s + wy * a.c;
+    }
+    float part_b = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int j = (i + 1) & 3;
+        float t0 = 0.0f, t1 = 1.0f;
+        const float dx = qx[j] - qx[i], dy = qy[j] - qy[i];
+        const float pd[4] = {dx, -dx, dy, -dy};
+        const float qd[4] = {a.hx - qx[i], a.hx + qx[i], a.hy - qy[i], a.hy + qy[i]};
+        bool ok = true;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (pd[e] == 0.0f) ok = ok && qd[e] > 0.0f;                       // open half-planes for b's edges
+            else { const float r = qd[e] / pd[e]; if (pd[e] > 0.0f) t1 = fminf(t1, r); else t0 = fmaxf(t0, r); }
         }
-        n = m;
-        for (int i = 0; i < n; ++i) { px[i] = qx[i]; py[i] = qy[i]; }
+        if (ok && t0 < t1) {                                                  // evaluate the piece in b's frame (origin = b's centre)
+            const float ex = lx[j] - lx[i], ey = ly[j] - ly[i];
+            const float ax = lx[i] + t0 * ex, ay = ly[i] + t0 * ey, bx = lx[i] + t1 * ex, by = ly[i] + t1 * ey;
+            part_b += 0.5f * (ax * by - bx * ay);
+        }
     }
-    if (n < 3) return 0.0f;
-    float area = 0.0f;
-    for (int i = 0; i < n; ++i) {
-        const int j = (i + 1 == n) ? 0 : i + 1;
-        area += px[i] * py[j] - px[j] * py[i];
-    }
-    return 0.5f * fabsf(area);
+    return fmaxf(part_a + part_b, 0.0f);
 }
 
 __global__ void __launch_bounds__(64) pp_iou_mask_kernel(const float *__restrict__ boxes, int64_t N, const unsigned long long *__restrict__ sorted,
@@ -190,24 +233,22 @@ __global__ void __launch_bounds__(64) pp_iou_mask_kernel(const float *__restrict
     if (cb < rb) return;                                  // upper triangle: a box only suppresses lower-scored ones
     const int n = nsel[f];
     if (rb * 64 >= n || cb * 64 >= n) return;
-    __shared__ float cbox[64][7];
+    __shared__ PpRect crect[64];                          // column rectangles, sin/cos evaluated once per box (not once per pair)
     const int t = threadIdx.x;
     const unsigned long long *keys = sorted + (int64_t)f * kPpMaxPre;
     const int cj = cb * 64 + t;
     if (cj < n) {
         const int64_t idx = (int64_t)(0xFFFFFFFFu - (uint32_t)(keys[cj] & 0xFFFFFFFFull));
-        const float *b = boxes + ((int64_t)f * N + idx) * 7;
-        for (int e = 0; e < 7; ++e) cbox[t][e] = b[e];
+        crect[t] = pp_rect(boxes + ((int64_t)f * N + idx) * 7);
     }
     __syncthreads();
     const int ri = rb * 64 + t;
     if (ri >= n) return;
-    const int64_t ridx = (int64_t)(0xFFFFFFFFu - (uint32_t)(keys[ri] & 0xFFFFFFFFull));
-    const PpRect a = pp_rect(boxes + ((int64_t)f * N + ridx) * 7);
+    const PpRect a = (rb == cb) ? crect[t] : pp_rect(boxes + ((int64_t)f * N + (int64_t)(0xFFFFFFFFu - (uint32_t)(keys[ri] & 0xFFFFFFFFull))) * 7);
     unsigned long long bits = 0ull;
     const int cols = (n - cb * 64) < 64 ? (n - cb * 64) : 64;
     for (int j = (rb == cb) ? t + 1 : 0; j < cols; ++j) {
-        const PpRect b = pp_rect(cbox[j]);
+        const PpRect b = crect[j];
         // cheap reject: circumscribed circles do not touch -> no overlap (most pairs of a 70 m x 80 m scene)
         const float ddx = a.cx - b.cx, ddy = a.cy - b.cy;
         const float rsum2 = a.rad2 + b.rad2 + 2.0f * sqrtf(a.rad2 * b.rad2);
@@ -237,7 +278,11 @@ __global__ void __launch_bounds__(64) pp_reduce_kernel(const float *__restrict__
     const unsigned long long *mk = mask + (int64_t)f * kPpMaxPre * kPpWords;
     if (t == 0) s_kept = 0;
     __syncthreads();
+    __shared__ unsigned long long s_diag[64];
     for (int blk = 0; blk < nblk; ++blk) {
+        // the 64 x 64 diagonal tile of this block: one coalesced-ish load per thread instead of 64 dependent global loads below
+        s_diag[t] = (blk * 64 + t < n) ? mk[(int64_t)(blk * 64 + t) * kPpWords + blk] : 0ull;
+        __syncthreads();
         if (t == blk) {
             // resolve the diagonal word serially: box j survives iff no kept box of higher score suppresses it
             unsigned long long alive = ~removed, keep = 0ull;
@@ -248,7 +293,7 @@ __global__ void __launch_bounds__(64) pp_reduce_kernel(const float *__restrict__
                     keep |= 1ull << j;
                     s_list[m++] = j;
                     ++kept;
-                    alive &= ~mk[(int64_t)(blk * 64 + j) * kPpWords + blk];
+                    alive &= ~s_diag[j];
                 }
             s_keep = keep;
         }
