@@ -12,7 +12,7 @@ __version__ = "0.1.0"
 def __getattr__(name):
     # torch-dependent modules are imported lazily so `import hvpr_b200` stays cheap
     import importlib
-    if name in ("vfe", "map_to_bev", "voxelizer", "frontend", "backbone", "dense_head", "pipeline", "_lib"):
+    if name in ("vfe", "map_to_bev", "voxelizer", "frontend", "backbone", "dense_head", "post_process", "pipeline", "_lib"):
         return importlib.import_module("." + name, __name__)
     if name in ("Voxelizer", "VoxelGenerator", "VoxelGeneratorV2"):
         return getattr(importlib.import_module(".voxelizer", __name__), name)

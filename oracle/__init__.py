@@ -19,4 +19,6 @@ Pinning status:
                          tests/golden/backbone_tiny.npz.
   * dense head (N2)    — oracle/dense_head.py: assembly restated (the head class is not importable: B5/B6), its decode / anchor /
                          limit_period building blocks pinned bit-exactly on the reference's own functions (tests/test_oracle_cpu.py).
+  * post-processing (N3) — oracle/post_process.py: PARITY UNPINNED for the NMS (the reference's iou3d_nms CUDA op is not in the tree);
+                         selection logic restated from the Python source, rotated IoU restated independently in float64.
 """
