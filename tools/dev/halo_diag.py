@@ -1,4 +1,5 @@
-"""Dev probe — what does tcgen05.mma read through the shifted halo descriptor?  Identity weights on ONE tap make the
+"""Dev probe (written for the first, single-patch halo variant; the shipped halo path uses aligned column-shifted patches) —
+what does tcgen05.mma read through a shifted halo descriptor?  Identity weights on ONE tap make the
 output a copy of the A operand; inputs encode the pixel id (pass A) or the 16-byte chunk id (pass B)."""
 import ctypes
 import os
@@ -12,6 +13,7 @@ from hvpr_b200 import _lib     # noqa: E402
 
 _lib.init_device()
 L = _lib.lib()
+L.hvpr_dbg_conv_halo_off(0)          # the halo operand path is off by default
 n, h, w, c = 1, 16, 8, 64
 
 
