@@ -158,18 +158,12 @@ __device__ __forceinline__ float pp_edge_integral(float x0, float y0, float x1, 
     // segment p(t) = p0 + t (p1 - p0), t in [0,1], clipped to |x| <= hx, |y| <= hy; returns 1/2 (xa*yb - xb*ya) of the clipped piece
     float t0 = 0.0f, t1 = 1.0f;
     const float dx = x1 - x0, dy = y1 - y0;
-    const float pd[4] = {dx, -dx, dy, -dy};
-    const float qd[4] = {hx - x0, hx + x0, hy - y0, hy + y0};          // distance to each boundary, >= 0 inside
     bool ok = true;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        if (pd[e] == 0.0f) {
-            ok = ok && (kClosed ? qd[e] >= 0.0f : qd[e] > 0.0f);
-        } else {
-            const float r = qd[e] / pd[e];
-            if (pd[e] > 0.0f) t1 = fminf(t1, r); else t0 = fmaxf(t0, r);
-        }
-    }
+    // x slab: -hx <= x0 + t dx <= hx ; y slab likewise.  One reciprocal per axis (the two half-planes of a slab share it).
+    if (dx == 0.0f) ok = kClosed ? (fabsf(x0) <= hx) : (fabsf(x0) < hx);
+    else { const float inv = 1.0f / dx; const float ra = (hx - x0) * inv, rb = (-hx - x0) * inv; t1 = fminf(t1, fmaxf(ra, rb)); t0 = fmaxf(t0, fminf(ra, rb)); }
+    if (dy == 0.0f) ok = ok && (kClosed ? (fabsf(y0) <= hy) : (fabsf(y0) < hy));
+    else { const float inv = 1.0f / dy; const float ra = (hy - y0) * inv, rb = (-hy - y0) * inv; t1 = fminf(t1, fmaxf(ra, rb)); t0 = fmaxf(t0, fminf(ra, rb)); }
     if (!ok || t0 >= t1) return 0.0f;
     const float ax = x0 + t0 * dx, ay = y0 + t0 * dy, bx = x0 + t1 * dx, by = y0 + t1 * dy;
     return 0.5f * (ax * by - bx * ay);
@@ -210,14 +204,11 @@ __device__ __forceinline__ float pp_intersection(const PpRect &a, const PpRect &
         const int j = (i + 1) & 3;
         float t0 = 0.0f, t1 = 1.0f;
         const float dx = qx[j] - qx[i], dy = qy[j] - qy[i];
-        const float pd[4] = {dx, -dx, dy, -dy};
-        const float qd[4] = {a.hx - qx[i], a.hx + qx[i], a.hy - qy[i], a.hy + qy[i]};
-        bool ok = true;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if (pd[e] == 0.0f) ok = ok && qd[e] > 0.0f;                       // open half-planes for b's edges
-            else { const float r = qd[e] / pd[e]; if (pd[e] > 0.0f) t1 = fminf(t1, r); else t0 = fmaxf(t0, r); }
-        }
+        bool ok = true;                                                       // open slabs for b's edges
+        if (dx == 0.0f) ok = fabsf(qx[i]) < a.hx;
+        else { const float inv = 1.0f / dx; const float ra = (a.hx - qx[i]) * inv, rb = (-a.hx - qx[i]) * inv; t1 = fminf(t1, fmaxf(ra, rb)); t0 = fmaxf(t0, fminf(ra, rb)); }
+        if (dy == 0.0f) ok = ok && fabsf(qy[i]) < a.hy;
+        else { const float inv = 1.0f / dy; const float ra = (a.hy - qy[i]) * inv, rb = (-a.hy - qy[i]) * inv; t1 = fminf(t1, fmaxf(ra, rb)); t0 = fmaxf(t0, fminf(ra, rb)); }
         if (ok && t0 < t1) {                                                  // evaluate the piece in b's frame (origin = b's centre)
             const float ex = lx[j] - lx[i], ey = ly[j] - ly[i];
             const float ax = lx[i] + t0 * ex, ay = ly[i] + t0 * ey, bx = lx[i] + t1 * ex, by = ly[i] + t1 * ey;
