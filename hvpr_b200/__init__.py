@@ -12,7 +12,7 @@ __version__ = "0.1.0"
 def __getattr__(name):
     # torch-dependent modules are imported lazily so `import hvpr_b200` stays cheap
     import importlib
-    if name in ("vfe", "map_to_bev", "voxelizer", "frontend", "backbone", "dense_head", "post_process", "pipeline", "_lib"):
+    if name in ("vfe", "map_to_bev", "voxelizer", "frontend", "backbone", "dense_head", "post_process", "pipeline", "detector", "_lib"):
         return importlib.import_module("." + name, __name__)
     if name in ("Voxelizer", "VoxelGenerator", "VoxelGeneratorV2"):
         return getattr(importlib.import_module(".voxelizer", __name__), name)
@@ -22,6 +22,8 @@ def __getattr__(name):
         return getattr(importlib.import_module(".map_to_bev", __name__), name)
     if name in ("BaseBEVBackbone", "BaseBEVBackbone_Scale"):
         return getattr(importlib.import_module(".backbone", __name__), name)
+    if name == "MixAnchor_Memory":
+        return importlib.import_module(".detector", __name__).MixAnchor_Memory
     if name == "AnchorHeadSingle":
         return importlib.import_module(".dense_head", __name__).AnchorHeadSingle
     if name == "HybridFrontEnd":

@@ -270,3 +270,23 @@ def test_post_process_abi_and_oracle_geometry_without_gpu():
     assert abs(op.iou_bev(b1, b2) - 1.0 / 3.0) < 1e-12
     sq, rot = np.array([0, 0, 0, 2, 2, 1, 0.0]), np.array([0, 0, 0, 2, 2, 1, np.pi / 4])
     assert abs(op.iou_bev(sq, rot) - (8 * (np.sqrt(2) - 1)) / (8 - 8 * (np.sqrt(2) - 1))) < 1e-9       # regular octagon of two unit squares
+
+
+def test_detector_state_dict_uses_the_reference_module_names():
+    """MixAnchor_Memory exposes vfe / map_to_bev_module / backbone_2d / dense_head (detector3d_template.py:30-33): the union of the
+    per-module reference state dicts, each under its reference prefix, and nothing else."""
+    if True:
+        # the detector allocates its voxelizer on the device; the key layout is checked through the parts on CPU
+        from hvpr_b200 import map_to_bev, vfe
+        from hvpr_b200.backbone import BaseBEVBackbone_Scale
+        from hvpr_b200.dense_head import AnchorHeadSingle
+        from hvpr_b200.pipeline import HVPR_BACKBONE_CFG, HVPR_HEAD_CFG
+        from oracle import backbone as ob, dense_head as od
+        parts = {"vfe": vfe.PillarVFE_Scale(config.HVPR_VFE_CFG, 4, list(G2.voxel_size), G2.range_f32),
+                 "map_to_bev_module": map_to_bev.PointPillarScatter_Agg_Memory_1_scale(config.HVPR_BEV_CFG, grid_size=G2.grid_size),
+                 "backbone_2d": BaseBEVBackbone_Scale(HVPR_BACKBONE_CFG, 128),
+                 "dense_head": AnchorHeadSingle(HVPR_HEAD_CFG, 384, 1, ["Car"], G2.grid_size, G2.point_cloud_range)}
+        keys = {"%s.%s" % (p, k) for p, m in parts.items() for k in m.state_dict() if not k.endswith("num_batches_tracked")}
+        want = (set(hybrid.random_weights(0)) | {"backbone_2d." + k for k in ob.random_backbone_weights(0)} |
+                {"dense_head." + k for k in od.random_head_weights(0)})
+        assert keys == want

@@ -108,3 +108,35 @@ def test_points_to_detections_pipeline():
         assert np.allclose(pd["pred_scores"].cpu().numpy(), sc, rtol=1e-6, atol=1e-7)
         total += len(sel)
     assert total > 0
+
+
+def test_detector_object_loads_reference_names_and_matches_the_pipeline():
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import load_small
+    from hvpr_b200 import synth
+    from hvpr_b200.detector import MixAnchor_Memory
+    from oracle import backbone as ob, dense_head as od, hybrid, post_process as op
+    z, geom, frames, overflow, wseed = load_small("tiny_continue")
+    det = MixAnchor_Memory(geom, overflow=overflow)
+    wh = od.random_head_weights(22)
+    wh["conv_cls.bias"] = wh["conv_cls.bias"] + 1.0
+    state = dict(hybrid.random_weights(wseed))
+    state.update({"backbone_2d." + k: torch.from_numpy(v) for k, v in ob.random_backbone_weights(21).items()})
+    state.update({"dense_head." + k: torch.from_numpy(v) for k, v in wh.items()})
+    state["backbone_3d.SA_modules.0.mlps.0.0.weight"] = torch.zeros(16, 4, 1, 1)      # train-only PointNet++ weights are ignored
+    det.load_reference_state(state)
+    assert {k.split(".")[0] for k in det.state_dict()} == {"vfe", "map_to_bev_module", "backbone_2d", "dense_head"}
+    pred_dicts, recall_dicts, bd = det({"points": torch.from_numpy(synth.collate_points(frames)).cuda(), "batch_size": len(frames)})
+    torch.cuda.synchronize()
+    assert len(pred_dicts) == len(frames) and recall_dicts == {}
+    cls, box = bd["batch_cls_preds"].cpu().numpy(), bd["batch_box_preds"].cpu().numpy()
+    n = 0
+    for f, pd in enumerate(pred_dicts):
+        sel, sc, lab, margin = op.post_process_frame(cls[f], box[f], return_margin=True)
+        if margin > 1e-5:
+            assert np.array_equal(pd["pred_boxes"].cpu().numpy(), box[f][sel]) and np.array_equal(pd["pred_labels"].cpu().numpy(), lab)
+            n += len(sel)
+    assert n > 0
+    with pytest.raises(KeyError):
+        det.load_reference_state({"vfe.bogus": torch.zeros(1)})
