@@ -26,7 +26,8 @@ with torch.no_grad():
     lv0, lv1, lv2 = pl["lv"]
     cases = [("L0 body 128->128", P["blocks"][0][1], lv0["a"], H, W, lv0["b"]),
              ("L1 body 256->256", P["blocks"][1][1], lv1["a"], lv1["h"], lv1["w"], lv1["b"]),
-             ("L2 body 512->512", P["blocks"][2][1], lv2["a"], lv2["h"], lv2["w"], lv2["b"])]
+             ("L2 body 512->512", P["blocks"][2][1], lv2["a"], lv2["h"], lv2["w"], lv2["b"]),
+             ("L0 scale 32->32 (64-ch rows)", P["scale"][0], y_in, H, W, lv0["y"])]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for label, lay, src, h, w, dst in cases:
         res = {k: [] for k in MODES}
