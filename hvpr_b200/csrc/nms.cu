@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(1024) pp_topk_kernel(const unsigned long long 
     __shared__ int hist[2048];
     __shared__ unsigned long long s_prefix;
     __shared__ int s_remaining, s_fill;
+    __shared__ int s_wsum[32];
     const int f = blockIdx.x, t = threadIdx.x;
     const unsigned long long *src = cand + (int64_t)f * N;
     const int n = count[f];
@@ -105,11 +106,26 @@ __global__ void __launch_bounds__(1024) pp_topk_kernel(const unsigned long long 
                 if (digit >= 0 && (t & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], __popc(peers));
             }
             __syncthreads();
-            if (t == 0) {
-                int rem = s_remaining, d = (1 << bits) - 1;
-                for (; d > 0; --d) { if (hist[d] >= rem) break; rem -= hist[d]; }
-                s_prefix = prefix | ((unsigned long long)d << sh);
-                s_remaining = rem;
+            // find the digit d with  sum(hist[d+1..]) < remaining <= sum(hist[d..])  in parallel: thread t owns bins 2t, 2t+1, a
+            // suffix scan inside each warp, then over the 32 warp totals (a serial scan of 2048 bins by one thread was 80 % of the kernel)
+            {
+                const int lane = t & 31, wid = t >> 5;
+                const int h0 = hist[2 * t], h1 = hist[2 * t + 1];
+                int suf = h0 + h1;                                   // inclusive suffix sum over the warp's lanes (higher bins first)
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_down_sync(0xffffffffu, suf, o); if (lane + o < 32) suf += v; }
+                if (lane == 0) s_wsum[wid] = suf;                    // total of this warp's 64 bins
+                const int rem = s_remaining;                         // read before the barrier: one thread rewrites it below
+                __syncthreads();
+                int above = 0;                                       // bins of all higher warps
+                for (int w2 = wid + 1; w2 < 32; ++w2) above += s_wsum[w2];
+                const int incl = above + suf;                        // sum over bins >= 2t
+                const int excl_pair = incl - (h0 + h1);              // sum over bins >= 2t+2
+                if (excl_pair < rem && rem <= incl) {                // the target digit is 2t+1 or 2t: exactly one thread gets here
+                    const int d = (excl_pair + h1 >= rem) ? 2 * t + 1 : 2 * t;
+                    s_prefix = prefix | ((unsigned long long)d << sh);
+                    s_remaining = rem - (d == 2 * t + 1 ? excl_pair : excl_pair + h1);
+                }
             }
             __syncthreads();
             if (sh == 0) break;
@@ -307,11 +323,14 @@ __global__ void __launch_bounds__(64) pp_reduce_kernel(const float *__restrict__
             out_index[(int64_t)f * post_max + o] = (int32_t)idx;
         }
         if (t > blk && t < nblk) {
-            unsigned long long k2 = keep;
-            while (k2) {
-                const int j = __ffsll((long long)k2) - 1;
-                k2 &= k2 - 1;
-                removed |= mk[(int64_t)(blk * 64 + j) * kPpWords + t];
+            // rows of the kept boxes, eight loads in flight at a time (a load-then-OR loop serialises one L2 round trip per kept box)
+            for (int q0 = 0; q0 < m; q0 += 8) {
+                unsigned long long rowsv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    rowsv[u] = (q0 + u < m) ? mk[(int64_t)(blk * 64 + s_list[q0 + u]) * kPpWords + t] : 0ull;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) removed |= rowsv[u];
             }
         }
         __syncthreads();
