@@ -9,7 +9,9 @@ collective on the data path; NCCL only reduces the timings).
     python bench.py [--gpus N] [--steps K] [--warmup W]           our arm
     python bench.py --impl reference ...                           the reference's CPU path (oracle port) on host cores
 
-Prints ONE JSON line (rank 0).
+Prints ONE JSON line (rank 0).  At N = 1 the line also carries `next_rows.bev_backbone`: the widened rows N1-N3 of SURVEY.md §8f measured on
+the same batch — BaseBEVBackbone_Scale on the tcgen05 conv kernel (ms, TFLOP/s vs the measured bf16 peak, the same network through cuDNN as the
+library baseline), the dense head, the NMS post-processing, and points -> features / boxes / detections end to end (`--no-backbone` skips it).
 """
 from __future__ import annotations
 
