@@ -64,6 +64,7 @@ struct TcSmem {
     uint16_t cand[kTcCandBufs][kTcCandCap][kTcTileM];
     int32_t cand_cnt[kTcCandBufs][kTcTileM];
     float gm[16][kTcTileM];                   // group maxima of the current chunk, one column per filter thread
+    alignas(16) uint32_t bcast[kTcTailWarps][2][32];   // per tail warp: candidate indices / softmax weights, read back as LDS.128 broadcasts
     uint64_t w_full[kTcWStages], w_empty[kTcWStages];
     uint64_t a_full[2], a_empty[2];
     uint64_t t_full[2];
@@ -261,18 +262,25 @@ __device__ __noinline__ void tail_slow_row(const float *__restrict__ prow, const
 // candidate, a single L2 round trip); the 32 per-candidate partial dots are transpose-reduced across the warp with 31
 // shuffles so that lane c ends up with the exact fp32 logit of candidate c; the rows stay in registers for the readout.
 __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, const float *__restrict__ W, int k, int cnt,
-                                              const uint16_t *__restrict__ cand_col /* stride kTcTileM */,
+                                              const uint16_t *__restrict__ cand_col /* stride kTcTileM */, uint32_t (*bc)[32],
                                               float *__restrict__ out_row, int32_t *__restrict__ idx_row, int lane TCP_ROW_ARG) {
     TCP_ROW_START;
     const float2 p2 = __ldg(reinterpret_cast<const float2 *>(prow) + lane);
     // slots past cnt replay candidate 0 (an L1 hit) so that all 32 gathers are unconditional and issue back to back:
     // any branch here makes the compiler merge registers per group and serialises the L2 round trips
     const int my_j = (int)cand_col[((lane < cnt) ? lane : 0) * kTcTileM];
+    // lane c's index / weight is needed by every lane: one store + eight 128-bit shared-memory broadcasts instead of 32 shuffles
+    __syncwarp();
+    bc[0][lane] = (uint32_t)my_j;
+    __syncwarp();
     float2 w2[32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-        const int j = __shfl_sync(0xffffffffu, my_j, c);
-        w2[c] = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)j * kTcK) + lane);
+    for (int c4 = 0; c4 < 8; ++c4) {
+        const uint4 jj = *reinterpret_cast<const uint4 *>(&bc[0][4 * c4]);
+        w2[4 * c4 + 0] = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)jj.x * kTcK) + lane);
+        w2[4 * c4 + 1] = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)jj.y * kTcK) + lane);
+        w2[4 * c4 + 2] = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)jj.z * kTcK) + lane);
+        w2[4 * c4 + 3] = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)jj.w * kTcK) + lane);
     }
     float s[32];
 #pragma unroll
@@ -308,10 +316,15 @@ __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, co
     const float a = ex / sum;
     TCP_ROW_T(2);
     float o0 = 0.0f, o1 = 0.0f;
+    bc[1][lane] = __float_as_uint(a);                          // 0 for dropped / absent candidates
+    __syncwarp();
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-        const float ac = __shfl_sync(0xffffffffu, a, c);       // 0 for dropped / absent candidates
-        o0 = fmaf(ac, w2[c].x, o0); o1 = fmaf(ac, w2[c].y, o1);
+    for (int c4 = 0; c4 < 8; ++c4) {
+        const uint4 aa = *reinterpret_cast<const uint4 *>(&bc[1][4 * c4]);
+        o0 = fmaf(__uint_as_float(aa.x), w2[4 * c4 + 0].x, o0); o1 = fmaf(__uint_as_float(aa.x), w2[4 * c4 + 0].y, o1);
+        o0 = fmaf(__uint_as_float(aa.y), w2[4 * c4 + 1].x, o0); o1 = fmaf(__uint_as_float(aa.y), w2[4 * c4 + 1].y, o1);
+        o0 = fmaf(__uint_as_float(aa.z), w2[4 * c4 + 2].x, o0); o1 = fmaf(__uint_as_float(aa.z), w2[4 * c4 + 2].y, o1);
+        o0 = fmaf(__uint_as_float(aa.w), w2[4 * c4 + 3].x, o0); o1 = fmaf(__uint_as_float(aa.w), w2[4 * c4 + 3].y, o1);
     }
     reinterpret_cast<float2 *>(out_row)[lane] = make_float2(o0, o1);
     TCP_ROW_T(3);
@@ -674,7 +687,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
                 const float *prow = pillars + grow * kTcK;
                 int32_t *idx_row = topk_idx_out ? topk_idx_out + grow * k : nullptr;
                 if (cnt >= k && cnt <= 32)
-                    tail_fast_row(prow, W, k, cnt, &S.cand[cb][0][r], readout + grow * kTcK, idx_row, lane TCP_ROW_PASS);
+                    tail_fast_row(prow, W, k, cnt, &S.cand[cb][0][r], S.bcast[tw], readout + grow * kTcK, idx_row, lane TCP_ROW_PASS);
                 else if (cnt > 32 && cnt <= kTcCandCap)
                     tail_medium_row(prow, W, k, cnt, &S.cand[cb][0][r], readout + grow * kTcK, idx_row, lane);
                 else
