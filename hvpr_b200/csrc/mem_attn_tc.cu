@@ -258,37 +258,58 @@ __device__ __noinline__ void tail_slow_row(const float *__restrict__ prow, const
     if (idx_row && lane < k) idx_row[lane] = my_idx;
 }
 
-// fast path: <= 32 candidates.  Every lane loads 2 channels of EVERY candidate row (one coalesced 256-B request per
-// candidate, a single L2 round trip); the 32 per-candidate partial dots are transpose-reduced across the warp with 31
-// shuffles so that lane c ends up with the exact fp32 logit of candidate c; the rows stay in registers for the readout.
+// packed fp32 pairs (sm_100 FMUL2 / FFMA2): one instruction for two channels
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long *>(&d))
+        : "l"(*reinterpret_cast<const unsigned long long *>(&a)), "l"(*reinterpret_cast<const unsigned long long *>(&b)));
+    return d;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(*reinterpret_cast<unsigned long long *>(&d))
+        : "l"(*reinterpret_cast<const unsigned long long *>(&a)), "l"(*reinterpret_cast<const unsigned long long *>(&b)),
+          "l"(*reinterpret_cast<const unsigned long long *>(&c)));
+    return d;
+}
+
+// fast path: <= 32 candidates.  The warp works as two half-warps of 16 candidates each: a lane loads 4 channels of every
+// candidate row of its half (one 256-B row per half-warp per request, a single L2 round trip for all 16), the 16
+// per-candidate partial dots are transpose-reduced across the half with 15 shuffles so that lane c ends up with the exact
+// fp32 logit of candidate c; the rows stay in registers for the readout, whose two half sums meet in one last exchange.
 __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, const float *__restrict__ W, int k, int cnt,
                                               const uint16_t *__restrict__ cand_col /* stride kTcTileM */, uint32_t (*bc)[32],
                                               float *__restrict__ out_row, int32_t *__restrict__ idx_row, int lane TCP_ROW_ARG) {
     TCP_ROW_START;
-    const float2 p2 = __ldg(reinterpret_cast<const float2 *>(prow) + lane);
-    // slots past cnt replay candidate 0 (an L1 hit) so that all 32 gathers are unconditional and issue back to back:
+    const int sub = lane & 15, hb = lane & 16;                // channel quad / first candidate slot of this half
+    const float4 p4 = __ldg(reinterpret_cast<const float4 *>(prow) + sub);
+    // slots past cnt replay candidate 0 (an L1 hit) so that all gathers are unconditional and issue back to back:
     // any branch here makes the compiler merge registers per group and serialises the L2 round trips
     const int my_j = (int)cand_col[((lane < cnt) ? lane : 0) * kTcTileM];
-    // lane c's index / weight is needed by every lane: one store + eight 128-bit shared-memory broadcasts instead of 32 shuffles
+    // lane c's index / weight is needed by every lane of its half: one store + four 128-bit shared-memory broadcasts
     __syncwarp();
     bc[0][lane] = (uint32_t)my_j;
     __syncwarp();
-    float2 w2[32];
+    float4 w4[16];
 #pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) {
-        const uint4 jj = *reinterpret_cast<const uint4 *>(&bc[0][4 * c4]);
-        w2[4 * c4 + 0] = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)jj.x * kTcK) + lane);
-        w2[4 * c4 + 1] = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)jj.y * kTcK) + lane);
-        w2[4 * c4 + 2] = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)jj.z * kTcK) + lane);
-        w2[4 * c4 + 3] = __ldg(reinterpret_cast<const float2 *>(W + (int64_t)jj.w * kTcK) + lane);
+    for (int c4 = 0; c4 < 4; ++c4) {
+        const uint4 jj = *reinterpret_cast<const uint4 *>(&bc[0][hb + 4 * c4]);
+        w4[4 * c4 + 0] = __ldg(reinterpret_cast<const float4 *>(W + (int64_t)jj.x * kTcK) + sub);
+        w4[4 * c4 + 1] = __ldg(reinterpret_cast<const float4 *>(W + (int64_t)jj.y * kTcK) + sub);
+        w4[4 * c4 + 2] = __ldg(reinterpret_cast<const float4 *>(W + (int64_t)jj.z * kTcK) + sub);
+        w4[4 * c4 + 3] = __ldg(reinterpret_cast<const float4 *>(W + (int64_t)jj.w * kTcK) + sub);
     }
-    float s[32];
+    float s[16];
+    const float2 pa = make_float2(p4.x, p4.y), pb = make_float2(p4.z, p4.w);
 #pragma unroll
-    for (int c = 0; c < 32; ++c) s[c] = fmaf(w2[c].y, p2.y, w2[c].x * p2.x);
+    for (int c = 0; c < 16; ++c) {
+        const float2 t = fma2(make_float2(w4[c].z, w4[c].w), pb, mul2(make_float2(w4[c].x, w4[c].y), pa));
+        s[c] = t.x + t.y;
+    }
     TCP_ROW_T(0);
-    // transpose-reduce: after the stage with xor-distance d, a lane keeps the half of the values selected by its bit d
+    // transpose-reduce inside the half: after the stage with xor-distance d, a lane keeps the half of the values selected by its bit d
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
+    for (int d = 8; d > 0; d >>= 1) {
         const bool up = (lane & d) != 0;
 #pragma unroll
         for (int i = 0; i < d; ++i) {
@@ -315,18 +336,26 @@ __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, co
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float a = ex / sum;
     TCP_ROW_T(2);
-    float o0 = 0.0f, o1 = 0.0f;
+    float2 oa = make_float2(0.0f, 0.0f), ob = oa;
     bc[1][lane] = __float_as_uint(a);                          // 0 for dropped / absent candidates
     __syncwarp();
 #pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) {
-        const uint4 aa = *reinterpret_cast<const uint4 *>(&bc[1][4 * c4]);
-        o0 = fmaf(__uint_as_float(aa.x), w2[4 * c4 + 0].x, o0); o1 = fmaf(__uint_as_float(aa.x), w2[4 * c4 + 0].y, o1);
-        o0 = fmaf(__uint_as_float(aa.y), w2[4 * c4 + 1].x, o0); o1 = fmaf(__uint_as_float(aa.y), w2[4 * c4 + 1].y, o1);
-        o0 = fmaf(__uint_as_float(aa.z), w2[4 * c4 + 2].x, o0); o1 = fmaf(__uint_as_float(aa.z), w2[4 * c4 + 2].y, o1);
-        o0 = fmaf(__uint_as_float(aa.w), w2[4 * c4 + 3].x, o0); o1 = fmaf(__uint_as_float(aa.w), w2[4 * c4 + 3].y, o1);
+    for (int c4 = 0; c4 < 4; ++c4) {
+        const uint4 aa = *reinterpret_cast<const uint4 *>(&bc[1][hb + 4 * c4]);
+        const float a0 = __uint_as_float(aa.x), a1 = __uint_as_float(aa.y), a2 = __uint_as_float(aa.z), a3 = __uint_as_float(aa.w);
+        oa = fma2(make_float2(w4[4 * c4 + 0].x, w4[4 * c4 + 0].y), make_float2(a0, a0), oa);
+        ob = fma2(make_float2(w4[4 * c4 + 0].z, w4[4 * c4 + 0].w), make_float2(a0, a0), ob);
+        oa = fma2(make_float2(w4[4 * c4 + 1].x, w4[4 * c4 + 1].y), make_float2(a1, a1), oa);
+        ob = fma2(make_float2(w4[4 * c4 + 1].z, w4[4 * c4 + 1].w), make_float2(a1, a1), ob);
+        oa = fma2(make_float2(w4[4 * c4 + 2].x, w4[4 * c4 + 2].y), make_float2(a2, a2), oa);
+        ob = fma2(make_float2(w4[4 * c4 + 2].z, w4[4 * c4 + 2].w), make_float2(a2, a2), ob);
+        oa = fma2(make_float2(w4[4 * c4 + 3].x, w4[4 * c4 + 3].y), make_float2(a3, a3), oa);
+        ob = fma2(make_float2(w4[4 * c4 + 3].z, w4[4 * c4 + 3].w), make_float2(a3, a3), ob);
     }
-    reinterpret_cast<float2 *>(out_row)[lane] = make_float2(o0, o1);
+    float4 o4 = make_float4(oa.x, oa.y, ob.x, ob.y);
+    o4.x += __shfl_xor_sync(0xffffffffu, o4.x, 16); o4.y += __shfl_xor_sync(0xffffffffu, o4.y, 16);
+    o4.z += __shfl_xor_sync(0xffffffffu, o4.z, 16); o4.w += __shfl_xor_sync(0xffffffffu, o4.w, 16);
+    if (lane < 16) reinterpret_cast<float4 *>(out_row)[sub] = o4;
     TCP_ROW_T(3);
     if (idx_row) {
         const uint32_t kept = __ballot_sync(0xffffffffu, valid);
@@ -423,6 +452,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
     TcSmem &S = *reinterpret_cast<TcSmem *>(smem_raw);
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef HVPR_TC_PROFILE
+    const long long tcp_kstart = clock64();
+#endif
     int64_t nP = n_pillars_dev ? (int64_t)*n_pillars_dev : n_rows_max;
     if (nP > n_rows_max) nP = n_rows_max;
     const int ntiles = (int)((nP + kTcTileM - 1) / kTcTileM);
@@ -702,7 +734,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
 #endif
     }
 #ifdef HVPR_TC_PROFILE
-    if (tid == 0 && dbg_logits) reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 16 + 15] = clock64();
+    if (tid == 0 && dbg_logits) reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 16 + 15] = clock64() - tcp_kstart;
 #endif
 
     tc_fence_before();

@@ -32,4 +32,5 @@ for rep in range(2):
 pr=prof.cpu().numpy().astype(np.float64)
 m=pr.mean(0)
 names=["mma.wait_a_full","mma.wait_w_full","mma.wait_t_empty","flt.s1.sort+merge","flt.wait_tfull_s1","flt.wait_tfull_s2","flt.wait_c_empty","flt.s1.ld+max","tail.wait_c_full","tail.work","row.gather+dot","row.butterfly","row.select+softmax","row.readout+store","flt.s2.loop"]
+print(f"CTA lifetime mean {m[15]/1e3:.1f} max {pr[:,15].max()/1e3:.1f} kcycles")
 for i,n in enumerate(names): print(f"{n:20s} {m[i]/1e3:10.1f} kcycles")
