@@ -31,7 +31,7 @@ namespace hvpr {
 #define TCP_ROW_START long long tcp_rt = clock64()
 #define TCP_BEGIN() tcp_t0 = clock64()
 #define TCP_END(i) tcp_acc[i] += clock64() - tcp_t0
-#define TCP_DUMP(base) do { if (lane == 0 && dbg_logits) { long long *o_ = reinterpret_cast<long long *>(dbg_logits) + (size_t)blockIdx.x * 16 + (base); \
+#define TCP_DUMP(base) do { if (lane == 0 && dbg_logits) { long long *o_ = reinterpret_cast<long long *>(dbg_logits) + (size_t)blockIdx.x * 24 + (base); \
     for (int i_ = 0; i_ < 4; ++i_) atomicAdd(reinterpret_cast<unsigned long long *>(o_ + i_), (unsigned long long)tcp_acc[i_]); } } while (0)
 #else
 #define TCP_DECL
@@ -69,6 +69,7 @@ struct TcSmem {
     uint64_t a_full[2], a_empty[2];
     uint64_t t_full[2];
     uint32_t tmem_base;
+    int32_t tile_ids[4];                      // ring of dynamically claimed tile indices (-1 = no more work), local tile ti -> slot ti & 3
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -97,6 +98,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
             if (spin > (1u << 26)) __trap();                  // watchdog: a protocol bug must not hang the GPU
         }
     }
+}
+__device__ __forceinline__ bool mbar_test(uint64_t *b, uint32_t parity) {   // non-blocking: has the phase with this parity completed?
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    return done != 0;
 }
 // Hardware named barriers: a waiting warp is descheduled (no polling), unlike an mbarrier try_wait loop.  Used for the long
 // thread-to-thread handoffs; mbarriers remain where the async proxy (TMA, tcgen05.commit) is the signaller.
@@ -444,6 +451,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
                                                                     int k, float *__restrict__ readout,
                                                                     int32_t *__restrict__ topk_idx_out,
                                                                     float *__restrict__ slow_scratch,
+                                                                    int32_t *__restrict__ tile_counter,
                                                                     float *__restrict__ dbg_logits) {
     // __align__(1024) (128-B swizzle atoms) instead of rounding the pointer up by hand: integer arithmetic on the address makes
     // the compiler lose the shared address space and emit generic LD.E / ST.E for every access to S (group maxima, candidate
@@ -454,6 +462,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef HVPR_TC_PROFILE
     const long long tcp_kstart = clock64();
+    unsigned long long tcp_gstart; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tcp_gstart));
 #endif
     int64_t nP = n_pillars_dev ? (int64_t)*n_pillars_dev : n_rows_max;
     if (nP > n_rows_max) nP = n_rows_max;
@@ -467,6 +476,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
         }
         fence_barrier_init();
     }
+    // Dynamic tile schedule: the first tile of a CTA is blockIdx.x, every later one is claimed from a global counter by ONE thread
+    // (tail warp 0, lane 0) two tiles ahead and published through S.tile_ids; the A-tile barrier a_full doubles as the "tile id is
+    // valid" signal for the MMA warp and the filter, and a negative id (still arrived on a_full) ends every role's loop.  On an idle
+    // GPU it equals the static round-robin (0.329 vs 0.331 ms); it keeps the CTAs level when other kernels share the SMs (streaming mode).
+    int next_id = -1;                                          // meaningful in thread 32 only
+    if (tid == 32) {
+#ifdef HVPR_K3_STATIC
+        const int t0 = (int)blockIdx.x, t1 = t0 + (int)gridDim.x, t2 = t1 + (int)gridDim.x;
+#else
+        const int base = atomicAdd(tile_counter, 2);
+        const int t0 = (int)blockIdx.x, t1 = (int)gridDim.x + base, t2 = t1 + 1;
+#endif
+        S.tile_ids[0] = (t0 < ntiles) ? t0 : -1;
+        S.tile_ids[1] = (t1 < ntiles) ? t1 : -1;
+        next_id = (t2 < ntiles) ? t2 : -1;
+    }
+    volatile int32_t *tile_ids = S.tile_ids;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -481,8 +507,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
         // idesc: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcChunkN >> 3) << 17) |
                                ((uint32_t)(kTcTileM >> 4) << 24);
-        const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-        const uint32_t total_it = (uint32_t)my_tiles * 2u * (uint32_t)nchunks;
         auto issue_load = [&](uint32_t itl) {                 // chunk sequence: tile-major, two sweeps, nchunks each
             const int s = itl % kTcWStages;
             const int c = (int)(itl % (uint32_t)nchunks);
@@ -490,20 +514,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
             mbar_arrive_expect_tx(&S.w_full[s], kTcChunkBytes);
             bulk_g2s(S.w[s], Wpk + (size_t)c * kTcChunkBytes, kTcChunkBytes, &S.w_full[s]);
         };
+        // W chunks are prefetched kTcWStages - 1 ahead, but never past the last tile KNOWN to exist (load_limit): a bulk copy
+        // nobody consumes must not be in flight when the CTA exits
+        const uint32_t per_tile = 2u * (uint32_t)nchunks;
+        uint32_t next_load = 0, load_limit = (tile_ids[0] >= 0) ? per_tile : 0u;
         if (lane == 0)
-            for (uint32_t p = 0; p < (uint32_t)(kTcWStages - 1) && p < total_it; ++p) issue_load(p);
+            while (next_load < load_limit && next_load < (uint32_t)(kTcWStages - 1)) issue_load(next_load++);
         uint32_t it = 0, ti = 0;
         TCP_DECL;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+        for (;; ++ti) {
             const int ab = ti & 1;
             TCP_BEGIN();
             mbar_wait(&S.a_full[ab], (ti >> 1) & 1);
             TCP_END(0);
+            if (tile_ids[ti & 3] < 0) break;
+            if (load_limit < (ti + 1) * per_tile) load_limit = (ti + 1) * per_tile;
             const uint64_t adesc = umma_desc_sw128(smem_u32(S.a[ab]));
             for (int sweep = 0; sweep < 2; ++sweep)
                 for (int c = 0; c < nchunks; ++c, ++it) {
                     const int s = it % kTcWStages, tb = it & 1;
-                    if (lane == 0 && it + kTcWStages - 1 < total_it) issue_load(it + kTcWStages - 1);
+                    if (lane == 0) {
+                        // the next tile's A barrier is normally complete long before this tile ends: peek, do not wait
+                        if (load_limit < it + kTcWStages && load_limit == (ti + 1) * per_tile &&
+                            mbar_test(&S.a_full[ab ^ 1], ((ti + 1) >> 1) & 1) && tile_ids[(ti + 1) & 3] >= 0)
+                            load_limit += per_tile;
+                        while (next_load < load_limit && next_load < it + kTcWStages) issue_load(next_load++);
+                    }
                     TCP_BEGIN();
                     mbar_wait(&S.w_full[s], (it / kTcWStages) & 1);
                     TCP_END(1);
@@ -541,7 +577,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
 #define FL_B()
 #define FL_E(i)
 #endif
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+        for (;; ++ti) {
+            mbar_wait(&S.a_full[ti & 1], (ti >> 1) & 1);        // the tile id is published before the A tile is (see the tail)
+            const int t = tile_ids[ti & 3];
+            if (t < 0) break;
             const int cb = ti % kTcCandBufs;
             // ---- sweep 1: group maxima -> tau ----
             float top[32];
@@ -611,7 +650,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
             TCP_BEGIN();
             if (ti >= (uint32_t)kTcCandBufs) named_bar_sync(kBarCEmpty + cb, 128 + 32 * kTcTailWarps);   // tail finished with this candidate buffer
             TCP_END(2);
-            int cnt = 0;
+            int cnt = ((int64_t)t * kTcTileM + row < nP) ? 0 : kTcCandCap;   // dead rows start "overflowed" (their count is never read)
             for (int c = 0; c < nchunks; ++c, ++it) {
                 const int tb = it & 1;
                 TCP_BEGIN();
@@ -633,6 +672,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
                     uint32_t m = ~((n0 << 24) | (n1 << 16) | (n2 << 8) | n3);
                     const int base = col0 + b * 32;
                     if (base + 32 > M) m = (base >= M) ? 0u : (m & ~(0xFFFFFFFFu >> (M - base)));
+                    // rows that already overflowed the candidate list, and rows past the end of the input (zero A rows: every logit
+                    // ties; they start at the cap), only need the count — extracting 2000 tied columns one by one stalled the whole
+                    // warp (the CTA that owned the last, partial tile ran 45 us longer than every other one)
+                    if (cnt >= kTcCandCap) { cnt += __popc(m); m = 0u; }
                     while (m) {
                         const int bit = 31 - __clz((int)m);     // highest set bit = lowest column first
                         m &= ~(1u << bit);
@@ -663,7 +706,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
         }
         if (q == 0) { TCP_DUMP(4); }
 #ifdef HVPR_TC_PROFILE
-        if (q == 0 && lane == 0 && dbg_logits) { reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 16 + 7] = fl_acc[0]; reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 16 + 3] = fl_acc[1]; reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 16 + 14] = fl_acc[2]; }
+        if (q == 0 && lane == 0 && dbg_logits) { reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 24 + 7] = fl_acc[0]; reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 24 + 3] = fl_acc[1]; reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 24 + 14] = fl_acc[2]; }
 #endif
     } else {
         // ===== tail: A-tile loads + exact fp32 re-score, top-k, softmax, readout — one warp per row =================
@@ -693,31 +736,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.a_full[ab]);
         };
+        auto stage_tile = [&](int t_load, uint32_t ti_load) {   // A tile of a claimed tile, or just the barrier arrival for "no more work"
+            if (t_load >= 0) load_a_tile(t_load, ti_load);
+            else { __syncwarp(); if (lane == 0) mbar_arrive(&S.a_full[ti_load & 1]); }
+        };
         // prologue: the first two tiles of this CTA
-        {
-            int t0 = blockIdx.x;
-            if (t0 < ntiles) load_a_tile(t0, 0);
-            if (t0 + (int)gridDim.x < ntiles) load_a_tile(t0 + gridDim.x, 1);
-        }
+        stage_tile(tile_ids[0], 0);
+        stage_tile(tile_ids[1], 1);
         uint32_t ti = 0;
         TCP_DECL;
 #ifdef HVPR_TC_PROFILE
         long long tcp_row_acc[4] = {0, 0, 0, 0};
 #endif
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+        for (;; ++ti) {
+            const int t = tile_ids[ti & 3];
+            if (t < 0) break;
             const int cb = ti % kTcCandBufs;
+            if (tid == 32) tile_ids[(ti + 2) & 3] = next_id;     // ordered before every tail warp's read by the barrier below
             TCP_BEGIN();
             named_bar_sync(kBarCFull + cb, 128 + 32 * kTcTailWarps);
             TCP_END(0);
             TCP_BEGIN();
-            // tile t's MMAs are complete (its candidates exist), so its A buffer is free: stage tile t + 2 into it
-            if (t + 2 * (int)gridDim.x < ntiles) load_a_tile(t + 2 * gridDim.x, ti + 2);
+            if (tid == 32) {                                     // claim the tile after next; the round trip hides behind this tile's rows
+#ifdef HVPR_K3_STATIC
+                const int v = (int)blockIdx.x + (int)(ti + 3) * (int)gridDim.x;
+#else
+                const int v = (int)gridDim.x + atomicAdd(tile_counter, 1);
+#endif
+                next_id = (v < ntiles) ? v : -1;
+            }
+            // tile t's MMAs are complete (its candidates exist), so its A buffer is free: stage tile ti + 2 into it
+            stage_tile(tile_ids[(ti + 2) & 3], ti + 2);
             for (int r = tw; r < kTcTileM; r += kTcTailWarps) {
                 const int64_t grow = (int64_t)t * kTcTileM + r;
                 if (grow >= nP) break;
                 const int cnt = S.cand_cnt[cb][r];
                 const float *prow = pillars + grow * kTcK;
                 int32_t *idx_row = topk_idx_out ? topk_idx_out + grow * k : nullptr;
+#ifdef HVPR_TC_PROFILE
+                if (lane == 0 && dbg_logits) atomicAdd(reinterpret_cast<unsigned long long *>(dbg_logits) + (size_t)blockIdx.x * 24 + ((cnt >= k && cnt <= 32) ? 19 : (cnt > 32 && cnt <= kTcCandCap) ? 20 : 21), 1ull);
+#endif
                 if (cnt >= k && cnt <= 32)
                     tail_fast_row(prow, W, k, cnt, &S.cand[cb][0][r], S.bcast[tw], readout + grow * kTcK, idx_row, lane TCP_ROW_PASS);
                 else if (cnt > 32 && cnt <= kTcCandCap)
@@ -730,11 +788,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
         }
         if (tw == 0) { TCP_DUMP(8); }
 #ifdef HVPR_TC_PROFILE
-        if (tw == 0 && lane == 0 && dbg_logits) for (int i_ = 0; i_ < 4; ++i_) reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 16 + 10 + i_] = tcp_row_acc[i_];
+        if (tw == 0 && lane == 0 && dbg_logits) for (int i_ = 0; i_ < 4; ++i_) reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 24 + 10 + i_] = tcp_row_acc[i_];
 #endif
     }
 #ifdef HVPR_TC_PROFILE
-    if (tid == 0 && dbg_logits) reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 16 + 15] = clock64() - tcp_kstart;
+    if (tid == 0 && dbg_logits) reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 24 + 15] = clock64() - tcp_kstart;
+    if (tid == 0 && dbg_logits) {
+        unsigned long long g1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        long long *o_ = reinterpret_cast<long long *>(dbg_logits) + (size_t)blockIdx.x * 24;
+        o_[16] = (long long)tcp_gstart; o_[17] = (long long)g1; o_[18] = smid;
+    }
 #endif
 
     tc_fence_before();
@@ -775,7 +839,7 @@ int hvpr_mem_attn_tc_init() {
 }
 
 size_t hvpr_mem_attn_tc_workspace_bytes(int64_t, int) {
-    return (size_t)kNumSMs * kTcTailWarps * kTcSlowScratch * sizeof(float) + 256;
+    return (size_t)kNumSMs * kTcTailWarps * kTcSlowScratch * sizeof(float) + 512;   // + alignment slack + the tile counter
 }
 
 int hvpr_mem_pack_bf16_impl(const float *W, int M, int C, void *out, cudaStream_t stream) {
@@ -795,13 +859,19 @@ static int tc_launch(const float *pillars, const int32_t *n_pillars_dev, int64_t
     if (((uintptr_t)W | (uintptr_t)Wpk | (uintptr_t)pillars | (uintptr_t)readout) % 16) return HVPR_ERR_ARG;
     if (!workspace || workspace_bytes < hvpr_mem_attn_tc_workspace_bytes(n_rows_max, M)) return HVPR_ERR_WORKSPACE;
     float *scratch = (float *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    int32_t *tile_counter = (int32_t *)(scratch + (size_t)kNumSMs * kTcTailWarps * kTcSlowScratch);
+#ifndef HVPR_K3_STATIC
+    // the dynamic tile schedule starts from zero on every launch; a memset node when the stream is being captured
+    cudaError_t me = cudaMemsetAsync(tile_counter, 0, sizeof(int32_t), stream);
+    if (me != cudaSuccess) { set_cuda_error(me); return HVPR_ERR_CUDA; }
+#endif
     const int nchunks = (M + kTcChunkN - 1) / kTcChunkN;
     int64_t tiles = (n_rows_max + kTcTileM - 1) / kTcTileM;
     int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
     if (grid < 1) grid = 1;
     mem_attn_tc_kernel<<<grid, kTcThreads, tc_smem_bytes(), stream>>>(pillars, n_pillars_dev, n_rows_max, W,
                                                                       (const uint8_t *)Wpk, M, nchunks, k, readout,
-                                                                      topk_idx_out, scratch, dbg_logits);
+                                                                      topk_idx_out, scratch, tile_counter, dbg_logits);
     HVPR_CHECK_LAUNCH();
     return HVPR_OK;
 }
