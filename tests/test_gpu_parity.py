@@ -252,6 +252,42 @@ def test_mem_attn_vs_oracle(precision, tol):
     assert bool((a[:, 1:] != a[:, :-1]).all()) and int(a.min()) >= 0 and int(a.max()) < 2000   # 20 distinct valid items
 
 
+def test_mem_attn_tc_many_tiles_dead_and_degenerate_rows():
+    """The tensor-core kernel's dynamic tile schedule (548 tiles: every CTA claims tiles beyond its prologue), a device-side row
+    count below the buffer size (the last live tile is partial, the tiles after it are dead) and degenerate all-zero pillar rows
+    (every logit ties: candidate overflow -> exact full-scan path).  Live rows match the oracle, dead rows are never written."""
+    from hvpr_b200.map_to_bev import MemoryUnit_Agg
+    rows, live = 70001, 65003
+    pil, W = _mem_inputs(rows, 11)
+    zero_rows = list(range(700, live, 1499)) + list(range(12790, 12810))      # isolated ones + a run across a tile boundary
+    pil[zero_rows] = 0.0
+    with torch.no_grad():
+        ref = hybrid.memory_attention(pil[:live], W, 20)
+    m = MemoryUnit_Agg(2000, 64).cuda().eval()
+    m.precision = "bf16_rescore"
+    with torch.no_grad():
+        m.weight.copy_(W)
+    n_dev = torch.tensor([live], dtype=torch.int32, device="cuda")
+    out = torch.full((rows, 64), float("nan"), device="cuda")
+    idx = torch.full((rows, 20), -1, dtype=torch.int32, device="cuda")
+    for _ in range(2):                                   # twice: the tile counter must restart from zero on every launch
+        out.fill_(float("nan"))
+        m.run(pil.cuda(), 20, n_pillars_dev=n_dev, out=out, topk_idx_out=idx)
+    torch.cuda.synchronize()
+    assert bool(torch.isnan(out[live:]).all()) and int(idx[live:].max()) == -1
+    got = out[:live].cpu()
+    assert bool(torch.isfinite(got).all())
+    zr = torch.tensor(zero_rows)
+    # an all-zero row: 20 equal logits -> uniform weights over the 20 lowest-numbered items (torch.topk's pick is unspecified)
+    assert bool((idx[:live].cpu()[zr].long() == torch.arange(20)).all())
+    assert float((got[zr] - W[:20].mean(0)).abs().max()) <= 1e-6
+    keep = torch.ones(live, dtype=torch.bool); keep[zr] = False
+    err, _ = tie_aware_readout_check(got[keep], ref[keep], pil[:live][keep], W, TOL_FP32, idx=idx[:live].cpu()[keep])
+    assert err <= TOL_FP32
+    a = torch.sort(idx[:live].cpu().long()[keep], 1)[0]
+    assert bool((a[:, 1:] != a[:, :-1]).all()) and int(a.min()) >= 0 and int(a.max()) < 2000
+
+
 def test_mem_attn_tc_gemm_logits():
     """tcgen05 plumbing in isolation: the TMEM accumulators equal a bf16-input / fp32-accumulate matmul
     (descriptors, 128-B swizzle, instruction descriptor, tcgen05.ld lane mapping)."""
