@@ -1,0 +1,23 @@
+"""Dev probe: time K1 (voxelize, 6 launches) alone on the bench workload; optional library variant suffix."""
+import sys, numpy as np, torch
+sys.path.insert(0, '.')
+from hvpr_b200 import _lib
+v = sys.argv[1] if len(sys.argv) > 1 else ""
+if v: _lib.LIB_PATH = _lib.LIB_PATH.replace("libhvpr_b200.so", "libhvpr_b200_%s.so" % v)
+from hvpr_b200 import synth
+from hvpr_b200.geometry import G2
+from hvpr_b200.frontend import HybridFrontEnd
+fe = HybridFrontEnd(G2).load_reference_weights(synth.random_frontend_weights(0))
+B, N = 8, 120000
+frames = synth.make_batch("L", N, G2.point_cloud_range, B)
+p = fe.plan(B, B * N, N, use_graph=False)
+p.points.copy_(torch.from_numpy(np.concatenate(frames, 0))); p.frame_offsets.copy_(torch.tensor(np.r_[0, np.cumsum([N] * B)], dtype=torch.int32))
+fe.run(); torch.cuda.synchronize()
+def k1(): fe.voxelizer.run(p.points, p.frame_offsets, B, N, out=p.vox)
+for _ in range(5): k1()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(30): k1()
+e1.record(); torch.cuda.synchronize()
+print("variant", v or "default", "K1 ms", round(e0.elapsed_time(e1) / 30, 4))
