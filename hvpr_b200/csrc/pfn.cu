@@ -265,21 +265,27 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_kernel(const __grid_consta
             for (int k4 = 0; k4 < 4; ++k4)
                 *reinterpret_cast<float4 *>(&xs[lane][4 * k4]) = make_float4(x0[4 * k4], x0[4 * k4 + 1], x0[4 * k4 + 2], x0[4 * k4 + 3]);
             pid[lane] = pl;
+            // bit r: row r starts a new pillar run (points arrive pillar by pillar).  The segmented maxima below test this
+            // register instead of loading and comparing the pillar id of every row (a dependent LDS -> compare -> branch per row)
+            const int pl_prev = __shfl_up_sync(0xffffffffu, pl, 1);
+            const uint32_t bnd = __ballot_sync(0xffffffffu, lane == 0 || pl != pl_prev);
             __syncwarp();
 
             // pillar max of the layer-0 activations: lane = (half, column); 16 rows each
             {
                 const int k = lane & 15, r0 = (lane >> 4) * 16;
+                const uint32_t b16 = bnd >> r0;
                 int cur = pid[r0];
                 float acc = 0.0f;
-#pragma unroll 4
+                float v[16];
+#pragma unroll
+                for (int r = 0; r < 16; ++r) v[r] = xs[r0 + r][k];      // all loads in flight before the dependent max chain
+#pragma unroll
                 for (int r = 0; r < 16; ++r) {
-                    const int pr = pid[r0 + r];
-                    const float v = xs[r0 + r][k];
-                    if (pr != cur) {
+                    if (r > 0 && ((b16 >> r) & 1u)) {
                         if (cur >= 0) atomicMax(&S.xmax[cur][k], __float_as_uint(acc));
-                        cur = pr; acc = v;
-                    } else acc = fmaxf(acc, v);
+                        cur = pid[r0 + r]; acc = v[r];
+                    } else acc = fmaxf(acc, v[r]);
                 }
                 if (cur >= 0) atomicMax(&S.xmax[cur][k], __float_as_uint(acc));
             }
@@ -315,16 +321,21 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_kernel(const __grid_consta
                 __syncwarp();
                 // pillar max over the 16 staged points: lane owns channels (2*lane, 2*lane+1)
                 {
+                    const uint32_t b16 = bnd >> (16 * mt);               // warp-uniform
                     int cur = pid[16 * mt];
                     float2 acc = make_float2(-INFINITY, -INFINITY);
-#pragma unroll 4
-                    for (int r = 0; r < 16; ++r) {
-                        const int pr = pid[16 * mt + r];
-                        const float2 v = *reinterpret_cast<const float2 *>(&ys[r][2 * lane]);
-                        if (pr != cur) {
-                            if (cur >= 0) { atomicMax(&S.m1[cur][2 * lane], pfn_key(acc.x)); atomicMax(&S.m1[cur][2 * lane + 1], pfn_key(acc.y)); }
-                            cur = pr; acc = v;
-                        } else { acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); }
+#pragma unroll
+                    for (int rb = 0; rb < 16; rb += 8) {
+                        float2 v[8];
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) v[r] = *reinterpret_cast<const float2 *>(&ys[rb + r][2 * lane]);
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            if (rb + r > 0 && ((b16 >> (rb + r)) & 1u)) {
+                                if (cur >= 0) { atomicMax(&S.m1[cur][2 * lane], pfn_key(acc.x)); atomicMax(&S.m1[cur][2 * lane + 1], pfn_key(acc.y)); }
+                                cur = pid[16 * mt + rb + r]; acc = v[r];
+                            } else { acc.x = fmaxf(acc.x, v[r].x); acc.y = fmaxf(acc.y, v[r].y); }
+                        }
                     }
                     if (cur >= 0) { atomicMax(&S.m1[cur][2 * lane], pfn_key(acc.x)); atomicMax(&S.m1[cur][2 * lane + 1], pfn_key(acc.y)); }
                 }
