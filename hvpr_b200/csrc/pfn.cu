@@ -12,6 +12,9 @@
 
 namespace hvpr {
 
+#ifndef HVPR_PFN_STRIDED
+#define HVPR_PFN_STRIDED 1
+#endif
 constexpr int kPfnThreads = 128;
 constexpr int kPfnG = 32;        // pillars per group (one group per block iteration)
 constexpr int kPfnXS = 20;       // row stride (floats) of the layer-0 activation staging: conflict-free fragment loads
@@ -159,12 +162,19 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_kernel(const __grid_consta
     }
 
     for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-        const int64_t g0 = grp * kPfnG;
+        // Pillar of group slot pl.  Slots are strided (pl * ngroups + grp), not consecutive: first-seen order puts the crowded
+        // near-field pillars (32 real points instead of ~4) into the lowest rows of every frame, so consecutive groups
+        // were 8x heavier there and the static round-robin left the blocks that drew them running alone at the end.
+#if HVPR_PFN_STRIDED
+#define PFN_ROW(pl) ((int64_t)(pl) * ngroups + grp)
+#else
+#define PFN_ROW(pl) (grp * kPfnG + (pl))
+#endif
         __syncthreads();      // previous group's readers are done (and the fragments above are visible)
 
         // ---- phase 0: counts, exclusive scan (one warp), pillar centres --------------------------------------
         if (t < kPfnG) {
-            const int64_t p = g0 + t;
+            const int64_t p = PFN_ROW(t);
             int n = 0;
             if (p < nP) {
                 n = num_points[p];
@@ -191,7 +201,7 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_kernel(const __grid_consta
         // ---- phase 1: per-pillar mean (4 threads per pillar, fixed combination order -> deterministic) --------
         {
             const int pl = lane, n = S.n[pl];
-            const int64_t p = g0 + pl;
+            const int64_t p = PFN_ROW(pl);
             float sx = 0.f, sy = 0.f, sz = 0.f;
             for (int j = q4; j < n; j += 4) {
                 float4 v = __ldg(vox4 + p * T + j);
@@ -224,7 +234,7 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_kernel(const __grid_consta
             __syncthreads();
             float o[8];
             PFN_DISPATCH_Q(q4, pfn_scale_out<Q>(P, S, pl, o));
-            const int64_t p = g0 + pl;
+            const int64_t p = PFN_ROW(pl);
             if (p < nP) {
                 float4 *dst = reinterpret_cast<float4 *>(scale_out + p * 32 + q4 * 8);
                 dst[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -244,7 +254,7 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_kernel(const __grid_consta
             if (qpt < total) {
                 pl = find_pillar(S.poff, qpt);
                 const int j = qpt - S.poff[pl];
-                const float4 v = __ldg(vox4 + (g0 + pl) * T + j);
+                const float4 v = __ldg(vox4 + PFN_ROW(pl) * T + j);
                 float f[10];
                 f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
                 f[4] = v.x - S.mean[pl][0]; f[5] = v.y - S.mean[pl][1]; f[6] = v.z - S.mean[pl][2];
@@ -374,7 +384,7 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_kernel(const __grid_consta
 #pragma unroll
                     for (int hrow = 0; hrow < 2; ++hrow) {
                         const int pl = 16 * mt + gid + 8 * hrow;
-                        const int64_t p = g0 + pl;
+                        const int64_t p = PFN_ROW(pl);
                         const float o0 = fmaxf(pfn_unkey(S.m1[pl][ch]) + (c[2 * hrow] + S.b1s[ch]), 0.0f);
                         const float o1 = fmaxf(pfn_unkey(S.m1[pl][ch + 1]) + (c[2 * hrow + 1] + S.b1s[ch + 1]), 0.0f);
                         if (p < nP) *reinterpret_cast<float2 *>(feats + p * 64 + ch) = make_float2(o0, o1);

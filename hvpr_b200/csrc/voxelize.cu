@@ -291,9 +291,19 @@ __device__ __forceinline__ int32_t bitonic_sort_bounded_asc(int32_t x, int lane,
     return x;
 }
 
-// One warp handles 32 consecutive voxel slots: lane <-> voxel for the metadata (coalesced), then the voxels are
-// materialised four at a time so that the CSR loads, the point gathers and the 512-byte row stores of four voxels are
-// in flight together (the kernel is latency-bound: each voxel needs two dependent loads).
+// One warp handles 32 voxel slots of one frame: lane <-> voxel for the metadata, then the voxels are materialised four
+// at a time so that the CSR loads, the point gathers and the 512-byte row stores of four voxels are in flight together
+// (each voxel needs two dependent loads).  The 32 slots are NOT consecutive: lane l of warp w takes slot
+// (l / kGatherRun * warps_per_frame + w) * kGatherRun + l % kGatherRun.  First-seen order puts the crowded near-field
+// pillars (n > 32: extra CSR chunks + sort/merge rounds, ~10x the work of a 1..4-point pillar) into the lowest ranks of
+// every frame, so consecutive slots gave a few warps 32 heavy pillars each and the kernel waited for them (ncu: SMs
+// active 57 % of the elapsed cycles); strided runs of kGatherRun slots give every warp at most kGatherRun of them and the same
+// number of live voxels: 60 -> 37 us on the headline batch (runs of 1 and 4 measure the same; 4 keeps 16-byte metadata
+// segments).
+#ifndef HVPR_GATHER_RUN
+#define HVPR_GATHER_RUN 4
+#endif
+constexpr int kGatherRun = HVPR_GATHER_RUN;      // consecutive slots per run (power of two <= 32)
 constexpr int kGatherGroup = 4;
 template <bool kVec4>
 __global__ void __launch_bounds__(256) vox_gather_kernel(const float *__restrict__ pts, int stride, int xyz_col,
@@ -318,24 +328,26 @@ __global__ void __launch_bounds__(256) vox_gather_kernel(const float *__restrict
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x <= B) voxel_offsets[threadIdx.x] = s_base[threadIdx.x];
 
-    const int64_t total_slots = (int64_t)B * max_vox;
+    const int runs_per_frame = (max_vox + kGatherRun - 1) / kGatherRun;
+    const int wpf = (runs_per_frame + 32 / kGatherRun - 1) / (32 / kGatherRun);      // warps per frame
+    const int64_t total_warps = (int64_t)B * wpf;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     float4 *vox4 = reinterpret_cast<float4 *>(voxels);
-    for (int64_t wbase = warp0 * 32; wbase < total_slots; wbase += nwarps * 32) {
+    for (int64_t gw = warp0; gw < total_warps; gw += nwarps) {
         // ---- lane <-> voxel metadata -------------------------------------------------------------------------
-        const int64_t w = wbase + lane;
-        int f = 0, n = 0, off = 0, cell = 0;
+        const int f = (int)(gw / wpf);
+        const int wl = (int)(gw - (int64_t)f * wpf);
+        const int run = (lane / kGatherRun) * wpf + wl;
+        const int v = run * kGatherRun + (lane % kGatherRun);
+        int n = 0, off = 0, cell = 0;
         int64_t row = 0;
-        if (w < total_slots) {
-            f = (int)(w / max_vox);
-            const int v = (int)(w - (int64_t)f * max_vox);
-            if (v < s_nvox[f]) {
-                n = cursor[w];
-                off = s_start[f] + seg_off[w];
-                cell = vox_cell[w];
-                row = (int64_t)s_base[f] + v;
-            }
+        if (run < runs_per_frame && v < s_nvox[f]) {
+            const int64_t w = (int64_t)f * max_vox + v;
+            n = cursor[w];
+            off = s_start[f] + seg_off[w];
+            cell = vox_cell[w];
+            row = (int64_t)s_base[f] + v;
         }
         const uint32_t live = __ballot_sync(0xffffffffu, n > 0);
         if (live == 0) continue;
@@ -387,11 +399,9 @@ __global__ void __launch_bounds__(256) vox_gather_kernel(const float *__restrict
             // point gathers of the group in flight (idx is frame-local)
 #pragma unroll
             for (int u = 0; u < kGatherGroup; ++u) {
-                const int sl = src[u] < 0 ? 0 : src[u];
-                const int fsrc = __shfl_sync(0xffffffffu, f, sl);
                 const int kept = nn[u] < max_points ? nn[u] : max_points;
                 if (lane < kept) {
-                    const int64_t gi = (int64_t)s_start[fsrc] + idx[u];
+                    const int64_t gi = (int64_t)s_start[f] + idx[u];
                     if (kVec4) pv[u] = __ldg(reinterpret_cast<const float4 *>(pts) + gi);
                     else {
                         const float *q = pts + gi * stride + xyz_col;
@@ -477,8 +487,8 @@ extern "C" int hvpr_voxelize(const float *points, int64_t n_total, int pts_strid
         HVPR_CHECK_LAUNCH();
     }
     {
-        int64_t slots = (int64_t)n_frames * max_voxels;
-        int64_t want = ceil_div64(slots, 8 * 32);   // 8 warps per block, 32 slots per warp
+        const int64_t runs = ceil_div64(max_voxels, kGatherRun);
+        int64_t want = ceil_div64((int64_t)n_frames * ceil_div64(runs, 32 / kGatherRun), 8);   // 8 warps per block, 32 slots per warp
         int blocks = (int)(want < 148 * 16 ? (want > 0 ? want : 1) : 148 * 16);
         if (vec4) vox_gather_kernel<true><<<blocks, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, n_frames, *geom, cells, max_voxels, max_points, w.vox_cell, w.seg_off, w.cursor, w.csr, w.frame_nvox, voxels, coords, num_points, voxel_offsets, cell_map);
         else vox_gather_kernel<false><<<blocks, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, n_frames, *geom, cells, max_voxels, max_points, w.vox_cell, w.seg_off, w.cursor, w.csr, w.frame_nvox, voxels, coords, num_points, voxel_offsets, cell_map);
