@@ -82,29 +82,50 @@ __device__ __forceinline__ int32_t point_cell(float x, float y, float z, const H
 }
 
 // grid: (blocks over max_frame_points, B).  Point index stored in the table is frame-local.
+// kVoxPPT points per thread, block-strided (coalesced), all loads issued before the first use: the kernel is one
+// dependent chain per point (load -> cell -> two REDs; ncu: long_scoreboard + drain, 11 % issue activity).  Measured for
+// hash + fill on the headline batch: 1 / 2 / 4 / 8 points per thread = 0.1076 / 0.1045 / 0.106 / 0.1081 ms for all of K1 —
+// per-thread latency is not the bound (the scattered REDs into the 13.7 MB table are), so 2 it is.
+#ifndef HVPR_VOX_PPT
+#define HVPR_VOX_PPT 2
+#endif
+constexpr int kVoxPPT = HVPR_VOX_PPT;
 template <bool kVec4>
 __global__ void __launch_bounds__(256) vox_hash_kernel(const float *__restrict__ pts, int stride, int xyz_col,
                                                        const int32_t *__restrict__ frame_off, HvprGeom g,
                                                        int64_t cells, int2 *table, int32_t *__restrict__ cellbuf) {
     const int f = blockIdx.y;
     const int32_t start = frame_off[f], n = frame_off[f + 1] - start;
-    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int64_t gi = (int64_t)start + i;
-    float x, y, z;
-    if (kVec4) {
-        float4 p = __ldg(reinterpret_cast<const float4 *>(pts) + gi);
-        x = p.x; y = p.y; z = p.z;
-    } else {
-        const float *p = pts + gi * stride + xyz_col;
-        x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+    const int32_t i0 = blockIdx.x * (256 * kVoxPPT) + threadIdx.x;
+    if (i0 >= n) return;
+    float x[kVoxPPT], y[kVoxPPT], z[kVoxPPT];
+#pragma unroll
+    for (int k = 0; k < kVoxPPT; ++k) {
+        const int32_t i = i0 + k * 256;
+        x[k] = y[k] = z[k] = 0.f;
+        if (i < n) {
+            const int64_t gi = (int64_t)start + i;
+            if (kVec4) {
+                float4 p = __ldg(reinterpret_cast<const float4 *>(pts) + gi);
+                x[k] = p.x; y[k] = p.y; z[k] = p.z;
+            } else {
+                const float *p = pts + gi * stride + xyz_col;
+                x[k] = __ldg(p); y[k] = __ldg(p + 1); z[k] = __ldg(p + 2);
+            }
+        }
     }
-    int32_t c = point_cell(x, y, z, g);
-    cellbuf[gi] = c;
-    if (c >= 0) {
-        int2 *e = table + (int64_t)f * cells + c;
-        atomicMin(&e->x, i);
-        atomicAdd(&e->y, 1);
+    int2 *tab = table + (int64_t)f * cells;
+#pragma unroll
+    for (int k = 0; k < kVoxPPT; ++k) {
+        const int32_t i = i0 + k * 256;
+        if (i < n) {
+            const int32_t c = point_cell(x[k], y[k], z[k], g);
+            cellbuf[(int64_t)start + i] = c;
+            if (c >= 0) {
+                atomicMin(&tab[c].x, i);
+                atomicAdd(&tab[c].y, 1);
+            }
+        }
     }
 }
 
@@ -235,6 +256,8 @@ __global__ void __launch_bounds__(kScanThreads) vox_assign_kernel(const int32_t 
     }
 }
 
+// kVoxPPT points per thread, stage by stage (cell -> voxel id -> cursor claim + segment offset -> CSR store) so that the
+// four dependent memory round trips of kVoxPPT points overlap.
 __global__ void __launch_bounds__(256) vox_fill_kernel(const int32_t *__restrict__ frame_off, int64_t cells,
                                                        const int2 *__restrict__ table,
                                                        const int32_t *__restrict__ cellbuf, int max_vox,
@@ -242,17 +265,35 @@ __global__ void __launch_bounds__(256) vox_fill_kernel(const int32_t *__restrict
                                                        int32_t *__restrict__ csr, const int32_t *__restrict__ istar,
                                                        int break_mode) {
     const int f = blockIdx.y;
-    const int32_t start = frame_off[f], n = frame_off[f + 1] - start;
-    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (break_mode && i >= istar[f]) return;
-    int32_t c = cellbuf[(int64_t)start + i];
-    if (c < 0) return;
-    int32_t e = table[(int64_t)f * cells + c].x;
-    if (e >= 0) return;                                   // cell belongs to a voxel beyond the cap
-    int32_t v = -e - 1;
-    int pos = atomicAdd(&cursor[(int64_t)f * max_vox + v], 1);
-    csr[(int64_t)start + seg_off[(int64_t)f * max_vox + v] + pos] = i;
+    const int32_t start = frame_off[f];
+    int32_t n = frame_off[f + 1] - start;
+    if (break_mode) { const int32_t is = istar[f]; n = is < n ? is : n; }       // points from istar on are dropped
+    const int32_t i0 = blockIdx.x * (256 * kVoxPPT) + threadIdx.x;
+    if (i0 >= n) return;
+    const int2 *tab = table + (int64_t)f * cells;
+    int32_t c[kVoxPPT], v[kVoxPPT];
+#pragma unroll
+    for (int k = 0; k < kVoxPPT; ++k) {
+        const int32_t i = i0 + k * 256;
+        c[k] = (i < n) ? cellbuf[(int64_t)start + i] : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < kVoxPPT; ++k) {
+        const int32_t e = (c[k] >= 0) ? tab[c[k]].x : 0;
+        v[k] = (e < 0) ? -e - 1 : -1;                      // e >= 0: the cell belongs to a voxel beyond the cap
+    }
+    int pos[kVoxPPT], so[kVoxPPT];
+#pragma unroll
+    for (int k = 0; k < kVoxPPT; ++k) {
+        pos[k] = 0; so[k] = 0;
+        if (v[k] >= 0) {
+            pos[k] = atomicAdd(&cursor[(int64_t)f * max_vox + v[k]], 1);
+            so[k] = seg_off[(int64_t)f * max_vox + v[k]];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kVoxPPT; ++k)
+        if (v[k] >= 0) csr[(int64_t)start + so[k] + pos[k]] = i0 + k * 256;
 }
 
 __device__ __forceinline__ int32_t bitonic_sort32_asc(int32_t x, int lane) {
@@ -471,7 +512,7 @@ extern "C" int hvpr_voxelize(const float *points, int64_t n_total, int pts_strid
     }
     const bool vec4 = (pts_stride == 4 && xyz_col == 0 && ((uintptr_t)points % 16 == 0));
     if (max_frame_points > 0) {
-        dim3 gridp((unsigned)ceil_div64(max_frame_points, 256), (unsigned)n_frames);
+        dim3 gridp((unsigned)ceil_div64(max_frame_points, 256 * kVoxPPT), (unsigned)n_frames);
         if (vec4) vox_hash_kernel<true><<<gridp, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, *geom, cells, w.table, w.cellbuf);
         else vox_hash_kernel<false><<<gridp, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, *geom, cells, w.table, w.cellbuf);
         HVPR_CHECK_LAUNCH();
