@@ -5,10 +5,10 @@
 // Parallel restatement (validated against the serial loop in NumPy: oracle/voxelize.py::voxelize_np):
 //   hash    per point: cell = floor((p-lo)/vs) per axis in IEEE fp32 (no FMA, no reciprocal);  dense per-frame table
 //           (a perfect hash for nz=1 pillar grids):  first[cell] = atomicMin(point index), cnt[cell] += 1
-//   count   per block: #first points and sum of their cell counts
-//   assign  exclusive scan in point order -> first-seen voxel rank + CSR segment offset; caps applied on the rank
+//   assign  single-pass exclusive scan of (is_first, cnt) in point order (block aggregates published with a ready bit)
+//           -> first-seen voxel rank + CSR segment offset; caps applied on the rank
 //   fill    unordered CSR fill of point indices per kept voxel
-//   gather  one warp per voxel: keep the 32 lowest point indices (bitonic sort / merge in registers) = arrival
+//   gather  a warp per 32 strided voxel slots: keep the 32 lowest point indices (bitonic sort / merge in registers) = arrival
 //           order of the serial loop; write the 512-byte zero-padded voxel row, coords, count and the cell->row map
 // All atomics are integer min/add, so the result does not depend on scheduling.
 #include "common.cuh"
@@ -23,7 +23,8 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 struct VoxWorkspace {
     int2 *table;        // [B*cells] {first, cnt}
     int32_t *cellbuf;   // [n_total]
-    int2 *agg;          // [B*blocks_per_frame] {n_first, sum_cnt}
+    unsigned long long *agg;  // [B*blocks_per_frame] block aggregates {sum_cnt : ready flag | n_first}, zeroed by init
+    int32_t *ticket;    // [B] scan-block tickets (dispatch order), zeroed by init
     int32_t *vox_cell;  // [B*max_vox]
     int32_t *seg_off;   // [B*max_vox]
     int32_t *cursor;    // [B*max_vox]
@@ -39,7 +40,8 @@ static VoxWorkspace carve(void *base, int64_t n_total, int B, int64_t cells, int
     auto take = [&](size_t bytes) { void *p = base ? (char *)base + off : nullptr; off += align_up(bytes, 256); return p; };
     w.table = (int2 *)take(sizeof(int2) * (size_t)B * cells);
     w.cellbuf = (int32_t *)take(sizeof(int32_t) * (size_t)n_total);
-    w.agg = (int2 *)take(sizeof(int2) * (size_t)B * blocks_per_frame);
+    w.agg = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)B * blocks_per_frame);
+    w.ticket = (int32_t *)take(sizeof(int32_t) * (size_t)B);
     w.vox_cell = (int32_t *)take(sizeof(int32_t) * (size_t)B * max_vox);
     w.seg_off = (int32_t *)take(sizeof(int32_t) * (size_t)B * max_vox);
     w.cursor = (int32_t *)take(sizeof(int32_t) * (size_t)B * max_vox);
@@ -52,7 +54,8 @@ static VoxWorkspace carve(void *base, int64_t n_total, int B, int64_t cells, int
 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void vox_init_kernel(int2 *table, int64_t n_table, int32_t *cell_map, int64_t n_map,
-                                int32_t *cursor, int64_t n_cursor, int32_t *frame_nvox, int32_t *istar, int B) {
+                                int32_t *cursor, int64_t n_cursor, unsigned long long *agg, int64_t n_agg,
+                                int32_t *frame_nvox, int32_t *istar, int32_t *ticket, int B) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     // table entries are 8 B; write two per thread as one 16-B store
@@ -67,7 +70,8 @@ __global__ void vox_init_kernel(int2 *table, int64_t n_table, int32_t *cell_map,
         for (int64_t j = nm4 * 4 + i; j < n_map; j += stride) cell_map[j] = -1;
     }
     for (int64_t j = i; j < n_cursor; j += stride) cursor[j] = 0;
-    if (i < B) { frame_nvox[i] = 0; istar[i] = INT_MAX; }
+    for (int64_t j = i; j < n_agg; j += stride) agg[j] = 0ull;
+    if (i < B) { frame_nvox[i] = 0; istar[i] = INT_MAX; ticket[i] = 0; }
 }
 
 // cell index of one point; -1 when outside the grid.  IEEE fp32 sub, div, floor — exactly the CPU arithmetic.
@@ -129,94 +133,50 @@ __global__ void __launch_bounds__(256) vox_hash_kernel(const float *__restrict__
     }
 }
 
-// block-wide sums of (is_first, cnt-of-first)
-__global__ void __launch_bounds__(kScanThreads) vox_count_kernel(const int32_t *__restrict__ frame_off, int64_t cells,
-                                                                 const int2 *__restrict__ table,
-                                                                 const int32_t *__restrict__ cellbuf,
-                                                                 int2 *__restrict__ agg, int blocks_per_frame) {
-    const int f = blockIdx.y;
-    const int32_t start = frame_off[f], n = frame_off[f + 1] - start;
-    const int32_t base = blockIdx.x * kScanTile;
-    if (base >= n) return;   // agg entries of blocks past the frame end are never read
-    int nf = 0, sc = 0;
-    const int2 *tab = table + (int64_t)f * cells;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        int32_t i = base + threadIdx.x * kScanItems + k;
-        if (i < n) {
-            int32_t c = cellbuf[(int64_t)start + i];
-            if (c >= 0) {
-                int2 e = tab[c];
-                if (e.x == i) { nf += 1; sc += e.y; }
-            }
-        }
-    }
-    __shared__ int s_nf[kScanThreads / 32], s_sc[kScanThreads / 32];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { nf += __shfl_xor_sync(0xffffffffu, nf, o); sc += __shfl_xor_sync(0xffffffffu, sc, o); }
-    if ((threadIdx.x & 31) == 0) { s_nf[threadIdx.x >> 5] = nf; s_sc[threadIdx.x >> 5] = sc; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int a = 0, b = 0;
-#pragma unroll
-        for (int w = 0; w < kScanThreads / 32; ++w) { a += s_nf[w]; b += s_sc[w]; }
-        agg[(int64_t)f * blocks_per_frame + blockIdx.x] = make_int2(a, b);
-    }
-}
-
-// exclusive scan in point order -> voxel rank / CSR offset for every first point
+// Exclusive scan in point order -> voxel rank / CSR offset for every first point.  Single pass: a block sums its own
+// (is_first, cnt-of-first) pairs, publishes the pair as ONE 64-bit word carrying a ready bit, then adds up the words of
+// the blocks in front of it in the same frame (a frame has a few dozen to a few hundred blocks, so a flat sum replaces a
+// look-back chain).  Blocks take their position from a per-frame ticket, so every block a block waits for is already
+// running, whatever order the hardware dispatches them in.
+constexpr unsigned long long kAggReady = 0x80000000ull;
 __global__ void __launch_bounds__(kScanThreads) vox_assign_kernel(const int32_t *__restrict__ frame_off, int64_t cells,
                                                                   int2 *table, const int32_t *__restrict__ cellbuf,
-                                                                  const int2 *__restrict__ agg, int blocks_per_frame,
+                                                                  unsigned long long *agg, int32_t *ticket,
+                                                                  int blocks_per_frame,
                                                                   int max_vox, int32_t *__restrict__ vox_cell,
                                                                   int32_t *__restrict__ seg_off,
                                                                   int32_t *__restrict__ frame_nvox,
                                                                   int32_t *__restrict__ istar) {
     const int f = blockIdx.y;
     const int32_t start = frame_off[f], n = frame_off[f + 1] - start;
-    const int32_t base = blockIdx.x * kScanTile;
-    if (base >= n) return;
-    __shared__ int s_a[kScanThreads / 32], s_b[kScanThreads / 32];
-    __shared__ int s_pref_a, s_pref_b;
+    if ((int64_t)blockIdx.x * kScanTile >= n) return;       // as many blocks take a ticket as the frame has tiles
+    __shared__ int s_a[kScanThreads / 32], s_b[kScanThreads / 32], s_pa[kScanThreads / 32], s_pb[kScanThreads / 32];
+    __shared__ int s_tile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    // prefix over preceding blocks of this frame (at most a few hundred entries)
-    {
-        int a = 0, b = 0;
-        for (int j = threadIdx.x; j < (int)blockIdx.x; j += kScanThreads) {
-            int2 v = agg[(int64_t)f * blocks_per_frame + j];
-            a += v.x; b += v.y;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-        if (lane == 0) { s_a[warp] = a; s_b[warp] = b; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int ta = 0, tb = 0;
-#pragma unroll
-            for (int w = 0; w < kScanThreads / 32; ++w) { ta += s_a[w]; tb += s_b[w]; }
-            s_pref_a = ta; s_pref_b = tb;
-        }
-        __syncthreads();
-    }
-    const int pref_a = s_pref_a, pref_b = s_pref_b;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&ticket[f], 1);
     __syncthreads();
+    const int tile = s_tile;
+    const int32_t base = tile * kScanTile;
+    unsigned long long *fagg = agg + (int64_t)f * blocks_per_frame;
 
     int2 *tab = table + (int64_t)f * cells;
     int32_t cell[kScanItems];
     int cnt[kScanItems];
     bool isf[kScanItems];
+    int32_t cc[kScanItems];
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int32_t i = base + threadIdx.x * kScanItems + k;
+        cc[k] = (i < n) ? cellbuf[(int64_t)start + i] : -1;
+    }
     int ta = 0, tb = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
-        int32_t i = base + threadIdx.x * kScanItems + k;
+        const int32_t i = base + threadIdx.x * kScanItems + k;
         isf[k] = false; cnt[k] = 0; cell[k] = -1;
-        if (i < n) {
-            int32_t c = cellbuf[(int64_t)start + i];
-            if (c >= 0) {
-                int2 e = tab[c];
-                if (e.x == i) { isf[k] = true; cnt[k] = e.y; cell[k] = c; ta += 1; tb += e.y; }
-            }
+        if (cc[k] >= 0) {
+            const int2 e = tab[cc[k]];
+            if (e.x == i) { isf[k] = true; cnt[k] = e.y; cell[k] = cc[k]; ta += 1; tb += e.y; }
         }
     }
     // block exclusive scan of (ta, tb)
@@ -228,11 +188,30 @@ __global__ void __launch_bounds__(kScanThreads) vox_assign_kernel(const int32_t 
     }
     if (lane == 31) { s_a[warp] = ia; s_b[warp] = ib; }
     __syncthreads();
-    int wa = 0, wb = 0;
+    int wa = 0, wb = 0, tot_a = 0, tot_b = 0;
 #pragma unroll
     for (int w = 0; w < kScanThreads / 32; ++w) {
         if (w < warp) { wa += s_a[w]; wb += s_b[w]; }
+        tot_a += s_a[w]; tot_b += s_b[w];
     }
+    if (threadIdx.x == 0)
+        atomicExch(&fagg[tile], ((unsigned long long)(uint32_t)tot_b << 32) | kAggReady | (unsigned long long)(uint32_t)tot_a);
+
+    // sum of the aggregates of the tiles in front (published before their owners wait, so this cannot deadlock)
+    int pa = 0, pb = 0;
+    for (int j = threadIdx.x; j < tile; j += kScanThreads) {
+        unsigned long long v;
+        do { v = *reinterpret_cast<volatile unsigned long long *>(fagg + j); } while (!(v & kAggReady));
+        pa += (int)(v & 0x7fffffffull); pb += (int)(v >> 32);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { pa += __shfl_xor_sync(0xffffffffu, pa, o); pb += __shfl_xor_sync(0xffffffffu, pb, o); }
+    if (lane == 0) { s_pa[warp] = pa; s_pb[warp] = pb; }
+    __syncthreads();
+    int pref_a = 0, pref_b = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w) { pref_a += s_pa[w]; pref_b += s_pb[w]; }
+
     int rank = pref_a + wa + (ia - ta);
     int off = pref_b + wb + (ib - tb);
 #pragma unroll
@@ -507,7 +486,8 @@ extern "C" int hvpr_voxelize(const float *points, int64_t n_total, int pts_strid
         int blocks = (int)(ceil_div64(work, 256) < 148 * 8 ? (ceil_div64(work, 256) > 0 ? ceil_div64(work, 256) : 1) : 148 * 8);
         vox_init_kernel<<<blocks, 256, 0, stream>>>(w.table, (int64_t)n_frames * cells, cell_map,
                                                    (int64_t)n_frames * cells, w.cursor,
-                                                   (int64_t)n_frames * max_voxels, w.frame_nvox, w.istar, n_frames);
+                                                   (int64_t)n_frames * max_voxels, w.agg, (int64_t)n_frames * bpf_ws,
+                                                   w.frame_nvox, w.istar, w.ticket, n_frames);
         HVPR_CHECK_LAUNCH();
     }
     const bool vec4 = (pts_stride == 4 && xyz_col == 0 && ((uintptr_t)points % 16 == 0));
@@ -518,9 +498,7 @@ extern "C" int hvpr_voxelize(const float *points, int64_t n_total, int pts_strid
         HVPR_CHECK_LAUNCH();
         const int bpf = (int)ceil_div64(max_frame_points, kScanTile);
         dim3 grids((unsigned)bpf, (unsigned)n_frames);
-        vox_count_kernel<<<grids, kScanThreads, 0, stream>>>(frame_offsets, cells, w.table, w.cellbuf, w.agg, (int)bpf_ws);
-        HVPR_CHECK_LAUNCH();
-        vox_assign_kernel<<<grids, kScanThreads, 0, stream>>>(frame_offsets, cells, w.table, w.cellbuf, w.agg, (int)bpf_ws,
+        vox_assign_kernel<<<grids, kScanThreads, 0, stream>>>(frame_offsets, cells, w.table, w.cellbuf, w.agg, w.ticket, (int)bpf_ws,
                                                              max_voxels, w.vox_cell, w.seg_off, w.frame_nvox, w.istar);
         HVPR_CHECK_LAUNCH();
         vox_fill_kernel<<<gridp, 256, 0, stream>>>(frame_offsets, cells, w.table, w.cellbuf, max_voxels, w.seg_off,
