@@ -84,7 +84,7 @@ class FrontEndWithBackbone(torch.nn.Module):
         bb = self.backbone_2d
         convs = sum(1 + n for n in bb.layer_nums) + sum(bb.sfm_layer_nums) + 2 * len(bb.num_filters)     # blocks + sfm + scale + deblock
         head = (2 if self.dense_head is not None else 0) + (4 if self.post is not None else 0)            # head GEMM + decode, 4 NMS kernels
-        return 6 + 1 + 1 + 2 + convs + 2 * len(bb.num_filters) + head                                     # K1 x6, K2, K3, K4 x2, convs, gate x2/level
+        return 5 + 1 + 1 + 2 + convs + 2 * len(bb.num_filters) + head                                     # K1 x5, K2, K3, K4 x2, convs, gate x2/level
 
     @torch.no_grad()
     def run(self):

@@ -1,4 +1,4 @@
-"""Dev probe: time K1 (voxelize, 6 launches) alone on the bench workload; optional library variant suffix."""
+"""Dev probe: time K1 (voxelize, 5 launches) alone on the bench workload; optional library variant suffix."""
 import sys, numpy as np, torch
 sys.path.insert(0, '.')
 from hvpr_b200 import _lib
