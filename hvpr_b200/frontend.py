@@ -21,6 +21,9 @@ from .voxelizer import Voxelizer
 
 
 class HybridFrontEnd(torch.nn.Module):
+    # hvpr_tune_pfn(blocks_per_sm, low_register_variant) used while the streaming graphs are captured
+    stream_pfn_knob = (3, 1)
+
     def __init__(self, geom: Geometry, vfe_cfg: Cfg = HVPR_VFE_CFG, bev_cfg: Cfg = HVPR_BEV_CFG,
                  overflow: str = "continue", mem_precision: str = "bf16_rescore", device="cuda"):
         super().__init__()
@@ -192,7 +195,7 @@ class HybridFrontEnd(torch.nn.Module):
             self._stage_bev(p, 0)
             torch.cuda.synchronize()
             # the low-register PFN variant leaves room for the canvas-fill blocks it runs beside (+10 % measured)
-            _lib.check(_lib.lib().hvpr_tune_pfn(3, 1))
+            _lib.check(_lib.lib().hvpr_tune_pfn(*self.stream_pfn_knob))
             for k in range(NS):
                 gr = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gr):
