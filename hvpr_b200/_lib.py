@@ -17,7 +17,7 @@ SYMBOLS = [
     "hvpr_voxelize_workspace_bytes", "hvpr_voxelize", "hvpr_frame_offsets",
     "hvpr_pfn", "hvpr_tune_pfn",
     "hvpr_mem_attn_workspace_bytes", "hvpr_mem_pack_bf16", "hvpr_mem_attn",
-    "hvpr_bev_fill", "hvpr_build_cell_map",
+    "hvpr_bev_fill", "hvpr_tune_bev_fill", "hvpr_build_cell_map",
     "hvpr_conv_packed_bytes", "hvpr_conv_pack_weights", "hvpr_conv2d", "hvpr_nchw_to_nhwc_bf16", "hvpr_attention_gate",
     "hvpr_bev_fill_nhwc_bf16", "hvpr_head_decode",
     "hvpr_post_process_workspace_bytes", "hvpr_post_process",
@@ -87,6 +87,8 @@ def lib():
     L.hvpr_pfn.restype = c_int
     L.hvpr_pfn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p,
                            c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.hvpr_tune_bev_fill.restype = c_int
+    L.hvpr_tune_bev_fill.argtypes = [c_int]
     L.hvpr_tune_pfn.restype = c_int
     L.hvpr_tune_pfn.argtypes = [c_int, c_int]
     L.hvpr_mem_attn_workspace_bytes.restype = c_size_t

@@ -25,43 +25,67 @@ struct BevArgs {
     int chunk_nc[16];    // channels in the chunk (multiple of 4)
 };
 constexpr int kBevChunk = 32;
+#ifndef HVPR_BEV_BPS
+#define HVPR_BEV_BPS 0
+#endif
 constexpr int kBevThreads = 128;   // small blocks: they slot in beside the register-heavy PFN blocks of the next batch
 
-// grid (ceil(cells/4/256), B, n_chunks)
-__global__ void __launch_bounds__(kBevThreads) bev_fill_kernel(const __grid_constant__ BevArgs A,
-                                                       const int32_t *__restrict__ cell_map, int64_t cells) {
-    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // group of 4 consecutive cells
+// Persistent form: gridDim.x blocks walk the (x-block, frame, channel-chunk) items with a grid stride and load the cell->row
+// map of their NEXT item before they write the current one, so the only DRAM round trip of an item (the map) is off the
+// critical path and a couple of small blocks per SM keep the store stream going.  That matters in the streaming mode, where
+// the register-heavy PFN blocks of the next batch leave room for just two fill blocks per SM: with one-item blocks every item
+// paid the map latency plus a block launch and the fill dropped below DRAM saturation (hvpr_tune_bev_fill(2): 0.723 -> 0.682 ms
+// per streaming step).  Alone, one block per item (n_items blocks, the default) is faster — 0.202 vs 0.227-0.244 ms: the
+// hardware block scheduler balances occupied and empty items, the static grid stride does not.
+__global__ void __launch_bounds__(kBevThreads, 8) bev_fill_kernel(const __grid_constant__ BevArgs A,
+                                                       const int32_t *__restrict__ cell_map, int64_t cells,
+                                                       int xblocks, int n_frames, int64_t n_items) {
     const int64_t groups = cells >> 2;
-    const int f = blockIdx.y, ch = blockIdx.z;
-    const bool live = g < groups;
-    int4 m = make_int4(-1, -1, -1, -1);
-    if (live) m = __ldg(reinterpret_cast<const int4 *>(cell_map + (int64_t)f * cells) + g);
-    const BevSrc &s = A.src[A.chunk_src[ch]];
-    const int c0 = A.chunk_c0[ch], nc = A.chunk_nc[ch];
-    float4 *out = reinterpret_cast<float4 *>(s.out + ((int64_t)f * s.Ctot + s.c_off + c0) * cells) + g;
-    const bool occupied = (m.x & m.y & m.z & m.w) != -1;   // row ids are >= 0, empties are exactly -1
-    if (!__any_sync(0xffffffffu, occupied)) {
-        if (live) {
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t item = blockIdx.x;
+    if (item >= n_items) return;
+    auto load_map = [&](int64_t it, int64_t &g, int &f, int &ch) -> int4 {
+        const int xb = (int)(it % xblocks);
+        const int64_t r = it / xblocks;
+        f = (int)(r % n_frames); ch = (int)(r / n_frames);
+        g = (int64_t)xb * kBevThreads + threadIdx.x;                    // group of 4 consecutive cells
+        return g < groups ? __ldg(reinterpret_cast<const int4 *>(cell_map + (int64_t)f * cells) + g) : make_int4(-1, -1, -1, -1);
+    };
+    int64_t g; int f, ch;
+    int4 m = load_map(item, g, f, ch);
+    while (true) {
+        const int64_t next = item + gridDim.x;
+        int64_t g_n = 0; int f_n = 0, ch_n = 0;
+        int4 m_n = make_int4(-1, -1, -1, -1);
+        if (next < n_items) m_n = load_map(next, g_n, f_n, ch_n);
+        const bool live = g < groups;
+        const BevSrc &s = A.src[A.chunk_src[ch]];
+        const int c0 = A.chunk_c0[ch], nc = A.chunk_nc[ch];
+        float4 *out = reinterpret_cast<float4 *>(s.out + ((int64_t)f * s.Ctot + s.c_off + c0) * cells) + g;
+        const bool occupied = (m.x & m.y & m.z & m.w) != -1;   // row ids are >= 0, empties are exactly -1
+        if (!__any_sync(0xffffffffu, occupied)) {
+            if (live) {
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
-            for (int c = 0; c < nc; ++c) st_stream_f4(out + (int64_t)c * groups, z);
-        }
-        return;
-    }
-    if (!live) return;
-    const float *fa = s.feat + c0;
-    const int C = s.C;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int c = 0; c < nc; ++c) st_stream_f4(out + (int64_t)c * groups, z);
+            }
+        } else if (live) {
+            const float *fa = s.feat + c0;
+            const int C = s.C;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
-    for (int c = 0; c < nc; c += 4) {
-        const float4 ra = m.x >= 0 ? __ldg(reinterpret_cast<const float4 *>(fa + (int64_t)m.x * C + c)) : z4;
-        const float4 rb = m.y >= 0 ? __ldg(reinterpret_cast<const float4 *>(fa + (int64_t)m.y * C + c)) : z4;
-        const float4 rc = m.z >= 0 ? __ldg(reinterpret_cast<const float4 *>(fa + (int64_t)m.z * C + c)) : z4;
-        const float4 rd = m.w >= 0 ? __ldg(reinterpret_cast<const float4 *>(fa + (int64_t)m.w * C + c)) : z4;
-        st_stream_f4(out + (int64_t)(c + 0) * groups, make_float4(ra.x, rb.x, rc.x, rd.x));
-        st_stream_f4(out + (int64_t)(c + 1) * groups, make_float4(ra.y, rb.y, rc.y, rd.y));
-        st_stream_f4(out + (int64_t)(c + 2) * groups, make_float4(ra.z, rb.z, rc.z, rd.z));
-        st_stream_f4(out + (int64_t)(c + 3) * groups, make_float4(ra.w, rb.w, rc.w, rd.w));
+            for (int c = 0; c < nc; c += 4) {
+                const float4 ra = m.x >= 0 ? __ldg(reinterpret_cast<const float4 *>(fa + (int64_t)m.x * C + c)) : z4;
+                const float4 rb = m.y >= 0 ? __ldg(reinterpret_cast<const float4 *>(fa + (int64_t)m.y * C + c)) : z4;
+                const float4 rc = m.z >= 0 ? __ldg(reinterpret_cast<const float4 *>(fa + (int64_t)m.z * C + c)) : z4;
+                const float4 rd = m.w >= 0 ? __ldg(reinterpret_cast<const float4 *>(fa + (int64_t)m.w * C + c)) : z4;
+                st_stream_f4(out + (int64_t)(c + 0) * groups, make_float4(ra.x, rb.x, rc.x, rd.x));
+                st_stream_f4(out + (int64_t)(c + 1) * groups, make_float4(ra.y, rb.y, rc.y, rd.y));
+                st_stream_f4(out + (int64_t)(c + 2) * groups, make_float4(ra.z, rb.z, rc.z, rd.z));
+                st_stream_f4(out + (int64_t)(c + 3) * groups, make_float4(ra.w, rb.w, rc.w, rd.w));
+            }
+        }
+        if (next >= n_items) break;
+        item = next; m = m_n; g = g_n; f = f_n; ch = ch_n;
     }
 }
 
@@ -118,6 +142,14 @@ __global__ void cell_map_kernel(const int32_t *__restrict__ coords, const int32_
 
 using namespace hvpr;
 
+static int g_bev_blocks_per_sm = HVPR_BEV_BPS;
+// launch-shape knob (include/hvpr_b200.h), read at launch time
+extern "C" int hvpr_tune_bev_fill(int blocks_per_sm) {
+    if (blocks_per_sm < 0 || blocks_per_sm > 16) return HVPR_ERR_ARG;
+    g_bev_blocks_per_sm = blocks_per_sm;
+    return HVPR_OK;
+}
+
 extern "C" int hvpr_bev_fill(const float *feat_a, int ca, const float *feat_b, int cb, const float *feat_s, int cs,
                              const int32_t *cell_map, int n_frames, int nx, int ny,
                              float *spatial, float *spatial_scale, void *stream_) {
@@ -142,8 +174,10 @@ extern "C" int hvpr_bev_fill(const float *feat_a, int ca, const float *feat_b, i
                 ++n;
             }
         for (int i = n; i < 16; ++i) { A.chunk_src[i] = 0; A.chunk_c0[i] = 0; A.chunk_nc[i] = 0; }
-        dim3 grid((unsigned)ceil_div64(cells / 4, kBevThreads), (unsigned)n_frames, (unsigned)n);
-        bev_fill_kernel<<<grid, kBevThreads, 0, stream>>>(A, cell_map, cells);
+        const int xblocks = (int)ceil_div64(cells / 4, kBevThreads);
+        const int64_t n_items = (int64_t)xblocks * n_frames * n;
+        const int64_t cap = g_bev_blocks_per_sm > 0 ? (int64_t)kNumSMs * g_bev_blocks_per_sm : n_items;
+        bev_fill_kernel<<<(unsigned)(n_items < cap ? n_items : cap), kBevThreads, 0, stream>>>(A, cell_map, cells, xblocks, n_frames, n_items);
         HVPR_CHECK_LAUNCH();
     } else {
         dim3 grid((unsigned)ceil_div64(cells, 256), (unsigned)n_frames);

@@ -361,6 +361,18 @@ def test_bev_fill_bitwise(gname):
                                         _lib.ptr(sp), _lib.ptr(sps), _lib.cur_stream()))
     torch.cuda.synchronize()
     assert torch.equal(sp.cpu().view(3, 128, -1), ref) and torch.equal(sps.cpu().view(3, 32, -1), refs)
+    # persistent form (grid-stride over the items, next item's map prefetched): 1, 2 and 8 blocks per SM, same bits
+    try:
+        for bps in (1, 2, 8):
+            _lib.check(_lib.lib().hvpr_tune_bev_fill(bps))
+            sp.fill_(float("nan")); sps.fill_(float("nan"))
+            _lib.check(_lib.lib().hvpr_bev_fill(_lib.ptr(a), 64, _lib.ptr(b_), 64, _lib.ptr(s), 32, _lib.ptr(cm), 3, nx, ny,
+                                                _lib.ptr(sp), _lib.ptr(sps), _lib.cur_stream()))
+            torch.cuda.synchronize()
+            assert torch.equal(sp.cpu().view(3, 128, -1), ref) and torch.equal(sps.cpu().view(3, 32, -1), refs), bps
+        assert _lib.lib().hvpr_tune_bev_fill(17) != 0 and _lib.lib().hvpr_tune_bev_fill(-1) != 0
+    finally:
+        _lib.check(_lib.lib().hvpr_tune_bev_fill(0))
     # vanilla PointPillarScatter module, fp32 coords, no batch_size key (falls back to the reference formula)
     mod = map_to_bev.PointPillarScatter(config.Cfg(NUM_BEV_FEATURES=64), grid_size=g.grid_size)
     bd = mod(dict(pillar_features=a, voxel_coords=coords.float()))

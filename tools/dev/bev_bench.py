@@ -15,12 +15,17 @@ fa, fb, fs = torch.randn(P, 64, device="cuda"), torch.randn(P, 64, device="cuda"
 sp = torch.empty((B, 128, ny, nx), device="cuda"); sps = torch.empty((B, 32, ny, nx), device="cuda")
 def run():
     _lib.check(L.hvpr_bev_fill(_lib.ptr(fa), 64, _lib.ptr(fb), 64, _lib.ptr(fs), 32, _lib.ptr(cm), B, nx, ny, _lib.ptr(sp), _lib.ptr(sps), _lib.cur_stream()))
-for _ in range(5): run()
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(50): run()
-e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / 50
 nbytes = 4 * 160 * nx * ny * B + 4 * nx * ny * B + 640 * P
-print("variant", variant, "ms", round(ms, 4), "GB/s", round(nbytes / ms / 1e6, 1))
+ref = None
+for knob in (0, 16, 8, 6, 4, 3, 2, 1):
+    _lib.check(L.hvpr_tune_bev_fill(knob))
+    for _ in range(5): run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50): run()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 50
+    chk = (float(sp.double().sum()), float(sps.double().sum()))
+    if ref is None: ref = chk
+    print("variant", variant, "blocks/SM", knob, "ms", round(ms, 4), "GB/s", round(nbytes / ms / 1e6, 1), "same" if chk == ref else "DIFFERENT")
