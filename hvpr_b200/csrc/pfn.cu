@@ -18,6 +18,9 @@ namespace hvpr {
 #ifndef HVPR_PFN_PREFETCH
 #define HVPR_PFN_PREFETCH 1
 #endif
+#ifndef HVPR_PFN_LOWREG_MINB
+#define HVPR_PFN_LOWREG_MINB 3   // 5 (96 regs, no spills) lets K1 co-run beside PFN + fill in the streaming step, which measured WORSE: 0.741 vs 0.685 ms
+#endif
 constexpr int kPfnThreads = 128;
 constexpr int kPfnG = 32;        // pillars per group (one group per block iteration)
 constexpr int kPfnXS = 20;       // row stride (floats) of the layer-0 activation staging: conflict-free fragment loads
@@ -121,7 +124,7 @@ __device__ __forceinline__ void pfn_scale_out(const PfnParams &P, PfnSmem &S, in
 // so ONE pass over the real points produces both x_max (layer 0) and max_p(W1a.x_p); c is applied per pillar afterwards.
 // Both 16->64 contractions (W1a.x per point, W1b.x_max per pillar) run on the tensor cores as 3xTF32 m16n8k8 MMAs.
 template <bool kScale, bool kFragRegs>
-__global__ void __launch_bounds__(kPfnThreads, 3) pfn_kernel(const __grid_constant__ PfnParams P,
+__global__ void __launch_bounds__(kPfnThreads, kFragRegs ? 3 : HVPR_PFN_LOWREG_MINB) pfn_kernel(const __grid_constant__ PfnParams P,
                                                           const float *__restrict__ voxels,
                                                           const int32_t *__restrict__ num_points,
                                                           const int32_t *__restrict__ coords,
