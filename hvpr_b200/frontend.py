@@ -25,6 +25,8 @@ class HybridFrontEnd(torch.nn.Module):
     stream_pfn_knob = (3, 1)
     # hvpr_tune_bev_fill(blocks_per_sm) for the canvas fill inside the streaming graphs (it shares the SMs with K1 / K2 there)
     stream_bev_knob = 2
+    # where K1 of batch k+2 sits in the step: "fork" (own stream from the start of the step), "before_k3" / "after_k3" / "last" (main stream)
+    stream_k1_order = "fork"
 
     def __init__(self, geom: Geometry, vfe_cfg: Cfg = HVPR_VFE_CFG, bev_cfg: Cfg = HVPR_BEV_CFG,
                  overflow: str = "continue", mem_precision: str = "bf16_rescore", device="cuda"):
@@ -210,12 +212,18 @@ class HybridFrontEnd(torch.nn.Module):
                 gr = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gr):
                     main = torch.cuda.current_stream()
+                    order = self.stream_k1_order
                     p.side2.wait_stream(main)           # fork
                     with torch.cuda.stream(p.side2):
                         p.cnt_stage[k].copy_(p.voxs[k].voxel_offsets)      # slot k is re-voxelized by the NEXT step
+                        if order == "fork":
+                            self._stage_vox(p, (k + 2) % NS)
+                    if order == "before_k3":
                         self._stage_vox(p, (k + 2) % NS)
 
                     def _fork_pfn(k=k):
+                        if order == "after_k3":
+                            self._stage_vox(p, (k + 2) % NS)
                         # K3 holds whole SMs; the PFN of the next batch starts when it retires and shares the SMs with K4
                         p.side1.wait_stream(main)
                         with torch.cuda.stream(p.side1):
@@ -223,6 +231,8 @@ class HybridFrontEnd(torch.nn.Module):
                     self._stage_bev(p, k, after_k3=_fork_pfn)
                     main.wait_stream(p.side1)           # join
                     main.wait_stream(p.side2)
+                    if order == "last":
+                        self._stage_vox(p, (k + 2) % NS)
                 p.graphs[k] = gr
             _lib.check(_lib.lib().hvpr_tune_pfn(3, 0))
             _lib.check(_lib.lib().hvpr_tune_bev_fill(0))

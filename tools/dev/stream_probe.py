@@ -10,9 +10,9 @@ B, N = 8, 120000
 frames = synth.make_batch("L", N, G2.point_cloud_range, B)
 pts = torch.from_numpy(np.concatenate(frames, 0)).cuda(); off = torch.tensor(np.r_[0, np.cumsum([N] * B)], dtype=torch.int32).cuda()
 import itertools
-for (bps, low), bev in itertools.product(((3, 1), (2, 1)), (0, 8, 4, 3, 2, 1)):
+for ((bps, low), bev), order in itertools.product((((3, 1), 2), ((3, 1), 4), ((3, 1), 0)), ("fork", "before_k3", "after_k3", "last")):
     fe = HybridFrontEnd(G2).load_reference_weights(w)
-    fe.stream_pfn_knob = (bps, low); fe.stream_bev_knob = bev
+    fe.stream_pfn_knob = (bps, low); fe.stream_bev_knob = bev; fe.stream_k1_order = order
     sp = fe.plan_stream(B, B * N, N)
     for sl in range(3):
         sp.in_points[sl].copy_(pts); sp.in_offsets[sl].copy_(off)
@@ -24,4 +24,4 @@ for (bps, low), bev in itertools.product(((3, 1), (2, 1)), (0, 8, 4, 3, 2, 1)):
     for _ in range(100): fe.stream_step()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 100
-    print("pfn knob", (bps, low), "bev knob", bev, "stream ms/step", round(ms, 4), "fps", round(B / ms * 1e3))
+    print("pfn knob", (bps, low), "bev knob", bev, "K1", order, "stream ms/step", round(ms, 4), "fps", round(B / ms * 1e3))
