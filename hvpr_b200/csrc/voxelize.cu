@@ -17,7 +17,10 @@
 namespace hvpr {
 
 constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;                       // points per thread in count/assign
+#ifndef HVPR_SCAN_ITEMS
+#define HVPR_SCAN_ITEMS 8
+#endif
+constexpr int kScanItems = HVPR_SCAN_ITEMS;                       // points per thread in count/assign
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 struct VoxWorkspace {
