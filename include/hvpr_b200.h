@@ -5,8 +5,8 @@
  * Every entry point
  *   - takes DEVICE pointers unless a parameter says "host";
  *   - enqueues all its work on `stream` (a cudaStream_t passed as void*), never synchronises the device,
- *     never allocates device memory, keeps no data state (the only process-wide setting is the launch-shape knob
- *     hvpr_tune_pfn) -> safe inside CUDA-graph capture and re-entrant across streams / devices
+ *     never allocates device memory, keeps no data state (the only process-wide settings are the launch-shape knobs
+ *     hvpr_tune_pfn / hvpr_tune_bev_fill) -> safe inside CUDA-graph capture and re-entrant across streams / devices
  *     (one process per GPU);
  *   - returns HVPR_OK (0) or a negative HvprStatus; it never throws.
  * The caller (hvpr_b200/*.py through ctypes, or any C/C++ host) owns every buffer.
