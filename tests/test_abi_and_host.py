@@ -290,3 +290,30 @@ def test_detector_state_dict_uses_the_reference_module_names():
         want = (set(hybrid.random_weights(0)) | {"backbone_2d." + k for k in ob.random_backbone_weights(0)} |
                 {"dense_head." + k for k in od.random_head_weights(0)})
         assert keys == want
+
+
+# ---------------------------------------------------------------------------------------------- work-assignment maps
+@pytest.mark.parametrize("max_vox,run", [(40000, 4), (80000, 4), (16000, 4), (37, 4), (1, 4), (130, 1), (4099, 4)])
+def test_gather_slot_assignment_covers_every_slot_once(max_vox, run):
+    """vox_gather_kernel (hvpr_b200/csrc/voxelize.cu): lane l of warp w takes slot (l // run * wpf + w) * run + l % run of its frame.
+    The strided runs must tile [0, max_vox) exactly once for any cap, including caps that are not multiples of 32 or of the run."""
+    runs = -(-max_vox // run)
+    wpf = -(-runs // (32 // run))
+    lane = np.arange(32)
+    seen = np.zeros(max_vox, dtype=np.int32)
+    for w in range(wpf):
+        r = (lane // run) * wpf + w
+        v = r * run + lane % run
+        ok = (r < runs) & (v < max_vox)
+        np.add.at(seen, v[ok], 1)
+    assert (seen == 1).all()
+
+
+@pytest.mark.parametrize("n_rows", [1, 31, 32, 33, 1000, 201833])
+def test_pfn_group_assignment_covers_every_row_once(n_rows):
+    """pfn_kernel (hvpr_b200/csrc/pfn.cu): slot pl of group grp is pillar row pl * ngroups + grp (strided, not consecutive)."""
+    ngroups = -(-n_rows // 32)
+    pl, grp = np.meshgrid(np.arange(32), np.arange(ngroups), indexing="ij")
+    rows = (pl.astype(np.int64) * ngroups + grp).ravel()
+    rows = rows[rows < n_rows]
+    assert len(rows) == n_rows and len(np.unique(rows)) == n_rows
