@@ -327,6 +327,9 @@ __device__ __forceinline__ int32_t bitonic_sort_bounded_asc(int32_t x, int lane,
 #define HVPR_GATHER_RUN 4
 #endif
 constexpr int kGatherRun = HVPR_GATHER_RUN;      // consecutive slots per run (power of two <= 32)
+#ifndef HVPR_GATHER_LOCKSTEP
+#define HVPR_GATHER_LOCKSTEP 1
+#endif
 constexpr int kGatherGroup = 4;
 template <bool kVec4>
 __global__ void __launch_bounds__(256) vox_gather_kernel(const float *__restrict__ pts, int stride, int xyz_col,
@@ -400,6 +403,37 @@ __global__ void __launch_bounds__(256) vox_gather_kernel(const float *__restrict
                 rr[u] = __shfl_sync(0xffffffffu, row, sl);
                 idx[u] = (lane < nn[u]) ? __ldg(csr + oo[u] + lane) : INT_MAX;          // CSR loads of the group in flight
             }
+#if HVPR_GATHER_LOCKSTEP
+            {   // the four voxels of the group go through ONE bitonic network sized for the largest of them (lane predicates and
+                // loop control shared, four independent shuffle chains in flight); rows with fewer entries hold INT_MAX above them
+                int nmax = nn[0];
+#pragma unroll
+                for (int u = 1; u < kGatherGroup; ++u) nmax = nn[u] > nmax ? nn[u] : nmax;
+                if (nmax > 1) {                                                          // warp-uniform
+                    int K = 2;
+                    while (K < nmax && K < 32) K <<= 1;
+                    for (int k = 2; k <= K; k <<= 1)
+                        for (int j = k >> 1; j > 0; j >>= 1) {
+                            const bool take_min = (((lane & k) == 0) == ((lane & j) == 0));
+#pragma unroll
+                            for (int u = 0; u < kGatherGroup; ++u) {
+                                const int32_t y = __shfl_xor_sync(0xffffffffu, idx[u], j);
+                                idx[u] = take_min ? min(idx[u], y) : max(idx[u], y);
+                            }
+                        }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kGatherGroup; ++u)
+                for (int c0 = 32; c0 < nn[u]; c0 += 32) {                                // > 32 candidates: keep the 32 lowest
+                    int32_t e = (c0 + lane < nn[u]) ? __ldg(csr + oo[u] + c0 + lane) : INT_MAX;
+                    const int32_t worst = __shfl_sync(0xffffffffu, idx[u], 31);
+                    if (!__any_sync(0xffffffffu, e < worst)) continue;
+                    e = bitonic_sort32_asc(e, lane);
+                    const int32_t er = __shfl_sync(0xffffffffu, e, 31 - lane);
+                    idx[u] = bitonic_merge32_asc(min(idx[u], er), lane);
+                }
+#else
 #pragma unroll
             for (int u = 0; u < kGatherGroup; ++u) {
                 if (nn[u] > 1) {                                                         // warp-uniform
@@ -416,6 +450,7 @@ __global__ void __launch_bounds__(256) vox_gather_kernel(const float *__restrict
                     }
                 }
             }
+#endif
             float4 pv[kGatherGroup];
 #pragma unroll
             for (int u = 0; u < kGatherGroup; ++u) pv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
