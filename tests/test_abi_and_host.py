@@ -317,3 +317,28 @@ def test_pfn_group_assignment_covers_every_row_once(n_rows):
     rows = (pl.astype(np.int64) * ngroups + grp).ravel()
     rows = rows[rows < n_rows]
     assert len(rows) == n_rows and len(np.unique(rows)) == n_rows
+
+
+@pytest.mark.parametrize("n,tile", [(1, 2048), (2047, 2048), (2048, 2048), (120000, 2048), (300000, 2048), (5000, 64)])
+def test_single_pass_assign_scan_model(n, tile):
+    """vox_assign_kernel (hvpr_b200/csrc/voxelize.cu): every tile publishes (n_first, sum of the first points' cell counts) as ONE 64-bit
+    word — count in the high half, ready bit 31 and n_first in the low half — and takes the sum of the words in front of it as its
+    prefix.  NumPy restatement of that arithmetic against a plain exclusive scan (what oracle/voxelize.py::voxelize_np uses)."""
+    rng = np.random.default_rng(n)
+    is_first = rng.random(n) < 0.25
+    cnt = np.where(is_first, rng.integers(1, 400, n), 0).astype(np.int64)
+    ready = np.uint64(0x80000000)
+    words = []
+    for t0 in range(0, n, tile):
+        a, b = int(is_first[t0:t0 + tile].sum()), int(cnt[t0:t0 + tile].sum())
+        assert a < 2 ** 31 and b < 2 ** 32
+        words.append((np.uint64(b) << np.uint64(32)) | ready | np.uint64(a))
+    rank = np.empty(n, dtype=np.int64); off = np.empty(n, dtype=np.int64)
+    for ti, t0 in enumerate(range(0, n, tile)):
+        w = np.array(words[:ti], dtype=np.uint64)
+        assert ((w & ready) != 0).all()
+        pa = int((w & np.uint64(0x7FFFFFFF)).sum()); pb = int((w >> np.uint64(32)).sum())
+        f, c = is_first[t0:t0 + tile], cnt[t0:t0 + tile]
+        rank[t0:t0 + tile] = pa + np.cumsum(f) - f
+        off[t0:t0 + tile] = pb + np.cumsum(c) - c
+    assert (rank == np.cumsum(is_first) - is_first).all() and (off == np.cumsum(cnt) - cnt).all()
