@@ -360,7 +360,7 @@ def run_gpu_arm(args):
     W_ = max(args.warmup, 3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    # ---- reference point: one batch at a time, single stream (graph replay of the 9-kernel chain) ---------------------
+    # ---- reference point: one batch at a time, single stream (graph replay of the 8-kernel chain) ---------------------
     for _ in range(W_):
         fe.run()
     barrier()
