@@ -11,7 +11,7 @@ from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhvpr_b200.so")
 
-# every symbol include/hvpr_b200.h declares (tests/test_abi.py checks the .so exports each one)
+# every symbol include/hvpr_b200.h declares (tests/test_abi_and_host.py checks the .so exports each one)
 SYMBOLS = [
     "hvpr_strerror", "hvpr_last_cuda_error", "hvpr_version", "hvpr_init",
     "hvpr_voxelize_workspace_bytes", "hvpr_voxelize", "hvpr_frame_offsets",

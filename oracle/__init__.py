@@ -8,12 +8,18 @@ leg and `bench.py --impl reference`.  Nothing under hvpr_b200/ imports it; the p
 when its CUDA extension is missing instead of falling back to anything here.
 
 Pinning status:
-  * voxelizer          — PARITY UNPINNED against upstream spconv (not vendored, not pinned, not installed; the
-                         reference has no tests).  Pinned against an independent dict-based model and the in-tree
-                         loop witness tools/vis.py:23-50.
+  * voxelizer          — loop structure PINNED ON REFERENCE-RUN CODE: the reference's own in-tree numba voxel loop
+                         (`_points_to_bevmap_reverse_kernel`, tools/vis.py:8-60 — same lineage as spconv's points_to_voxel)
+                         is executed here (oracle/ref_loader.load_vis_voxel_kernel) and oracle/voxelize_ref.c reproduces its
+                         coor_to_voxelidx table and per-cell point counts exactly (cell arithmetic, x->y->z reject order,
+                         reversed coords, first-seen ids, the `break` cap): tests/test_oracle_cpu.py::
+                         test_voxelizer_oracle_vs_live_reference_loop + fixtures tests/golden/vis_kernel_pins.json
+                         (oracle/make_golden_vis.py).  Still unpinned against UPSTREAM spconv (not vendored, not pinned, not
+                         installed): the `continue` overflow mode and the 32-point append, which vis.py replaces with a height
+                         map, rest on the published algorithm + an independent dict-based model.
   * VFE / memory / BEV — pinned against the reference's OWN Python modules imported from /root/reference in the
                          build container (oracle/ref_loader.py, 3 in-memory patches) — see oracle/make_golden.py and
-                         tests/golden/*.npz, and tests/test_oracle_vs_reference.py (runs wherever /root/reference exists).
+                         tests/golden/*.npz, and tests/test_oracle_cpu.py::test_oracle_vs_live_reference (runs wherever /root/reference exists).
   * 2-D backbone (N1)  — oracle/backbone.py, pinned against the reference's OWN BaseBEVBackbone_Scale
                          (oracle/ref_loader.load_backbone, one in-memory patch: breakage B4) — oracle/make_golden_backbone.py,
                          tests/golden/backbone_tiny.npz.

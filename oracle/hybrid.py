@@ -5,7 +5,7 @@ whose keys are the reference's state_dict names:
     vfe.pfn_layers.{0,1}.linear.weight, vfe.pfn_layers.{0,1}.norm.{weight,bias,running_mean,running_var}
     vfe.pfn_scale_layers.{0,1}.0.weight, vfe.pfn_scale_layers.{0,1}.1.{weight,bias,running_mean,running_var}
     map_to_bev_module.memory.weight
-Pinned against the reference's own modules (oracle/ref_loader.py) by tests/test_oracle_vs_reference.py and the
+Pinned against the reference's own modules (oracle/ref_loader.py) by tests/test_oracle_cpu.py::test_oracle_vs_live_reference and the
 fixtures under tests/golden/.
 """
 from __future__ import annotations

@@ -2,7 +2,8 @@
 
 Only usable where /root/reference exists (the build container); the GPU box never has it, so nothing in the
 `-m gpu` tests, smoke() or bench.py calls this.  It is used by oracle/make_golden.py (to mint tests/golden/) and by
-tests/test_oracle_vs_reference.py (CPU, skipped when the tree is absent) to pin oracle/hybrid.py.
+tests/test_oracle_cpu.py (CPU, live-reference cases skipped when the tree is absent) to pin oracle/hybrid.py and
+oracle/voxelize_ref.c.
 
 Nothing is copied: sources are read, patched IN MEMORY and exec'd into fresh module objects:
   (1) delete memory_module.py:75  (stray prose line -> SyntaxError)
@@ -109,3 +110,50 @@ def load_backbone():
                                SpatialAttention=sa.SpatialAttention)
     _CACHE["bb"] = ns
     return ns
+
+
+def load_vis_voxel_kernel():
+    """-> the reference's OWN in-tree point->voxel loop, `_points_to_bevmap_reverse_kernel` (tools/vis.py:8-60), jitted by
+    numba exactly as the reference declares it (`@numba.jit(nopython=True)`).
+
+    tools/vis.py cannot be imported as a module (it pulls cv2 / matplotlib / the broken pcdet package at :1-6), so the
+    source text of that ONE function (decorator line to the line before `def points_to_bev`) is exec'd in memory with
+    `numba` and `np` in scope — nothing is copied into the repo.  This loop is the same lineage as spconv's
+    `points_to_voxel` (floor / per-axis reject in x,y,z order / reversed coor / dense coor_to_voxelidx table / first-seen
+    id / `break` at max_voxels); the per-voxel point append is replaced by a height map, and `bev_map[-1]` counts the
+    points of every cell.  It pins: cell arithmetic, reject order, reversed coords, first-seen rank, the `break` cap and
+    per-cell point counts of oracle/voxelize_ref.c on code the reference itself ships and runs.
+    """
+    if "vis" in _CACHE:
+        return _CACHE["vis"]
+    path = os.path.join(REF, "tools/vis.py")
+    if not os.path.isfile(path):
+        raise RuntimeError("reference tree not present at %s" % REF)
+    import numba
+    import numpy as np
+    lines = open(path).read().split("\n")
+    start = next(i for i, l in enumerate(lines) if l.startswith("@numba.jit"))
+    assert lines[start + 1].startswith("def _points_to_bevmap_reverse_kernel("), "reference tools/vis.py:8-9 changed"
+    end = next(i for i, l in enumerate(lines) if l.startswith("def points_to_bev("))
+    ns = {"numba": numba, "np": np}
+    exec(compile("\n".join(lines[start:end]), "tools/vis.py[%d:%d]" % (start + 1, end), "exec"), ns)
+    _CACHE["vis"] = ns["_points_to_bevmap_reverse_kernel"]
+    return _CACHE["vis"]
+
+
+def run_vis_voxel_kernel(points, pc_range, voxel_size, max_voxels):
+    """Calls the reference loop the way its own caller does (tools/vis.py:86-104: dtype casts, DHW table of -1, zero
+    bev_map with one extra plane, height_lowers).  -> (coor_to_voxelidx (nz,ny,nx) int32, per-cell point counts (ny,nx) int32)."""
+    import numpy as np
+    k = load_vis_voxel_kernel()
+    points = np.ascontiguousarray(points, dtype=np.float32)
+    vs = np.array(voxel_size, dtype=points.dtype)                                      # vis.py:86-87
+    cr = np.array(pc_range, dtype=points.dtype)                                        # vis.py:88-89
+    shape = tuple(np.round((cr[3:] - cr[:3]) / vs).astype(np.int32).tolist())[::-1]    # vis.py:90-92
+    table = -np.ones(shape=shape, dtype=np.int32)                                      # vis.py:93
+    bshape = list(shape)
+    bshape[0] += 1                                                                     # vis.py:95-96
+    lowers = np.linspace(cr[2], cr[5], shape[0], endpoint=False)                       # vis.py:97-98
+    bev = np.zeros(shape=bshape, dtype=points.dtype)                                   # vis.py:101
+    k(points, vs, cr, table, bev, lowers, False, max_voxels)                           # vis.py:102-104
+    return table, bev[-1].astype(np.int32)

@@ -75,6 +75,30 @@ def voxelize_c(points, pc_range, voxel_size, max_points=32, max_voxels=40000, ov
     return out + (pv, ps) if return_assignment else out
 
 
+def cell_table_c(points, pc_range, voxel_size, max_voxels=40000, overflow="break", max_points=None):
+    """The C loop run WITHOUT a payload (nfeat = 0): -> (coor_to_voxelidx table (nz,ny,nx) int32, per-cell point counts
+    (nz,ny,nx) int32, coords (P,3)).  With max_points=None the counts are uncapped — exactly what the reference's in-tree
+    loop tools/vis.py:8-60 leaves in `coor_to_voxelidx` and `bev_map[-1]`; this is the function pinned against it."""
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    n = pts.shape[0]
+    r = np.ascontiguousarray(pc_range, dtype=np.float32)
+    v = np.ascontiguousarray(voxel_size, dtype=np.float32)
+    gx, gy, gz = grid_size(r, v)
+    dummy = np.zeros((1,), dtype=np.float32)
+    coords = np.zeros((max_voxels, 3), dtype=np.int32)
+    nump = np.zeros((max_voxels,), dtype=np.int32)
+    table = np.full((gz * gy * gx,), -1, dtype=np.int32)
+    p = _lib().hvpr_oracle_voxelize(
+        pts.ctypes.data, n, pts.shape[1], 0, 0, r.ctypes.data, v.ctypes.data,
+        int(max_points) if max_points is not None else max(n, 1), max_voxels, {"continue": 0, "break": 1}[overflow],
+        dummy.ctypes.data, coords.ctypes.data, nump.ctypes.data, table.ctypes.data, None, None)
+    assert p >= 0
+    counts = np.zeros_like(table)
+    c = coords[:p]
+    counts[(c[:, 0] * gy + c[:, 1]) * gx + c[:, 2]] = nump[:p]
+    return table.reshape(gz, gy, gx), counts.reshape(gz, gy, gx), c
+
+
 def voxelize_py(points, pc_range, voxel_size, max_points=32, max_voxels=40000, overflow="continue"):
     """Dict-based model written from the prose spec — deliberately NOT a transliteration
     of the C loop: cells are keyed by tuple, voxels are Python lists, caps are applied when reading out."""

@@ -18,9 +18,13 @@
  * plus the per-voxel append that vis.py replaces with a height map:
  *     num = num_points_per_voxel[id]; if (num < max_points) { voxels[id,num] = point; num++ }
  *
- * PARITY UNPINNED: the reference ships no tests / golden vectors for this path.
- * The restatement is pinned only against an independent dict-based Python model (oracle/voxelize_py.py)
- * and the committed fixtures under tests/golden/ that it produced.
+ * PINNED on reference-run code for everything tools/vis.py:8-60 contains: that numba loop is executed in the build
+ * container (oracle/ref_loader.load_vis_voxel_kernel) and this function reproduces its coor_to_voxelidx table and its
+ * per-cell point counts bev_map[-1] array-for-array (tests/test_oracle_cpu.py, tests/golden/vis_kernel_pins.json).
+ * UNPINNED against upstream spconv itself (not vendored / installed): the `continue` mode and the max_points append
+ * are checked against an independent dict-based Python model (oracle/voxelize.py::voxelize_py) only.
+ * One deliberate difference: NaN coordinates are rejected here; in the reference loop `c < 0 or c >= grid` is false
+ * for NaN and the int cast indexes out of bounds (undefined behaviour).
  *
  * Build: see oracle/Makefile  (gcc -O2 -ffp-contract=off, no -ffast-math: fp32 sub/div/floor must be IEEE).
  */

@@ -89,6 +89,27 @@ def test_voxelize_golden_hashes():
         assert sha(v.view(np.int32), c[:, 1:].copy(), k) == ref["sha256"], key
 
 
+def test_voxelize_vs_reference_loop_pins():
+    """K1's cell map and per-pillar counts against fixtures minted by the REFERENCE'S OWN voxel loop (tools/vis.py:8-60 run
+    under numba by oracle/make_golden_vis.py; tests/golden/vis_kernel_pins.json): `break` mode, caps 5 000 / 40 000 / 80 000."""
+    from oracle.make_golden_vis import GEOM, case_frame, digest
+    with open(os.path.join(GOLDEN, "vis_kernel_pins.json")) as fh:
+        pins = json.load(fh)
+    for key, ref in pins.items():
+        gname, dist, n, mv = key.split("/")
+        g0 = GEOM[gname]
+        g = Geometry(g0.point_cloud_range, g0.voxel_size, 32, int(mv))
+        f = case_frame(gname, dist, int(n))
+        out, vo, v, c, k = _voxelize_gpu([f], g, "break")
+        assert len(k) == ref["P"], key
+        cm = out.cell_map.cpu().numpy().reshape(-1)
+        assert digest(cm) == ref["table_sha256"], key
+        nx, ny, nz = g.grid_size
+        counts = np.zeros(ny * nx, dtype=np.int32)
+        counts[c[:, 2] * nx + c[:, 3]] = k
+        assert digest(counts) == ref["counts_cap32_sha256"], key
+
+
 def test_voxelize_ragged_and_empty_frames():
     g = G2
     frames = [synth.make_frame("L", 5000, g.point_cloud_range, 1), np.zeros((0, 4), np.float32),

@@ -86,6 +86,53 @@ def test_voxel_hashes_golden():
         assert sha(v.view(np.int32), c, k) == ref["sha256"], key
 
 
+def _vis_pins():
+    with open(os.path.join(GOLDEN, "vis_kernel_pins.json")) as fh:
+        return json.load(fh)
+
+
+def test_voxelizer_oracle_vs_reference_loop_golden():
+    """The C restatement reproduces what the REFERENCE'S OWN in-tree voxel loop (tools/vis.py:8-60, run under numba by
+    oracle/make_golden_vis.py) left in coor_to_voxelidx and bev_map[-1]: cell arithmetic, x->y->z reject order, reversed
+    coords, first-seen ids, the `break` cap, per-cell point counts.  Runs on any box (sha256 fixtures)."""
+    from oracle.make_golden_vis import GEOM, case_frame, digest
+    for key, ref in _vis_pins().items():
+        gname, dist, n, mv = key.split("/")
+        g = GEOM[gname]
+        f = case_frame(gname, dist, int(n))
+        table, counts, c = ov.cell_table_c(f, g.range_f32, g.voxel_f32, int(mv), "break")
+        assert len(c) == ref["P"] and int(counts.sum()) == ref["points_counted"], key
+        assert digest(table.reshape(-1)) == ref["table_sha256"], key
+        assert digest(counts[0].reshape(-1)) == ref["counts_sha256"], key
+        assert digest(np.minimum(counts[0], 32).reshape(-1)) == ref["counts_cap32_sha256"], key
+        # table[c_z, c_y, c_x] == arange(P): coords are the first-seen order of the reference table
+        assert np.array_equal(table[c[:, 0], c[:, 1], c[:, 2]], np.arange(len(c), dtype=np.int32)), key
+        # and the full voxelizer (payload, 32-point cap) agrees with the payload-free run on ids and capped counts
+        v, c2, k2 = ov.voxelize_c(f, g.range_f32, g.voxel_f32, 32, int(mv), "break")
+        assert np.array_equal(c2, c) and np.array_equal(k2, np.minimum(counts[c[:, 0], c[:, 1], c[:, 2]], 32)), key
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present on this box")
+@pytest.mark.parametrize("gname,dist,n,mv,seed", [("G1", "U", 120000, 40000, 5), ("G1", "L", 50000, 5000, 6), ("G2", "U", 120000, 5000, 7),
+                                                  ("G2", "L", 120000, 40000, 8), ("G2", "U", 3000, 1, 9), ("G3", "L", 200000, 80000, 10),
+                                                  ("G2", "L", 0, 40000, 11)])
+def test_voxelizer_oracle_vs_live_reference_loop(gname, dist, n, mv, seed):
+    """Where the reference tree exists: run its numba loop itself and compare ARRAYS (not hashes) with the C restatement,
+    on other seeds than the fixtures, a 1-voxel cap and an empty frame; +-inf rows are rejected by both.  (NaN is NOT fed
+    to the reference loop: `c < 0 or c >= grid` is false for NaN there and the int cast indexes out of bounds — the
+    restatement and the CUDA kernel reject NaN instead, see test_edge_cases_semantics.)"""
+    g = {"G1": G1, "G2": G2, "G3": G3}[gname]
+    f = synth.make_frame(dist, n, g.point_cloud_range, seed, edge_cases=True) if n else np.zeros((0, 4), np.float32)
+    if n > 100:
+        f[6::1019, 0] = np.inf
+        f[7::1021, 2] = -np.inf
+    rt, rc = ref_loader.run_vis_voxel_kernel(f, g.range_f32, g.voxel_f32, mv)
+    table, counts, c = ov.cell_table_c(f, g.range_f32, g.voxel_f32, mv, "break")
+    assert np.array_equal(rt, table)
+    assert np.array_equal(rc, counts[0])
+    assert np.array_equal(table[c[:, 0], c[:, 1], c[:, 2]], np.arange(len(c), dtype=np.int32))
+
+
 @pytest.mark.parametrize("name", SMALL)
 def test_oracle_matches_reference_fixture(name):
     """oracle/hybrid.py + C voxelizer vs tensors produced by the REFERENCE'S OWN modules (tests/golden, committed)."""
