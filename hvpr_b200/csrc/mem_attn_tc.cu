@@ -4,10 +4,12 @@
 //   logits (bf16 x bf16 -> fp32, TMEM)   :64     tcgen05.mma cta_group::1, M128 x N256 x K16, 4 k-steps per chunk,
 //                                                8 chunks of 256 memory items; W chunks stream through a 4-stage
 //                                                cp.async.bulk (TMA engine) ring from a pre-swizzled bf16 image
-//   top-k (softmax is monotone)          :65-66  two sweeps over the accumulators, one row per thread:
-//                                                sweep 1: maxima of 16-column groups -> the 24th largest group maximum
-//                                                         tau is a lower bound of the 24th largest logit (24 distinct
-//                                                         elements are >= tau) and is tight (~25 elements pass);
+//   top-k (softmax is monotone)          :65-66  two sweeps over the accumulators; a row is shared by TWO filter threads
+//                                                (same TMEM lane, the two 128-column halves of every chunk; 8 filter warps):
+//                                                sweep 1: maxima of 16-column groups (3-input FMNMX), each thread keeps the
+//                                                         sorted top-16 of its 64 group maxima; tau = 24th largest of the
+//                                                         union of the two lists = min_i max(a_i, b_{23-i}): a lower bound
+//                                                         of the 24th largest logit (24 distinct elements are >= tau), ~26.5 pass;
 //                                                sweep 2: sign-bit masks of (logit - tau) -> candidate list
 //   exact re-score of the candidates     :70-71  fp32 FFMA against the fp32 memory rows (warp per row, coalesced)
 //   top-20, softmax, weighted readout    :72-74  fp32
@@ -18,6 +20,7 @@
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <math.h>
+#include <type_traits>
 
 namespace hvpr {
 
@@ -53,8 +56,23 @@ constexpr int kTcChunkBytes = kTcChunkN * kTcK * 2;      // 32 KB
 constexpr int kTcATileBytes = kTcTileM * kTcK * 2;       // 16 KB
 constexpr int kTcCandCap = 64;         // candidate slots per row (<= 32: fast tail, <= 64: two-round tail)
 constexpr int kTcKPrime = 24;          // tau = kTcKPrime-th largest group maximum
-constexpr int kTcThreads = 512;        // warp 0 TMEM alloc + TMA + MMA, warps 4-7 filter, warps 1-3 + 8-15 tail (+ A-tile loads)
-constexpr int kTcTailWarps = 11;
+#ifndef HVPR_K3_TAIL_WARPS
+#define HVPR_K3_TAIL_WARPS 11
+#endif
+#ifndef HVPR_K3_TAIL_LOWREG
+#define HVPR_K3_TAIL_LOWREG 0   // 1: the tail fetches candidate rows twice instead of caching them (for builds with < 128 registers per thread)
+#endif
+#ifndef HVPR_K3_FILTER_WARPS
+#define HVPR_K3_FILTER_WARPS 4
+#endif
+constexpr int kTcFilterWarps = HVPR_K3_FILTER_WARPS;   // 4: one thread per row; 8: warp 4 + q + 4 * half owns columns [128 * half, +128) of every chunk
+static_assert(kTcFilterWarps == 4 || kTcFilterWarps == 8, "filter warps: one or two per TMEM lane quadrant");
+constexpr int kTcTailWarps = HVPR_K3_TAIL_WARPS;       // warps 1-3 and 4 + kTcFilterWarps ...
+constexpr int kTcWarps = 4 + kTcFilterWarps + kTcTailWarps - 3;
+constexpr int kTcThreads = 32 * kTcWarps;   // warp 0 TMEM alloc + TMA + MMA, warps 4-11 filter, the rest tail (+ A-tile loads)
+constexpr int kTcFilterThreads = 32 * kTcFilterWarps;
+constexpr int kTcHalfCap = 32;         // candidate slots per half row
+constexpr int kTcOverflow = 99;        // cand_cnt value of a half row that overflowed its slots
 constexpr int kTcCandBufs = 3;         // candidate-list ring between the filter and the tail
 constexpr int kTcSlowScratch = 2048;   // floats per tail warp (global workspace) for the overflow path
 
@@ -62,8 +80,8 @@ struct TcSmem {
     uint8_t w[kTcWStages][kTcChunkBytes];     // 1024-aligned
     uint8_t a[2][kTcATileBytes];
     uint16_t cand[kTcCandBufs][kTcCandCap][kTcTileM];
-    int32_t cand_cnt[kTcCandBufs][kTcTileM];
-    float gm[16][kTcTileM];                   // group maxima of the current chunk, one column per filter thread
+    int32_t cand_cnt[kTcCandBufs][2][kTcTileM];
+    float tx[9][2 * kTcTileM];                // entries 7..15 of each filter thread's sorted top-16 group maxima (tau exchange)
     alignas(16) uint32_t bcast[kTcTailWarps][2][32];   // per tail warp: candidate indices / softmax weights, read back as LDS.128 broadcasts
     uint64_t w_full[kTcWStages], w_empty[kTcWStages];
     uint64_t a_full[2], a_empty[2];
@@ -111,7 +129,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 constexpr int kBarCFull = 1;    // +cb (3 ids): filter (128 arrive) -> tail warps (sync)
 constexpr int kBarCEmpty = 4;   // +cb (3 ids): tail warps (arrive)  -> filter (128 sync)
-constexpr int kBarTEmpty = 7;   // +tb (2 ids): filter (128 arrive) -> MMA warp (32 sync)
+constexpr int kBarTEmpty = 7;   // +tb (2 ids): filter (256 arrive) -> MMA warp (32 sync)
+constexpr int kBarFilter = 9;   // the 256 filter threads among themselves (tau exchange)
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -159,6 +178,25 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
                       "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
 }
 
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                      "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
+// 3-input maximum (sm_100: one FMNMX3 on the ALU pipe instead of two FMNMX)
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 // ---------------------------------------------------------------------------------------------- register sorting nets
 __device__ __forceinline__ void cex_desc(float &a, float &b) {   // a >= b afterwards
     const float hi = fmaxf(a, b), lo = fminf(a, b);
@@ -191,6 +229,16 @@ __device__ __forceinline__ void bitonic_merge_desc(float (&x)[N]) {   // x biton
             if (l > i) cex_desc(x[i], x[l]);
         }
     }
+}
+
+// 19-comparator network for 8 values (descending)
+__device__ __forceinline__ void sort8_desc(float (&x)[8]) {
+    cex_desc(x[0], x[2]); cex_desc(x[1], x[3]); cex_desc(x[4], x[6]); cex_desc(x[5], x[7]);
+    cex_desc(x[0], x[4]); cex_desc(x[1], x[5]); cex_desc(x[2], x[6]); cex_desc(x[3], x[7]);
+    cex_desc(x[0], x[1]); cex_desc(x[2], x[3]); cex_desc(x[4], x[5]); cex_desc(x[6], x[7]);
+    cex_desc(x[2], x[4]); cex_desc(x[3], x[5]);
+    cex_desc(x[1], x[4]); cex_desc(x[3], x[6]);
+    cex_desc(x[1], x[2]); cex_desc(x[3], x[4]); cex_desc(x[5], x[6]);
 }
 
 __device__ __forceinline__ uint32_t float_key(float f) {   // order-preserving float -> uint
@@ -272,6 +320,12 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
         : "l"(*reinterpret_cast<const unsigned long long *>(&a)), "l"(*reinterpret_cast<const unsigned long long *>(&b)));
     return d;
 }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long *>(&d))
+        : "l"(*reinterpret_cast<const unsigned long long *>(&a)), "l"(*reinterpret_cast<const unsigned long long *>(&b)));
+    return d;
+}
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
     float2 d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(*reinterpret_cast<unsigned long long *>(&d))
@@ -284,35 +338,56 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
 // candidate row of its half (one 256-B row per half-warp per request, a single L2 round trip for all 16), the 16
 // per-candidate partial dots are transpose-reduced across the half with 15 shuffles so that lane c ends up with the exact
 // fp32 logit of candidate c; the rows stay in registers for the readout, whose two half sums meet in one last exchange.
-__device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, const float *__restrict__ W, int k, int cnt,
+__device__ __forceinline__ int cand_at(const uint16_t *__restrict__ cand_col /* stride kTcTileM */, int e, int cnt_a) {
+    return (int)cand_col[((e < cnt_a) ? e : kTcHalfCap + e - cnt_a) * kTcTileM];
+}
+__device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, const float *__restrict__ W, int k, int cnt, int cnt_a,
                                               const uint16_t *__restrict__ cand_col /* stride kTcTileM */, uint32_t (*bc)[32],
                                               float *__restrict__ out_row, int32_t *__restrict__ idx_row, int lane TCP_ROW_ARG) {
     TCP_ROW_START;
     const int sub = lane & 15, hb = lane & 16;                // channel quad / first candidate slot of this half
+    const float4 *__restrict__ Wq = reinterpret_cast<const float4 *>(W) + sub;     // this lane's 16-byte piece of every memory row
     const float4 p4 = __ldg(reinterpret_cast<const float4 *>(prow) + sub);
     // slots past cnt replay candidate 0 (an L1 hit) so that all gathers are unconditional and issue back to back:
     // any branch here makes the compiler merge registers per group and serialises the L2 round trips
-    const int my_j = (int)cand_col[((lane < cnt) ? lane : 0) * kTcTileM];
-    // lane c's index / weight is needed by every lane of its half: one store + four 128-bit shared-memory broadcasts
+    const int my_j = cand_at(cand_col, (lane < cnt) ? lane : 0, cnt_a);
+    // lane c's index / weight is needed by every lane of its half: one store + 128-bit shared-memory broadcasts
     __syncwarp();
-    bc[0][lane] = (uint32_t)my_j;
+    bc[0][lane] = (uint32_t)my_j * (uint32_t)(kTcK / 4);      // row offset in float4 units
     __syncwarp();
+    const float2 pa = make_float2(p4.x, p4.y), pb = make_float2(p4.z, p4.w);
+    float s[16];
+#if HVPR_K3_TAIL_LOWREG
+    // pass 1: exact partial dots, eight candidate rows in flight per batch; the rows are NOT kept (a 64-register row cache
+    // needs 128 registers per thread) and the readout below fetches the kept rows again, from L1 / L2
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+        const uint4 ja = *reinterpret_cast<const uint4 *>(&bc[0][hb + 8 * h2]);
+        const uint4 jb = *reinterpret_cast<const uint4 *>(&bc[0][hb + 8 * h2 + 4]);
+        float4 w[8];
+        w[0] = __ldg(Wq + ja.x); w[1] = __ldg(Wq + ja.y); w[2] = __ldg(Wq + ja.z); w[3] = __ldg(Wq + ja.w);
+        w[4] = __ldg(Wq + jb.x); w[5] = __ldg(Wq + jb.y); w[6] = __ldg(Wq + jb.z); w[7] = __ldg(Wq + jb.w);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float2 t = fma2(make_float2(w[c].z, w[c].w), pb, mul2(make_float2(w[c].x, w[c].y), pa));
+            s[8 * h2 + c] = t.x + t.y;
+        }
+    }
+#else
+    // all 16 candidate rows of this half in flight at once (one L2 round trip per pillar row) and kept for the readout
     float4 w4[16];
 #pragma unroll
     for (int c4 = 0; c4 < 4; ++c4) {
         const uint4 jj = *reinterpret_cast<const uint4 *>(&bc[0][hb + 4 * c4]);
-        w4[4 * c4 + 0] = __ldg(reinterpret_cast<const float4 *>(W + (int64_t)jj.x * kTcK) + sub);
-        w4[4 * c4 + 1] = __ldg(reinterpret_cast<const float4 *>(W + (int64_t)jj.y * kTcK) + sub);
-        w4[4 * c4 + 2] = __ldg(reinterpret_cast<const float4 *>(W + (int64_t)jj.z * kTcK) + sub);
-        w4[4 * c4 + 3] = __ldg(reinterpret_cast<const float4 *>(W + (int64_t)jj.w * kTcK) + sub);
+        w4[4 * c4 + 0] = __ldg(Wq + jj.x); w4[4 * c4 + 1] = __ldg(Wq + jj.y);
+        w4[4 * c4 + 2] = __ldg(Wq + jj.z); w4[4 * c4 + 3] = __ldg(Wq + jj.w);
     }
-    float s[16];
-    const float2 pa = make_float2(p4.x, p4.y), pb = make_float2(p4.z, p4.w);
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
         const float2 t = fma2(make_float2(w4[c].z, w4[c].w), pb, mul2(make_float2(w4[c].x, w4[c].y), pa));
         s[c] = t.x + t.y;
     }
+#endif
     TCP_ROW_T(0);
     // transpose-reduce inside the half: after the stage with xor-distance d, a lane keeps the half of the values selected by its bit d
 #pragma unroll
@@ -341,24 +416,43 @@ __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, co
     float sum = ex;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float a = ex / sum;
+    const float a = ex * __frcp_rn(sum);                       // sum >= 1 (the maximum contributes exp(0)); a 0 / sum division takes the slow path
     TCP_ROW_T(2);
     float2 oa = make_float2(0.0f, 0.0f), ob = oa;
     bc[1][lane] = __float_as_uint(a);                          // 0 for dropped / absent candidates
     __syncwarp();
+#if HVPR_K3_TAIL_LOWREG
+    // pass 2: readout over the kept rows (weight 0 = dropped or absent slot: no load)
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+        const uint4 ja = *reinterpret_cast<const uint4 *>(&bc[0][hb + 8 * h2]);
+        const uint4 jb = *reinterpret_cast<const uint4 *>(&bc[0][hb + 8 * h2 + 4]);
+        const uint4 xa = *reinterpret_cast<const uint4 *>(&bc[1][hb + 8 * h2]);
+        const uint4 xb = *reinterpret_cast<const uint4 *>(&bc[1][hb + 8 * h2 + 4]);
+        const uint32_t jj[8] = {ja.x, ja.y, ja.z, ja.w, jb.x, jb.y, jb.z, jb.w};
+        const uint32_t xx[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        float4 w[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) w[c] = (xx[c] != 0u) ? __ldg(Wq + jj[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float ac = __uint_as_float(xx[c]);
+            oa = fma2(make_float2(w[c].x, w[c].y), make_float2(ac, ac), oa);
+            ob = fma2(make_float2(w[c].z, w[c].w), make_float2(ac, ac), ob);
+        }
+    }
+#else
 #pragma unroll
     for (int c4 = 0; c4 < 4; ++c4) {
         const uint4 aa = *reinterpret_cast<const uint4 *>(&bc[1][hb + 4 * c4]);
-        const float a0 = __uint_as_float(aa.x), a1 = __uint_as_float(aa.y), a2 = __uint_as_float(aa.z), a3 = __uint_as_float(aa.w);
-        oa = fma2(make_float2(w4[4 * c4 + 0].x, w4[4 * c4 + 0].y), make_float2(a0, a0), oa);
-        ob = fma2(make_float2(w4[4 * c4 + 0].z, w4[4 * c4 + 0].w), make_float2(a0, a0), ob);
-        oa = fma2(make_float2(w4[4 * c4 + 1].x, w4[4 * c4 + 1].y), make_float2(a1, a1), oa);
-        ob = fma2(make_float2(w4[4 * c4 + 1].z, w4[4 * c4 + 1].w), make_float2(a1, a1), ob);
-        oa = fma2(make_float2(w4[4 * c4 + 2].x, w4[4 * c4 + 2].y), make_float2(a2, a2), oa);
-        ob = fma2(make_float2(w4[4 * c4 + 2].z, w4[4 * c4 + 2].w), make_float2(a2, a2), ob);
-        oa = fma2(make_float2(w4[4 * c4 + 3].x, w4[4 * c4 + 3].y), make_float2(a3, a3), oa);
-        ob = fma2(make_float2(w4[4 * c4 + 3].z, w4[4 * c4 + 3].w), make_float2(a3, a3), ob);
+        const float av[4] = {__uint_as_float(aa.x), __uint_as_float(aa.y), __uint_as_float(aa.z), __uint_as_float(aa.w)};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            oa = fma2(make_float2(w4[4 * c4 + u].x, w4[4 * c4 + u].y), make_float2(av[u], av[u]), oa);
+            ob = fma2(make_float2(w4[4 * c4 + u].z, w4[4 * c4 + u].w), make_float2(av[u], av[u]), ob);
+        }
     }
+#endif
     float4 o4 = make_float4(oa.x, oa.y, ob.x, ob.y);
     o4.x += __shfl_xor_sync(0xffffffffu, o4.x, 16); o4.y += __shfl_xor_sync(0xffffffffu, o4.y, 16);
     o4.z += __shfl_xor_sync(0xffffffffu, o4.z, 16); o4.w += __shfl_xor_sync(0xffffffffu, o4.w, 16);
@@ -394,13 +488,13 @@ __device__ __forceinline__ float cand_logits32(const float2 p2, const float *__r
 }
 
 // 33..64 candidates (about 1 % of rows at kTcKPrime = 24): two rounds of 32, then the kept rows are gathered again
-__device__ __noinline__ void tail_medium_row(const float *__restrict__ prow, const float *__restrict__ W, int k, int cnt,
+__device__ __noinline__ void tail_medium_row(const float *__restrict__ prow, const float *__restrict__ W, int k, int cnt, int cnt_a,
                                              const uint16_t *__restrict__ cand_col, float *__restrict__ out_row,
                                              int32_t *__restrict__ idx_row, int lane) {
     const float2 p2 = __ldg(reinterpret_cast<const float2 *>(prow) + lane);
-    const int j0 = (int)cand_col[lane * kTcTileM];
+    const int j0 = cand_at(cand_col, lane, cnt_a);
     const int n1 = cnt - 32;
-    const int j1 = (lane < n1) ? (int)cand_col[(32 + lane) * kTcTileM] : 0;
+    const int j1 = cand_at(cand_col, (lane < n1) ? 32 + lane : 0, cnt_a);
     const float l0 = cand_logits32(p2, W, j0, 32, lane);
     const float l1 = cand_logits32(p2, W, j1, n1, lane);
     const uint32_t k0 = float_key(l0), k1 = (lane < n1) ? float_key(l1) : 0u;
@@ -544,7 +638,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
                     mbar_wait(&S.w_full[s], (it / kTcWStages) & 1);
                     TCP_END(1);
                     TCP_BEGIN();
-                    if (it >= 2) named_bar_sync(kBarTEmpty + tb, 128 + 32);     // filter drained this accumulator buffer
+                    if (it >= 2) named_bar_sync(kBarTEmpty + tb, kTcFilterThreads + 32);     // filter drained this accumulator buffer
                     TCP_END(2);
                     tc_fence_after();
                     if (lane == 0) {
@@ -562,9 +656,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
             __syncwarp();
         }
         TCP_DUMP(0);
-    } else if (warp >= 4 && warp < 8) {
-        // ===== filter: one accumulator row per thread ===============================================================
-        const int q = warp & 3;                 // TMEM lane quadrant of this warp
+    } else if (warp >= 4 && warp < 4 + kTcFilterWarps) {
+        // ===== filter: one accumulator row per thread (4 filter warps) or per thread pair (8 filter warps) ===============
+        // A row's 256 columns of every chunk are handled as two halves of 128; with 8 filter warps the halves belong to two
+        // threads (same TMEM lane, warps 4 + q and 8 + q), with 4 filter warps one thread walks both.
+        constexpr int kH = 8 / kTcFilterWarps;  // halves per thread
+        const int q = warp & 3;                 // TMEM lane quadrant of this warp (a warp may only read lanes 32 * (warp % 4) ...)
+        const int half0 = (kH == 2) ? 0 : ((warp - 4) >> 2);
         const int row = q * 32 + lane;          // row within the tile
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t it = 0, ti = 0;
@@ -582,135 +680,174 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
             const int t = tile_ids[ti & 3];
             if (t < 0) break;
             const int cb = ti % kTcCandBufs;
-            // ---- sweep 1: group maxima -> tau ----
-            float top[32];
+            const bool live = (int64_t)t * kTcTileM + row < nP;
+            // ---- sweep 1: maxima of 16-column groups -> sorted top-16 of each half row (64 group maxima per half) ----
+            float top[kH][16];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) top[i] = -INFINITY;
+            for (int h = 0; h < kH; ++h)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) top[h][i] = -INFINITY;
             for (int c = 0; c < nchunks; ++c, ++it) {
                 const int tb = it & 1;
                 TCP_BEGIN();
                 mbar_wait(&S.t_full[tb], (it >> 1) & 1);
                 TCP_END(0);
                 tc_fence_after();
-                const int col0 = c * kTcChunkN;
                 FL_B();
-                auto s1_block = [&](const uint32_t (&r)[32], int b) {
-                    float v[32];
+                float g[kH][8];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                    if (col0 + b * 32 + 32 > M) {             // warp-uniform: chunk straddles the end of the memory
+                for (int h = 0; h < kH; ++h) {
+                    const int col0 = c * kTcChunkN + (half0 + h) * 128;
+                    const uint32_t cbase = lane_addr + (uint32_t)(tb * kTcChunkN + (half0 + h) * 128);
+                    // kSlow: this half chunk straddles the end of the memory (columns >= M count as -inf) or the debug dump is on
+                    auto s1_half_chunk = [&](auto slow_tag) {
+                        constexpr bool kSlow = decltype(slow_tag)::value;
+                        auto s1_group = [&](const uint32_t (&r)[16], int gi) -> float {
+                            float v[16];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = (col0 + b * 32 + i < M) ? v[i] : -INFINITY;
-                    }
+                            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+                            if (kSlow) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] = (col0 + gi * 16 + i < M) ? v[i] : -INFINITY;
 #ifndef HVPR_TC_PROFILE
-                    if (dbg_logits) {
-                        const int64_t grow = (int64_t)t * kTcTileM + row;
-                        if (grow < nP)
+                                if (dbg_logits) {
+                                    const int64_t grow = (int64_t)t * kTcTileM + row;
+                                    if (grow < nP)
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) dbg_logits[grow * (nchunks * kTcChunkN) + col0 + b * 32 + i] = v[i];
-                    }
+                                        for (int i = 0; i < 16; ++i) dbg_logits[grow * (nchunks * kTcChunkN) + col0 + gi * 16 + i] = v[i];
+                                }
 #endif
+                            }
+                            // 16 -> 1 with eight maxima, seven of them 3-input (FMNMX3)
+                            const float a0 = max3(v[0], v[1], v[2]), a1 = max3(v[3], v[4], v[5]), a2 = max3(v[6], v[7], v[8]);
+                            const float a3 = max3(v[9], v[10], v[11]), a4 = max3(v[12], v[13], v[14]);
+                            return fmaxf(max3(a0, a1, a2), max3(a3, a4, v[15]));
+                        };
+                        uint32_t ra[16], rb[16];
+                        tmem_ld16_issue(cbase, ra);
 #pragma unroll
-                    for (int h2 = 0; h2 < 2; ++h2) {          // tree max of 16
-                        float m8[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) m8[i] = fmaxf(v[h2 * 16 + i], v[h2 * 16 + 8 + i]);
-                        const float a0 = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
-                        const float a1 = fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7]));
-                        S.gm[b * 2 + h2][row] = fmaxf(a0, a1);
-                    }
-                };
-                {
-                    // single-buffered here: top[32] is live in this sweep, a second 32-register buffer would spill
-                    const uint32_t cbase = lane_addr + (uint32_t)(tb * kTcChunkN);
-#pragma unroll 1
-                    for (int b = 0; b < 8; ++b) {               // rolled: keeps the hot code inside the instruction cache
-                        uint32_t ra[32];
-                        tmem_ld32_issue(cbase + (uint32_t)(b * 32), ra);
-                        tmem_ld32_wait(ra);
-                        s1_block(ra, b);
-                    }
+                        for (int gi = 0; gi < 8; gi += 2) {
+                            tmem_ld16_wait(ra);
+                            tmem_ld16_issue(cbase + (uint32_t)((gi + 1) * 16), rb);
+                            g[h][gi] = s1_group(ra, gi);
+                            tmem_ld16_wait(rb);
+                            if (gi + 2 < 8) tmem_ld16_issue(cbase + (uint32_t)((gi + 2) * 16), ra);
+                            g[h][gi + 1] = s1_group(rb, gi + 1);
+                        }
+                    };
+                    if (col0 + 128 > M || dbg_logits != nullptr) s1_half_chunk(std::true_type{});
+                    else s1_half_chunk(std::false_type{});
                 }
                 FL_E(0);
                 tc_fence_before();
-                named_bar_arrive(kBarTEmpty + tb, 128 + 32);
+                named_bar_arrive(kBarTEmpty + tb, kTcFilterThreads + 32);
                 FL_B();
-                // merge the 16 new group maxima into the running top-32 (descending)
-                float g[16];
+                // top-16 of (top, g): sort the 8 new maxima, half-cleaner against the lower half of the list, bitonic merge
 #pragma unroll
-                for (int i = 0; i < 16; ++i) g[i] = S.gm[i][row];
-                bitonic_sort_desc<16>(g);
+                for (int h = 0; h < kH; ++h) {
+                    sort8_desc(g[h]);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) top[16 + i] = fmaxf(top[16 + i], g[15 - i]);
-                bitonic_merge_desc<32>(top);
+                    for (int i = 0; i < 8; ++i) top[h][8 + i] = fmaxf(top[h][8 + i], g[h][7 - i]);
+                    bitonic_merge_desc<16>(top[h]);
+                }
                 FL_E(1);
             }
-            const float tau = top[kTcKPrime - 1];
+            // ---- tau = 24th largest of the union of the two half-row lists a, b (each the sorted top-16 of 64 group maxima):
+            //      min(a_7, b_7, min_{i=8..15} max(a_i, b_{23-i})).  A half that holds more than 16 of the 24 only lowers tau.
+            float tau;
+            if (kH == 2) {
+                tau = fminf(top[0][7], top[kH - 1][7]);
+#pragma unroll
+                for (int i = 8; i < 16; ++i) tau = fminf(tau, fmaxf(top[0][i], top[kH - 1][23 - i]));
+            } else {
+                const int me = half0 * kTcTileM + row, other = (half0 ^ 1) * kTcTileM + row;
+#pragma unroll
+                for (int i = 7; i < 16; ++i) S.tx[i - 7][me] = top[0][i];
+                named_bar_sync(kBarFilter, kTcFilterThreads);
+                tau = fminf(top[0][7], S.tx[0][other]);
+#pragma unroll
+                for (int i = 8; i < 16; ++i) tau = fminf(tau, fmaxf(top[0][i], S.tx[(23 - i) - 7][other]));
+                named_bar_sync(kBarFilter, kTcFilterThreads);   // everyone has read tx before the next tile overwrites it
+            }
+            if (!live) tau = INFINITY;            // rows past the end of the input (zero A rows: every logit ties) nominate nothing
             // ---- sweep 2: candidates = { j : logit_j >= tau } ----
             TCP_BEGIN();
-            if (ti >= (uint32_t)kTcCandBufs) named_bar_sync(kBarCEmpty + cb, 128 + 32 * kTcTailWarps);   // tail finished with this candidate buffer
+            if (ti >= (uint32_t)kTcCandBufs) named_bar_sync(kBarCEmpty + cb, kTcFilterThreads + 32 * kTcTailWarps);   // tail finished with this candidate buffer
             TCP_END(2);
-            int cnt = ((int64_t)t * kTcTileM + row < nP) ? 0 : kTcCandCap;   // dead rows start "overflowed" (their count is never read)
+            uint32_t cstart[kH], caddr[kH];
+            bool over[kH];
+#pragma unroll
+            for (int h = 0; h < kH; ++h) {
+                cstart[h] = smem_u32(&S.cand[cb][(half0 + h) * kTcHalfCap][row]);
+                caddr[h] = cstart[h];
+                over[h] = false;
+            }
+            const float2 ntau2 = make_float2(-tau, -tau);
             for (int c = 0; c < nchunks; ++c, ++it) {
                 const int tb = it & 1;
                 TCP_BEGIN();
                 mbar_wait(&S.t_full[tb], (it >> 1) & 1);
                 TCP_END(1);
                 tc_fence_after();
-                const int col0 = c * kTcChunkN;
                 FL_B();
-                auto s2_block = [&](const uint32_t (&r)[32], int b) {
-                    // bit (31 - i) of `neg` = sign of (logit_i - tau); four independent 8-deep funnel-shift chains
-                    uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+                // bit (15 - i) of the result = sign of (logit_i - tau); two independent 8-deep funnel-shift chains
+                auto s2_signs = [&](const uint32_t (&r)[16]) -> uint32_t {
+                    uint32_t n0 = 0, n1 = 0;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        n0 = __funnelshift_l(__float_as_uint(__uint_as_float(r[i]) - tau), n0, 1);
-                        n1 = __funnelshift_l(__float_as_uint(__uint_as_float(r[8 + i]) - tau), n1, 1);
-                        n2 = __funnelshift_l(__float_as_uint(__uint_as_float(r[16 + i]) - tau), n2, 1);
-                        n3 = __funnelshift_l(__float_as_uint(__uint_as_float(r[24 + i]) - tau), n3, 1);
+                    for (int i = 0; i < 8; i += 2) {
+                        const float2 d0 = add2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), ntau2);
+                        const float2 d1 = add2(make_float2(__uint_as_float(r[8 + i]), __uint_as_float(r[8 + i + 1])), ntau2);
+                        n0 = __funnelshift_l(__float_as_uint(d0.x), n0, 1); n0 = __funnelshift_l(__float_as_uint(d0.y), n0, 1);
+                        n1 = __funnelshift_l(__float_as_uint(d1.x), n1, 1); n1 = __funnelshift_l(__float_as_uint(d1.y), n1, 1);
                     }
-                    uint32_t m = ~((n0 << 24) | (n1 << 16) | (n2 << 8) | n3);
-                    const int base = col0 + b * 32;
-                    if (base + 32 > M) m = (base >= M) ? 0u : (m & ~(0xFFFFFFFFu >> (M - base)));
-                    // rows that already overflowed the candidate list, and rows past the end of the input (zero A rows: every logit
-                    // ties; they start at the cap), only need the count — extracting 2000 tied columns one by one stalled the whole
-                    // warp (the CTA that owned the last, partial tile ran 45 us longer than every other one)
-                    if (cnt >= kTcCandCap) { cnt += __popc(m); m = 0u; }
-                    while (m) {
-                        const int bit = 31 - __clz((int)m);     // highest set bit = lowest column first
-                        m &= ~(1u << bit);
-                        if (cnt < kTcCandCap) S.cand[cb][cnt][row] = (uint16_t)(base + 31 - bit);
-                        ++cnt;
-                    }
+                    return (n0 << 8) | n1;
                 };
-                {
-                    uint32_t ra[32], rb[32];
-                    const uint32_t cbase = lane_addr + (uint32_t)(tb * kTcChunkN);
-                    tmem_ld32_issue(cbase, ra);
+#pragma unroll
+                for (int h = 0; h < kH; ++h) {
+                    const int col0 = c * kTcChunkN + (half0 + h) * 128;
+                    const bool ragged = col0 + 128 > M;           // warp-uniform: only the last half chunk can straddle the end of the memory
+                    const uint32_t cend = cstart[h] + (uint32_t)(kTcHalfCap * kTcTileM * 2);
+                    const uint32_t cbase = lane_addr + (uint32_t)(tb * kTcChunkN + (half0 + h) * 128);
+                    uint32_t ra[16], rb[16];
+                    tmem_ld16_issue(cbase, ra);
 #pragma unroll 1
-                    for (int b = 0; b < 8; b += 2) {
-                        tmem_ld32_wait(ra);
-                        tmem_ld32_issue(cbase + (uint32_t)((b + 1) * 32), rb);
-                        s2_block(ra, b);
-                        tmem_ld32_wait(rb);
-                        if (b + 2 < 8) tmem_ld32_issue(cbase + (uint32_t)((b + 2) * 32), ra);
-                        s2_block(rb, b + 1);
+                    for (int b = 0; b < 4; ++b) {
+                        tmem_ld16_wait(ra);
+                        tmem_ld16_issue(cbase + (uint32_t)(b * 32 + 16), rb);
+                        const uint32_t hi = s2_signs(ra);
+                        tmem_ld16_wait(rb);
+                        if (b + 1 < 4) tmem_ld16_issue(cbase + (uint32_t)((b + 1) * 32), ra);
+                        const uint32_t lo = s2_signs(rb);
+                        uint32_t m = ~((hi << 16) | lo);           // bit (31 - i) <-> column base + i passes
+                        const int base = col0 + b * 32;
+                        if (ragged && base + 32 > M) m = (base >= M) ? 0u : (m & ~(0xFFFFFFFFu >> (M - base)));
+                        // a half row that filled its slots (massive ties, e.g. an all-zero pillar row) stops extracting: the tail
+                        // sees kTcOverflow and takes the exact full scan
+                        while (m != 0u && caddr[h] < cend) {
+                            const int bit = 31 - __clz((int)m);     // highest set bit = lowest column first
+                            m &= ~(1u << bit);
+                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(caddr[h]), "h"((uint16_t)(base + 31 - bit)) : "memory");
+                            caddr[h] += (uint32_t)(kTcTileM * 2);
+                        }
+                        over[h] |= (m != 0u);
                     }
                 }
                 FL_E(2);
                 tc_fence_before();
-                named_bar_arrive(kBarTEmpty + tb, 128 + 32);
+                named_bar_arrive(kBarTEmpty + tb, kTcFilterThreads + 32);
             }
-            S.cand_cnt[cb][row] = cnt;
-            named_bar_arrive(kBarCFull + cb, 128 + 32 * kTcTailWarps);   // orders the candidate stores before the tail's reads
+#pragma unroll
+            for (int h = 0; h < kH; ++h)
+                S.cand_cnt[cb][half0 + h][row] = over[h] ? kTcOverflow : (int)((caddr[h] - cstart[h]) / (uint32_t)(kTcTileM * 2));
+            named_bar_arrive(kBarCFull + cb, kTcFilterThreads + 32 * kTcTailWarps);   // orders the candidate stores before the tail's reads
         }
-        if (q == 0) { TCP_DUMP(4); }
+        if (q == 0 && half0 == 0) { TCP_DUMP(4); }
 #ifdef HVPR_TC_PROFILE
-        if (q == 0 && lane == 0 && dbg_logits) { reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 24 + 7] = fl_acc[0]; reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 24 + 3] = fl_acc[1]; reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 24 + 14] = fl_acc[2]; }
+        if (q == 0 && half0 == 0 && lane == 0 && dbg_logits) { reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 24 + 7] = fl_acc[0]; reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 24 + 3] = fl_acc[1]; reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 24 + 14] = fl_acc[2]; }
 #endif
     } else {
         // ===== tail: A-tile loads + exact fp32 re-score, top-k, softmax, readout — one warp per row =================
-        const int tw = (warp < 4) ? (warp - 1) : (warp - 5);    // 0..10
+        const int tw = (warp < 4) ? (warp - 1) : (warp - (4 + kTcFilterWarps) + 3);    // 0 .. kTcTailWarps - 1
         float *scratch = slow_scratch + ((size_t)blockIdx.x * kTcTailWarps + tw) * kTcSlowScratch;
         // fp32 pillar rows -> bf16, 128-B-swizzled K-major tile; this warp converts rows tw, tw+10, ...
         auto load_a_tile = [&](int t_load, uint32_t ti_load) {
@@ -754,7 +891,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
             const int cb = ti % kTcCandBufs;
             if (tid == 32) tile_ids[(ti + 2) & 3] = next_id;     // ordered before every tail warp's read by the barrier below
             TCP_BEGIN();
-            named_bar_sync(kBarCFull + cb, 128 + 32 * kTcTailWarps);
+            named_bar_sync(kBarCFull + cb, kTcFilterThreads + 32 * kTcTailWarps);
             TCP_END(0);
             TCP_BEGIN();
             if (tid == 32) {                                     // claim the tile after next; the round trip hides behind this tile's rows
@@ -770,20 +907,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
             for (int r = tw; r < kTcTileM; r += kTcTailWarps) {
                 const int64_t grow = (int64_t)t * kTcTileM + r;
                 if (grow >= nP) break;
-                const int cnt = S.cand_cnt[cb][r];
+                const int cnt_a = S.cand_cnt[cb][0][r], cnt_b = S.cand_cnt[cb][1][r];
+                const int cnt = (cnt_a > kTcHalfCap || cnt_b > kTcHalfCap) ? 2 * kTcCandCap : cnt_a + cnt_b;   // a half row overflowed -> full scan
                 const float *prow = pillars + grow * kTcK;
                 int32_t *idx_row = topk_idx_out ? topk_idx_out + grow * k : nullptr;
 #ifdef HVPR_TC_PROFILE
                 if (lane == 0 && dbg_logits) atomicAdd(reinterpret_cast<unsigned long long *>(dbg_logits) + (size_t)blockIdx.x * 24 + ((cnt >= k && cnt <= 32) ? 19 : (cnt > 32 && cnt <= kTcCandCap) ? 20 : 21), 1ull);
 #endif
                 if (cnt >= k && cnt <= 32)
-                    tail_fast_row(prow, W, k, cnt, &S.cand[cb][0][r], S.bcast[tw], readout + grow * kTcK, idx_row, lane TCP_ROW_PASS);
+                    tail_fast_row(prow, W, k, cnt, cnt_a, &S.cand[cb][0][r], S.bcast[tw], readout + grow * kTcK, idx_row, lane TCP_ROW_PASS);
                 else if (cnt > 32 && cnt <= kTcCandCap)
-                    tail_medium_row(prow, W, k, cnt, &S.cand[cb][0][r], readout + grow * kTcK, idx_row, lane);
+                    tail_medium_row(prow, W, k, cnt, cnt_a, &S.cand[cb][0][r], readout + grow * kTcK, idx_row, lane);
                 else
                     tail_slow_row(prow, W, M, k, scratch, readout + grow * kTcK, idx_row, lane);
             }
-            named_bar_arrive(kBarCEmpty + cb, 128 + 32 * kTcTailWarps);
+            named_bar_arrive(kBarCEmpty + cb, kTcFilterThreads + 32 * kTcTailWarps);
             TCP_END(1);
         }
         if (tw == 0) { TCP_DUMP(8); }
@@ -830,7 +968,8 @@ __global__ void pack_bf16_kernel(const float *__restrict__ W, int M, int Mpad, u
 }  // namespace hvpr
 using namespace hvpr;
 
-static size_t tc_smem_bytes() { return sizeof(TcSmem) + 1024; }
+static size_t tc_smem_bytes() { return sizeof(TcSmem); }   // the extern array is declared __align__(1024)
+static_assert(sizeof(TcSmem) <= 232448, "TcSmem exceeds the 227 KB opt-in shared memory of sm_100");
 
 int hvpr_mem_attn_tc_init() {
     cudaError_t e = cudaFuncSetAttribute(mem_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes());

@@ -7,4 +7,4 @@ echo "# cuobjdump -sass hvpr_b200/libhvpr_b200.so | mnemonic counts per kernel (
 cuobjdump -sass hvpr_b200/libhvpr_b200.so | awk '
 /Function :/ {fn=$3; next}
 { for (i=1;i<=NF;i++) if ($i ~ /^(UTCHMMA|UTCQMMA|UTCOMMA|LDTM|STTM|UBLKCP|UTMALDG|UTMASTG|UTCBAR|UTCCP|HMMA|SYNCS|REDUX|ATOMS|RED\.|ATOMG)/) { sub(/;$/,"",$i); c[fn"\t"$i]++ } }
-END { for (k in c) print k"\t"c[k] }' | sort | c++filt | column -t -s$'\t'
+END { for (k in c) print k"\t"c[k] }' | sort | c++filt
