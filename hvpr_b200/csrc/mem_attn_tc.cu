@@ -51,7 +51,10 @@ constexpr int kTcTileM = 128;          // pillar rows per tile (UMMA M)
 constexpr int kTcChunkN = 256;         // memory items per MMA (UMMA N)
 constexpr int kTcK = 64;               // feature dim
 constexpr int kTcMaxChunks = 8;        // M_pad <= 2048
-constexpr int kTcWStages = 4;
+#ifndef HVPR_K3_W_STAGES
+#define HVPR_K3_W_STAGES 3
+#endif
+constexpr int kTcWStages = HVPR_K3_W_STAGES;   // the filter takes a chunk every ~3.5 k cycles, an L2 round trip is ~1-2 k: three stages keep the MMA fed (two exposed the L2 latency once the filter got faster)
 constexpr int kTcChunkBytes = kTcChunkN * kTcK * 2;      // 32 KB
 constexpr int kTcATileBytes = kTcTileM * kTcK * 2;       // 16 KB
 constexpr int kTcCandCap = 64;         // candidate slots per row (<= 32: fast tail, <= 64: two-round tail)
@@ -62,16 +65,28 @@ constexpr int kTcKPrime = 24;          // tau = kTcKPrime-th largest group maxim
 #ifndef HVPR_K3_TAIL_LOWREG
 #define HVPR_K3_TAIL_LOWREG 0   // 1: the tail fetches candidate rows twice instead of caching them (for builds with < 128 registers per thread)
 #endif
+#ifndef HVPR_K3_SETMAXNREG
+#define HVPR_K3_SETMAXNREG 0
+#endif
+#ifndef HVPR_K3_FILTER_REGS
+#define HVPR_K3_FILTER_REGS 64
+#endif
+#ifndef HVPR_K3_TAIL_REGS
+#define HVPR_K3_TAIL_REGS 112
+#endif
 #ifndef HVPR_K3_FILTER_WARPS
 #define HVPR_K3_FILTER_WARPS 4
 #endif
 constexpr int kTcFilterWarps = HVPR_K3_FILTER_WARPS;   // 4: one thread per row; 8: warp 4 + q + 4 * half owns columns [128 * half, +128) of every chunk
 static_assert(kTcFilterWarps == 4 || kTcFilterWarps == 8, "filter warps: one or two per TMEM lane quadrant");
 constexpr int kTcTailWarps = HVPR_K3_TAIL_WARPS;       // warps 1-3 and 4 + kTcFilterWarps ...
-constexpr int kTcWarps = 4 + kTcFilterWarps + kTcTailWarps - 3;
+constexpr int kTcWarps = 1 + kTcTailWarps + kTcFilterWarps;   // warp 0: TMEM alloc + TMA + MMA; warps 1..: tail; the last kTcFilterWarps: filter
+constexpr int kTcFilterBase = 1 + kTcTailWarps;
+static_assert(kTcFilterBase % 4 == 0, "filter warp w reads TMEM lane quadrant w % 4: the first filter warp must be a multiple of 4");
 constexpr int kTcThreads = 32 * kTcWarps;   // warp 0 TMEM alloc + TMA + MMA, warps 4-11 filter, the rest tail (+ A-tile loads)
 constexpr int kTcFilterThreads = 32 * kTcFilterWarps;
 constexpr int kTcHalfCap = 32;         // candidate slots per half row
+constexpr int kTcTrStride = 36;        // row stride (floats) of the transpose buffer: conflict-free 128-bit reads of 8 consecutive rows
 constexpr int kTcOverflow = 99;        // cand_cnt value of a half row that overflowed its slots
 constexpr int kTcCandBufs = 3;         // candidate-list ring between the filter and the tail
 constexpr int kTcSlowScratch = 2048;   // floats per tail warp (global workspace) for the overflow path
@@ -82,7 +97,8 @@ struct TcSmem {
     uint16_t cand[kTcCandBufs][kTcCandCap][kTcTileM];
     int32_t cand_cnt[kTcCandBufs][2][kTcTileM];
     float tx[9][2 * kTcTileM];                // entries 7..15 of each filter thread's sorted top-16 group maxima (tau exchange)
-    alignas(16) uint32_t bcast[kTcTailWarps][2][32];   // per tail warp: candidate indices / softmax weights, read back as LDS.128 broadcasts
+    alignas(16) uint32_t bcast[kTcTailWarps][2][32];   // per tail warp: candidate indices / keys, then softmax weights, read back as LDS.128 broadcasts
+    alignas(16) float tr[kTcTailWarps][16][kTcTrStride];   // per tail warp: partial dots [candidate of the half][lane] for the transpose-reduce
     uint64_t w_full[kTcWStages], w_empty[kTcWStages];
     uint64_t a_full[2], a_empty[2];
     uint64_t t_full[2];
@@ -342,18 +358,19 @@ __device__ __forceinline__ int cand_at(const uint16_t *__restrict__ cand_col /* 
     return (int)cand_col[((e < cnt_a) ? e : kTcHalfCap + e - cnt_a) * kTcTileM];
 }
 __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, const float *__restrict__ W, int k, int cnt, int cnt_a,
-                                              const uint16_t *__restrict__ cand_col /* stride kTcTileM */, uint32_t (*bc)[32],
+                                              const uint16_t *__restrict__ cand_col /* stride kTcTileM */, uint32_t (*bc)[32], float *__restrict__ tr,
                                               float *__restrict__ out_row, int32_t *__restrict__ idx_row, int lane TCP_ROW_ARG) {
     TCP_ROW_START;
     const int sub = lane & 15, hb = lane & 16;                // channel quad / first candidate slot of this half
-    const float4 *__restrict__ Wq = reinterpret_cast<const float4 *>(W) + sub;     // this lane's 16-byte piece of every memory row
+    const char *__restrict__ Wq = reinterpret_cast<const char *>(W) + sub * 16;     // this lane's 16-byte piece of every memory row
+#define HVPR_WROW(j) reinterpret_cast<const float4 *>(Wq + (size_t)(j) * (kTcK * 4))
     const float4 p4 = __ldg(reinterpret_cast<const float4 *>(prow) + sub);
     // slots past cnt replay candidate 0 (an L1 hit) so that all gathers are unconditional and issue back to back:
     // any branch here makes the compiler merge registers per group and serialises the L2 round trips
     const int my_j = cand_at(cand_col, (lane < cnt) ? lane : 0, cnt_a);
     // lane c's index / weight is needed by every lane of its half: one store + 128-bit shared-memory broadcasts
     __syncwarp();
-    bc[0][lane] = (uint32_t)my_j * (uint32_t)(kTcK / 4);      // row offset in float4 units
+    bc[0][lane] = (uint32_t)my_j;
     __syncwarp();
     const float2 pa = make_float2(p4.x, p4.y), pb = make_float2(p4.z, p4.w);
     float s[16];
@@ -365,8 +382,8 @@ __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, co
         const uint4 ja = *reinterpret_cast<const uint4 *>(&bc[0][hb + 8 * h2]);
         const uint4 jb = *reinterpret_cast<const uint4 *>(&bc[0][hb + 8 * h2 + 4]);
         float4 w[8];
-        w[0] = __ldg(Wq + ja.x); w[1] = __ldg(Wq + ja.y); w[2] = __ldg(Wq + ja.z); w[3] = __ldg(Wq + ja.w);
-        w[4] = __ldg(Wq + jb.x); w[5] = __ldg(Wq + jb.y); w[6] = __ldg(Wq + jb.z); w[7] = __ldg(Wq + jb.w);
+        w[0] = __ldg(HVPR_WROW(ja.x)); w[1] = __ldg(HVPR_WROW(ja.y)); w[2] = __ldg(HVPR_WROW(ja.z)); w[3] = __ldg(HVPR_WROW(ja.w));
+        w[4] = __ldg(HVPR_WROW(jb.x)); w[5] = __ldg(HVPR_WROW(jb.y)); w[6] = __ldg(HVPR_WROW(jb.z)); w[7] = __ldg(HVPR_WROW(jb.w));
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             const float2 t = fma2(make_float2(w[c].z, w[c].w), pb, mul2(make_float2(w[c].x, w[c].y), pa));
@@ -379,8 +396,8 @@ __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, co
 #pragma unroll
     for (int c4 = 0; c4 < 4; ++c4) {
         const uint4 jj = *reinterpret_cast<const uint4 *>(&bc[0][hb + 4 * c4]);
-        w4[4 * c4 + 0] = __ldg(Wq + jj.x); w4[4 * c4 + 1] = __ldg(Wq + jj.y);
-        w4[4 * c4 + 2] = __ldg(Wq + jj.z); w4[4 * c4 + 3] = __ldg(Wq + jj.w);
+        w4[4 * c4 + 0] = __ldg(HVPR_WROW(jj.x)); w4[4 * c4 + 1] = __ldg(HVPR_WROW(jj.y));
+        w4[4 * c4 + 2] = __ldg(HVPR_WROW(jj.z)); w4[4 * c4 + 3] = __ldg(HVPR_WROW(jj.w));
     }
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
@@ -389,34 +406,45 @@ __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, co
     }
 #endif
     TCP_ROW_T(0);
-    // transpose-reduce inside the half: after the stage with xor-distance d, a lane keeps the half of the values selected by its bit d
+    // transpose-reduce through shared memory: lane l stores its 16 partial dots as column l, then lane (half, c) sums the 16 partials
+    // of candidate c of its half (row c, columns 16 * half .. +16) — 16 STS + 4 LDS.128 + 15 FADD and one shared-memory round trip
+    // instead of a four-stage shuffle butterfly (15 SHFL + 30 FSEL + 15 FADD, four dependent shuffle latencies)
 #pragma unroll
-    for (int d = 8; d > 0; d >>= 1) {
-        const bool up = (lane & d) != 0;
-#pragma unroll
-        for (int i = 0; i < d; ++i) {
-            const float send = up ? s[i] : s[i + d];
-            const float keep = up ? s[i + d] : s[i];
-            s[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
-        }
+    for (int c = 0; c < 16; ++c) tr[c * kTcTrStride + lane] = s[c];
+    __syncwarp();
+    float logit;
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(tr + sub * kTcTrStride + hb);
+        const float4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
+        logit = (((q0.x + q0.y) + (q0.z + q0.w)) + ((q1.x + q1.y) + (q1.z + q1.w))) +
+                (((q2.x + q2.y) + (q2.z + q2.w)) + ((q3.x + q3.y) + (q3.z + q3.w)));      // exact fp32 logit of candidate `lane`
     }
-    const float logit = s[0];                                  // exact fp32 logit of candidate `lane`
     TCP_ROW_T(1);
-    bool valid = lane < cnt;
-    uint32_t key = valid ? float_key(logit) : 0xFFFFFFFFu;
-    const uint32_t kmax = __reduce_max_sync(0xffffffffu, valid ? key : 0u);
-    // drop the (cnt - k) smallest exact logits, one warp-min each (ties: lowest lane first)
-    for (int e = cnt; e > k; --e) {
-        const uint32_t mn = __reduce_min_sync(0xffffffffu, key);
-        const int victim = __ffs(__ballot_sync(0xffffffffu, key == mn)) - 1;
-        if (lane == victim) { valid = false; key = 0xFFFFFFFFu; }
+    // top-k by rank: every lane reads all 32 keys (broadcast) and counts the larger ones — 32 independent compares instead of
+    // (cnt - k) dependent warp-min / ballot / find-first rounds; equal keys (exact fp32 ties) rank by lane
+    const uint32_t key = (lane < cnt) ? float_key(logit) : 0u;            // absent slots rank last (a real key is never 0: -NaN aside)
+    bc[1][lane] = key;
+    __syncwarp();
+    int rank = 0;
+#pragma unroll
+    for (int m4 = 0; m4 < 8; ++m4) {
+        const uint4 kk = *reinterpret_cast<const uint4 *>(&bc[1][4 * m4]);
+        rank += (kk.x > key) ? 1 : 0; rank += (kk.y > key) ? 1 : 0; rank += (kk.z > key) ? 1 : 0; rank += (kk.w > key) ? 1 : 0;
     }
+    bool valid = (lane < cnt) && rank < k;
+    if (__popc(__ballot_sync(0xffffffffu, valid)) != k) {      // an exact fp32 tie straddles the cut: equal keys rank by lane
+        const uint32_t same = __match_any_sync(0xffffffffu, key);
+        rank += __popc(same & ((1u << lane) - 1u));
+        valid = (lane < cnt) && rank < k;
+    }
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
     const float mx = key_float(kmax);
     const float ex = valid ? expf(logit - mx) : 0.0f;
     float sum = ex;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float a = ex * __frcp_rn(sum);                       // sum >= 1 (the maximum contributes exp(0)); a 0 / sum division takes the slow path
+    __syncwarp();                                              // every lane has read the keys before the weights overwrite them
     TCP_ROW_T(2);
     float2 oa = make_float2(0.0f, 0.0f), ob = oa;
     bc[1][lane] = __float_as_uint(a);                          // 0 for dropped / absent candidates
@@ -433,7 +461,7 @@ __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, co
         const uint32_t xx[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
         float4 w[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) w[c] = (xx[c] != 0u) ? __ldg(Wq + jj[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < 8; ++c) w[c] = (xx[c] != 0u) ? __ldg(HVPR_WROW(jj[c])) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             const float ac = __uint_as_float(xx[c]);
@@ -596,6 +624,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
     tc_fence_after();
     const uint32_t tmem_base = S.tmem_base;
 
+    // Per-role register budgets (setmaxnreg works per warpgroup of four consecutive warps): with eight filter warps the kernel
+    // is launched at 96 registers per thread; the two filter warpgroups (warps 4-11) hand registers back and the warpgroups
+    // that hold tail warps take them, so the tail keeps its 16-row register cache without spilling.
+#if HVPR_K3_FILTER_WARPS == 8 && HVPR_K3_SETMAXNREG
+    if (warp >= kTcFilterBase) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HVPR_K3_FILTER_REGS));
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(HVPR_K3_TAIL_REGS));
+#endif
+
     if (warp == 0) {
         // ===== W producer + MMA issuer: the whole warp stays converged (it blocks on named barriers), lane 0 issues ==========
         // idesc: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
@@ -656,13 +692,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
             __syncwarp();
         }
         TCP_DUMP(0);
-    } else if (warp >= 4 && warp < 4 + kTcFilterWarps) {
+    } else if (warp >= kTcFilterBase) {
         // ===== filter: one accumulator row per thread (4 filter warps) or per thread pair (8 filter warps) ===============
         // A row's 256 columns of every chunk are handled as two halves of 128; with 8 filter warps the halves belong to two
         // threads (same TMEM lane, warps 4 + q and 8 + q), with 4 filter warps one thread walks both.
         constexpr int kH = 8 / kTcFilterWarps;  // halves per thread
         const int q = warp & 3;                 // TMEM lane quadrant of this warp (a warp may only read lanes 32 * (warp % 4) ...)
-        const int half0 = (kH == 2) ? 0 : ((warp - 4) >> 2);
+        const int half0 = (kH == 2) ? 0 : ((warp - kTcFilterBase) >> 2);
         const int row = q * 32 + lane;          // row within the tile
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t it = 0, ti = 0;
@@ -847,7 +883,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
 #endif
     } else {
         // ===== tail: A-tile loads + exact fp32 re-score, top-k, softmax, readout — one warp per row =================
-        const int tw = (warp < 4) ? (warp - 1) : (warp - (4 + kTcFilterWarps) + 3);    // 0 .. kTcTailWarps - 1
+        const int tw = warp - 1;    // 0 .. kTcTailWarps - 1
         float *scratch = slow_scratch + ((size_t)blockIdx.x * kTcTailWarps + tw) * kTcSlowScratch;
         // fp32 pillar rows -> bf16, 128-B-swizzled K-major tile; this warp converts rows tw, tw+10, ...
         auto load_a_tile = [&](int t_load, uint32_t ti_load) {
@@ -915,7 +951,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float 
                 if (lane == 0 && dbg_logits) atomicAdd(reinterpret_cast<unsigned long long *>(dbg_logits) + (size_t)blockIdx.x * 24 + ((cnt >= k && cnt <= 32) ? 19 : (cnt > 32 && cnt <= kTcCandCap) ? 20 : 21), 1ull);
 #endif
                 if (cnt >= k && cnt <= 32)
-                    tail_fast_row(prow, W, k, cnt, cnt_a, &S.cand[cb][0][r], S.bcast[tw], readout + grow * kTcK, idx_row, lane TCP_ROW_PASS);
+                    tail_fast_row(prow, W, k, cnt, cnt_a, &S.cand[cb][0][r], S.bcast[tw], &S.tr[tw][0][0], readout + grow * kTcK, idx_row, lane TCP_ROW_PASS);
                 else if (cnt > 32 && cnt <= kTcCandCap)
                     tail_medium_row(prow, W, k, cnt, cnt_a, &S.cand[cb][0][r], readout + grow * kTcK, idx_row, lane);
                 else
