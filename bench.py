@@ -443,7 +443,7 @@ def run_gpu_arm(args):
             from hvpr_b200 import _lib
             _lib.check(_lib.lib().hvpr_bev_fill(_lib.ptr(p.pillar_features), 64, _lib.ptr(p.readout), 64,
                                                 _lib.ptr(p.pillar_scale), 32, _lib.ptr(vox.cell_map), B, nx, ny,
-                                                _lib.ptr(p.spatial), _lib.ptr(p.spatial_scale), _lib.cur_stream()))
+                                                _lib.ptr(p.spatial), _lib.ptr(p.spatial_scale), None, _lib.cur_stream()))
             evs[4].record(stream)
             torch.cuda.synchronize()
             if it >= 2:

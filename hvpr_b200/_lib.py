@@ -15,9 +15,9 @@ LIB_PATH = os.path.join(_HERE, "libhvpr_b200.so")
 SYMBOLS = [
     "hvpr_strerror", "hvpr_last_cuda_error", "hvpr_version", "hvpr_init",
     "hvpr_voxelize_workspace_bytes", "hvpr_voxelize", "hvpr_frame_offsets",
-    "hvpr_pfn", "hvpr_tune_pfn",
+    "hvpr_pfn",
     "hvpr_mem_attn_workspace_bytes", "hvpr_mem_pack_bf16", "hvpr_mem_attn",
-    "hvpr_bev_fill", "hvpr_tune_bev_fill", "hvpr_build_cell_map",
+    "hvpr_bev_fill", "hvpr_build_cell_map",
     "hvpr_conv_packed_bytes", "hvpr_conv_pack_weights", "hvpr_conv2d", "hvpr_nchw_to_nhwc_bf16", "hvpr_attention_gate",
     "hvpr_bev_fill_nhwc_bf16", "hvpr_head_decode",
     "hvpr_post_process_workspace_bytes", "hvpr_post_process",
@@ -35,6 +35,17 @@ class HvprPfnWeights(ctypes.Structure):
     _fields_ = [("w0", c_float * 160), ("b0", c_float * 16), ("w1a", c_float * 1024), ("w1b", c_float * 1024),
                 ("b1", c_float * 64), ("ws0", c_float * 80), ("bs0", c_float * 16), ("ws1", c_float * 512),
                 ("bs1", c_float * 32)]
+
+
+class HvprLaunchCfg(ctypes.Structure):
+    _fields_ = [("blocks_per_sm", c_int32), ("variant", c_int32)]
+
+
+def launch_cfg(cfg):
+    """(blocks_per_sm, variant) tuple or None -> pointer argument for hvpr_pfn / hvpr_bev_fill (None = library defaults)."""
+    if cfg is None:
+        return None
+    return ctypes.byref(HvprLaunchCfg(int(cfg[0]), int(cfg[1])))
 
 
 class HvprConvArgs(ctypes.Structure):
@@ -86,11 +97,7 @@ def lib():
     L.hvpr_frame_offsets.argtypes = [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]
     L.hvpr_pfn.restype = c_int
     L.hvpr_pfn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p,
-                           c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]
-    L.hvpr_tune_bev_fill.restype = c_int
-    L.hvpr_tune_bev_fill.argtypes = [c_int]
-    L.hvpr_tune_pfn.restype = c_int
-    L.hvpr_tune_pfn.argtypes = [c_int, c_int]
+                           c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, ctypes.POINTER(HvprLaunchCfg), c_void_p]
     L.hvpr_mem_attn_workspace_bytes.restype = c_size_t
     L.hvpr_mem_attn_workspace_bytes.argtypes = [c_int64, c_int, c_int]
     L.hvpr_mem_pack_bf16.restype = c_int
@@ -100,7 +107,7 @@ def lib():
                                 c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     L.hvpr_bev_fill.restype = c_int
     L.hvpr_bev_fill.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
-                                c_void_p, c_void_p, c_void_p]
+                                c_void_p, c_void_p, ctypes.POINTER(HvprLaunchCfg), c_void_p]
     L.hvpr_build_cell_map.restype = c_int
     L.hvpr_build_cell_map.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]
     L.hvpr_conv_packed_bytes.restype = c_size_t

@@ -13,6 +13,18 @@ int hvpr_conv_init();
 int hvpr_mem_pack_bf16_impl(const float *, int, int, void *, cudaStream_t);
 
 namespace hvpr {
+int num_sms() {
+    static int cached[64] = {0};                 // 0 = not queried yet; racing first calls write the same value
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { (void)cudaGetLastError(); return kMaxSMs; }
+    int n = cached[dev];
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); return kMaxSMs; }
+        if (n > kMaxSMs) n = kMaxSMs;            // workspaces are sized for kMaxSMs persistent blocks
+        cached[dev] = n;
+    }
+    return n;
+}
 static thread_local char g_cuda_err[256] = "";
 void set_cuda_error(cudaError_t e) {
     strncpy(g_cuda_err, cudaGetErrorString(e), sizeof(g_cuda_err) - 1);

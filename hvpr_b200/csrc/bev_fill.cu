@@ -34,7 +34,7 @@ constexpr int kBevThreads = 128;   // small blocks: they slot in beside the regi
 // map of their NEXT item before they write the current one, so the only DRAM round trip of an item (the map) is off the
 // critical path and a couple of small blocks per SM keep the store stream going.  That matters in the streaming mode, where
 // the register-heavy PFN blocks of the next batch leave room for just two fill blocks per SM: with one-item blocks every item
-// paid the map latency plus a block launch and the fill dropped below DRAM saturation (hvpr_tune_bev_fill(2): 0.723 -> 0.682 ms
+// paid the map latency plus a block launch and the fill dropped below DRAM saturation (HvprLaunchCfg{2, 0}: 0.723 -> 0.682 ms
 // per streaming step).  Alone, one block per item (n_items blocks, the default) is faster — 0.202 vs 0.227-0.244 ms: the
 // hardware block scheduler balances occupied and empty items, the static grid stride does not.
 __global__ void __launch_bounds__(kBevThreads, 8) bev_fill_kernel(const __grid_constant__ BevArgs A,
@@ -142,18 +142,12 @@ __global__ void cell_map_kernel(const int32_t *__restrict__ coords, const int32_
 
 using namespace hvpr;
 
-static int g_bev_blocks_per_sm = HVPR_BEV_BPS;
-// launch-shape knob (include/hvpr_b200.h), read at launch time
-extern "C" int hvpr_tune_bev_fill(int blocks_per_sm) {
-    if (blocks_per_sm < 0 || blocks_per_sm > 16) return HVPR_ERR_ARG;
-    g_bev_blocks_per_sm = blocks_per_sm;
-    return HVPR_OK;
-}
-
 extern "C" int hvpr_bev_fill(const float *feat_a, int ca, const float *feat_b, int cb, const float *feat_s, int cs,
                              const int32_t *cell_map, int n_frames, int nx, int ny,
-                             float *spatial, float *spatial_scale, void *stream_) {
+                             float *spatial, float *spatial_scale, const HvprLaunchCfg *launch, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    const int bev_bps = launch ? launch->blocks_per_sm : HVPR_BEV_BPS;
+    if (bev_bps < 0 || bev_bps > 16) return HVPR_ERR_ARG;
     if (!cell_map || !spatial || !feat_a || ca <= 0 || cb < 0 || cs < 0 || n_frames <= 0 || nx <= 0 || ny <= 0) return HVPR_ERR_ARG;
     if ((cb > 0 && !feat_b) || (cs > 0 && (!feat_s || !spatial_scale))) return HVPR_ERR_ARG;
     const int64_t cells = (int64_t)nx * ny;
@@ -176,7 +170,7 @@ extern "C" int hvpr_bev_fill(const float *feat_a, int ca, const float *feat_b, i
         for (int i = n; i < 16; ++i) { A.chunk_src[i] = 0; A.chunk_c0[i] = 0; A.chunk_nc[i] = 0; }
         const int xblocks = (int)ceil_div64(cells / 4, kBevThreads);
         const int64_t n_items = (int64_t)xblocks * n_frames * n;
-        const int64_t cap = g_bev_blocks_per_sm > 0 ? (int64_t)kNumSMs * g_bev_blocks_per_sm : n_items;
+        const int64_t cap = bev_bps > 0 ? (int64_t)num_sms() * bev_bps : n_items;
         bev_fill_kernel<<<(unsigned)(n_items < cap ? n_items : cap), kBevThreads, 0, stream>>>(A, cell_map, cells, xblocks, n_frames, n_items);
         HVPR_CHECK_LAUNCH();
     } else {

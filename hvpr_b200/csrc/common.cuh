@@ -6,7 +6,9 @@
 
 namespace hvpr {
 
-constexpr int kNumSMs = 148;  // B200
+constexpr int kMaxSMs = 148;  // B200; sizes host-side workspace queries that must work without a device
+// SM count of the CURRENT device, queried once per device and cached (immutable, so not "state"); kMaxSMs when no device answers
+int num_sms();
 
 void set_cuda_error(cudaError_t e);
 

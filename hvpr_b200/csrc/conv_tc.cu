@@ -643,14 +643,14 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
     P.w_out = a->w_in / a->stride;
     // patch shape: the power-of-two split of 128 pixels that wastes the fewest out-of-image pixels (ties: wider rows)
     // two 128-pixel sub-tiles per tile when the column tile is narrow: halves the weight traffic per MAC
-    P.msub = (a->bn <= 128 && (int64_t)a->n * P.h_out * P.w_out >= 2 * 128 * (int64_t)kNumSMs) ? 2 : 1;
+    P.msub = (a->bn <= 128 && (int64_t)a->n * P.h_out * P.w_out >= 2 * 128 * (int64_t)num_sms()) ? 2 : 1;
     if (g_cv_force_msub == 1 || (g_cv_force_msub == 2 && a->bn <= 128)) P.msub = g_cv_force_msub;
     // automatic policy (measured per layer with tools/dev/backbone_bench.py, 432 x 496 canvases, batch 8): the pair kernel wins
     // 6-9 % on the 256-column 3x3 layers (weight traffic and operand reads halved per SM); narrow layers and the transposed
     // convolutions (short K loops, store-bound epilogue) are faster on the single-CTA kernel
     const bool pair = g_cv_pair_mode == 2 ||
                       (g_cv_pair_mode == 0 && a->bn == 256 && a->ksize == 3 && a->out_mode == 0 &&
-                       (int64_t)a->n * P.h_out * P.w_out >= 256 * (int64_t)(kNumSMs / 2) * 4);
+                       (int64_t)a->n * P.h_out * P.w_out >= 256 * (int64_t)(num_sms() / 2) * 4);
     P.pair = pair ? 1 : 0;
     P.halo = (a->ksize == 3 && a->stride == 1 && !g_cv_halo_off) ? 1 : 0;
     if (P.halo) P.msub = 1;      // two double-buffered patch triples of a 256-pixel tile (2 x 102 KB) do not fit beside the weight ring
@@ -745,11 +745,11 @@ extern "C" int hvpr_conv2d(const HvprConvArgs *a, void *stream) {
     const size_t smem = cv_smem_bytes();
     cudaStream_t st = (cudaStream_t)stream;
     if (pair) {
-        const unsigned grid = 2u * (unsigned)(total_tiles < kNumSMs / 2 ? total_tiles : kNumSMs / 2);
+        const unsigned grid = 2u * (unsigned)(total_tiles < num_sms() / 2 ? total_tiles : num_sms() / 2);
         if (P.msub == 2) { if (P.halo) conv_tc2_kernel<2, true><<<grid, kCvThreads, smem, st>>>(P); else conv_tc2_kernel<2, false><<<grid, kCvThreads, smem, st>>>(P); }
         else { if (P.halo) conv_tc2_kernel<1, true><<<grid, kCvThreads, smem, st>>>(P); else conv_tc2_kernel<1, false><<<grid, kCvThreads, smem, st>>>(P); }
     } else {
-        const unsigned grid = (unsigned)(total_tiles < kNumSMs ? total_tiles : kNumSMs);
+        const unsigned grid = (unsigned)(total_tiles < num_sms() ? total_tiles : num_sms());
         if (P.msub == 2) { if (P.halo) conv_tc_kernel<2, true><<<grid, kCvThreads, smem, st>>>(P); else conv_tc_kernel<2, false><<<grid, kCvThreads, smem, st>>>(P); }
         else { if (P.halo) conv_tc_kernel<1, true><<<grid, kCvThreads, smem, st>>>(P); else conv_tc_kernel<1, false><<<grid, kCvThreads, smem, st>>>(P); }
     }

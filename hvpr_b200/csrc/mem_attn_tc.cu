@@ -1014,7 +1014,7 @@ int hvpr_mem_attn_tc_init() {
 }
 
 size_t hvpr_mem_attn_tc_workspace_bytes(int64_t, int) {
-    return (size_t)kNumSMs * kTcTailWarps * kTcSlowScratch * sizeof(float) + 512;   // + alignment slack + the tile counter
+    return (size_t)kMaxSMs * kTcTailWarps * kTcSlowScratch * sizeof(float) + 512;   // + alignment slack + the tile counter
 }
 
 int hvpr_mem_pack_bf16_impl(const float *W, int M, int C, void *out, cudaStream_t stream) {
@@ -1034,7 +1034,7 @@ static int tc_launch(const float *pillars, const int32_t *n_pillars_dev, int64_t
     if (((uintptr_t)W | (uintptr_t)Wpk | (uintptr_t)pillars | (uintptr_t)readout) % 16) return HVPR_ERR_ARG;
     if (!workspace || workspace_bytes < hvpr_mem_attn_tc_workspace_bytes(n_rows_max, M)) return HVPR_ERR_WORKSPACE;
     float *scratch = (float *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    int32_t *tile_counter = (int32_t *)(scratch + (size_t)kNumSMs * kTcTailWarps * kTcSlowScratch);
+    int32_t *tile_counter = (int32_t *)(scratch + (size_t)kMaxSMs * kTcTailWarps * kTcSlowScratch);
 #ifndef HVPR_K3_STATIC
     // the dynamic tile schedule starts from zero on every launch; a memset node when the stream is being captured
     cudaError_t me = cudaMemsetAsync(tile_counter, 0, sizeof(int32_t), stream);
@@ -1042,7 +1042,8 @@ static int tc_launch(const float *pillars, const int32_t *n_pillars_dev, int64_t
 #endif
     const int nchunks = (M + kTcChunkN - 1) / kTcChunkN;
     int64_t tiles = (n_rows_max + kTcTileM - 1) / kTcTileM;
-    int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+    const int nsm = num_sms();
+    int grid = (int)(tiles < nsm ? tiles : nsm);
     if (grid < 1) grid = 1;
     mem_attn_tc_kernel<<<grid, kTcThreads, tc_smem_bytes(), stream>>>(pillars, n_pillars_dev, n_rows_max, W,
                                                                       (const uint8_t *)Wpk, M, nchunks, k, readout,

@@ -424,16 +424,6 @@ __global__ void __launch_bounds__(kPfnThreads, kFragRegs ? 3 : HVPR_PFN_LOWREG_M
 
 using namespace hvpr;
 
-static int g_pfn_blocks_per_sm = 3;
-static int g_pfn_frag_regs = 1;
-// launch-shape knob (include/hvpr_b200.h), read at launch time
-extern "C" int hvpr_tune_pfn(int blocks_per_sm, int low_register_variant) {
-    if (blocks_per_sm < 1 || blocks_per_sm > 3) return HVPR_ERR_ARG;
-    g_pfn_blocks_per_sm = blocks_per_sm;
-    g_pfn_frag_regs = low_register_variant ? 0 : 1;
-    return HVPR_OK;
-}
-
 int hvpr_pfn_init() {
     cudaError_t e;
     e = cudaFuncSetAttribute(pfn_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PfnSmem));
@@ -450,12 +440,15 @@ int hvpr_pfn_init() {
 extern "C" int hvpr_pfn(const float *voxels, const int32_t *num_points, const int32_t *coords,
                         const int32_t *n_pillars_dev, int64_t n_rows_max, int max_points,
                         const HvprPfnWeights *weights_host, const HvprGeom *geom, float x_off, float y_off, float z_off,
-                        float *pillar_features, float *scale_out, float *mask_out, void *stream_) {
+                        float *pillar_features, float *scale_out, float *mask_out, const HvprLaunchCfg *launch, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!weights_host || !geom || n_rows_max < 0) return HVPR_ERR_ARG;
     if (n_rows_max == 0) return HVPR_OK;
     if (!voxels || !num_points || !coords || !pillar_features) return HVPR_ERR_ARG;
     if (max_points < 1 || max_points > 32) return HVPR_ERR_UNSUPPORTED;
+    const int bps = (launch && launch->blocks_per_sm != 0) ? launch->blocks_per_sm : 3;
+    const bool frag_regs = !(launch && launch->variant != 0);
+    if (bps < 1 || bps > 3 || (launch && (launch->variant < 0 || launch->variant > 1))) return HVPR_ERR_ARG;
     if (((uintptr_t)voxels | (uintptr_t)coords | (uintptr_t)scale_out | (uintptr_t)pillar_features) % 16) return HVPR_ERR_ARG;
     PfnParams P;
     P.w = *weights_host;
@@ -466,14 +459,14 @@ extern "C" int hvpr_pfn(const float *voxels, const int32_t *num_points, const in
         P.v1[c] = a;
     }
     int64_t want = ceil_div64(n_rows_max, kPfnG);
-    const int64_t cap = (int64_t)kNumSMs * g_pfn_blocks_per_sm;                              // persistent blocks
+    const int64_t cap = (int64_t)num_sms() * bps;                              // persistent blocks
     const int blocks = (int)(want < cap ? want : cap);
 #define HVPR_PFN_LAUNCH(SC, FR)                                                                                  \
     pfn_kernel<SC, FR><<<blocks, kPfnThreads, sizeof(PfnSmem), stream>>>(                                         \
         P, voxels, num_points, coords, n_pillars_dev, n_rows_max, max_points, geom->vs[0], geom->vs[1], geom->vs[2], \
         x_off, y_off, z_off, pillar_features, scale_out, mask_out)
-    if (scale_out) { if (g_pfn_frag_regs) HVPR_PFN_LAUNCH(true, true); else HVPR_PFN_LAUNCH(true, false); }
-    else { if (g_pfn_frag_regs) HVPR_PFN_LAUNCH(false, true); else HVPR_PFN_LAUNCH(false, false); }
+    if (scale_out) { if (frag_regs) HVPR_PFN_LAUNCH(true, true); else HVPR_PFN_LAUNCH(true, false); }
+    else { if (frag_regs) HVPR_PFN_LAUNCH(false, true); else HVPR_PFN_LAUNCH(false, false); }
     HVPR_CHECK_LAUNCH();
     return HVPR_OK;
 }

@@ -21,10 +21,10 @@ from .voxelizer import Voxelizer
 
 
 class HybridFrontEnd(torch.nn.Module):
-    # hvpr_tune_pfn(blocks_per_sm, low_register_variant) used while the streaming graphs are captured
+    # HvprLaunchCfg (blocks_per_sm, variant) of the PFN inside the streaming graphs: the low-register variant leaves room for the fill blocks
     stream_pfn_knob = (3, 1)
-    # hvpr_tune_bev_fill(blocks_per_sm) for the canvas fill inside the streaming graphs (it shares the SMs with K1 / K2 there)
-    stream_bev_knob = 2
+    # HvprLaunchCfg of the canvas fill inside the streaming graphs (persistent blocks per SM; it shares the SMs with K1 / K2 there)
+    stream_bev_knob = (2, 0)
     # where K1 of batch k+2 sits in the step: "fork" (own stream from the start of the step), "before_k3" / "after_k3" / "last" (main stream)
     stream_k1_order = "fork"
 
@@ -170,11 +170,11 @@ class HybridFrontEnd(torch.nn.Module):
     def _stage_vox(self, p, slot):      # K1
         self.voxelizer.run(p.in_points[slot], p.in_offsets[slot], p.B, p.max_frame_points, out=p.voxs[slot])
 
-    def _stage_pfn(self, p, slot):      # K2
+    def _stage_pfn(self, p, slot, launch=None):      # K2
         vox = p.voxs[slot]
-        self.vfe.run(vox.voxels, vox.num_points, vox.coords, vox.n_pillars_dev, out=p.pfs[slot], scale_out=p.pss[slot])
+        self.vfe.run(vox.voxels, vox.num_points, vox.coords, vox.n_pillars_dev, out=p.pfs[slot], scale_out=p.pss[slot], launch=launch)
 
-    def _stage_bev(self, p, slot, after_k3=None):      # K3 + K4
+    def _stage_bev(self, p, slot, after_k3=None, launch=None):      # K3 + K4
         vox = p.voxs[slot]
         m = self.map_to_bev_module
         m.memory.run(p.pfs[slot], m.k, vox.n_pillars_dev, out=p.readout)
@@ -182,7 +182,7 @@ class HybridFrontEnd(torch.nn.Module):
             after_k3()
         st = _lib.lib().hvpr_bev_fill(_lib.ptr(p.pfs[slot]), 64, _lib.ptr(p.readout), 64, _lib.ptr(p.pss[slot]), 32,
                                       _lib.ptr(vox.cell_map), p.B, m.nx, m.ny, _lib.ptr(p.spatial),
-                                      _lib.ptr(p.spatial_scale), _lib.cur_stream())
+                                      _lib.ptr(p.spatial_scale), _lib.launch_cfg(launch), _lib.cur_stream())
         _lib.check(st, "hvpr_bev_fill")
 
     @torch.no_grad()
@@ -205,9 +205,8 @@ class HybridFrontEnd(torch.nn.Module):
                 self._stage_vox(p, slot); self._stage_pfn(p, slot)
             self._stage_bev(p, 0)
             torch.cuda.synchronize()
-            # the low-register PFN variant leaves room for the canvas-fill blocks it runs beside (+10 % measured)
-            _lib.check(_lib.lib().hvpr_tune_pfn(*self.stream_pfn_knob))
-            _lib.check(_lib.lib().hvpr_tune_bev_fill(self.stream_bev_knob))
+            # launch shapes travel with the calls (HvprLaunchCfg): the low-register PFN variant leaves room for the canvas-fill
+            # blocks it runs beside (+10 % measured); nothing process-wide is touched, so several front ends can capture at once
             for k in range(NS):
                 gr = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gr):
@@ -227,15 +226,13 @@ class HybridFrontEnd(torch.nn.Module):
                         # K3 holds whole SMs; the PFN of the next batch starts when it retires and shares the SMs with K4
                         p.side1.wait_stream(main)
                         with torch.cuda.stream(p.side1):
-                            self._stage_pfn(p, (k + 1) % NS)
-                    self._stage_bev(p, k, after_k3=_fork_pfn)
+                            self._stage_pfn(p, (k + 1) % NS, launch=self.stream_pfn_knob)
+                    self._stage_bev(p, k, after_k3=_fork_pfn, launch=self.stream_bev_knob)
                     main.wait_stream(p.side1)           # join
                     main.wait_stream(p.side2)
                     if order == "last":
                         self._stage_vox(p, (k + 2) % NS)
                 p.graphs[k] = gr
-            _lib.check(_lib.lib().hvpr_tune_pfn(3, 0))
-            _lib.check(_lib.lib().hvpr_tune_bev_fill(0))
         self._stage_vox(p, 0); self._stage_pfn(p, 0)
         self._stage_vox(p, 1)
         p.k, p.primed = 0, True

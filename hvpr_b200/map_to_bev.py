@@ -109,7 +109,7 @@ class PointPillarScatter(nn.Module):
         C = pf.shape[1]
         out = torch.empty((B, C * self.nz, self.ny, self.nx), dtype=torch.float32, device=pf.device)
         st = _lib.lib().hvpr_bev_fill(_lib.ptr(pf), C, None, 0, None, 0, _lib.ptr(cm), B, self.nx, self.ny,
-                                      _lib.ptr(out), None, _lib.cur_stream())
+                                      _lib.ptr(out), None, None, _lib.cur_stream())
         _lib.check(st, "hvpr_bev_fill")
         batch_dict["spatial_features"] = out
         return batch_dict
@@ -147,7 +147,7 @@ class PointPillarScatter_Agg_Memory_1_scale(nn.Module):
             spatial_scale = torch.empty((B, Cs * self.nz, self.ny, self.nx), dtype=torch.float32, device=dev)
         st = _lib.lib().hvpr_bev_fill(_lib.ptr(pillar_features), C, _lib.ptr(readout), C,
                                       _lib.ptr(pillar_scale_features), Cs, _lib.ptr(cell_map), B, self.nx, self.ny,
-                                      _lib.ptr(spatial), _lib.ptr(spatial_scale), _lib.cur_stream())
+                                      _lib.ptr(spatial), _lib.ptr(spatial_scale), None, _lib.cur_stream())
         _lib.check(st, "hvpr_bev_fill")
         return spatial, spatial_scale, readout
 

@@ -145,7 +145,7 @@ class _PillarVFEBase(VFETemplate):
         """Drop the folded-weight cache (needed only after raw `.data` edits, which bypass tensor version counters)."""
         self._wcache = None
 
-    def run(self, voxels, num_points, coords, n_pillars_dev=None, out=None, scale_out=None, mask_out=None):
+    def run(self, voxels, num_points, coords, n_pillars_dev=None, out=None, scale_out=None, mask_out=None, launch=None):
         """Enqueue the fused PFN on the current stream.  int32 coords/counts; returns (features, scale, mask)."""
         _lib.init_device()
         rows, T = voxels.shape[0], voxels.shape[1]
@@ -158,7 +158,8 @@ class _PillarVFEBase(VFETemplate):
             _lib.ptr(voxels), _lib.ptr(num_points), _lib.ptr(coords), _lib.ptr(n_pillars_dev), rows, T,
             ctypes.byref(self._weights()), ctypes.byref(self._geom_c),
             float(self.x_offset), float(self.y_offset), float(self.z_offset),
-            _lib.ptr(out), _lib.ptr(scale_out) if self._HAS_SCALE else None, _lib.ptr(mask_out), _lib.cur_stream())
+            _lib.ptr(out), _lib.ptr(scale_out) if self._HAS_SCALE else None, _lib.ptr(mask_out), _lib.launch_cfg(launch),
+            _lib.cur_stream())
         _lib.check(st, "hvpr_pfn")
         return out, scale_out, mask_out
 

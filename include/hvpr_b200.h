@@ -5,9 +5,9 @@
  * Every entry point
  *   - takes DEVICE pointers unless a parameter says "host";
  *   - enqueues all its work on `stream` (a cudaStream_t passed as void*), never synchronises the device,
- *     never allocates device memory, keeps no data state (the only process-wide settings are the launch-shape knobs
- *     hvpr_tune_pfn / hvpr_tune_bev_fill) -> safe inside CUDA-graph capture and re-entrant across streams / devices
- *     (one process per GPU);
+ *     never allocates device memory and keeps NO mutable state: launch-shape choices travel with the call
+ *     (HvprLaunchCfg), the only cached datum is the immutable SM count of each device -> safe inside CUDA-graph
+ *     capture and re-entrant across streams, threads and devices;
  *   - returns HVPR_OK (0) or a negative HvprStatus; it never throws.
  * The caller (hvpr_b200/*.py through ctypes, or any C/C++ host) owns every buffer.
  *
@@ -66,6 +66,18 @@ typedef struct HvprPfnWeights {
     float bs1[32];
 } HvprPfnWeights;
 
+/* Optional launch shape of hvpr_pfn / hvpr_bev_fill, passed with the call (NULL = defaults).  Replaces the round-1
+ * process-global hvpr_tune_* knobs: two front ends in one process can no longer race on them.
+ *   hvpr_pfn:      blocks_per_sm 1..3 persistent blocks per SM (0 = default 3); variant 0 = W1a tensor-core fragments in
+ *                  registers (fastest alone), 1 = fragments in shared memory (fewer registers: the canvas-fill blocks of
+ *                  hvpr_bev_fill fit beside the PFN blocks in the streaming schedule)
+ *   hvpr_bev_fill: blocks_per_sm 0 = one 128-thread block per work item (fastest alone), 1..16 = that many persistent
+ *                  blocks per SM walking the items with a grid stride; variant unused (0)                              */
+typedef struct HvprLaunchCfg {
+    int32_t blocks_per_sm;
+    int32_t variant;
+} HvprLaunchCfg;
+
 const char *hvpr_strerror(int status);
 const char *hvpr_last_cuda_error(void);
 int hvpr_version(void);
@@ -102,13 +114,7 @@ int hvpr_frame_offsets(const float *points5, int64_t n_total, int pts_stride, in
 int hvpr_pfn(const float *voxels, const int32_t *num_points, const int32_t *coords,
              const int32_t *n_pillars_dev, int64_t n_rows_max, int max_points,
              const HvprPfnWeights *weights_host, const HvprGeom *geom, float x_off, float y_off, float z_off,
-             float *pillar_features, float *scale_out, float *mask_out, void *stream);
-
-/* Launch-shape knob, read at launch.  blocks_per_sm: persistent PFN blocks per SM (1..3, default 3).
- * low_register_variant: 0 (default) keeps the W1a tensor-core fragments in registers (168 regs/thread, fastest alone);
- * 1 reads them from shared memory (106 regs/thread) so that the small canvas-fill blocks of hvpr_bev_fill fit beside the PFN
- * blocks when the PFN of the next batch runs concurrently with the fill of the current one (streaming mode).          */
-int hvpr_tune_pfn(int blocks_per_sm, int low_register_variant);
+             float *pillar_features, float *scale_out, float *mask_out, const HvprLaunchCfg *launch, void *stream);
 
 /* ---- K3 memory attention -----------------------------------------------------------------------------------------
  * pillars (rows,64) fp32; mem_weight (M,64) fp32; readout (rows,64) fp32.
@@ -128,13 +134,7 @@ int hvpr_mem_attn(const float *pillars, const int32_t *n_pillars_dev, int64_t n_
  * cell_map (n_frames, ny*nx) int32: cell -> pillar row or -1.                                                        */
 int hvpr_bev_fill(const float *feat_a, int ca, const float *feat_b, int cb, const float *feat_s, int cs,
                   const int32_t *cell_map, int n_frames, int nx, int ny,
-                  float *spatial, float *spatial_scale, void *stream);
-
-/* Launch-shape knob, read at launch.  blocks_per_sm = 0 (default): one 128-thread block per work item, fastest when the fill
- * has the GPU to itself (0.202 ms, 6.1 TB/s on the headline batch).  1..16: that many persistent blocks per SM walk the items
- * with a grid stride and prefetch the next item's cell->row map; the streaming schedule uses 2, which keeps the store stream
- * going from the two block slots the PFN of the next batch leaves free per SM (0.723 -> 0.682 ms per streaming step).     */
-int hvpr_tune_bev_fill(int blocks_per_sm);
+                  float *spatial, float *spatial_scale, const HvprLaunchCfg *launch, void *stream);
 
 /* cell_map from externally supplied coords (rows,4) int32 [b,z,y,x] (module API fed by a foreign voxelizer).         */
 int hvpr_build_cell_map(const int32_t *coords, const int32_t *n_pillars_dev, int64_t n_rows_max,

@@ -173,7 +173,7 @@ def test_bev_fill_nhwc_bf16_matches_the_nchw_fill():
     cmap = cmap.cuda()
     fa, fb, fs = torch.randn(P, 64).cuda(), torch.randn(P, 64).cuda(), torch.randn(P, 32).cuda()
     sp = torch.empty(B, 128, ny, nx, device="cuda"); sc = torch.empty(B, 32, ny, nx, device="cuda")
-    L.check(L.lib().hvpr_bev_fill(L.ptr(fa), 64, L.ptr(fb), 64, L.ptr(fs), 32, L.ptr(cmap), B, nx, ny, L.ptr(sp), L.ptr(sc), L.cur_stream()))
+    L.check(L.lib().hvpr_bev_fill(L.ptr(fa), 64, L.ptr(fb), 64, L.ptr(fs), 32, L.ptr(cmap), B, nx, ny, L.ptr(sp), L.ptr(sc), None, L.cur_stream()))
     xo = torch.full((B, ny, nx, 128), 9.0, dtype=torch.bfloat16, device="cuda")
     yo = torch.full((B, ny, nx, 64), 9.0, dtype=torch.bfloat16, device="cuda")
     L.check(L.lib().hvpr_bev_fill_nhwc_bf16(L.ptr(fa), 64, L.ptr(fb), 64, L.ptr(fs), 32, L.ptr(cmap), B, nx, ny,

@@ -379,21 +379,19 @@ def test_bev_fill_bitwise(gname):
     sp = torch.full((3, 128, ny, nx), float("nan"), device="cuda"); sps = torch.full((3, 32, ny, nx), float("nan"), device="cuda")
     a, b_, s = pf.cuda(), ro.cuda(), ps.cuda()
     _lib.check(_lib.lib().hvpr_bev_fill(_lib.ptr(a), 64, _lib.ptr(b_), 64, _lib.ptr(s), 32, _lib.ptr(cm), 3, nx, ny,
-                                        _lib.ptr(sp), _lib.ptr(sps), _lib.cur_stream()))
+                                        _lib.ptr(sp), _lib.ptr(sps), None, _lib.cur_stream()))
     torch.cuda.synchronize()
     assert torch.equal(sp.cpu().view(3, 128, -1), ref) and torch.equal(sps.cpu().view(3, 32, -1), refs)
     # persistent form (grid-stride over the items, next item's map prefetched): 1, 2 and 8 blocks per SM, same bits
-    try:
-        for bps in (1, 2, 8):
-            _lib.check(_lib.lib().hvpr_tune_bev_fill(bps))
-            sp.fill_(float("nan")); sps.fill_(float("nan"))
-            _lib.check(_lib.lib().hvpr_bev_fill(_lib.ptr(a), 64, _lib.ptr(b_), 64, _lib.ptr(s), 32, _lib.ptr(cm), 3, nx, ny,
-                                                _lib.ptr(sp), _lib.ptr(sps), _lib.cur_stream()))
-            torch.cuda.synchronize()
-            assert torch.equal(sp.cpu().view(3, 128, -1), ref) and torch.equal(sps.cpu().view(3, 32, -1), refs), bps
-        assert _lib.lib().hvpr_tune_bev_fill(17) != 0 and _lib.lib().hvpr_tune_bev_fill(-1) != 0
-    finally:
-        _lib.check(_lib.lib().hvpr_tune_bev_fill(0))
+    for bps in (1, 2, 8):
+        sp.fill_(float("nan")); sps.fill_(float("nan"))
+        _lib.check(_lib.lib().hvpr_bev_fill(_lib.ptr(a), 64, _lib.ptr(b_), 64, _lib.ptr(s), 32, _lib.ptr(cm), 3, nx, ny,
+                                            _lib.ptr(sp), _lib.ptr(sps), _lib.launch_cfg((bps, 0)), _lib.cur_stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(sp.cpu().view(3, 128, -1), ref) and torch.equal(sps.cpu().view(3, 32, -1), refs), bps
+    for bad in (17, -1):       # the launch shape is validated per call (there is no process-wide knob any more)
+        assert _lib.lib().hvpr_bev_fill(_lib.ptr(a), 64, _lib.ptr(b_), 64, _lib.ptr(s), 32, _lib.ptr(cm), 3, nx, ny,
+                                        _lib.ptr(sp), _lib.ptr(sps), _lib.launch_cfg((bad, 0)), _lib.cur_stream()) == -1
     # vanilla PointPillarScatter module, fp32 coords, no batch_size key (falls back to the reference formula)
     mod = map_to_bev.PointPillarScatter(config.Cfg(NUM_BEV_FEATURES=64), grid_size=g.grid_size)
     bd = mod(dict(pillar_features=a, voxel_coords=coords.float()))
@@ -419,7 +417,7 @@ def test_bev_fill_odd_shapes_fallback():
     cd, pd = coords.cuda(), pf.cuda()
     _lib.check(_lib.lib().hvpr_build_cell_map(_lib.ptr(cd), None, P, B, nx, ny, _lib.ptr(cm), _lib.cur_stream()))
     out = torch.full((B, 6, ny, nx), float("nan"), device="cuda")
-    _lib.check(_lib.lib().hvpr_bev_fill(_lib.ptr(pd), 6, None, 0, None, 0, _lib.ptr(cm), B, nx, ny, _lib.ptr(out), None, _lib.cur_stream()))
+    _lib.check(_lib.lib().hvpr_bev_fill(_lib.ptr(pd), 6, None, 0, None, 0, _lib.ptr(cm), B, nx, ny, _lib.ptr(out), None, None, _lib.cur_stream()))
     torch.cuda.synchronize()
     assert torch.equal(out.cpu().view(B, 6, -1), ref)
 
@@ -600,3 +598,55 @@ def test_streaming_mode_is_bit_identical_to_single_stream():
         torch.cuda.synchronize()
         assert torch.equal(sp.spatial, ref[b][0]) and torch.equal(sp.spatial_scale, ref[b][1]), (i, b)
         assert torch.equal(cnt, ref[b][2].cpu())
+
+
+def test_two_front_ends_two_streams_with_different_launch_shapes():
+    """SURVEY §8b #3 (no global state, re-entrant across streams): two front ends in ONE process, on two streams, with
+    different HvprLaunchCfg shapes for the PFN and the canvas fill, interleaved call by call, produce the bits each one
+    produces alone.  (Round 1 had process-global hvpr_tune_* knobs that two front ends could race on.)"""
+    from hvpr_b200 import _lib
+    g = G1
+    w1, w2 = hybrid.random_weights(21), hybrid.random_weights(22)
+    fr1 = synth.make_batch("L", 30000, g.point_cloud_range, 2, first_frame=40)
+    fr2 = synth.make_batch("U", 25000, g.point_cloud_range, 2, first_frame=50)
+    shapes = [((3, 0), None), ((1, 1), (2, 0))]
+    alone = []
+    for fr, w, (pfn_cfg, bev_cfg) in ((fr1, w1, shapes[0]), (fr2, w2, shapes[1])):
+        fe = _frontend(g, w)
+        p = fe.plan(2, sum(len(f) for f in fr), max(len(f) for f in fr), use_graph=False)
+        pts, off = to_dev(fr)
+        p.points.copy_(pts); p.frame_offsets.copy_(off)
+        fe.run(); torch.cuda.synchronize()
+        alone.append((p.spatial.clone(), p.spatial_scale.clone()))
+    fes, plans, streams = [], [], [torch.cuda.Stream(), torch.cuda.Stream()]
+    for fr, w in ((fr1, w1), (fr2, w2)):
+        fe = _frontend(g, w)
+        p = fe.plan(2, sum(len(f) for f in fr), max(len(f) for f in fr), use_graph=False)
+        pts, off = to_dev(fr)
+        p.points.copy_(pts); p.frame_offsets.copy_(off)
+        fes.append(fe); plans.append(p)
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for p in plans:
+            p.spatial.fill_(float("nan")); p.spatial_scale.fill_(float("nan"))
+        torch.cuda.synchronize()
+        # stage by stage, alternating between the two front ends / streams, each with its own launch shape
+        voxs = []
+        for i in (0, 1):
+            with torch.cuda.stream(streams[i]):
+                voxs.append(fes[i].voxelizer.run(plans[i].points, plans[i].frame_offsets, 2, plans[i].max_frame_points, out=plans[i].vox))
+        for i in (1, 0):
+            with torch.cuda.stream(streams[i]):
+                v, p = voxs[i], plans[i]
+                fes[i].vfe.run(v.voxels, v.num_points, v.coords, v.n_pillars_dev, out=p.pillar_features,
+                               scale_out=p.pillar_scale, launch=shapes[i][0])
+        for i in (0, 1):
+            with torch.cuda.stream(streams[i]):
+                v, p, m = voxs[i], plans[i], fes[i].map_to_bev_module
+                m.memory.run(p.pillar_features, m.k, v.n_pillars_dev, out=p.readout)
+                _lib.check(_lib.lib().hvpr_bev_fill(_lib.ptr(p.pillar_features), 64, _lib.ptr(p.readout), 64, _lib.ptr(p.pillar_scale), 32,
+                                                    _lib.ptr(v.cell_map), 2, m.nx, m.ny, _lib.ptr(p.spatial), _lib.ptr(p.spatial_scale),
+                                                    _lib.launch_cfg(shapes[i][1]), _lib.cur_stream()))
+        torch.cuda.synchronize()
+        for i in (0, 1):
+            assert torch.equal(plans[i].spatial, alone[i][0]) and torch.equal(plans[i].spatial_scale, alone[i][1]), (rep, i)

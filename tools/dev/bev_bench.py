@@ -16,11 +16,10 @@ sp = torch.empty((B, 128, ny, nx), device="cuda"); sps = torch.empty((B, 32, ny,
 import os
 if os.environ.get('EMPTY'): cm.fill_(-1)          # EMPTY=1: zero-fill only (no occupied cells), isolates the store stream from the gathers
 def run():
-    _lib.check(L.hvpr_bev_fill(_lib.ptr(fa), 64, _lib.ptr(fb), 64, _lib.ptr(fs), 32, _lib.ptr(cm), B, nx, ny, _lib.ptr(sp), _lib.ptr(sps), _lib.cur_stream()))
+    _lib.check(L.hvpr_bev_fill(_lib.ptr(fa), 64, _lib.ptr(fb), 64, _lib.ptr(fs), 32, _lib.ptr(cm), B, nx, ny, _lib.ptr(sp), _lib.ptr(sps), _lib.launch_cfg((knob, 0)) if knob else None, _lib.cur_stream()))
 nbytes = 4 * 160 * nx * ny * B + 4 * nx * ny * B + 640 * P
 ref = None
 for knob in (0, 16, 8, 4, 3, 2, 1):
-    _lib.check(L.hvpr_tune_bev_fill(knob))
     for _ in range(5): run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

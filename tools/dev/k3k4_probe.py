@@ -16,7 +16,7 @@ m = fe.map_to_bev_module
 def k3(): m.memory.run(p.pillar_features, 20, p.vox.n_pillars_dev, out=ro2)
 def k4():
     _lib.check(_lib.lib().hvpr_bev_fill(_lib.ptr(p.pillar_features), 64, _lib.ptr(p.readout), 64, _lib.ptr(p.pillar_scale), 32,
-               _lib.ptr(p.vox.cell_map), B, m.nx, m.ny, _lib.ptr(p.spatial), _lib.ptr(p.spatial_scale), _lib.cur_stream()))
+               _lib.ptr(p.vox.cell_map), B, m.nx, m.ny, _lib.ptr(p.spatial), _lib.ptr(p.spatial_scale), None, _lib.cur_stream()))
 hi = torch.cuda.Stream(priority=-1); lo = torch.cuda.Stream()
 def timeit(fn, reps=20):
     for _ in range(3): fn()
