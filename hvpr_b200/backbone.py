@@ -271,7 +271,8 @@ class BaseBEVBackbone_Scale(nn.Module):
         if self._WITH_SCALE:
             sc = data_dict["spatial_scale_features"].contiguous().float()
             _lib.check(L.hvpr_nchw_to_nhwc_bf16(_lib.ptr(sc), B, sc.shape[1], H, W, _lib.ptr(pl["y_in"]), pl["y_in"].shape[-1], st), "nchw_to_nhwc")
-        data_dict["spatial_features_2d"] = self.run_nhwc(pl["x_in"], pl.get("y_in"), B, H, W)
+        # a fresh tensor, like the reference module: run_nhwc() writes a persistent per-shape buffer that the next call overwrites
+        data_dict["spatial_features_2d"] = self.run_nhwc(pl["x_in"], pl.get("y_in"), B, H, W).clone()
         return data_dict
 
 

@@ -166,72 +166,71 @@ __device__ __forceinline__ PpRect pp_rect(const float *b) {
 }
 // Area of (rectangle a) ∩ (rectangle b) without building the intersection polygon: by Green's theorem the area is the boundary integral
 // 1/2 ∮ (x dy - y dx), and the boundary of the intersection consists of the parts of a's edges inside b plus the parts of b's edges
-// inside a (both counter-clockwise).  Each edge is clipped against the other rectangle's four half-planes (Liang-Barsky) in that
-// rectangle's local frame, where they are axis-aligned — eight segments, fully unrolled, registers only.  Edges of a use CLOSED
-// half-planes and edges of b OPEN ones, so coincident boundaries (e.g. identical boxes) are counted once.
-template <bool kClosed>
-__device__ __forceinline__ float pp_edge_integral(float x0, float y0, float x1, float y1, float hx, float hy) {
-    // segment p(t) = p0 + t (p1 - p0), t in [0,1], clipped to |x| <= hx, |y| <= hy; returns 1/2 (xa*yb - xb*ya) of the clipped piece
-    float t0 = 0.0f, t1 = 1.0f;
-    const float dx = x1 - x0, dy = y1 - y0;
+// inside a (both counter-clockwise).  Each edge is clipped against the other rectangle's slabs (Liang-Barsky) in that rectangle's
+// local frame, where they are axis-aligned — eight segments, fully unrolled, registers only.
+//
+// Coincident / collinear edges (exact duplicates, heading + pi duplicates, same-heading boxes sharing an edge line — the boxes NMS
+// exists to remove) must be counted exactly ONCE.  A closed-vs-open test on `dx == 0` cannot do that in fp32: after the rotate /
+// translate round trip a coincident edge sits ~1e-6 m off the slab face and lands inside, outside or astride it at random (round 1:
+// inter/area spread over [0, 2] for bit-identical boxes).  Instead the two clip regions are made decisively different:
+//     a's edges are clipped against b GROWN by kPpEps   (an edge of a along b's boundary is inside  -> counted),
+//     b's edges are clipped against a SHRUNK by kPpEps  (the same edge of b is outside               -> not counted),
+// and every corner is formed as (centre difference) + (local offset), so the coordinate noise is an ulp of a few metres (~5e-7 m),
+// far below kPpEps.  The price is an area error of at most kPpEps x perimeter (~1e-4 m^2 on a 6 m^2 car box: 2e-5 relative).
+constexpr float kPpEps = 1e-5f;
+// segment p(t) = p0 + t (p1 - p0), t in [0,1], clipped to |x| <= hx, |y| <= hy: the surviving parameter range [t0, t1] (empty: t0 >= t1)
+__device__ __forceinline__ bool pp_clip(float x0, float y0, float dx, float dy, float hx, float hy, float &t0, float &t1) {
+    t0 = 0.0f; t1 = 1.0f;
     bool ok = true;
-    // x slab: -hx <= x0 + t dx <= hx ; y slab likewise.  One reciprocal per axis (the two half-planes of a slab share it).
-    if (dx == 0.0f) ok = kClosed ? (fabsf(x0) <= hx) : (fabsf(x0) < hx);
+    // |d| below 1e-12: the edge is parallel to the slab (a reciprocal would overflow); one reciprocal per axis otherwise
+    if (fabsf(dx) < 1e-12f) ok = fabsf(x0) <= hx;
     else { const float inv = 1.0f / dx; const float ra = (hx - x0) * inv, rb = (-hx - x0) * inv; t1 = fminf(t1, fmaxf(ra, rb)); t0 = fmaxf(t0, fminf(ra, rb)); }
-    if (dy == 0.0f) ok = ok && (kClosed ? (fabsf(y0) <= hy) : (fabsf(y0) < hy));
+    if (fabsf(dy) < 1e-12f) ok = ok && fabsf(y0) <= hy;
     else { const float inv = 1.0f / dy; const float ra = (hy - y0) * inv, rb = (-hy - y0) * inv; t1 = fminf(t1, fmaxf(ra, rb)); t0 = fmaxf(t0, fminf(ra, rb)); }
-    if (!ok || t0 >= t1) return 0.0f;
-    const float ax = x0 + t0 * dx, ay = y0 + t0 * dy, bx = x0 + t1 * dx, by = y0 + t1 * dy;
-    return 0.5f * (ax * by - bx * ay);
-}
-// corners of rectangle `a` (counter-clockwise) expressed in the local frame of `b`, then its four edges integrated inside b
-template <bool kClosed>
-__device__ __forceinline__ float pp_boundary_inside(const PpRect &a, const PpRect &b) {
-    const float lx[4] = {a.hx, -a.hx, -a.hx, a.hx}, ly[4] = {a.hy, a.hy, -a.hy, -a.hy};
-    float px[4], py[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float wx = a.cx + lx[i] * a.c - ly[i] * a.s - b.cx, wy = a.cy + lx[i] * a.s + ly[i] * a.c - b.cy;
-        px[i] = wx * b.c + wy * b.s;
-        py[i] = -wx * b.s + wy * b.c;
-    }
-    float acc = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc += pp_edge_integral<kClosed>(px[i], py[i], px[(i + 1) & 3], py[(i + 1) & 3], b.hx, b.hy);
-    return acc;
+    return ok && t0 < t1;
 }
 __device__ __forceinline__ float pp_intersection(const PpRect &a, const PpRect &b) {
     // Every piece is evaluated in ONE coordinate system (b's local frame): the closed integral is origin-independent, its parts are not.
-    // a's edges: clipped and evaluated in b's frame.  b's edges: clip parameters from a's frame (they are frame-independent), positions
-    // taken in b's frame, where b's corners are simply (+-hx, +-hy).
-    const float part_a = pp_boundary_inside<true>(a, b);
-    // b's edges: corners in b's frame are (±hx, ±hy); clip parameters come from a's frame
-    const float lx[4] = {b.hx, -b.hx, -b.hx, b.hx}, ly[4] = {b.hy, b.hy, -b.hy, -b.hy};
-    float qx[4], qy[4];
+    const float lxa[4] = {a.hx, -a.hx, -a.hx, a.hx}, lya[4] = {a.hy, a.hy, -a.hy, -a.hy};
+    const float lxb[4] = {b.hx, -b.hx, -b.hx, b.hx}, lyb[4] = {b.hy, b.hy, -b.hy, -b.hy};
+    const float ddx = a.cx - b.cx, ddy = a.cy - b.cy;          // exact or nearly so: the centres are close whenever the boxes can overlap
+    float px[4], py[4], qx[4], qy[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {            // b's corners in a's frame
-        const float wx = b.cx + lx[i] * b.c - ly[i] * b.s - a.cx, wy = b.cy + lx[i] * b.s + ly[i] * b.c - a.cy;
-        qx[i] = wx * a.c + wy * a.s;
-        qy[i] = -wx * a.s + wy * a.c;
+    for (int i = 0; i < 4; ++i) {
+        // a's corners (counter-clockwise) in b's frame
+        const float wx = ddx + (lxa[i] * a.c - lya[i] * a.s), wy = ddy + (lxa[i] * a.s + lya[i] * a.c);
+        px[i] = wx * b.c + wy * b.s;
+        py[i] = -wx * b.s + wy * b.c;
+        // b's corners in a's frame
+        const float vx = (lxb[i] * b.c - lyb[i] * b.s) - ddx, vy = (lxb[i] * b.s + lyb[i] * b.c) - ddy;
+        qx[i] = vx * a.c + vy * a.s;
+        qy[i] = -vx * a.s + vy * a.c;
     }
-    float part_b = 0.0f;
+    float acc = 0.0f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int j = (i + 1) & 3;
-        float t0 = 0.0f, t1 = 1.0f;
-        const float dx = qx[j] - qx[i], dy = qy[j] - qy[i];
-        bool ok = true;                                                       // open slabs for b's edges
-        if (dx == 0.0f) ok = fabsf(qx[i]) < a.hx;
-        else { const float inv = 1.0f / dx; const float ra = (a.hx - qx[i]) * inv, rb = (-a.hx - qx[i]) * inv; t1 = fminf(t1, fmaxf(ra, rb)); t0 = fmaxf(t0, fminf(ra, rb)); }
-        if (dy == 0.0f) ok = ok && fabsf(qy[i]) < a.hy;
-        else { const float inv = 1.0f / dy; const float ra = (a.hy - qy[i]) * inv, rb = (-a.hy - qy[i]) * inv; t1 = fminf(t1, fmaxf(ra, rb)); t0 = fmaxf(t0, fminf(ra, rb)); }
-        if (ok && t0 < t1) {                                                  // evaluate the piece in b's frame (origin = b's centre)
-            const float ex = lx[j] - lx[i], ey = ly[j] - ly[i];
-            const float ax = lx[i] + t0 * ex, ay = ly[i] + t0 * ey, bx = lx[i] + t1 * ex, by = ly[i] + t1 * ey;
-            part_b += 0.5f * (ax * by - bx * ay);
+        float t0, t1;
+        // a's edge i inside b grown by eps, evaluated where it lies (b's frame)
+        {
+            const float dx = px[j] - px[i], dy = py[j] - py[i];
+            if (pp_clip(px[i], py[i], dx, dy, b.hx + kPpEps, b.hy + kPpEps, t0, t1)) {
+                const float ax = px[i] + t0 * dx, ay = py[i] + t0 * dy, bx = px[i] + t1 * dx, by = py[i] + t1 * dy;
+                acc += 0.5f * (ax * by - bx * ay);
+            }
+        }
+        // b's edge i inside a shrunk by eps: clip parameters from a's frame (they are frame-independent), positions taken in b's
+        // frame, where b's corners are simply (+-hx, +-hy)
+        {
+            const float dx = qx[j] - qx[i], dy = qy[j] - qy[i];
+            if (pp_clip(qx[i], qy[i], dx, dy, a.hx - kPpEps, a.hy - kPpEps, t0, t1)) {
+                const float ex = lxb[j] - lxb[i], ey = lyb[j] - lyb[i];
+                const float ax = lxb[i] + t0 * ex, ay = lyb[i] + t0 * ey, bx = lxb[i] + t1 * ex, by = lyb[i] + t1 * ey;
+                acc += 0.5f * (ax * by - bx * ay);
+            }
         }
     }
-    return fmaxf(part_a + part_b, 0.0f);
+    return fminf(fmaxf(acc, 0.0f), fminf(a.area, b.area));
 }
 
 __global__ void __launch_bounds__(64) pp_iou_mask_kernel(const float *__restrict__ boxes, int64_t N, const unsigned long long *__restrict__ sorted,

@@ -99,10 +99,11 @@ __device__ __forceinline__ int32_t point_cell(float x, float y, float z, const H
 constexpr int kVoxPPT = HVPR_VOX_PPT;
 template <bool kVec4>
 __global__ void __launch_bounds__(256) vox_hash_kernel(const float *__restrict__ pts, int stride, int xyz_col,
-                                                       const int32_t *__restrict__ frame_off, HvprGeom g,
+                                                       const int32_t *__restrict__ frame_off, int32_t frame_cap, HvprGeom g,
                                                        int64_t cells, int2 *table, int32_t *__restrict__ cellbuf) {
     const int f = blockIdx.y;
-    const int32_t start = frame_off[f], n = frame_off[f + 1] - start;
+    const int32_t start = frame_off[f];
+    const int32_t n = min(frame_off[f + 1] - start, frame_cap);      // a frame longer than the caller's bound is cut, identically in every kernel
     const int32_t i0 = blockIdx.x * (256 * kVoxPPT) + threadIdx.x;
     if (i0 >= n) return;
     float x[kVoxPPT], y[kVoxPPT], z[kVoxPPT];
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(256) vox_hash_kernel(const float *__restrict__
 // look-back chain).  Blocks take their position from a per-frame ticket, so every block a block waits for is already
 // running, whatever order the hardware dispatches them in.
 constexpr unsigned long long kAggReady = 0x80000000ull;
-__global__ void __launch_bounds__(kScanThreads) vox_assign_kernel(const int32_t *__restrict__ frame_off, int64_t cells,
+__global__ void __launch_bounds__(kScanThreads) vox_assign_kernel(const int32_t *__restrict__ frame_off, int32_t frame_cap, int64_t cells,
                                                                   int2 *table, const int32_t *__restrict__ cellbuf,
                                                                   unsigned long long *agg, int32_t *ticket,
                                                                   int blocks_per_frame,
@@ -151,7 +152,8 @@ __global__ void __launch_bounds__(kScanThreads) vox_assign_kernel(const int32_t 
                                                                   int32_t *__restrict__ frame_nvox,
                                                                   int32_t *__restrict__ istar) {
     const int f = blockIdx.y;
-    const int32_t start = frame_off[f], n = frame_off[f + 1] - start;
+    const int32_t start = frame_off[f];
+    const int32_t n = min(frame_off[f + 1] - start, frame_cap);
     if ((int64_t)blockIdx.x * kScanTile >= n) return;       // as many blocks take a ticket as the frame has tiles
     __shared__ int s_a[kScanThreads / 32], s_b[kScanThreads / 32], s_pa[kScanThreads / 32], s_pb[kScanThreads / 32];
     __shared__ int s_tile;
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(kScanThreads) vox_assign_kernel(const int32_t 
 
 // kVoxPPT points per thread, stage by stage (cell -> voxel id -> cursor claim + segment offset -> CSR store) so that the
 // four dependent memory round trips of kVoxPPT points overlap.
-__global__ void __launch_bounds__(256) vox_fill_kernel(const int32_t *__restrict__ frame_off, int64_t cells,
+__global__ void __launch_bounds__(256) vox_fill_kernel(const int32_t *__restrict__ frame_off, int32_t frame_cap, int64_t cells,
                                                        const int2 *__restrict__ table,
                                                        const int32_t *__restrict__ cellbuf, int max_vox,
                                                        const int32_t *__restrict__ seg_off, int32_t *cursor,
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(256) vox_fill_kernel(const int32_t *__restrict
                                                        int break_mode) {
     const int f = blockIdx.y;
     const int32_t start = frame_off[f];
-    int32_t n = frame_off[f + 1] - start;
+    int32_t n = min(frame_off[f + 1] - start, frame_cap);
     if (break_mode) { const int32_t is = istar[f]; n = is < n ? is : n; }       // points from istar on are dropped
     const int32_t i0 = blockIdx.x * (256 * kVoxPPT) + threadIdx.x;
     if (i0 >= n) return;
@@ -512,6 +514,7 @@ extern "C" int hvpr_voxelize(const float *points, int64_t n_total, int pts_strid
     const int64_t cells = (int64_t)geom->grid[0] * geom->grid[1] * geom->grid[2];
     if (cells <= 0 || cells > INT_MAX || n_total > INT_MAX) return HVPR_ERR_UNSUPPORTED;
     if (max_frame_points <= 0 || max_frame_points > n_total) max_frame_points = n_total;
+    const int32_t frame_cap = (int32_t)max_frame_points;     // grids are sized from this bound; the kernels clamp every frame to it
 
     const int64_t bpf_ws = ceil_div64(n_total > 0 ? n_total : 1, kScanTile);
     // 256-B align the caller's pointer
@@ -531,15 +534,15 @@ extern "C" int hvpr_voxelize(const float *points, int64_t n_total, int pts_strid
     const bool vec4 = (pts_stride == 4 && xyz_col == 0 && ((uintptr_t)points % 16 == 0));
     if (max_frame_points > 0) {
         dim3 gridp((unsigned)ceil_div64(max_frame_points, 256 * kVoxPPT), (unsigned)n_frames);
-        if (vec4) vox_hash_kernel<true><<<gridp, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, *geom, cells, w.table, w.cellbuf);
-        else vox_hash_kernel<false><<<gridp, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, *geom, cells, w.table, w.cellbuf);
+        if (vec4) vox_hash_kernel<true><<<gridp, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, frame_cap, *geom, cells, w.table, w.cellbuf);
+        else vox_hash_kernel<false><<<gridp, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, frame_cap, *geom, cells, w.table, w.cellbuf);
         HVPR_CHECK_LAUNCH();
         const int bpf = (int)ceil_div64(max_frame_points, kScanTile);
         dim3 grids((unsigned)bpf, (unsigned)n_frames);
-        vox_assign_kernel<<<grids, kScanThreads, 0, stream>>>(frame_offsets, cells, w.table, w.cellbuf, w.agg, w.ticket, (int)bpf_ws,
+        vox_assign_kernel<<<grids, kScanThreads, 0, stream>>>(frame_offsets, frame_cap, cells, w.table, w.cellbuf, w.agg, w.ticket, (int)bpf_ws,
                                                              max_voxels, w.vox_cell, w.seg_off, w.frame_nvox, w.istar);
         HVPR_CHECK_LAUNCH();
-        vox_fill_kernel<<<gridp, 256, 0, stream>>>(frame_offsets, cells, w.table, w.cellbuf, max_voxels, w.seg_off,
+        vox_fill_kernel<<<gridp, 256, 0, stream>>>(frame_offsets, frame_cap, cells, w.table, w.cellbuf, max_voxels, w.seg_off,
                                                   w.cursor, w.csr, w.istar, overflow_mode == HVPR_OVERFLOW_BREAK);
         HVPR_CHECK_LAUNCH();
     }

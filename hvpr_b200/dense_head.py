@@ -164,8 +164,8 @@ class AnchorHeadSingle(nn.Module):
         _lib.check(_lib.lib().hvpr_nchw_to_nhwc_bf16(_lib.ptr(x.contiguous().float()), B, C, H, W, _lib.ptr(x_nhwc), C,
                                                      _lib.cur_stream()), "nchw_to_nhwc")
         cls, box = self.run_nhwc(x_nhwc, B, H, W)
-        data_dict["batch_cls_preds"] = cls
-        data_dict["batch_box_preds"] = box
+        data_dict["batch_cls_preds"] = cls.clone()                     # fresh tensors (run_nhwc() reuses per-shape buffers)
+        data_dict["batch_box_preds"] = box.clone()
         data_dict["cls_preds_normalized"] = False                      # anchor_head_single.py:143
         return data_dict
 

@@ -49,6 +49,11 @@ class HybridFrontEnd(torch.nn.Module):
         assert not missing and not unexpected, (missing, unexpected)
         return self
 
+    def weights_version(self):
+        """(data_ptr, version) of every parameter / buffer: a captured graph bakes the folded PFN weights in by value and reads the
+        packed memory image, so a load_state_dict() after the first run must invalidate it (checked at every run / stream_step)."""
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
     # ---------------------------------------------------------------------------------------------------------
     class _Plan:
         pass
@@ -92,7 +97,11 @@ class HybridFrontEnd(torch.nn.Module):
         if not p.use_graph:
             self._enqueue(p)
             return p
+        wkey = self.weights_version()
+        if p.graph is not None and p.graph_wkey != wkey:
+            p.graph = None                                # weights changed since capture: fold / pack / capture again
         if p.graph is None:
+            p.graph_wkey = wkey
             self.vfe._weights()                         # host-side folding happens outside capture
             if self.map_to_bev_module.memory.precision == "bf16_rescore":
                 self.map_to_bev_module.memory._packed_bf16()
@@ -200,7 +209,11 @@ class HybridFrontEnd(torch.nn.Module):
         self.vfe._weights()
         if self.map_to_bev_module.memory.precision == "bf16_rescore":
             self.map_to_bev_module.memory._packed_bf16()
+        wkey = self.weights_version()
+        if p.graphs[0] is not None and p.graphs_wkey != wkey:
+            p.graphs = [None] * NS                        # weights changed since capture
         if p.graphs[0] is None:                         # warm every kernel up outside capture, then capture the NS phases
+            p.graphs_wkey = wkey
             for slot in range(NS):
                 self._stage_vox(p, slot); self._stage_pfn(p, slot)
             self._stage_bev(p, 0)

@@ -50,7 +50,12 @@ class FrontEndWithBackbone(torch.nn.Module):
         self.post = PostProcessor(post_cfg) if (post_cfg is not None and head_cfg is not None) else None
         self._p = None
 
+    def weights_version(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
     def plan(self, n_frames: int, n_total_points: int, max_frame_points: int = 0):
+        """Buffers (and, at the first run, one CUDA graph) for up to `n_total_points` points in `n_frames` frames.  The kernels take
+        the live extents from the device-side frame offsets, so any batch that fits the capacity replays the same graph."""
         fe = self.frontend
         p = fe.plan(n_frames, n_total_points, max_frame_points, use_graph=False)
         nx, ny, _ = fe.geom.grid_size
@@ -91,7 +96,11 @@ class FrontEndWithBackbone(torch.nn.Module):
         """points / frame_offsets already resident in plan.points -> plan.out = spatial_features_2d (B,384,ny,nx) fp32."""
         p = self._p
         _lib.init_device()
+        wkey = self.weights_version()
+        if p.graph is not None and p.graph_wkey != wkey:
+            p.graph = None                                # load_state_dict() after the first run: fold / pack / capture again
         if p.graph is None:
+            p.graph_wkey = wkey
             fe = self.frontend
             fe.vfe._weights()
             if fe.map_to_bev_module.memory.precision == "bf16_rescore":
@@ -121,20 +130,22 @@ class FrontEndWithBackbone(torch.nn.Module):
             raise _lib.HvprError("FrontEndWithBackbone needs CUDA tensors; there is no CPU path")
         B = int(batch_dict["batch_size"])
         n = pts.shape[0]
-        if self._p is None or self._p.B != B or self._p.n_total != n:
-            self.plan(B, n)
+        if self._p is None or self._p.B != B or self._p.n_total < n:
+            # plan for a CAPACITY (25 % headroom, 64 Ki granularity): real collated batches differ in point count every time, and
+            # re-planning reallocates > 1.5 GB at G2 / B = 8 and re-captures the graph
+            self.plan(B, max(65536, -(-(n + n // 4) // 65536) * 65536))
         p = self._p
-        p.points.copy_(pts[:, 1:5])
+        p.points[:n].copy_(pts[:, 1:5])
         st = _lib.lib().hvpr_frame_offsets(_lib.ptr(pts.contiguous()), n, 5, B, _lib.ptr(p.frame_offsets), _lib.cur_stream())
         _lib.check(st, "hvpr_frame_offsets")
         self.run()
         if self.dense_head is None:
-            batch_dict["spatial_features_2d"] = p.out
+            batch_dict["spatial_features_2d"] = p.out.clone()       # the reference returns fresh tensors; plan.out is overwritten by the next call
         else:
-            batch_dict["batch_cls_preds"], batch_dict["batch_box_preds"] = p.cls_preds, p.box_preds
+            batch_dict["batch_cls_preds"], batch_dict["batch_box_preds"] = p.cls_preds.clone(), p.box_preds.clone()
             batch_dict["cls_preds_normalized"] = False
             if self.post is not None:                    # pred_dicts as Detector3DTemplate.post_processing returns them (one D2H of the counts)
                 counts = p.det["count"].cpu().tolist()
-                batch_dict["pred_dicts"] = [{"pred_boxes": p.det["boxes"][i, :k], "pred_scores": p.det["scores"][i, :k],
+                batch_dict["pred_dicts"] = [{"pred_boxes": p.det["boxes"][i, :k].clone(), "pred_scores": p.det["scores"][i, :k].clone(),
                                              "pred_labels": p.det["labels"][i, :k].long()} for i, k in enumerate(counts)]
         return batch_dict

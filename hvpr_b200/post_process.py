@@ -55,5 +55,6 @@ class PostProcessor:
         (one device->host read of the per-frame counts, like the reference's data-dependent indexing)."""
         b = self.run(batch_dict["batch_cls_preds"], batch_dict["batch_box_preds"], bool(batch_dict.get("cls_preds_normalized", False)))
         counts = b["count"].cpu().tolist()
-        return [{"pred_boxes": b["boxes"][i, :k], "pred_scores": b["scores"][i, :k], "pred_labels": b["labels"][i, :k].long(),
+        # fresh tensors, like the reference: the (B, post_max, ...) buffers of run() are overwritten by the next call
+        return [{"pred_boxes": b["boxes"][i, :k].clone(), "pred_scores": b["scores"][i, :k].clone(), "pred_labels": b["labels"][i, :k].long(),
                  "pred_anchor_index": b["index"][i, :k].long()} for i, k in enumerate(counts)]

@@ -87,7 +87,8 @@ int hvpr_init(void);
 /* ---- K1 voxelize -------------------------------------------------------------------------------------------------
  * points        (n_total, pts_stride) fp32; x,y,z,intensity at columns xyz_col..xyz_col+3 (4 features are copied)
  * frame_offsets (n_frames+1) int32: frame f owns points [off[f], off[f+1])
- * max_frame_points  upper bound on any frame's point count (sizes the grid; 0 -> n_total)
+ * max_frame_points  upper bound on any frame's point count (sizes the grid; 0 -> n_total); a frame that is longer is
+ *                   truncated to its first max_frame_points points — by every kernel alike, never silently emptied
  * outputs (rows frame-major, first-seen order inside a frame, exactly as dataset.py:159-166 would collate):
  *   voxels        (>= n_frames*max_voxels rows, max_points, 4) fp32, zero-padded rows
  *   coords        (rows, 4) int32 [b, z, y, x]

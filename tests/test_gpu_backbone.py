@@ -430,3 +430,41 @@ def test_points_to_boxes_pipeline_vs_oracle_chain():
     assert np.abs(cls - cls_ref).max() <= 3e-2 * max(1.0, np.abs(cls_ref).max(), fscale)
     assert np.abs(box[..., :2] - box_ref[..., :2]).max() <= 5e-2 * float(np.sqrt(3.9 ** 2 + 1.6 ** 2))
     assert np.abs(box[..., 3:6] / box_ref[..., 3:6] - 1).max() <= 5e-2
+
+
+def test_pipeline_plans_for_a_capacity_and_follows_weight_reloads():
+    """(1) collated batches differ in point count every time -> the module entry point plans ONCE for a capacity and
+    replays the same graph (no per-batch reallocation / re-capture); (2) a load_state_dict() after the first forward must reach
+    the captured graph (folded PFN weights are baked in by value); (3) outputs are fresh tensors, not views of plan buffers."""
+    from helpers import load_small
+    from hvpr_b200 import synth
+    from hvpr_b200.pipeline import FrontEndWithBackbone
+    from oracle import backbone as ob, hybrid
+    z, geom, frames, overflow, wseed = load_small("tiny_continue")
+    w_a, w_b, w_bb = hybrid.random_weights(wseed), hybrid.random_weights(wseed + 1), ob.random_backbone_weights(21)
+
+    def make(w):
+        pipe = FrontEndWithBackbone(geom, overflow=overflow)
+        pipe.frontend.load_reference_weights(w)
+        pipe.backbone_2d.load_state_dict({k: torch.from_numpy(v) for k, v in w_bb.items()}, strict=False)
+        return pipe
+
+    batch1 = frames
+    batch2 = [f[: max(1, len(f) * 2 // 3)] for f in frames]           # fewer points: fits the planned capacity
+    bd = lambda fr: {"points": torch.from_numpy(synth.collate_points(fr)).cuda(), "batch_size": len(fr)}
+    pipe = make(w_a)
+    out1 = pipe(bd(batch1))["spatial_features_2d"]
+    plan = pipe._p
+    out2 = pipe(bd(batch2))["spatial_features_2d"]
+    assert pipe._p is plan and plan.graph is not None                 # same buffers, same graph
+    assert out1.data_ptr() != out2.data_ptr() and not torch.equal(out1, out2)
+    ref2 = make(w_a)(bd(batch2))["spatial_features_2d"]
+    assert torch.equal(out2, ref2)
+    ref1 = make(w_a)(bd(batch1))["spatial_features_2d"]
+    assert torch.equal(out1, ref1)                                    # out1 was not clobbered by the second call
+    # weight reload after the first forward
+    pipe.frontend.load_reference_weights(w_b)
+    out3 = pipe(bd(batch2))["spatial_features_2d"]
+    ref3 = make(w_b)(bd(batch2))["spatial_features_2d"]
+    torch.cuda.synchronize()
+    assert torch.equal(out3, ref3) and not torch.equal(out3, out2)

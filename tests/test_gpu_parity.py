@@ -133,6 +133,26 @@ def test_voxelize_all_points_one_pillar_and_tiny_caps():
     _assert_vox_equal([f], g1, "break")
 
 
+def test_voxelize_truncates_frames_longer_than_the_stated_bound():
+    """max_frame_points is a promise of the caller; a frame that breaks it is cut to its first max_frame_points points
+    by every kernel alike (it used to lose its last scan tile and come out with ZERO pillars)."""
+    from hvpr_b200.voxelizer import Voxelizer
+    g = G2
+    frames = [synth.make_frame("L", 9000, g.point_cloud_range, 31), synth.make_frame("U", 3000, g.point_cloud_range, 32),
+              synth.make_frame("L", 5000, g.point_cloud_range, 33)]
+    cap = 4100
+    for mode in ("continue", "break"):
+        vz = Voxelizer(g, mode)
+        pts, off = to_dev(frames)
+        out = vz.run(pts, off, len(frames), cap)
+        torch.cuda.synchronize()
+        P = int(out.voxel_offsets[-1])
+        rv, rc, rn = ov.voxelize_batch([f[:cap] for f in frames], g.range_f32, g.voxel_f32, 32, g.max_voxels, mode)
+        assert P == len(rn) and P > 0
+        assert np.array_equal(out.num_points[:P].cpu().numpy(), rn) and np.array_equal(out.coords[:P].cpu().numpy(), rc)
+        assert np.array_equal(out.voxels[:P].cpu().numpy().view(np.int32), rv.view(np.int32))
+
+
 def test_voxelize_collated_points_with_batch_column():
     """batch_dict path: (sum N, 5) [b,x,y,z,r] exactly as collate_batch pads it (dataset.py:161-166)."""
     from hvpr_b200.voxelizer import Voxelizer
