@@ -16,7 +16,7 @@ SYMBOLS = [
     "hvpr_strerror", "hvpr_last_cuda_error", "hvpr_version", "hvpr_init",
     "hvpr_voxelize_workspace_bytes", "hvpr_voxelize", "hvpr_frame_offsets",
     "hvpr_pfn",
-    "hvpr_mem_attn_workspace_bytes", "hvpr_mem_pack_bf16", "hvpr_mem_attn",
+    "hvpr_mem_attn_workspace_bytes", "hvpr_mem_pack_bf16", "hvpr_mem_attn", "hvpr_mem_train_forward", "hvpr_mse_loss",
     "hvpr_bev_fill", "hvpr_build_cell_map",
     "hvpr_conv_packed_bytes", "hvpr_conv_pack_weights", "hvpr_conv2d", "hvpr_nchw_to_nhwc_bf16", "hvpr_attention_gate",
     "hvpr_bev_fill_nhwc_bf16", "hvpr_head_decode",
@@ -105,6 +105,10 @@ def lib():
     L.hvpr_mem_attn.restype = c_int
     L.hvpr_mem_attn.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    L.hvpr_mem_train_forward.restype = c_int
+    L.hvpr_mem_train_forward.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]
+    L.hvpr_mse_loss.restype = c_int
+    L.hvpr_mse_loss.argtypes = [c_void_p, c_void_p, c_int64, ctypes.c_double, c_void_p, c_void_p, c_void_p]
     L.hvpr_bev_fill.restype = c_int
     L.hvpr_bev_fill.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                 c_void_p, c_void_p, ctypes.POINTER(HvprLaunchCfg), c_void_p]

@@ -10,6 +10,7 @@ size_t hvpr_mem_attn_tc_workspace_bytes(int64_t n_rows_max, int M);
 int hvpr_mem_attn_tc(const float *, const int32_t *, int64_t, const float *, const void *, int, int, int, float *,
                      int32_t *, void *, size_t, cudaStream_t);
 int hvpr_conv_init();
+int hvpr_mem_train_init();
 int hvpr_mem_pack_bf16_impl(const float *, int, int, void *, cudaStream_t);
 
 namespace hvpr {
@@ -51,6 +52,7 @@ extern "C" int hvpr_init(void) {
     if ((s = hvpr_mem_attn_fp32_init()) != HVPR_OK) return s;
     if ((s = hvpr_mem_attn_tc_init()) != HVPR_OK) return s;
     if ((s = hvpr_conv_init()) != HVPR_OK) return s;
+    if ((s = hvpr_mem_train_init()) != HVPR_OK) return s;
     return HVPR_OK;
 }
 

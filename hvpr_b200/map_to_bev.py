@@ -1,6 +1,7 @@
 """Drop-in boundary #2b — map_to_bev modules with the reference's constructor signature, parameter names and
 batch_dict contract (pcdet/models/backbones_2d/map_to_bev/pointpillar_scatter.py:5-222, memory_module.py:11-82,
-map_to_bev/__init__.py:1-8).  Inference (eval) path only.
+map_to_bev/__init__.py:1-8).  The eval path is the accelerated hot path; the training branch (row N4) is implemented
+FORWARD ONLY: it runs under torch.no_grad semantics and its outputs carry no autograd graph.
 """
 from __future__ import annotations
 
@@ -60,9 +61,26 @@ class MemoryUnit_Agg(nn.Module):
         _lib.check(st, "hvpr_mem_attn")
         return out
 
+    @torch.no_grad()
+    def run_train(self, input1, input2, k):
+        """Training branch forward (memory_module.py:31-59): input1 (nv, d) pillars, input2 (nv, k, d) the k positive point features of
+        every pillar -> output (nv, d).  No autograd graph is built (backward is out of scope)."""
+        _lib.init_device()
+        nv, d = input1.shape
+        assert input2.shape == (nv, k, d), (tuple(input2.shape), (nv, k, d))
+        pil = input1.contiguous().float()
+        pos = input2.contiguous().float().view(nv * k, d)
+        ws = torch.empty((nv * k, d), dtype=torch.float32, device=pil.device)
+        out = torch.empty((nv, d), dtype=torch.float32, device=pil.device)
+        st = _lib.lib().hvpr_mem_train_forward(_lib.ptr(pil), nv, _lib.ptr(pos), _lib.ptr(self.weight.detach()), self.mem_dim, d, int(k),
+                                               float(self.shrink_thres), _lib.ptr(ws), _lib.ptr(out), _lib.cur_stream())
+        _lib.check(st, "hvpr_mem_train_forward")
+        return out, ws.view(nv, k, d)
+
     def forward(self, input1, input2, k):
         if self.training:
-            raise NotImplementedError("hvpr_b200 implements the eval branch (memory_module.py:60-77) only")
+            out, _ = self.run_train(input1, input2, k)
+            return {"output": out, "att": None}   # `att` (nv*k, M) is collected and never read (pointpillar_scatter.py:139,152)
         out = self.run(input1.contiguous().float(), k)
         return {"output": out, "att": None}   # `att` (nv, M) is never read at eval (pointpillar_scatter.py:201,212)
 
@@ -163,9 +181,76 @@ class PointPillarScatter_Agg_Memory_1_scale(nn.Module):
         _lib.check(st, "hvpr_bev_fill_nhwc_bf16")
         return spatial_nhwc, scale_nhwc, readout
 
+    @torch.no_grad()
+    def get_score(self, points, pillars, return_positive=False):
+        """pointpillar_scatter.py:67-83.  points (np, d), pillars (d, nv) -> {'output': (nv, d), 'att': None}.  The softmax over the
+        points is monotone, so the top-k points of a pillar are taken on the logits; the (np, nv) score matrix (`att`, never read:
+        :136-137) is not materialised.  Runs hvpr_mem_attn with the point features in the role of the memory (exact fp32, any np)."""
+        _lib.init_device()
+        pts = points.contiguous().float()
+        pil = pillars.t().contiguous().float()
+        nv, d = pil.shape
+        npts = pts.shape[0]
+        out = torch.empty((nv, d), dtype=torch.float32, device=pts.device)
+        idx = torch.empty((nv, self.k), dtype=torch.int32, device=pts.device)
+        st = _lib.lib().hvpr_mem_attn(_lib.ptr(pil), None, nv, _lib.ptr(pts), None, npts, d, int(self.k), _lib.MEM_FP32,
+                                      _lib.ptr(out), _lib.ptr(idx), None, 0, _lib.cur_stream())
+        _lib.check(st, "hvpr_mem_attn(get_score)")
+        res = {"output": out, "att": None}
+        if return_positive:
+            res["points_positive"] = pts[idx.long()]          # (nv, k, d), pointpillar_scatter.py:76
+            res["indices"] = idx
+        return res
+
+    @torch.no_grad()
+    def forward_train(self, batch_dict):
+        """Training branch, forward only (pointpillar_scatter.py:87-167): per frame get_score + memory train forward, then three
+        gather-fills.  ONE repaired call: the reference invokes `self.memory(pillars.t(), self.k)` (:133) against the signature
+        forward(input1, input2, k) — a TypeError as shipped; input2 is what memory_module.py:30,33 documents: the k positive point
+        features of every pillar (`points_positive`, :76)."""
+        pf, psf, coords = batch_dict["pillar_features"], batch_dict["pillar_scale_features"], batch_dict["voxel_coords"]
+        point_features, point_coords = batch_dict["point_features"], batch_dict["point_coords"]
+        if not pf.is_cuda:
+            raise _lib.HvprError("hvpr_b200 has no CPU path: batch_dict tensors must be on a CUDA device")
+        _lib.init_device()
+        pf, psf = pf.contiguous().float(), psf.contiguous().float()
+        coords_i = (coords if coords.dtype == torch.int32 else coords.to(torch.int32)).contiguous()
+        B = _batch_size(batch_dict, coords)
+        cm = _cell_map(batch_dict, coords_i, B, self.nx, self.ny)
+        C, Cs, dev = pf.shape[1], psf.shape[1], pf.device
+        pos_pt = torch.empty_like(pf)
+        pos_mem = torch.empty_like(pf)
+        pb = point_coords[:, 0].long()
+        cb = coords_i[:, 0].long()
+        for b in range(B):                                    # the per-frame loop of :103 (frames differ in point and pillar counts)
+            m = (cb == b).nonzero()[:, 0]
+            if m.numel() == 0:
+                continue
+            pil = pf[m]
+            pts = point_features[pb == b].contiguous().float()
+            gs = self.get_score(pts, pil.t(), return_positive=True)
+            mem_out, _ = self.memory.run_train(pil, gs["points_positive"], self.k)
+            pos_pt[m] = gs["output"]
+            pos_mem[m] = mem_out
+        sp = torch.empty((B, 2 * C, self.ny, self.nx), dtype=torch.float32, device=dev)
+        sp_pt = torch.empty_like(sp)
+        sps = torch.empty((B, Cs, self.ny, self.nx), dtype=torch.float32, device=dev)
+        L, st_ = _lib.lib(), _lib.cur_stream()
+        _lib.check(L.hvpr_bev_fill(_lib.ptr(pf), C, _lib.ptr(pos_mem), C, _lib.ptr(psf), Cs, _lib.ptr(cm), B, self.nx, self.ny,
+                                   _lib.ptr(sp), _lib.ptr(sps), None, st_), "hvpr_bev_fill")
+        _lib.check(L.hvpr_bev_fill(_lib.ptr(pf), C, _lib.ptr(pos_pt), C, None, 0, _lib.ptr(cm), B, self.nx, self.ny,
+                                   _lib.ptr(sp_pt), None, None, st_), "hvpr_bev_fill")
+        batch_dict["spatial_features"] = sp                                   # :160
+        batch_dict["spatial_features_point"] = sp_pt                          # :161
+        batch_dict["spatial_scale_features"] = sps                            # :162
+        batch_dict["point_positive_features"] = pos_pt                        # :163
+        batch_dict["memory_positive_features"] = pos_mem                      # :164
+        batch_dict["memory_items"] = self.memory.weight                       # :165
+        return batch_dict
+
     def forward(self, batch_dict, **kwargs):
         if self.training:
-            raise NotImplementedError("hvpr_b200 implements the eval branch (pointpillar_scatter.py:169-220) only")
+            return self.forward_train(batch_dict)
         pf, psf, coords = batch_dict["pillar_features"], batch_dict["pillar_scale_features"], batch_dict["voxel_coords"]
         if not pf.is_cuda:
             raise _lib.HvprError("hvpr_b200 has no CPU path: batch_dict tensors must be on a CUDA device")
@@ -179,6 +264,21 @@ class PointPillarScatter_Agg_Memory_1_scale(nn.Module):
         batch_dict["spatial_scale_features"] = sps
         batch_dict["memory_readout"] = ro
         return batch_dict
+
+
+@torch.no_grad()
+def mem_loss(memory, target, mem_weight=1.0):
+    """AnchorHeadTemplate.get_mem_loss (anchor_head_template.py:262-275), forward only:
+    MSELoss(memory, target) / target.shape[0] * LOSS_WEIGHTS['mem_weight']  ->  0-dim CUDA tensor."""
+    _lib.init_device()
+    a, b = memory.contiguous().float(), target.contiguous().float()
+    assert a.shape == b.shape and a.is_cuda
+    n = a.numel()
+    ws = torch.empty(1024, dtype=torch.float32, device=a.device)
+    out = torch.empty(1, dtype=torch.float32, device=a.device)
+    scale = float(mem_weight) / (float(n) * float(int(b.shape[0])))
+    _lib.check(_lib.lib().hvpr_mse_loss(_lib.ptr(a), _lib.ptr(b), n, scale, _lib.ptr(ws), _lib.ptr(out), _lib.cur_stream()), "hvpr_mse_loss")
+    return out[0]
 
 
 __all__ = {

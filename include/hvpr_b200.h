@@ -141,6 +141,19 @@ int hvpr_bev_fill(const float *feat_a, int ca, const float *feat_b, int cb, cons
 int hvpr_build_cell_map(const int32_t *coords, const int32_t *n_pillars_dev, int64_t n_rows_max,
                         int n_frames, int nx, int ny, int32_t *cell_map, void *stream);
 
+/* ==== N4: training-branch hybrid aggregation, FORWARD only ============================================
+ * get_score (pointpillar_scatter.py:67-83: softmax over the frame's points, top-k points per pillar, exact re-score, softmax_k,
+ * readout) is hvpr_mem_attn with the frame's point features (np, 64) as `mem_weight`, M = np and HVPR_MEM_FP32 (exact, any M);
+ * topk_idx_out then names the k positive points of every pillar.
+ * hvpr_mem_train_forward = MemoryUnit_Agg.forward training branch (memory_module.py:31-59, hard_shrink_relu :85-87):
+ *   pillars (nv,64); points_positive (nv*k,64) the k positive point features of every pillar, pillar-major;
+ *   memory_positive_ws (nv*k,64) scratch that receives `memory_positive` (:49-50); output (nv,64).  M <= 2048.
+ * hvpr_mse_loss = get_mem_loss (anchor_head_template.py:262-275): loss_out[0] = scale * sum((a-b)^2) over n elements, with
+ *   scale = mem_weight / (n * rows) set by the caller; partials_ws: 1024 floats.  Deterministic (no atomics).                 */
+int hvpr_mem_train_forward(const float *pillars, int64_t nv, const float *points_positive, const float *mem_weight,
+                           int M, int C, int k, float shrink_thres, float *memory_positive_ws, float *output, void *stream);
+int hvpr_mse_loss(const float *a, const float *b, int64_t n, double scale, float *partials_ws, float *loss_out, void *stream);
+
 /* ==== N1 (first "next" row): BaseBEVBackbone_Scale convolutions ======================================
  * Replaces the nn.Conv2d / nn.ConvTranspose2d + BatchNorm2d + ReLU stacks built at
  * pcdet/models/backbones_2d/base_bev_backbone.py:150-213 and run by the eval forward at :280-315, and the

@@ -285,3 +285,42 @@ def test_dense_head_oracle_assembly_is_self_consistent():
     rot = box[..., 6] - od.HEAD_CFG["DIR_OFFSET"]
     lab = dir_raw.reshape(2, -1, 2).argmax(-1)
     assert np.all((rot - period * lab > -1e-4) & (rot - period * lab < period + 1e-4))      # limit_period range + label shift
+
+
+# ------------------------------------------------------------------------------------------------ row N4: training branch (forward)
+def test_train_branch_oracle_matches_reference_golden():
+    """oracle/train_branch.py vs tests/golden/train_small.npz, minted by the reference's OWN get_score and MemoryUnit_Agg(train)."""
+    from oracle import train_branch as tb
+    z = np.load(os.path.join(GOLDEN, "train_small.npz"))
+    pil, pts, w = torch.from_numpy(z["pillars"]), torch.from_numpy(z["points"]), torch.from_numpy(z["weight"])
+    k, shrink = int(z["k"]), float(z["shrink"])
+    out, pos, _ = tb.get_score(pts, pil.t(), k, return_positive=True)
+    torch.testing.assert_close(out, torch.from_numpy(z["get_score_output"]), rtol=2e-6, atol=2e-6)
+    assert torch.equal(pos, torch.from_numpy(z["positive"]))
+    mo = tb.memory_train(pil, pos, w, k, shrink)
+    torch.testing.assert_close(mo, torch.from_numpy(z["memory_output"]), rtol=2e-6, atol=2e-6)
+    assert float(mo.abs().max()) > 0.01                        # the shrinkage left something (inputs are scaled for that)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present on this box")
+def test_train_branch_oracle_vs_live_reference():
+    """get_score (pointpillar_scatter.py:67-83) and the memory unit's training forward (memory_module.py:31-59) of the reference,
+    run unmodified, against the restatement: bit-identical."""
+    from oracle import train_branch as tb
+    from oracle.make_golden_train import inputs
+    ns = ref_loader.load()
+    for seed, nv, npts, M, shrink in ((1, 37, 500, 2000, 0.0025), (2, 64, 900, 256, 0.01), (3, 1, 64, 256, 0.0)):
+        cfg = ref_loader.Cfg(dict(ref_loader.BEV_CFG), NUM_M=M, SHRINK_TH=shrink)
+        bev = ns.PointPillarScatter_Agg_Memory_1_scale(cfg, grid_size=(16, 16, 1))
+        pil, pts, w = inputs(seed, nv, npts, M)
+        pts = pts * 3.0
+        with torch.no_grad():
+            bev.memory.weight.copy_(w)
+            out, pos, _ = tb.get_score(pts, pil.t(), cfg.NUM_K, return_positive=True)
+            if nv > 1:                                     # nv == 1: the reference's .squeeze() (:77) breaks its own softmax(dim=1)
+                assert torch.equal(bev.get_score(pts, pil.t())["output"], out)
+            ref = bev.memory.train()(pil, pos, cfg.NUM_K)["output"]
+            assert torch.equal(ref, tb.memory_train(pil, pos, w, cfg.NUM_K, shrink))
+    # get_mem_loss arithmetic (anchor_head_template.py:262-275)
+    a, b = torch.randn(40, 64), torch.randn(40, 64)
+    assert torch.equal(tb.mem_loss(a, b, 0.5), torch.nn.MSELoss()(a, b) / 40 * 0.5)
