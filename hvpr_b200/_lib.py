@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libhvpr_b200.so")
 SYMBOLS = [
     "hvpr_strerror", "hvpr_last_cuda_error", "hvpr_version", "hvpr_init",
     "hvpr_voxelize_workspace_bytes", "hvpr_voxelize", "hvpr_frame_offsets",
-    "hvpr_pfn",
+    "hvpr_pfn", "hvpr_pfn_pack", "hvpr_pfn_packed_bytes",
     "hvpr_mem_attn_workspace_bytes", "hvpr_mem_pack_bf16", "hvpr_mem_attn", "hvpr_mem_train_forward", "hvpr_mse_loss",
     "hvpr_bev_fill", "hvpr_build_cell_map",
     "hvpr_conv_packed_bytes", "hvpr_conv_pack_weights", "hvpr_conv2d", "hvpr_nchw_to_nhwc_bf16", "hvpr_attention_gate",
@@ -97,7 +97,10 @@ def lib():
     L.hvpr_frame_offsets.argtypes = [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]
     L.hvpr_pfn.restype = c_int
     L.hvpr_pfn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p,
-                           c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, ctypes.POINTER(HvprLaunchCfg), c_void_p]
+                           c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(HvprLaunchCfg), c_void_p]
+    L.hvpr_pfn_pack.restype = c_int
+    L.hvpr_pfn_pack.argtypes = [c_void_p, c_void_p, c_void_p]
+    L.hvpr_pfn_packed_bytes.restype = c_size_t
     L.hvpr_mem_attn_workspace_bytes.restype = c_size_t
     L.hvpr_mem_attn_workspace_bytes.argtypes = [c_int64, c_int, c_int]
     L.hvpr_mem_pack_bf16.restype = c_int

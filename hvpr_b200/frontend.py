@@ -22,7 +22,7 @@ from .voxelizer import Voxelizer
 
 class HybridFrontEnd(torch.nn.Module):
     # HvprLaunchCfg (blocks_per_sm, variant) of the PFN inside the streaming graphs: the low-register variant leaves room for the fill blocks
-    stream_pfn_knob = (3, 1)
+    stream_pfn_knob = (2, 1)
     # HvprLaunchCfg of the canvas fill inside the streaming graphs (persistent blocks per SM; it shares the SMs with K1 / K2 there)
     stream_bev_knob = (2, 0)
     # where K1 of batch k+2 sits in the step: "fork" (own stream from the start of the step), "before_k3" / "after_k3" / "last" (main stream)
@@ -102,7 +102,7 @@ class HybridFrontEnd(torch.nn.Module):
             p.graph = None                                # weights changed since capture: fold / pack / capture again
         if p.graph is None:
             p.graph_wkey = wkey
-            self.vfe._weights()                         # host-side folding happens outside capture
+            self.vfe._weights_packed(self.dev)            # host-side folding + fragment packing happen outside capture
             if self.map_to_bev_module.memory.precision == "bf16_rescore":
                 self.map_to_bev_module.memory._packed_bf16()
             s = torch.cuda.Stream()
@@ -206,7 +206,7 @@ class HybridFrontEnd(torch.nn.Module):
             if b is not None:
                 p.in_points[slot].copy_(b[0], non_blocking=True)
                 p.in_offsets[slot].copy_(b[1], non_blocking=True)
-        self.vfe._weights()
+        self.vfe._weights_packed(self.dev)
         if self.map_to_bev_module.memory.precision == "bf16_rescore":
             self.map_to_bev_module.memory._packed_bf16()
         wkey = self.weights_version()

@@ -102,7 +102,7 @@ class FrontEndWithBackbone(torch.nn.Module):
         if p.graph is None:
             p.graph_wkey = wkey
             fe = self.frontend
-            fe.vfe._weights()
+            fe.vfe._weights_packed(p.points.device)
             if fe.map_to_bev_module.memory.precision == "bf16_rescore":
                 fe.map_to_bev_module.memory._packed_bf16()
             self.backbone_2d._ensure_packed(p.points.device)

@@ -139,7 +139,17 @@ class _PillarVFEBase(VFETemplate):
                 ws1, bs1 = _fold_seq(self.pfn_scale_layers[1])
                 put("ws0", ws0); put("bs0", bs0); put("ws1", ws1); put("bs1", bs1)
             self._wcache, self._wkey = W, key
+            self._wpacked = None
         return self._wcache
+
+    def _weights_packed(self, device):
+        """Device image of the tensor-core weight fragments (hvpr_pfn_pack), rebuilt when the folded weights change."""
+        W = self._weights()
+        if getattr(self, "_wpacked", None) is None or self._wpacked.device != device:
+            buf = torch.empty(int(_lib.lib().hvpr_pfn_packed_bytes()), dtype=torch.uint8, device=device)
+            _lib.check(_lib.lib().hvpr_pfn_pack(ctypes.byref(W), _lib.ptr(buf), _lib.cur_stream()), "hvpr_pfn_pack")
+            self._wpacked = buf
+        return self._wpacked
 
     def invalidate_weights(self):
         """Drop the folded-weight cache (needed only after raw `.data` edits, which bypass tensor version counters)."""
@@ -158,7 +168,8 @@ class _PillarVFEBase(VFETemplate):
             _lib.ptr(voxels), _lib.ptr(num_points), _lib.ptr(coords), _lib.ptr(n_pillars_dev), rows, T,
             ctypes.byref(self._weights()), ctypes.byref(self._geom_c),
             float(self.x_offset), float(self.y_offset), float(self.z_offset),
-            _lib.ptr(out), _lib.ptr(scale_out) if self._HAS_SCALE else None, _lib.ptr(mask_out), _lib.launch_cfg(launch),
+            _lib.ptr(out), _lib.ptr(scale_out) if self._HAS_SCALE else None, _lib.ptr(mask_out), _lib.ptr(self._weights_packed(dev)),
+            _lib.launch_cfg(launch),
             _lib.cur_stream())
         _lib.check(st, "hvpr_pfn")
         return out, scale_out, mask_out

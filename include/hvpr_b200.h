@@ -68,7 +68,7 @@ typedef struct HvprPfnWeights {
 
 /* Optional launch shape of hvpr_pfn / hvpr_bev_fill, passed with the call (NULL = defaults).  Replaces the round-1
  * process-global hvpr_tune_* knobs: two front ends in one process can no longer race on them.
- *   hvpr_pfn:      blocks_per_sm 1..3 persistent blocks per SM (0 = default 3); variant 0 = W1a tensor-core fragments in
+ *   hvpr_pfn:      blocks_per_sm 1..3 persistent blocks of five warps per SM (0 = default 2: what shared memory admits); variant 0 = W1a tensor-core fragments in
  *                  registers (fastest alone), 1 = fragments in shared memory (fewer registers: the canvas-fill blocks of
  *                  hvpr_bev_fill fit beside the PFN blocks in the streaming schedule)
  *   hvpr_bev_fill: blocks_per_sm 0 = one 128-thread block per work item (fastest alone), 1..16 = that many persistent
@@ -111,11 +111,16 @@ int hvpr_frame_offsets(const float *points5, int64_t n_total, int pts_stride, in
  * voxels (rows,max_points,4), num_points (rows), coords (rows,4) as produced above.
  * n_pillars_dev: device int32 holding the live row count (e.g. &voxel_offsets[n_frames]); NULL -> n_rows_max rows.
  * x_off/y_off/z_off: voxel/2 + range_min built by the caller with the reference's expression (pillar_vfe.py:169-171).
- * pillar_features (rows,64); scale_out (rows,32) or NULL; mask_out (rows,max_points) or NULL.                        */
+ * pillar_features (rows,64); scale_out (rows,32) or NULL; mask_out (rows,max_points) or NULL.
+ * weights_packed: DEVICE image made by hvpr_pfn_pack from the same weights_host (hvpr_pfn_packed_bytes() bytes), or NULL
+ * (every block then rebuilds its tensor-core weight fragments from the by-value weights: ~10 % slower).              */
+size_t hvpr_pfn_packed_bytes(void);
+int hvpr_pfn_pack(const HvprPfnWeights *weights_host, void *weights_packed, void *stream);
 int hvpr_pfn(const float *voxels, const int32_t *num_points, const int32_t *coords,
              const int32_t *n_pillars_dev, int64_t n_rows_max, int max_points,
              const HvprPfnWeights *weights_host, const HvprGeom *geom, float x_off, float y_off, float z_off,
-             float *pillar_features, float *scale_out, float *mask_out, const HvprLaunchCfg *launch, void *stream);
+             float *pillar_features, float *scale_out, float *mask_out, const void *weights_packed,
+             const HvprLaunchCfg *launch, void *stream);
 
 /* ---- K3 memory attention -----------------------------------------------------------------------------------------
  * pillars (rows,64) fp32; mem_weight (M,64) fp32; readout (rows,64) fp32.

@@ -14,7 +14,7 @@ p = fe.plan(B, B * N, N, use_graph=False)
 p.points.copy_(torch.from_numpy(np.concatenate(frames, 0))); p.frame_offsets.copy_(torch.tensor(np.r_[0, np.cumsum([N] * B)], dtype=torch.int32))
 fe.run(); torch.cuda.synchronize()
 vox = p.vox
-def k2(): fe.vfe.run(vox.voxels, vox.num_points, vox.coords, vox.n_pillars_dev, out=p.pillar_features, scale_out=p.pillar_scale, launch=(3, lowreg))
+def k2(): fe.vfe.run(vox.voxels, vox.num_points, vox.coords, vox.n_pillars_dev, out=p.pillar_features, scale_out=p.pillar_scale, launch=(2, lowreg))
 res = {}
 for lowreg in (0, 1):
     for _ in range(5): k2()
