@@ -6,8 +6,11 @@ synthetic frames: BASELINE.json configs[1] = G2 (pillar 0.16x0.16x4 m, 432x496 g
 B = 8 frames of 120 000 points per GPU.  N GPUs => N ranks (torchrun), each with its own 8 frames (weak scaling, no
 collective on the data path; NCCL only reduces the timings).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]           our arm
+    python bench.py [--gpus N] [--steps K] [--warmup W]           our arm (BASELINE.json configs[1], "cfg2")
     python bench.py --impl reference ...                           the reference's CPU path (oracle port) on host cores
+    python bench.py --config cfg3|cfg4 [--dist U]                  the other measured configs of BASELINE.json / SURVEY.md §8d:
+        cfg3 = 64 frames split frame-wise over the ranks (strong scaling; N = 1 runs all 64), cfg4 = G3 640x640 grid,
+        300 000 points per frame, 80 000 max pillars, 8 frames per GPU; --dist U = uniform frames (the 40 000-pillar cap is hit)
 
 Prints ONE JSON line (rank 0).  At N = 1 the line also carries `next_rows.bev_backbone`: the widened rows N1-N3 of SURVEY.md §8f measured on
 the same batch — BaseBEVBackbone_Scale on the tcgen05 conv kernel (ms, TFLOP/s vs the measured bf16 peak, the same network through cuDNN as the
@@ -33,6 +36,77 @@ UNIT = "frames/s"
 FRAMES_PER_GPU = 8
 POINTS_PER_FRAME = 120000
 DIST = "L"
+NOMINAL_HBM_GBS = 8000.0          # BASELINE.json: "roughly 8 TB/s"; fractions are quoted against the measured AND the nominal peak
+NOMINAL_BF16_TFLOPS = 2250.0
+
+# BASELINE.json configs[1..3] as concretised by SURVEY.md §8d
+WORKLOADS = {
+    "cfg2": dict(geom="G2", frames_per_gpu=8, frames_total=None, points=120000, scaling="weak",
+                 what="BASELINE.json configs[1]: batch of 8 frames per GPU"),
+    "cfg3": dict(geom="G2", frames_per_gpu=None, frames_total=64, points=120000, scaling="strong",
+                 what="BASELINE.json configs[2]: 64 frames sharded frame-wise over the ranks (frame i -> rank i mod W)"),
+    "cfg4": dict(geom="G3", frames_per_gpu=8, frames_total=None, points=300000, scaling="weak",
+                 what="BASELINE.json configs[3]: dense 300k-point frames, extended range (640x640 grid), 80k max pillars"),
+}
+
+
+def workload(args, rank, world):
+    """-> (geom, frame ids of this rank, points per frame, frames per step over all ranks)"""
+    from hvpr_b200 import sharding
+    from hvpr_b200.geometry import GEOMETRIES
+    wl = WORKLOADS[args.config]
+    geom = GEOMETRIES[wl["geom"]]
+    if wl["frames_total"]:
+        ids = sharding.frames_of_rank(wl["frames_total"], rank, world)
+        total = wl["frames_total"]
+    else:
+        ids = sharding.weak_scaling_frames(wl["frames_per_gpu"], rank)
+        total = wl["frames_per_gpu"] * world
+    return geom, ids, wl["points"], total
+
+
+def bind_numa(local_rank, world):
+    """Before any pinned allocation: run this rank (and first-touch its pinned buffers) on ONE NUMA node — the GPU's own when
+    NVML can tell them apart, else ranks are spread round-robin over the nodes.  Round 1 left every rank's pinned batch on
+    node 0 and the 8-GPU end-to-end efficiency dropped to 0.93 while the device-resident one stayed at 0.99."""
+    import glob
+    nodes = []
+    for d in sorted(glob.glob("/sys/devices/system/node/node[0-9]*"), key=lambda s: int(s.rsplit("node", 1)[1])):
+        try:
+            cpus = set()
+            for part in open(os.path.join(d, "cpulist")).read().strip().split(","):
+                if part:
+                    a, _, b = part.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+            if cpus:
+                nodes.append(cpus)
+        except Exception:
+            pass
+    allowed = os.sched_getaffinity(0)
+    nodes = [n & allowed for n in nodes if n & allowed]
+    info = {"numa_nodes": len(nodes), "bound_node": None, "how": "single node or no topology: not bound"}
+    if len(nodes) < 2:
+        return info
+    target, how = None, ""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(max(n) for n in nodes) + 64) // 64)
+        gpu_cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1} & allowed
+        hits = [i for i, n in enumerate(nodes) if n & gpu_cpus]
+        if len(hits) == 1:
+            target, how = hits[0], "NVML cpu affinity of the GPU"
+    except Exception:
+        pass
+    if target is None:
+        target, how = (local_rank * len(nodes)) // max(world, 1) % len(nodes), "round-robin over nodes (GPU affinity spans several)"
+    try:
+        os.sched_setaffinity(0, nodes[target])
+        info.update(bound_node=target, how=how, cpus=len(nodes[target]))
+    except Exception as e:
+        info["how"] = "sched_setaffinity failed: %r" % (e,)
+    return info
 
 
 def algorithmic_bytes(N, P, K, nx, ny):
@@ -96,17 +170,19 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def make_frames(geom, rank, n_frames=FRAMES_PER_GPU):
-    from hvpr_b200 import sharding, synth
-    ids = sharding.weak_scaling_frames(n_frames, rank)
-    return [synth.make_frame(DIST, POINTS_PER_FRAME, geom.point_cloud_range, 1024 + i) for i in ids]
+def make_frames(geom, ids, points, dist):
+    from hvpr_b200 import synth
+    return [synth.make_frame(dist, points, geom.point_cloud_range, 1024 + i) for i in ids]
 
 
 # --------------------------------------------------------------------------------------------------- CPU arms
-def cpu_reference_run(geom, frames, w, steps, warmup, frames_per_step, workers=4):
-    """The reference's CPU path, as the oracle port: spconv-style voxelizer single-threaded per frame (one frame per
-    DataLoader worker, `--workers 4` default, tools/test.py:25) + PillarVFE_Scale + PointPillarScatter_Agg_Memory_1_scale
-    on torch CPU with every host thread."""
+def cpu_reference_run(geom, frames, w, steps, warmup, frames_per_step, workers=4, components=False, gpu_check=None):
+    """The reference's CPU path, as the oracle port (oracle/: the same torch CPU fp32 ops as the reference's modules, pinned
+    bit-exactly on them where /root/reference exists; the GPU box has no reference tree, and the reference ships nothing to
+    compile): spconv-style voxelizer single-threaded per frame (one frame per DataLoader worker, `--workers 4` default,
+    tools/test.py:25) + PillarVFE_Scale + PointPillarScatter_Agg_Memory_1_scale on torch CPU with every host thread.
+    components=True adds BASELINE.md §3.4's breakdown (t_vox single thread / x4 workers / x n_cores, t_vfe, t_bev);
+    gpu_check(frames) -> dict of GPU tensors: the same frames through the CUDA path, compared with the oracle's outputs."""
     import concurrent.futures as cf
     import torch
     from oracle import hybrid
@@ -115,18 +191,22 @@ def cpu_reference_run(geom, frames, w, steps, warmup, frames_per_step, workers=4
     torch.set_num_threads(ncores)
     nx, ny, _ = geom.grid_size
     pool = cf.ThreadPoolExecutor(max_workers=min(workers, ncores))
+    vox1 = lambda f: ov.voxelize_c(f, geom.range_f32, geom.voxel_f32, geom.max_points_per_voxel, geom.max_voxels, "continue")
+    last = {}
 
-    def step(i):
-        fs = [frames[(i * frames_per_step + j) % len(frames)] for j in range(frames_per_step)]
-        outs = list(pool.map(lambda f: ov.voxelize_c(f, geom.range_f32, geom.voxel_f32, geom.max_points_per_voxel,
-                                                     geom.max_voxels, "continue"), fs))
+    def collate(outs):
         vox = np.concatenate([o[0] for o in outs], 0)
         coords = np.concatenate([np.pad(o[1], ((0, 0), (1, 0)), constant_values=b) for b, o in enumerate(outs)], 0)
         nump = np.concatenate([o[2] for o in outs], 0)
+        return torch.from_numpy(vox), torch.from_numpy(coords), torch.from_numpy(nump)
+
+    def step(i):
+        fs = [frames[(i * frames_per_step + j) % len(frames)] for j in range(frames_per_step)]
+        tv, tc, tn = collate(list(pool.map(vox1, fs)))
         with torch.no_grad():
-            tv, tc, tn = torch.from_numpy(vox), torch.from_numpy(coords), torch.from_numpy(nump)
             pf, psf, _ = hybrid.pillar_vfe(tv, tn, tc, w, list(geom.voxel_size), geom.range_f32)
-            sp, sps, _ = hybrid.scatter_agg_memory(pf, psf, tc, w["map_to_bev_module.memory.weight"], len(fs), nx, ny)
+            sp, sps, ro = hybrid.scatter_agg_memory(pf, psf, tc, w["map_to_bev_module.memory.weight"], len(fs), nx, ny)
+        last.update(frames=fs, pf=pf, ro=ro, sp=sp, sps=sps, tc=tc, tn=tn)
         return float(sp[0, 0, 0, 0])
 
     for i in range(warmup):
@@ -135,44 +215,93 @@ def cpu_reference_run(geom, frames, w, steps, warmup, frames_per_step, workers=4
     for i in range(steps):
         step(i)
     dt = time.perf_counter() - t0
-    return frames_per_step * steps / dt, dt / steps * 1e3, ncores
+    res = {"fps": frames_per_step * steps / dt, "ms_per_step": dt / steps * 1e3, "cores": ncores}
+    if components:
+        fs = [frames[j % len(frames)] for j in range(max(frames_per_step, 2))]
+        t0 = time.perf_counter(); outs = [vox1(f) for f in fs]; t_vox1 = (time.perf_counter() - t0) / len(fs)
+        many = [frames[j % len(frames)] for j in range(max(8, min(2 * ncores, 32)))]
+
+        def pooled(nw):
+            with cf.ThreadPoolExecutor(max_workers=nw) as ex:
+                t0 = time.perf_counter(); list(ex.map(vox1, many)); return (time.perf_counter() - t0) / len(many)
+        t_vox4, t_voxn = pooled(min(4, ncores)), pooled(ncores)
+        tv, tc, tn = collate(outs)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            pf, psf, _ = hybrid.pillar_vfe(tv, tn, tc, w, list(geom.voxel_size), geom.range_f32)
+            t_vfe = (time.perf_counter() - t0) / len(fs)
+            t0 = time.perf_counter()
+            hybrid.scatter_agg_memory(pf, psf, tc, w["map_to_bev_module.memory.weight"], len(fs), nx, ny)
+            t_bev = (time.perf_counter() - t0) / len(fs)
+        res["components"] = {
+            "t_vox_ms_per_frame": {"1_thread": t_vox1 * 1e3, "4_workers": t_vox4 * 1e3, "%d_cores" % ncores: t_voxn * 1e3},
+            "t_vfe_ms_per_frame": t_vfe * 1e3, "t_bev_ms_per_frame": t_bev * 1e3,
+            "frames_per_sec": {"vox_1_thread": 1.0 / (t_vox1 + t_vfe + t_bev), "vox_4_workers": 1.0 / (t_vox4 + t_vfe + t_bev),
+                               "vox_all_cores": 1.0 / (t_voxn + t_vfe + t_bev)},
+            "note": "frames/s = 1 / (t_vox + t_vfe + t_bev) as SURVEY.md §8d defines it; t_vfe / t_bev = oracle/hybrid.py (the reference's torch "
+                    "CPU ops) on all %d cores" % ncores}
+    if gpu_check is not None and last:
+        # the oracle as CHECKER: the last sample step's frames through the CUDA path vs the oracle's tensors
+        g = gpu_check(last["frames"])
+        scale = float(last["ro"].abs().max())
+        row_err = (g["readout"].double().cpu() - last["ro"].double()).abs().max(1)[0] / max(scale, 1e-30)
+        off = row_err > 1e-4
+        rel = lambda a, b: float((a.double().cpu() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+        res["parity_sample"] = {
+            "frames": len(last["frames"]), "pillars": int(last["tn"].shape[0]),
+            "coords_counts_bit_exact": bool(torch.equal(g["coords"].cpu(), last["tc"].int()) and torch.equal(g["num_points"].cpu(), last["tn"].int())),
+            "pillar_features_max_rel_err": rel(g["pillar_features"], last["pf"]),
+            "readout_rows_off_by_more_than_1e-4": int(off.sum()), "readout_tie_row_fraction": float(off.double().mean()),
+            "readout_max_rel_err_other_rows": float(row_err[~off].max()) if (~off).any() else 0.0,
+            "spatial_scale_features_bit_exact_given_inputs": rel(g["spatial_scale"], last["sps"]) <= 1e-4,
+            "note": "top-20 is discontinuous: rows whose 20th/21st logits tie within fp32 summation noise legitimately pick another item "
+                    "(tests/helpers.py::tie_aware_readout_check proves the near-tie in fp64 for every such row)"}
+    return res
 
 
 def run_reference_arm(args):
     from hvpr_b200 import sharding
-    from hvpr_b200.geometry import G2
     from oracle import hybrid
     rank, _, world = sharding.dist_env()
     if rank != 0:
         return 0
+    geom, ids, points, total = workload(args, 0, 1)
     fps_step = 2
-    frames = make_frames(G2, 0)
+    frames = make_frames(geom, ids[:8], points, args.dist)
     w = hybrid.random_weights(0)
     steps, warmup = args.steps, args.warmup
-    fps, ms, ncores = cpu_reference_run(G2, frames, w, steps, warmup, fps_step)
-    sample = "%d frames/step of the %d-frame batch (G2, %d pts/frame, dist %s)" % (fps_step, FRAMES_PER_GPU, POINTS_PER_FRAME, DIST)
+    r = cpu_reference_run(geom, frames, w, steps, warmup, fps_step)
+    fps, ms, ncores = r["fps"], r["ms_per_step"], r["cores"]
+    sample = "%d frames/step out of the workload's frames (%s, %d pts/frame, dist %s)" % (fps_step, WORKLOADS[args.config]["geom"], points, args.dist)
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": WORKLOADS[args.config]["scaling"], "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(G2),
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
+        "config": workload_config(geom, args, total, world),
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample,
+                         "what": "oracle/ port of the reference's CPU path: C voxelizer (1 thread per frame, 4 workers) + the reference's torch "
+                                 "CPU ops for VFE / memory / scatter on all cores; /root/reference is 100 % Python and absent on the GPU box"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
 
 
-def workload_config(geom):
+def workload_config(geom, args, frames_total, world):
     nx, ny, _ = geom.grid_size
-    return {"workload": "HVPR KITTI cfg, G2 pillars 0.16x0.16x4 m, %dx%d grid, 32 pts/pillar, 40k max pillars; "
-                        "batch of %d synthetic LiDAR-like frames x %d pts per GPU; voxelize+PFN+memory attention+BEV fill"
-                        % (nx, ny, FRAMES_PER_GPU, POINTS_PER_FRAME),
-            "frames_per_gpu": FRAMES_PER_GPU, "points_per_frame": POINTS_PER_FRAME, "distribution": DIST,
-            "weights": "random-init (seed 0), BN stats randomised",
-            "l2": "each step streams 1.1 GB of canvas writes (>8x the 126 MB L2), so inputs are evicted between steps",
+    wl = WORKLOADS[args.config]
+    fpg = frames_total // max(world, 1)
+    return {"workload": "%s — HVPR KITTI cfg, %s pillars %.2fx%.2fx%g m, %dx%d grid, 32 pts/pillar, %dk max pillars; "
+                        "%d synthetic %s frames x %d pts per step over %d GPU(s) (%d per GPU); voxelize+PFN+memory attention+BEV fill"
+                        % (wl["what"], wl["geom"], geom.voxel_size[0], geom.voxel_size[1], geom.voxel_size[2], nx, ny, geom.max_voxels // 1000,
+                           frames_total, {"L": "LiDAR-like", "U": "uniform"}[args.dist], wl["points"], world, fpg),
+            "name": args.config, "frames_per_gpu": fpg, "frames_per_step": frames_total, "points_per_frame": wl["points"],
+            "distribution": args.dist, "weights": "random-init (seed 0), BN stats randomised",
+            "l2": "each step streams %.1f GB of canvas writes per GPU (> 8x the 126 MB L2), so inputs are evicted between steps"
+                  % (fpg * 160 * nx * ny * 4 / 1e9),
             "streaming": "batches are software-pipelined 3 deep over CUDA streams: K1 voxelize of batch k+2 and K2 PFN of batch k+1 "
-                         "overlap K3/K4 of batch k; every batch runs the same 8 kernels (value_single_stream = no overlap)"}
+                         "overlap K3/K4 of batch k; every batch runs the same 8 kernels (value_single_stream = no overlap); a batch's "
+                         "canvases are complete two steps after it was submitted (latency = 3 x ms_per_step)"}
 
 
 # --------------------------------------------------------------------------------------------------- GPU arm
@@ -320,27 +449,117 @@ def bench_backbone(geom, w, host_pts, host_off, B, N, dev, mem_precision, steps=
     return out
 
 
+def library_baseline(geom, vox, P_total, B, w, dev, reps=5):
+    """SURVEY §8d / BASELINE.md §3.5: the reference's OWN formulation of the stages run by PyTorch's library kernels (cuBLAS SGEMM,
+    ATen elementwise / reduce / topk / index_put) on the same B200, same batch, CUDA-event timed — the number each hand-written
+    kernel has to beat.  A plain torch restatement of pillar_vfe.py:184-221, memory_module.py:60-77 and
+    pointpillar_scatter.py:169-220 (fp32, TF32 off); the voxelizer has no library counterpart (spconv is CPU code)."""
+    import torch
+    import torch.nn.functional as F
+    nx, ny, _ = geom.grid_size
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    wd = {k: v.to(dev) for k, v in w.items()}
+    voxels, coords, nump = vox.voxels[:P_total], vox.coords[:P_total], vox.num_points[:P_total]
+    vs, rng = [float(v) for v in geom.voxel_size], [float(v) for v in geom.point_cloud_range]
+    offs = [vs[i] / 2 + rng[i] for i in range(3)]
+
+    def bn(x, prefix):
+        return F.batch_norm(x, wd[prefix + ".running_mean"], wd[prefix + ".running_var"], wd[prefix + ".weight"], wd[prefix + ".bias"],
+                            False, 0.0, 1e-3)
+
+    def pfn_layer(x, i, last):
+        x = F.linear(x, wd["vfe.pfn_layers.%d.linear.weight" % i])
+        x = bn(x.permute(0, 2, 1), "vfe.pfn_layers.%d.norm" % i).permute(0, 2, 1)
+        x = F.relu(x)
+        xm = torch.max(x, dim=1, keepdim=True)[0]
+        return xm if last else torch.cat([x, xm.repeat(1, x.shape[1], 1)], dim=2)
+
+    def vfe():
+        n = nump.to(voxels.dtype).view(-1, 1, 1)
+        mean = voxels[:, :, :3].sum(dim=1, keepdim=True) / n
+        f_cluster = voxels[:, :, :3] - mean
+        c = coords.to(voxels.dtype)
+        f_center = torch.stack([voxels[:, :, 0] - (c[:, 3:4] * vs[0] + offs[0]), voxels[:, :, 1] - (c[:, 2:3] * vs[1] + offs[1]),
+                                voxels[:, :, 2] - (c[:, 1:2] * vs[2] + offs[2])], dim=2)
+        feats = torch.cat([voxels, f_cluster, f_center], dim=-1)
+        mask = (torch.arange(voxels.shape[1], device=dev).view(1, -1) < nump.view(-1, 1)).unsqueeze(-1).to(voxels.dtype)
+        feats = feats * mask
+        x = pfn_layer(pfn_layer(feats, 0, False), 1, True).squeeze(1)
+        sc = torch.cat([n.view(-1, 1), mean.norm(dim=2), mean.squeeze(1)], dim=1)
+        for i in range(2):
+            sc = F.relu(bn(F.linear(sc, wd["vfe.pfn_scale_layers.%d.0.weight" % i]), "vfe.pfn_scale_layers.%d.1" % i))
+        return x, sc
+
+    W = wd["map_to_bev_module.memory.weight"]
+
+    def memory(pil):
+        score = F.softmax(F.linear(pil, W), dim=1)
+        _, idx = torch.topk(score, 20, dim=1)
+        mem = W[idx]
+        agg = F.softmax((mem * pil.unsqueeze(1)).sum(dim=2), dim=1)
+        return (agg.unsqueeze(2) * mem).sum(dim=1)
+
+    def mem_and_scatter(pf, psf):
+        sp_l, sc_l = [], []
+        for b in range(B):
+            m = coords[:, 0] == b
+            tc = coords[m]
+            idx = (tc[:, 1] + tc[:, 2] * nx + tc[:, 3]).long()
+            pil = pf[m]
+            out = memory(pil)
+            canvas = torch.zeros(128, nx * ny, device=dev)
+            canvas_s = torch.zeros(32, nx * ny, device=dev)
+            canvas[:, idx] = torch.cat((pil.t(), out.t()), dim=0)
+            canvas_s[:, idx] = psf[m].t()
+            sp_l.append(canvas); sc_l.append(canvas_s)
+        return torch.stack(sp_l, 0).view(B, 128, ny, nx), torch.stack(sc_l, 0).view(B, 32, ny, nx)
+
+    def mem_only(pf):
+        return [memory(pf[coords[:, 0] == b]) for b in range(B)]
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    t = {"pfn": 0.0, "mem_attn+bev_fill": 0.0, "mem_attn": 0.0}
+    with torch.no_grad():
+        for it in range(reps + 2):
+            ev[0].record(); pf, psf = vfe(); ev[1].record(); sp, sps = mem_and_scatter(pf, psf); ev[2].record(); mem_only(pf); ev[3].record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                t["pfn"] += ev[0].elapsed_time(ev[1]) / reps
+                t["mem_attn+bev_fill"] += ev[1].elapsed_time(ev[2]) / reps
+                t["mem_attn"] += ev[2].elapsed_time(ev[3]) / reps
+            del sp, sps
+    t["bev_fill"] = max(t["mem_attn+bev_fill"] - t["mem_attn"], 0.0)
+    out = {"what": "the reference's formulation of PFN / memory attention / scatter through PyTorch's library kernels (cuBLAS + ATen, fp32, "
+                   "TF32 off, eager) on this GPU, same %d-frame batch, device-resident, CUDA events; voxelization excluded (no library path)" % B,
+           "ms": t, "ms_pfn_mem_bev": t["pfn"] + t["mem_attn+bev_fill"],
+           "frames_per_sec_excluding_voxelize": B / ((t["pfn"] + t["mem_attn+bev_fill"]) * 1e-3)}
+    del wd
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     from hvpr_b200 import sharding
     from hvpr_b200.frontend import HybridFrontEnd
-    from hvpr_b200.geometry import G2
     from hvpr_b200 import synth
 
     rank, local_rank, world = sharding.dist_env()
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback for the product path")
+    numa = bind_numa(local_rank, world)                  # before the first pinned allocation
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
         dist = sharding.init_process_group("nccl", device_id=dev)
 
-    geom = G2
+    geom, ids, N, frames_total = workload(args, rank, world)
     nx, ny, _ = geom.grid_size
-    B, N = FRAMES_PER_GPU, POINTS_PER_FRAME
-    frames = make_frames(geom, rank)
+    B = len(ids)
+    frames = make_frames(geom, ids, N, args.dist)
     w = synth.random_frontend_weights(0)     # synthetic weights under the reference's state_dict names
     fe = HybridFrontEnd(geom, mem_precision=args.mem_precision, device=dev).load_reference_weights(w)
     p = fe.plan(B, B * N, N, use_graph=not args.no_graph)
@@ -358,18 +577,31 @@ def run_gpu_arm(args):
 
     stream = torch.cuda.current_stream()
     W_ = max(args.warmup, 3)
+    K = args.steps
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(step_fn, finish=None, n=None):
+        """n (default: exactly K) steps between barriers; one event per step for the median / p95 of the step time."""
+        n = n or K
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        barrier()
+        marks[0].record(stream)
+        for i in range(n):
+            step_fn()
+            marks[i + 1].record(stream)
+        if finish is not None:
+            finish()
+        e1.record(stream)
+        barrier()
+        total = marks[0].elapsed_time(e1)
+        per = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(n))
+        return total, per[len(per) // 2], per[int(0.95 * (len(per) - 1))]
 
     # ---- reference point: one batch at a time, single stream (graph replay of the 8-kernel chain) ---------------------
     for _ in range(W_):
         fe.run()
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        fe.run()
-    e1.record(stream)
-    barrier()
-    ms_serial = sharding.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+    t_serial, med_serial, _ = timed(fe.run)
+    ms_serial = sharding.max_over_ranks(t_serial, dev) / K
 
     # ---- device-resident throughput (`value`): streaming mode, inputs of both slots already in HBM ---------------------
     sp = fe.plan_stream(B, B * N, N)
@@ -381,58 +613,62 @@ def run_gpu_arm(args):
         fe.stream_step()
     barrier()
     with ClockSampler(local_rank) as clk:
-        barrier()
-        e0.record(stream)
-        for _ in range(args.steps):
-            fe.stream_step()
-        e1.record(stream)
-        barrier()
-    ms_total = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
-    ms_step = ms_total / args.steps
-    value = world * B * args.steps / (ms_total * 1e-3)
+        t_dev, med_dev, p95_dev = timed(fe.stream_step)
+        n_stats = K
+        if K < 100:                              # SURVEY §8d asks for >= 100 timed iterations and the median: a second, longer region
+            n_stats = 100
+            _, med_dev, p95_dev = timed(fe.stream_step, n=n_stats)
+    ms_total = sharding.max_over_ranks(t_dev, dev)
+    ms_step = ms_total / K
+    med_dev = sharding.max_over_ranks(med_dev, dev)
+    value = frames_total * K / (ms_total * 1e-3)
 
     # ---- end-to-end through the public call with HOST buffers (`e2e`): H2D of every batch inside the timed region -------
     fe.stream_prime((host_pts, host_off), (host_pts, host_off))
-    for _ in range(3):
+    for _ in range(max(3, W_ // 2)):
         fe.stream_step(host_pts, host_off, host_cnt)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        fe.stream_step(host_pts, host_off, host_cnt)
-    fe.stream_wait_outputs()                      # the last read-back of the pillar offsets is inside the timed region
-    e1.record(stream)
-    barrier()
-    ms_e2e = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
-    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    t_e2e, med_e2e, _ = timed(lambda: fe.stream_step(host_pts, host_off, host_cnt), finish=fe.stream_wait_outputs)
+    ms_e2e = sharding.max_over_ranks(t_e2e, dev)
+    e2e_value = frames_total * K / (ms_e2e * 1e-3)
     h2d = host_pts.numel() * 4 + host_off.numel() * 4
     d2h = host_cnt.numel() * 4
     P_total = int(host_cnt[-1])
+    h2d_gbs_ranks = sharding.gather_scalars(h2d / (t_e2e / K * 1e-3) / 1e9, dev)
 
+    peak, peak_src = measured_peaks()
+    peaks_json = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC if N == POINTS_PER_FRAME else "vfe_frames_per_sec_%dk_pts" % (N // 1000), "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": K, "warmup": W_, "ms_per_step": ms_step, "higher_is_better": True, "scaling": WORKLOADS[args.config]["scaling"],
+        "vs_baseline": None,
         "dtype": "f32" if args.mem_precision == "fp32" else "f32 (bf16 tensor-core candidate GEMM in memory attention)",
-        "data": "synthetic", "config": workload_config(geom),
+        "data": "synthetic", "config": workload_config(geom, args, frames_total, world),
         "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps,
+                "ms_per_step": ms_e2e / K, "ms_per_step_median": sharding.max_over_ranks(med_e2e, dev),
+                "h2d_gbs_per_rank": [round(v, 2) for v in h2d_gbs_ranks],
                 "note": "host pinned points -> H2D (copy stream, overlapped with the previous batch) -> kernel chain -> D2H of "
                         "per-frame pillar offsets; BEV canvases stay in HBM for the 2D backbone, as in the reference "
-                        "(base_bev_backbone.py:281-282)"},
-        "gpu_launches": fe.kernel_launches_per_run() * args.steps,
+                        "(base_bev_backbone.py:281-282); h2d_gbs_per_rank = input bytes / step time (the link is shared with nothing else)"},
+        "gpu_launches": fe.kernel_launches_per_run() * K,
         "mem_precision": args.mem_precision,
+        "ms_per_step_median": med_dev, "ms_per_step_p95": p95_dev, "value_from_median_step": frames_total / (med_dev * 1e-3),
+        "median_over_steps": n_stats,
+        "latency_ms_streaming": 3 * ms_step,
         "ms_per_step_single_stream": ms_serial,
-        "value_single_stream": world * B / (ms_serial * 1e-3),
+        "value_single_stream": frames_total / (ms_serial * 1e-3),
+        "numa": numa,
     }
 
     if rank == 0:
         # ---- per-kernel timing (eager, CUDA events between stages, same stream) -> roofline --------------------
-        per = {"voxelize": 0.0, "pfn": 0.0, "mem_attn": 0.0, "bev_fill": 0.0}
+        per = {"voxelize": [], "pfn": [], "mem_attn": [], "bev_fill": []}
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         vox = p.vox
         nP = vox.n_pillars_dev
-        reps = min(args.steps, 20)
-        for it in range(reps + 2):
+        reps = min(max(K, 20), 100)
+        from hvpr_b200 import _lib
+        for it in range(reps + 3):
             evs[0].record(stream)
             fe.voxelizer.run(p.points, p.frame_offsets, B, N, out=vox)
             evs[1].record(stream)
@@ -440,23 +676,27 @@ def run_gpu_arm(args):
             evs[2].record(stream)
             fe.map_to_bev_module.memory.run(p.pillar_features, 20, nP, out=p.readout)
             evs[3].record(stream)
-            from hvpr_b200 import _lib
             _lib.check(_lib.lib().hvpr_bev_fill(_lib.ptr(p.pillar_features), 64, _lib.ptr(p.readout), 64,
                                                 _lib.ptr(p.pillar_scale), 32, _lib.ptr(vox.cell_map), B, nx, ny,
                                                 _lib.ptr(p.spatial), _lib.ptr(p.spatial_scale), None, _lib.cur_stream()))
             evs[4].record(stream)
             torch.cuda.synchronize()
-            if it >= 2:
+            if it >= 3:
                 for i, k in enumerate(per):
-                    per[k] += evs[i].elapsed_time(evs[i + 1]) / reps
+                    per[k].append(evs[i].elapsed_time(evs[i + 1]))
+        per = {k: statistics.median(v) for k, v in per.items()}
         K_total = int(vox.num_points[:P_total].sum())
         alg = algorithmic_bytes(N, P_total / B, K_total / B, nx, ny)
-        peak, peak_src = measured_peaks()
         kern = {}
         for k in per:
             gbs = alg[k] * B / (per[k] * 1e-3) / 1e9
-            kern[k] = {"ms": per[k], "alg_bytes": int(alg[k] * B), "gbs": gbs, "frac_hbm": gbs / peak}
+            kern[k] = {"ms": per[k], "alg_bytes": int(alg[k] * B), "gbs": gbs, "frac_hbm": gbs / peak, "frac_hbm_nominal": gbs / NOMINAL_HBM_GBS}
+        flops = 256000.0 * P_total
+        tf = flops / (per["mem_attn"] * 1e-3) / 1e12
+        bf16_peak = peaks_json.get("bf16_tflops", 1590.0)
+        kern["mem_attn"].update(gflop=flops / 1e9, tflops=tf, frac_tensor=tf / bf16_peak, frac_tensor_nominal=tf / NOMINAL_BF16_TFLOPS)
         line["kernels"] = kern
+        line["kernels_note"] = "median of %d eager launches per stage, CUDA events on the launching stream" % reps
         line["pillars_per_frame"] = P_total / B
         line["kept_points_per_frame"] = K_total / B
         dom = max(per, key=lambda k: per[k])
@@ -465,30 +705,51 @@ def run_gpu_arm(args):
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(dom)
         if dom == "mem_attn" and args.mem_precision != "fp32":
-            flops = 256000.0 * P_total
-            line["roofline"] = {"bound": "tensor", "kernel": dom, "achieved": flops / (per[dom] * 1e-3) / 1e12,
-                                "peak": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]
-                                if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0,
-                                "unit": "TFLOP/s", "traffic": traffic}
-            line["roofline"]["frac"] = line["roofline"]["achieved"] / line["roofline"]["peak"]
+            line["roofline"] = {"bound": "tensor", "kernel": dom, "achieved": tf, "peak": bf16_peak, "unit": "TFLOP/s", "frac": tf / bf16_peak,
+                                "frac_nominal": tf / NOMINAL_BF16_TFLOPS, "traffic": traffic,
+                                "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks_json else "fallback (B200_PROFILING.md)"}
         else:
             line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak,
-                                "unit": "GB/s", "frac": kern[dom]["frac_hbm"], "traffic": traffic, "peak_source": peak_src}
+                                "unit": "GB/s", "frac": kern[dom]["frac_hbm"], "frac_nominal": kern[dom]["frac_hbm_nominal"],
+                                "traffic": traffic, "peak_source": peak_src}
         total_alg = sum(alg.values()) * B
         line["path_roofline"] = {"alg_bytes_per_step": int(total_alg), "achieved_gbs": total_alg / (ms_step * 1e-3) / 1e9,
-                                 "frac_hbm": total_alg / (ms_step * 1e-3) / 1e9 / peak}
+                                 "frac_hbm": total_alg / (ms_step * 1e-3) / 1e9 / peak,
+                                 "frac_hbm_nominal": total_alg / (ms_step * 1e-3) / 1e9 / NOMINAL_HBM_GBS}
+        # ---- library baseline: the reference's formulation through cuBLAS / ATen on this GPU -------------------------------
+        if world == 1 and not args.no_library_baseline:
+            try:
+                lb = library_baseline(geom, vox, P_total, B, w, dev)
+                lb["speedup_of_hand_written_kernels"] = {"pfn": lb["ms"]["pfn"] / per["pfn"], "mem_attn": lb["ms"]["mem_attn"] / per["mem_attn"],
+                                                        "bev_fill": lb["ms"]["bev_fill"] / per["bev_fill"] if lb["ms"]["bev_fill"] > 0 else None,
+                                                        "pfn+mem_attn+bev_fill": lb["ms_pfn_mem_bev"] / (per["pfn"] + per["mem_attn"] + per["bev_fill"])}
+                line["library_baseline"] = lb
+            except Exception as e:
+                line["library_baseline"] = {"error": repr(e)[:300]}
         # ---- next row N1: BaseBEVBackbone_Scale on the tcgen05 conv kernel, reported beside the headline ----
-        if world == 1 and not args.no_backbone:
+        if world == 1 and not args.no_backbone and B <= 8:
             try:
                 line["next_rows"] = {"bev_backbone": bench_backbone(geom, w, host_pts, host_off, B, N, dev, args.mem_precision)}
             except Exception as e:   # the headline line must survive a failure of the widened row
                 line["next_rows"] = {"bev_backbone": {"error": repr(e)[:300]}}
         # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ---------------------------
         if world == 1 and not args.no_cpu_baseline:
-            fps, ms, ncores = cpu_reference_run(geom, frames, w, steps=3, warmup=1, frames_per_step=2)
-            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": ncores, "kind": "port",
-                                    "sample": "3 steps x 2 frames of the same 8-frame batch (C voxelizer 1 thread/frame + "
-                                              "torch CPU VFE/memory/scatter on all cores)"}
+            def gpu_check(fs):
+                q = fe.plan(len(fs), sum(len(f) for f in fs), max(len(f) for f in fs), use_graph=False)
+                q.points.copy_(torch.from_numpy(np.ascontiguousarray(np.concatenate(fs, 0))))
+                q.frame_offsets.copy_(torch.tensor(np.r_[0, np.cumsum([len(f) for f in fs])], dtype=torch.int32))
+                fe.run(); torch.cuda.synchronize()
+                Pq = int(q.vox.voxel_offsets[-1])
+                return {"coords": q.vox.coords[:Pq], "num_points": q.vox.num_points[:Pq], "pillar_features": q.pillar_features[:Pq],
+                        "readout": q.readout[:Pq], "spatial_scale": q.spatial_scale}
+            r = cpu_reference_run(geom, frames, w, steps=3, warmup=1, frames_per_step=2, components=True, gpu_check=gpu_check)
+            line["cpu_baseline"] = {"value": r["fps"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                    "sample": "3 steps x 2 frames of the same batch (C voxelizer 1 thread/frame, 4 workers + "
+                                              "torch CPU VFE/memory/scatter on all cores)",
+                                    "what": "oracle/ port: the reference's own torch CPU ops (pinned bit-exactly on its modules where the reference "
+                                            "tree exists) + a C restatement of the spconv voxel loop; the reference ships no compilable source",
+                                    "components": r.get("components")}
+            line["parity_sample"] = r.get("parity_sample")
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -499,8 +760,11 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--dist", default=DIST, choices=["L", "U"], help="synthetic frame distribution (SURVEY.md Appendix A)")
+    ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mem-precision", default=os.environ.get("HVPR_MEM_PRECISION", "bf16_rescore"), choices=["fp32", "bf16_rescore"])
     ap.add_argument("--no-graph", action="store_true")

@@ -37,7 +37,10 @@ constexpr int kBevThreads = 128;   // small blocks: they slot in beside the regi
 // paid the map latency plus a block launch and the fill dropped below DRAM saturation (HvprLaunchCfg{2, 0}: 0.723 -> 0.682 ms
 // per streaming step).  Alone, one block per item (n_items blocks, the default) is faster — 0.202 vs 0.227-0.244 ms: the
 // hardware block scheduler balances occupied and empty items, the static grid stride does not.
-__global__ void __launch_bounds__(kBevThreads, 8) bev_fill_kernel(const __grid_constant__ BevArgs A,
+#ifndef HVPR_BEV_MINB
+#define HVPR_BEV_MINB 8
+#endif
+__global__ void __launch_bounds__(kBevThreads, HVPR_BEV_MINB) bev_fill_kernel(const __grid_constant__ BevArgs A,
                                                        const int32_t *__restrict__ cell_map, int64_t cells,
                                                        int xblocks, int n_frames, int64_t n_items) {
     const int64_t groups = cells >> 2;

@@ -566,7 +566,13 @@ __device__ __noinline__ void tail_medium_row(const float *__restrict__ prow, con
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-__global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(const float *__restrict__ pillars,
+#ifdef HVPR_K3_MAXREG
+// register cap below 65536 / kTcThreads: leaves room for the canvas-fill blocks of another batch beside the persistent CTA
+__global__ void __maxnreg__(HVPR_K3_MAXREG) mem_attn_tc_kernel(
+#else
+__global__ void __launch_bounds__(kTcThreads, 1) mem_attn_tc_kernel(
+#endif
+const float *__restrict__ pillars,
                                                                     const int32_t *__restrict__ n_pillars_dev,
                                                                     int64_t n_rows_max, const float *__restrict__ W,
                                                                     const uint8_t *__restrict__ Wpk, int M, int nchunks,

@@ -24,7 +24,7 @@ class HybridFrontEnd(torch.nn.Module):
     # HvprLaunchCfg (blocks_per_sm, variant) of the PFN inside the streaming graphs: the low-register variant leaves room for the fill blocks
     stream_pfn_knob = (2, 1)
     # HvprLaunchCfg of the canvas fill inside the streaming graphs (persistent blocks per SM; it shares the SMs with K1 / K2 there)
-    stream_bev_knob = (2, 0)
+    stream_bev_knob = None   # one block per item (round 2: the persistent form lost once the PFN blocks shrank; tools/dev/stream_probe.py)
     # where K1 of batch k+2 sits in the step: "fork" (own stream from the start of the step), "before_k3" / "after_k3" / "last" (main stream)
     stream_k1_order = "fork"
 

@@ -68,7 +68,7 @@ typedef struct HvprPfnWeights {
 
 /* Optional launch shape of hvpr_pfn / hvpr_bev_fill, passed with the call (NULL = defaults).  Replaces the round-1
  * process-global hvpr_tune_* knobs: two front ends in one process can no longer race on them.
- *   hvpr_pfn:      blocks_per_sm 1..3 persistent blocks of five warps per SM (0 = default 2: what shared memory admits); variant 0 = W1a tensor-core fragments in
+ *   hvpr_pfn:      blocks_per_sm 1..3 persistent blocks of four warps per SM (0 = default 2: what shared memory admits); variant 0 = W1a tensor-core fragments in
  *                  registers (fastest alone), 1 = fragments in shared memory (fewer registers: the canvas-fill blocks of
  *                  hvpr_bev_fill fit beside the PFN blocks in the streaming schedule)
  *   hvpr_bev_fill: blocks_per_sm 0 = one 128-thread block per work item (fastest alone), 1..16 = that many persistent

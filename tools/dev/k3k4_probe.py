@@ -1,6 +1,8 @@
 import sys, numpy as np, torch
 sys.path.insert(0, '.')
 from hvpr_b200 import _lib, synth
+v = sys.argv[1] if len(sys.argv) > 1 else ''
+if v: _lib.LIB_PATH = _lib.LIB_PATH.replace('libhvpr_b200.so', 'libhvpr_b200_%s.so' % v)
 from hvpr_b200.geometry import G2
 from hvpr_b200.frontend import HybridFrontEnd
 from oracle import hybrid
@@ -16,7 +18,7 @@ m = fe.map_to_bev_module
 def k3(): m.memory.run(p.pillar_features, 20, p.vox.n_pillars_dev, out=ro2)
 def k4():
     _lib.check(_lib.lib().hvpr_bev_fill(_lib.ptr(p.pillar_features), 64, _lib.ptr(p.readout), 64, _lib.ptr(p.pillar_scale), 32,
-               _lib.ptr(p.vox.cell_map), B, m.nx, m.ny, _lib.ptr(p.spatial), _lib.ptr(p.spatial_scale), None, _lib.cur_stream()))
+               _lib.ptr(p.vox.cell_map), B, m.nx, m.ny, _lib.ptr(p.spatial), _lib.ptr(p.spatial_scale), _lib.launch_cfg(K4CFG), _lib.cur_stream()))
 hi = torch.cuda.Stream(priority=-1); lo = torch.cuda.Stream()
 def timeit(fn, reps=20):
     for _ in range(3): fn()
@@ -27,7 +29,8 @@ def timeit(fn, reps=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 main = torch.cuda.current_stream()
-print("K3 alone", timeit(k3)); print("K4 alone", timeit(k4))
+K4CFG = None
+print("variant", v or "default", "K3 alone", round(timeit(k3), 4))
 def both(first_k3=True):
     hi.wait_stream(main); lo.wait_stream(main)
     if first_k3:
@@ -37,5 +40,6 @@ def both(first_k3=True):
         with torch.cuda.stream(lo): k4()
         with torch.cuda.stream(hi): k3()
     main.wait_stream(hi); main.wait_stream(lo)
-print("K3(hi) || K4(lo), K3 launched first", timeit(lambda: both(True)))
-print("K3(hi) || K4(lo), K4 launched first", timeit(lambda: both(False)))
+for cfg in (None, (1, 0), (2, 0), (4, 0)):
+    K4CFG = cfg
+    print("K4 cfg", cfg, "alone", round(timeit(k4), 4), "K3||K4 K3 first", round(timeit(lambda: both(True)), 4), "K4 first", round(timeit(lambda: both(False)), 4))

@@ -1,6 +1,8 @@
 import ctypes, sys, numpy as np, torch
 sys.path.insert(0, '.')
 from hvpr_b200 import _lib, synth
+v = sys.argv[1] if len(sys.argv) > 1 else ''
+if v: _lib.LIB_PATH = _lib.LIB_PATH.replace('libhvpr_b200.so', 'libhvpr_b200_%s.so' % v)
 from hvpr_b200.geometry import G2
 from hvpr_b200.frontend import HybridFrontEnd
 from oracle import hybrid
@@ -10,9 +12,9 @@ B, N = 8, 120000
 frames = synth.make_batch("L", N, G2.point_cloud_range, B)
 pts = torch.from_numpy(np.concatenate(frames, 0)).cuda(); off = torch.tensor(np.r_[0, np.cumsum([N] * B)], dtype=torch.int32).cuda()
 import itertools
-for ((bps, low), bev), order in itertools.product((((3, 1), 2), ((3, 1), 4), ((3, 1), 0)), ("fork", "before_k3", "after_k3", "last")):
+for ((bps, low), bev), order in itertools.product((((2, 1), 2), ((2, 0), 2), ((1, 0), 2), ((2, 1), 4), ((2, 0), 4), ((2, 1), 0), ((2, 0), 0), ((1, 0), 0)), ("fork",)):
     fe = HybridFrontEnd(G2).load_reference_weights(w)
-    fe.stream_pfn_knob = (bps, low); fe.stream_bev_knob = bev; fe.stream_k1_order = order
+    fe.stream_pfn_knob = (bps, low); fe.stream_bev_knob = (bev, 0) if bev else None; fe.stream_k1_order = order
     sp = fe.plan_stream(B, B * N, N)
     for sl in range(3):
         sp.in_points[sl].copy_(pts); sp.in_offsets[sl].copy_(off)
