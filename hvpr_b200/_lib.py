@@ -20,7 +20,7 @@ SYMBOLS = [
     "hvpr_bev_fill", "hvpr_build_cell_map",
     "hvpr_conv_packed_bytes", "hvpr_conv_pack_weights", "hvpr_conv2d", "hvpr_nchw_to_nhwc_bf16", "hvpr_attention_gate",
     "hvpr_bev_fill_nhwc_bf16", "hvpr_head_decode",
-    "hvpr_post_process_workspace_bytes", "hvpr_post_process",
+    "hvpr_post_process_workspace_bytes", "hvpr_post_process", "hvpr_boxes_iou3d",
 ]
 
 OVERFLOW = {"continue": 0, "break": 1}
@@ -131,6 +131,8 @@ def lib():
     L.hvpr_post_process.restype = c_int
     L.hvpr_post_process.argtypes = [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_float, c_int, c_int, c_float,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    L.hvpr_boxes_iou3d.restype = c_int
+    L.hvpr_boxes_iou3d.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]
     L.hvpr_head_decode.restype = c_int
     L.hvpr_head_decode.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                    c_float, c_float, c_void_p, c_void_p, c_void_p]

@@ -340,8 +340,35 @@ __global__ void __launch_bounds__(64) pp_reduce_kernel(const float *__restrict__
     if (t == 0) out_count[f] = s_kept;
 }
 
+// pairwise 3-D IoU of upright boxes [x, y, z, dx, dy, dz, heading] (z = box centre): rotated-BEV overlap x height overlap over the
+// union volume — the published boxes_iou3d_gpu the reference calls from generate_recall_record (detector3d_template.py:277-310)
+__global__ void __launch_bounds__(256) pp_iou3d_kernel(const float *__restrict__ a, int n, const float *__restrict__ b, int m,
+                                                       float *__restrict__ iou) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n * m) return;
+    const float *pa = a + (i / m) * 7, *pb = b + (i % m) * 7;
+    const PpRect ra = pp_rect(pa), rb = pp_rect(pb);
+    float inter = 0.0f;
+    const float ddx = ra.cx - rb.cx, ddy = ra.cy - rb.cy;
+    const float rsum2 = ra.rad2 + rb.rad2 + 2.0f * sqrtf(ra.rad2 * rb.rad2);
+    if (ddx * ddx + ddy * ddy <= rsum2) inter = pp_intersection(ra, rb);
+    const float top = fminf(pa[2] + 0.5f * pa[5], pb[2] + 0.5f * pb[5]), bot = fmaxf(pa[2] - 0.5f * pa[5], pb[2] - 0.5f * pb[5]);
+    const float o3d = inter * fmaxf(top - bot, 0.0f);
+    const float va = pa[3] * pa[4] * pa[5], vb = pb[3] * pb[4] * pb[5];
+    iou[i] = o3d / fmaxf(va + vb - o3d, 1e-6f);
+}
+
 }  // namespace hvpr
 using namespace hvpr;
+
+extern "C" int hvpr_boxes_iou3d(const float *boxes_a, int n, const float *boxes_b, int m, float *iou, void *stream_) {
+    if (n < 0 || m < 0) return HVPR_ERR_ARG;
+    if (n == 0 || m == 0) return HVPR_OK;
+    if (!boxes_a || !boxes_b || !iou) return HVPR_ERR_ARG;
+    pp_iou3d_kernel<<<(unsigned)ceil_div64((int64_t)n * m, 256), 256, 0, (cudaStream_t)stream_>>>(boxes_a, n, boxes_b, m, iou);
+    HVPR_CHECK_LAUNCH();
+    return HVPR_OK;
+}
 
 extern "C" size_t hvpr_post_process_workspace_bytes(int n_frames, int64_t n_boxes) {
     if (n_frames <= 0 || n_boxes <= 0) return 0;

@@ -232,6 +232,10 @@ int hvpr_post_process(const float *cls_preds, const float *box_preds, int n_fram
                       int cls_normalized, float score_thresh, int nms_pre_max, int nms_post_max, float nms_thresh,
                       float *out_boxes, float *out_scores, int32_t *out_labels, int32_t *out_index, int32_t *out_count,
                       void *workspace, size_t workspace_bytes, void *stream);
+/* Pairwise 3-D IoU (n, m) of boxes [x, y, z, dx, dy, dz, heading] (z = centre): the boxes_iou3d_gpu of the reference's absent iou3d_nms
+ * op, used by generate_recall_record (detector3d_template.py:277-310).                                                              */
+int hvpr_boxes_iou3d(const float *boxes_a, int n, const float *boxes_b, int m, float *iou, void *stream);
+
 
 #ifdef __cplusplus
 }

@@ -102,3 +102,42 @@ def random_detections(seed, n, n_clusters=150, extent=(0.0, -39.68, 69.12, 39.68
     box[:, 6] = rng.uniform(-np.pi, np.pi, n)
     cls = rng.normal(-2.5, 1.5, (n, 1)).astype(np.float32)
     return cls, box
+
+
+def multi_classes_frame(cls_preds, box_preds, cfg=POST_CFG, normalized=False):
+    """model_nms_utils.multi_classes_nms (:28-65) for one frame and one head: class by class the class-agnostic procedure on that class's
+    score column; labels k + 1 (see hvpr_b200/post_process.py for the reference's off-by-one in the single-head label mapping)."""
+    boxes, scores, labels = [], [], []
+    for k in range(cls_preds.shape[1]):
+        sel, sc, _ = post_process_frame(cls_preds[:, k:k + 1], box_preds, cfg, normalized)
+        boxes.append(box_preds[sel]); scores.append(sc); labels.append(np.full(len(sel), k + 1, np.int64))
+    return np.concatenate(boxes, 0), np.concatenate(scores, 0), np.concatenate(labels, 0)
+
+
+def iou3d(b1, b2):
+    """published boxes_iou3d_gpu: rotated-BEV overlap x height overlap over the union volume (z = box centre), float64"""
+    inter_bev = iou_bev(b1, b2)
+    a1, a2 = b1[3] * b1[4], b2[3] * b2[4]
+    inter = inter_bev * (a1 + a2) / (1.0 + inter_bev)                       # invert iou = i / (a1 + a2 - i)
+    top = min(b1[2] + b1[5] / 2, b2[2] + b2[5] / 2)
+    bot = max(b1[2] - b1[5] / 2, b2[2] - b2[5] / 2)
+    o3d = inter * max(top - bot, 0.0)
+    return o3d / max(b1[3] * b1[4] * b1[5] + b2[3] * b2[4] * b2[5] - o3d, 1e-6)
+
+
+def recall_record(pred_boxes, gt_boxes, thresh_list=(0.3, 0.5, 0.7)):
+    """generate_recall_record (detector3d_template.py:277-318), single-stage case, one frame -> {'gt': n, 'rcnn_t': count}"""
+    gt = np.asarray(gt_boxes, np.float64)
+    k = len(gt) - 1
+    while k > 0 and gt[k].sum() == 0:
+        k -= 1
+    gt = gt[:k + 1]
+    out = {"gt": len(gt)}
+    for t in thresh_list:
+        out["rcnn_%s" % str(t)] = 0
+    if len(gt) and len(pred_boxes):
+        m = np.array([[iou3d(np.asarray(p, np.float64), g) for g in gt] for p in pred_boxes])
+        best = m.max(0)
+        for t in thresh_list:
+            out["rcnn_%s" % str(t)] = int((best > t).sum())
+    return out

@@ -259,9 +259,16 @@ def test_post_process_abi_and_oracle_geometry_without_gpu():
     assert L.hvpr_post_process(buf, buf, 1, 10, 1, 0, 0.1, 8192, 500, 0.1, buf, buf, buf, buf, buf, buf, 64, None) == -2   # pre > 4096
     assert L.hvpr_post_process(buf, buf, 1, 10, 1, 0, 0.1, 4096, 500, 0.1, buf, buf, buf, buf, buf, buf, 64, None) == -3   # workspace
     from hvpr_b200.post_process import PostProcessor
+    assert PostProcessor(config.Cfg(SCORE_THRESH=0.1, NMS_CONFIG=config.Cfg(MULTI_CLASSES_NMS=True, NMS_THRESH=0.1, NMS_PRE_MAXSIZE=4096,
+                                                                            NMS_POST_MAXSIZE=500))).multi_classes      # round 2: built
     with pytest.raises(NotImplementedError):
-        PostProcessor(config.Cfg(SCORE_THRESH=0.1, NMS_CONFIG=config.Cfg(MULTI_CLASSES_NMS=True, NMS_THRESH=0.1, NMS_PRE_MAXSIZE=4096,
+        PostProcessor(config.Cfg(SCORE_THRESH=0.1, NMS_CONFIG=config.Cfg(MULTI_CLASSES_NMS=False, NMS_THRESH=0.1, NMS_PRE_MAXSIZE=8192,
                                                                          NMS_POST_MAXSIZE=500)))
+    # 3-D IoU oracle: two unit-height boxes, half overlapping in x, same z -> 1/3; shifted by half their height -> (1/2 * 1/2) / (2 - 1/4)
+    b1z, b2z = np.array([0, 0, 0, 4, 2, 1, 0.0]), np.array([2, 0, 0.5, 4, 2, 1, 0.0])
+    from oracle import post_process as op3
+    assert abs(op3.iou3d(b1z, b1z + np.array([2, 0, 0, 0, 0, 0, 0])) - 1.0 / 3.0) < 1e-9
+    assert abs(op3.iou3d(b1z, b2z) - (4 * 0.5) / (16 - 2)) < 1e-9
     # oracle geometry: known answers of the rotated IoU
     from oracle import post_process as op
     b = np.array([0, 0, 0, 4, 2, 1, 0.3])

@@ -187,3 +187,57 @@ def test_nms_exact_duplicates_flipped_duplicates_and_shared_edge_lines():
     sel2 = op.post_process_frame(cls, box, cfg2)[0]
     got2 = _run([cls], [box], cfg2)[0]["pred_anchor_index"].cpu().numpy()
     assert got2.tolist() == sel2.tolist() and set(got2.tolist()) == exp
+
+
+def test_multi_classes_nms_branch_matches_oracle():
+    """MULTI_CLASSES_NMS (detector3d_template.py:214-233, model_nms_utils.py:28-65): class-by-class NMS, results concatenated."""
+    from hvpr_b200.config import Cfg
+    from hvpr_b200.post_process import PostProcessor
+    from oracle import post_process as op
+    cfg = dict(SCORE_THRESH=0.1, NMS_PRE_MAXSIZE=1000, NMS_POST_MAXSIZE=50, NMS_THRESH=0.1)
+    rng = np.random.default_rng(5)
+    frames = []
+    for seed in (60, 61):
+        cls, box = op.random_detections(seed, 6000, n_clusters=60)
+        cls3 = np.concatenate([cls, rng.normal(-2.5, 1.5, (6000, 2)).astype(np.float32)], 1)
+        frames.append((cls3, box))
+    pp = PostProcessor(Cfg(SCORE_THRESH=cfg["SCORE_THRESH"], NMS_CONFIG=Cfg(MULTI_CLASSES_NMS=True, NMS_TYPE="nms_gpu", NMS_THRESH=cfg["NMS_THRESH"],
+                                                                          NMS_PRE_MAXSIZE=cfg["NMS_PRE_MAXSIZE"], NMS_POST_MAXSIZE=cfg["NMS_POST_MAXSIZE"])))
+    out = pp.post_processing({"batch_cls_preds": torch.from_numpy(np.stack([f[0] for f in frames])).cuda(),
+                              "batch_box_preds": torch.from_numpy(np.stack([f[1] for f in frames])).cuda(), "cls_preds_normalized": False})
+    torch.cuda.synchronize()
+    for (cls3, box), o in zip(frames, out):
+        rb, rs, rl = op.multi_classes_frame(cls3, box, cfg)
+        assert np.array_equal(o["pred_labels"].cpu().numpy(), rl)
+        assert np.array_equal(o["pred_boxes"].cpu().numpy(), rb)
+        assert np.allclose(o["pred_scores"].cpu().numpy(), rs, rtol=1e-6, atol=1e-7)
+        assert set(rl.tolist()) == {1, 2, 3}
+
+
+def test_boxes_iou3d_and_recall_record_match_oracle():
+    """generate_recall_record (detector3d_template.py:277-318): pairwise 3-D IoU + per-threshold recall counts, zero-padded gt rows stripped."""
+    from hvpr_b200 import _lib
+    from hvpr_b200.config import Cfg
+    from hvpr_b200.post_process import PostProcessor
+    from oracle import post_process as op
+    rng = np.random.default_rng(9)
+    gt = np.zeros((12, 8), np.float32)
+    gt[:9, 0] = rng.uniform(5, 60, 9); gt[:9, 1] = rng.uniform(-30, 30, 9); gt[:9, 2] = rng.uniform(-1.5, -0.5, 9)
+    gt[:9, 3:6] = [3.9, 1.6, 1.56]; gt[:9, 6] = rng.uniform(-3, 3, 9); gt[:9, 7] = 1
+    pred = np.concatenate([gt[:6, :7] + rng.normal(0, 0.08, (6, 7)).astype(np.float32),          # close hits
+                           gt[6:8, :7] + np.array([1.2, 0.5, 0.3, 0, 0, 0, 0.4], np.float32),    # poor hits
+                           rng.uniform(-5, 5, (5, 7)).astype(np.float32) + np.array([30, 0, -1, 4, 2, 1.5, 0], np.float32)], 0).astype(np.float32)
+    pred[:, 3:6] = np.abs(pred[:, 3:6]) + 0.1
+    a, b = torch.from_numpy(pred).cuda(), torch.from_numpy(gt[:9, :7].copy()).cuda()
+    iou = torch.empty((len(pred), 9), device="cuda")
+    _lib.check(_lib.lib().hvpr_boxes_iou3d(_lib.ptr(a), len(pred), _lib.ptr(b), 9, _lib.ptr(iou), _lib.cur_stream()))
+    ref = np.array([[op.iou3d(p.astype(np.float64), g.astype(np.float64)) for g in gt[:9, :7]] for p in pred])
+    assert np.abs(iou.cpu().numpy() - ref).max() <= 2e-5
+    pp = PostProcessor(Cfg(SCORE_THRESH=0.1, RECALL_THRESH_LIST=[0.3, 0.5, 0.7],
+                           NMS_CONFIG=Cfg(MULTI_CLASSES_NMS=False, NMS_TYPE="nms_gpu", NMS_THRESH=0.1, NMS_PRE_MAXSIZE=4096, NMS_POST_MAXSIZE=500)))
+    rec = pp.generate_recall_record(a, {}, 0, {"gt_boxes": torch.from_numpy(gt).cuda()[None]}, [0.3, 0.5, 0.7])
+    exp = op.recall_record(pred, gt[:, :7])
+    assert rec["gt"] == exp["gt"] == 9
+    for t in (0.3, 0.5, 0.7):
+        assert rec["rcnn_%s" % t] == exp["rcnn_%s" % t], (t, rec, exp)
+    assert rec["rcnn_0.3"] >= 6 and pp.generate_recall_record(a, {}, 0, {}, None) == {}
