@@ -38,8 +38,13 @@ class MixAnchor_Memory(nn.Module):
     @torch.no_grad()
     def forward(self, batch_dict):
         """batch_dict['points'] (sum N, 5) [b,x,y,z,r] on the GPU + 'batch_size' -> (pred_dicts, recall_dicts, batch_dict),
-        the eval return of pointpillar.py:52-56 (recall bookkeeping is not computed: recall_dicts is empty)."""
+        the eval return of pointpillar.py:52-56; recall_dicts follows generate_recall_record (detector3d_template.py:277-318) when
+        batch_dict carries 'gt_boxes', else it is empty."""
         if self.training:
             raise NotImplementedError("hvpr_b200.MixAnchor_Memory implements the eval branch (pointpillar.py:52-56) only")
         batch_dict = self._pipe(batch_dict)
-        return batch_dict["pred_dicts"], {}, batch_dict
+        recall = {}
+        if "gt_boxes" in batch_dict:
+            for i, p in enumerate(batch_dict["pred_dicts"]):
+                recall = self._pipe.post.generate_recall_record(p["pred_boxes"], recall, i, batch_dict)
+        return batch_dict["pred_dicts"], recall, batch_dict

@@ -10,6 +10,8 @@ host synchronisation happens inside `run()`, and the kernel chain is captured in
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -25,6 +27,8 @@ class HybridFrontEnd(torch.nn.Module):
     stream_pfn_knob = (2, 1)
     # HvprLaunchCfg of the canvas fill inside the streaming graphs (persistent blocks per SM; it shares the SMs with K1 / K2 there)
     stream_bev_knob = None   # one block per item (round 2: the persistent form lost once the PFN blocks shrank; tools/dev/stream_probe.py)
+    if os.environ.get("HVPR_STREAM_BEV_BPS"):          # dev override for tools/dev probes
+        stream_bev_knob = (int(os.environ["HVPR_STREAM_BEV_BPS"]), 0) if int(os.environ["HVPR_STREAM_BEV_BPS"]) else None
     # where K1 of batch k+2 sits in the step: "fork" (own stream from the start of the step), "before_k3" / "after_k3" / "last" (main stream)
     stream_k1_order = "fork"
 
