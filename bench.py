@@ -445,6 +445,34 @@ def bench_backbone(geom, w, host_pts, host_off, B, N, dev, mem_precision, steps=
         out["dense_head"] = {"error": repr(e)[:200]}
     # library baseline on the same box: the same network through torch's own layers (cuDNN, bf16 channels_last, eager).
     # The module's nn.Sequential parameter containers are ordinary torch layers, so they can simply be called.
+    # accuracy of the bf16-operand backbone at FULL size against the same network in fp32 (torch layers, TF32 off) on the same
+    # (bf16-quantised) canvases, one frame: north_star gives no tolerance for this row; the tests state 2e-2 max-norm / 1e-2 L2
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+
+        def torch_forward(m, x, y):
+            ups, a = [], m.attention.spatial
+            for i in range(len(m.blocks)):
+                x = m.blocks[i](x)
+                y = m.scale_layers[i](y)
+                gate = torch.sigmoid(a.norm(a.conv(torch.cat((y.max(1, keepdim=True)[0], y.mean(1, keepdim=True)), 1))))
+                xa = x
+                for _ in range(m.sfm_layer_nums[i]):
+                    xa = gate * m.sfmblocks_down[i](xa) + xa
+                ups.append(m.deblocks[i](xa))
+            return torch.cat(ups, 1)
+        with torch.no_grad():
+            ours = bb.run_nhwc(p.x_nhwc[:1].contiguous(), p.y_nhwc[:1].contiguous(), 1, ny, nx).float().clone()
+            ref32 = torch_forward(bb, p.x_nhwc[:1, ..., :128].permute(0, 3, 1, 2).float().contiguous(),
+                                  p.y_nhwc[:1, ..., :32].permute(0, 3, 1, 2).float().contiguous())
+            d = (ours - ref32).double()
+            out["accuracy_vs_fp32"] = {"what": "spatial_features_2d of one G2-size frame: bf16-operand tcgen05 backbone vs the same torch layers in fp32 "
+                                               "(cuDNN, TF32 off) on identical canvases", "max_abs_err_over_max_abs_ref": float(d.abs().max() / ref32.abs().max()),
+                                       "rel_l2": float(d.norm() / ref32.double().norm()), "stated_tolerance": {"max_norm": 2e-2, "rel_l2": 1e-2}}
+            del ours, ref32, d
+    except Exception as e:
+        out["accuracy_vs_fp32"] = {"error": repr(e)[:200]}
     try:
         torch.backends.cudnn.benchmark = True
         mb = bb.to(memory_format=torch.channels_last).bfloat16()
