@@ -349,3 +349,29 @@ def test_single_pass_assign_scan_model(n, tile):
         rank[t0:t0 + tile] = pa + np.cumsum(f) - f
         off[t0:t0 + tile] = pb + np.cumsum(c) - c
     assert (rank == np.cumsum(is_first) - is_first).all() and (off == np.cumsum(cnt) - cnt).all()
+
+
+def test_bench_workloads_partition_frames_and_numa_binding_is_harmless():
+    """bench.py host logic (no GPU): cfg3 splits its 64 frames frame-wise over the ranks (every frame exactly once, frame i -> rank
+    i mod W), cfg2 / cfg4 / cfg5 give every rank 8 distinct frames; bind_numa never raises and leaves a usable affinity."""
+    import argparse
+    import bench
+    for W in (1, 2, 4, 8):
+        seen = []
+        for r in range(W):
+            geom, ids, pts, total = bench.workload(argparse.Namespace(config="cfg3"), r, W)
+            assert total == 64 and pts == 120000 and geom.grid_size == (432, 496, 1)
+            assert ids == list(range(r, 64, W))
+            seen += ids
+        assert sorted(seen) == list(range(64))
+        for cfg, grid, npts in (("cfg2", (432, 496, 1), 120000), ("cfg4", (640, 640, 1), 300000), ("cfg5", (432, 496, 1), 120000)):
+            all_ids = [bench.workload(argparse.Namespace(config=cfg), r, W)[1] for r in range(W)]
+            assert all(len(i) == 8 for i in all_ids) and len({x for i in all_ids for x in i}) == 8 * W
+            g, _, p, total = bench.workload(argparse.Namespace(config=cfg), 0, W)
+            assert g.grid_size == grid and p == npts and total == 8 * W
+    before = os.sched_getaffinity(0)
+    info = bench.bind_numa(0, 8)
+    assert "numa_nodes" in info and len(os.sched_getaffinity(0)) >= 1
+    os.sched_setaffinity(0, before)
+    a = bench.algorithmic_bytes(120000, 25229, 102786, 432, 496)
+    assert a["voxelize"] == 16 * 120000 + 532 * 25229 and a["bev_fill"] == 4 * 160 * 432 * 496 + 4 * 432 * 496 + 640 * 25229
