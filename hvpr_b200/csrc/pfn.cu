@@ -31,6 +31,11 @@ constexpr int kPfnG = 32;        // pillars per task; a task belongs to ONE warp
 constexpr int kPfnXS = 20;       // row stride (floats) of the layer-0 activation staging: conflict-free fragment loads
 constexpr int kPfnYS = 72;       // row stride of the accumulator staging: conflict-free 64-bit fragment stores
 constexpr int kPfnMS = 64;       // row stride of the per-pillar running maxima of W1a.x (lane l owns columns 2l, 2l+1: conflict-free)
+// pillars per sub-task: with the W1a fragments in registers (the stand-alone shape) the point pass and the epilogue run in two halves
+// of 16 pillars, so that the maxima buffer is 4 KB instead of 8 and THREE blocks of four warps fit an SM (0.154 -> 0.139 ms alone);
+// the low-register shape used beside the canvas fill in the streaming schedule keeps whole tasks (its two blocks per SM are set
+// by the fill's needs, and halves only add partially filled 32-point chunks: 0.180 -> 0.195 ms)
+template <bool kFragRegs> struct PfnSub { static constexpr int kH = kFragRegs ? 16 : 32; };
 
 struct PfnParams {
     HvprPfnWeights w;
@@ -39,7 +44,8 @@ struct PfnParams {
 };
 
 // private to one warp
-struct PfnWarpSmem {
+template <int kPfnH>
+struct PfnWarpSmemT {
     int poff[kPfnG + 1];
     int pid[32];                                // pillar of each staged point (-1: none)
     float mean[kPfnG][4];
@@ -47,12 +53,15 @@ struct PfnWarpSmem {
     alignas(16) uint32_t xmax[kPfnG][kPfnXS];   // running max of the layer-0 activations (>= 0: float bits order as uints)
     alignas(16) float xs[32][kPfnXS];           // layer-0 activations of the current 32 points, one row per point
     alignas(16) float ys[16][kPfnYS];           // W1a.x tile (16 points x 64 channels)
-    alignas(16) float m1[kPfnG][kPfnMS];        // running max over a pillar's points of W1a.x
+    alignas(16) float m1[kPfnH][kPfnMS];        // running max over a pillar's points of W1a.x, current half task
 };
-struct PfnSmem {
-    alignas(16) uint32_t bfrag[2][8][2][2][2][32];  // [W1a|W1b][n-tile][k-step][reg][hi|lo][lane] tf32 B fragments
+constexpr int kPfnFragWords = 8 * 2 * 2 * 2 * 32;   // one matrix: [n-tile][k-step][reg][hi|lo][lane] tf32 B fragments
+// kFragRegs: the W1a fragments live in registers, only W1b's sit in shared memory (8 KB instead of 16)
+template <bool kFragRegs>
+struct PfnSmemT {
+    alignas(16) uint32_t bfrag[kFragRegs ? 1 : 2][8][2][2][2][32];  // [W1a|W1b] or [W1b]
     float b1s[64];                                  // layer-1 BN shift
-    PfnWarpSmem w[kPfnWarps];
+    PfnWarpSmemT<PfnSub<kFragRegs>::kH> w[kPfnWarps];
 };
 
 __device__ __forceinline__ int find_pillar(const int *poff, int q) {
@@ -92,7 +101,7 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) 
 // ever touches (lane l owns channels 2l, 2l+1 and carries its running value in registers across m-tiles), and the only
 // synchronisation is __syncwarp.
 template <bool kScale, bool kFragRegs>
-__global__ void __launch_bounds__(kPfnThreads, kFragRegs ? 2 : HVPR_PFN_LOWREG_MINB) pfn_kernel(const __grid_constant__ PfnParams P,
+__global__ void __launch_bounds__(kPfnThreads, kFragRegs ? 3 : HVPR_PFN_LOWREG_MINB) pfn_kernel(const __grid_constant__ PfnParams P,
                                                           const float *__restrict__ voxels,
                                                           const int32_t *__restrict__ num_points,
                                                           const int32_t *__restrict__ coords,
@@ -102,7 +111,9 @@ __global__ void __launch_bounds__(kPfnThreads, kFragRegs ? 2 : HVPR_PFN_LOWREG_M
                                                           float *__restrict__ feats, float *__restrict__ scale_out,
                                                           float *__restrict__ mask_out, const uint4 *__restrict__ frag_image) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    using PfnSmem = PfnSmemT<kFragRegs>;
     PfnSmem &S = *reinterpret_cast<PfnSmem *>(smem_raw);
+    constexpr int kB = kFragRegs ? 0 : 1;               // index of W1b's fragments in S.bfrag
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const int gid = lane >> 2, tig = lane & 3;          // mma fragment coordinates
     int64_t nP = n_pillars_dev ? (int64_t)*n_pillars_dev : n_rows_max;
@@ -112,36 +123,51 @@ __global__ void __launch_bounds__(kPfnThreads, kFragRegs ? 2 : HVPR_PFN_LOWREG_M
 
     // ---- once per (persistent) block: tf32 hi/lo B fragments of W1a and W1b ------------------------------------------
     // B(k, n) = W[n][k];  b0: k = 8*ks + tig, b1: k = 8*ks + tig + 4;  n = 8*nt + gid
+    uint32_t wah[kFragRegs ? 8 : 1][2][2], wal[kFragRegs ? 8 : 1][2][2];     // W1a fragments in registers (kFragRegs)
     if (frag_image) {
-        // packed once per weight version by hvpr_pfn_pack: a coalesced 16 KB copy.  Building the image here reads the by-value weights
+        // packed once per weight version by hvpr_pfn_pack: coalesced copies.  Building the image here reads the by-value weights
         // with a different constant address per lane (serialised, cold constant cache): ncu put 11 % of the kernel's stall samples
         // on that prologue, repeated by every block
+        const uint4 *src = frag_image + (kFragRegs ? kPfnFragWords / 4 : 0);
         uint4 *dst = reinterpret_cast<uint4 *>(&S.bfrag[0][0][0][0][0][0]);
-        for (int e = t; e < (int)(sizeof(S.bfrag) / 16); e += kPfnThreads) dst[e] = __ldg(frag_image + e);
+        for (int e = t; e < (int)(sizeof(S.bfrag) / 16); e += kPfnThreads) dst[e] = __ldg(src + e);
+        if (kFragRegs) {
+            const uint32_t *img = reinterpret_cast<const uint32_t *>(frag_image);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                    for (int rg = 0; rg < 2; ++rg) {
+                        const int base = (((nt * 2 + ks) * 2 + rg) * 2) * 32 + lane;
+                        wah[kFragRegs ? nt : 0][ks][rg] = __ldg(img + base); wal[kFragRegs ? nt : 0][ks][rg] = __ldg(img + base + 32);
+                    }
+        }
     } else {
-        for (int e = t; e < 2 * 8 * 2 * 2 * 32; e += kPfnThreads) {
+        for (int e = t; e < 2 * kPfnFragWords / 2; e += kPfnThreads) {
             const int ln = e & 31, reg = (e >> 5) & 1, ks = (e >> 6) & 1, nt = (e >> 7) & 7, mat = e >> 10;
             const int nn = 8 * nt + (ln >> 2), kk = 8 * ks + (ln & 3) + 4 * reg;
+            if (kFragRegs && mat == 0) continue;
             const float wv = mat ? P.w.w1b[nn][kk] : P.w.w1a[nn][kk];
             uint32_t hi, lo;
             split_tf32(wv, hi, lo);
-            S.bfrag[mat][nt][ks][reg][0][ln] = hi;
-            S.bfrag[mat][nt][ks][reg][1][ln] = lo;
+            S.bfrag[kFragRegs ? 0 : mat][nt][ks][reg][0][ln] = hi;
+            S.bfrag[kFragRegs ? 0 : mat][nt][ks][reg][1][ln] = lo;
+        }
+        if (kFragRegs) {
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                    for (int rg = 0; rg < 2; ++rg)
+                        split_tf32(P.w.w1a[8 * nt + gid][8 * ks + tig + 4 * rg], wah[kFragRegs ? nt : 0][ks][rg], wal[kFragRegs ? nt : 0][ks][rg]);
         }
     }
     if (t < 64) S.b1s[t] = P.w.b1[t];
     __syncthreads();                                    // the only block barrier of the kernel
-    // W1a fragments live in registers for the whole (persistent) block: no shared-memory traffic in the MMA loop
-    uint32_t wah[kFragRegs ? 8 : 1][2][2], wal[kFragRegs ? 8 : 1][2][2];
-    if (kFragRegs) {
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-                for (int rg = 0; rg < 2; ++rg) { wah[nt][ks][rg] = S.bfrag[0][nt][ks][rg][0][lane]; wal[nt][ks][rg] = S.bfrag[0][nt][ks][rg][1][lane]; }
-    }
-    PfnWarpSmem &W = S.w[wid];
+    constexpr int kPfnH = PfnSub<kFragRegs>::kH;
+    PfnWarpSmemT<kPfnH> &W = S.w[wid];
     const int64_t warp0 = (int64_t)blockIdx.x * kPfnWarps + wid, nwarps = (int64_t)gridDim.x * kPfnWarps;
 
     for (int64_t grp = warp0; grp < ngroups; grp += nwarps) {
@@ -216,11 +242,6 @@ __global__ void __launch_bounds__(kPfnThreads, kFragRegs ? 2 : HVPR_PFN_LOWREG_M
                     padded ? make_uint4(__float_as_uint(P.rb0[4 * k4]), __float_as_uint(P.rb0[4 * k4 + 1]),
                                         __float_as_uint(P.rb0[4 * k4 + 2]), __float_as_uint(P.rb0[4 * k4 + 3]))
                            : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-            for (int c4 = 0; c4 < 16; ++c4)
-                *reinterpret_cast<float4 *>(&W.m1[lane][4 * c4]) =
-                    padded ? make_float4(P.v1[4 * c4], P.v1[4 * c4 + 1], P.v1[4 * c4 + 2], P.v1[4 * c4 + 3])
-                           : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         }
         // scale MLP on [n, |mean|, mean_xyz]  (pillar_vfe.py:213-216)
         if (kScale) {
@@ -252,15 +273,34 @@ __global__ void __launch_bounds__(kPfnThreads, kFragRegs ? 2 : HVPR_PFN_LOWREG_M
         }
         __syncwarp();
 
-        // ---- single pass over the real points of the task, 32 at a time, lane = point -------------------------------
-        int run_pl = -1;                                     // pillar whose running W1a.x maximum this lane carries
+        // ---- the task's two halves of 16 pillars: single pass over the half's real points, 32 at a time, lane = point ----
+        (void)total;
+#pragma unroll 1
+        for (int hf = 0; hf < kPfnG / kPfnH; ++hf) {
+        const int c_begin = W.poff[kPfnH * hf], c_end = W.poff[kPfnH * hf + kPfnH];
+        // seeds of this half's running maxima of W1a.x: the virtual zero-padded row when the pillar has padding, else the identity;
+        // lane = (pillar of the half, 32-channel half of its row)
+        {
+            // lane = (pillar of the sub-task, channel range): 16 pillars x 2 ranges of 32 channels, or 32 pillars x all 64 channels
+            constexpr int kRanges = 32 / kPfnH, kChan = 64 / kRanges;
+            const int pl_s = lane % kPfnH, cb0 = (lane / kPfnH) * kChan;
+            const int n_p = __shfl_sync(0xffffffffu, n, kPfnH * hf + pl_s);
+            const bool padded_p = n_p < T;
+#pragma unroll
+            for (int c4 = 0; c4 < kChan / 4; ++c4)
+                *reinterpret_cast<float4 *>(&W.m1[pl_s][cb0 + 4 * c4]) =
+                    padded_p ? make_float4(P.v1[cb0 + 4 * c4], P.v1[cb0 + 4 * c4 + 1], P.v1[cb0 + 4 * c4 + 2], P.v1[cb0 + 4 * c4 + 3])
+                             : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+        __syncwarp();
+        int run_pl = -1;                                     // pillar (of the half) whose running W1a.x maximum this lane carries
         float2 run = make_float2(-INFINITY, -INFINITY);      // channels (2*lane, 2*lane+1)
-        for (int c0 = 0; c0 < total; c0 += 32) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
             const int qpt = c0 + lane;
             // layer 0 (10 -> 16, ReLU) on CUDA cores, one point per lane
             float x0[16];
             int pl = -1;
-            if (qpt < total) {
+            if (qpt < c_end) {
                 pl = find_pillar(W.poff, qpt);
                 const int j = qpt - W.poff[pl];
                 const float4 v = __ldg(vox4 + PFN_ROW(pl) * T + j);
@@ -312,7 +352,7 @@ __global__ void __launch_bounds__(kPfnThreads, kFragRegs ? 2 : HVPR_PFN_LOWREG_M
             // W1a . x on the tensor cores, one 16-point m-tile at a time
 #pragma unroll 1
             for (int mt = 0; mt < 2; ++mt) {
-                if (c0 + 16 * mt >= total) break;           // warp-uniform: this 16-point m-tile holds no real point
+                if (c0 + 16 * mt >= c_end) break;           // warp-uniform: this 16-point m-tile holds no real point
                 uint32_t ahi[2][4], alo[2][4];
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
@@ -355,7 +395,7 @@ __global__ void __launch_bounds__(kPfnThreads, kFragRegs ? 2 : HVPR_PFN_LOWREG_M
                                     const float2 old = *m;
                                     *m = make_float2(fmaxf(old.x, run.x), fmaxf(old.y, run.y));
                                 }
-                                run_pl = W.pid[16 * mt + rb + r]; run = v[r];
+                                run_pl = W.pid[16 * mt + rb + r] - kPfnH * hf; run = v[r];
                             } else { run.x = fmaxf(run.x, v[r].x); run.y = fmaxf(run.y, v[r].y); }
                         }
                     }
@@ -370,44 +410,46 @@ __global__ void __launch_bounds__(kPfnThreads, kFragRegs ? 2 : HVPR_PFN_LOWREG_M
         }
         __syncwarp();
 
-        // ---- per pillar: c = b1 + W1b.x_max (tensor cores) ; pillar_features = ReLU(max + c) --------------------
+        // ---- the half's 16 pillars: c = b1 + W1b.x_max (tensor cores) ; pillar_features = ReLU(max + c) --------------------
         {
             const float (*xm)[kPfnXS] = reinterpret_cast<const float (*)[kPfnXS]>(W.xmax);
 #pragma unroll 1
-            for (int mt = 0; mt < 2; ++mt) {
-                uint32_t ahi[2][4], alo[2][4];
+            for (int mt = hf * (kPfnH / 16); mt < (hf + 1) * (kPfnH / 16); ++mt) {     // m-tiles (16 pillars each) of this sub-task
+            uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                split_tf32(xm[16 * mt + gid][8 * ks + tig], ahi[ks][0], alo[ks][0]);
+                split_tf32(xm[16 * mt + gid + 8][8 * ks + tig], ahi[ks][1], alo[ks][1]);
+                split_tf32(xm[16 * mt + gid][8 * ks + tig + 4], ahi[ks][2], alo[ks][2]);
+                split_tf32(xm[16 * mt + gid + 8][8 * ks + tig + 4], ahi[ks][3], alo[ks][3]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
-                    split_tf32(xm[16 * mt + gid][8 * ks + tig], ahi[ks][0], alo[ks][0]);
-                    split_tf32(xm[16 * mt + gid + 8][8 * ks + tig], ahi[ks][1], alo[ks][1]);
-                    split_tf32(xm[16 * mt + gid][8 * ks + tig + 4], ahi[ks][2], alo[ks][2]);
-                    split_tf32(xm[16 * mt + gid + 8][8 * ks + tig + 4], ahi[ks][3], alo[ks][3]);
+                    const uint32_t bh0 = S.bfrag[kB][nt][ks][0][0][lane], bl0 = S.bfrag[kB][nt][ks][0][1][lane];
+                    const uint32_t bh1 = S.bfrag[kB][nt][ks][1][0][lane], bl1 = S.bfrag[kB][nt][ks][1][1][lane];
+                    mma_tf32(c, alo[ks], bh0, bh1);
+                    mma_tf32(c, ahi[ks], bl0, bl1);
+                    mma_tf32(c, ahi[ks], bh0, bh1);
                 }
+                const int ch = 8 * nt + 2 * tig;
+                const float2 bb = *reinterpret_cast<const float2 *>(&S.b1s[ch]);
 #pragma unroll
-                for (int nt = 0; nt < 8; ++nt) {
-                    float c[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        const uint32_t bh0 = S.bfrag[1][nt][ks][0][0][lane], bl0 = S.bfrag[1][nt][ks][0][1][lane];
-                        const uint32_t bh1 = S.bfrag[1][nt][ks][1][0][lane], bl1 = S.bfrag[1][nt][ks][1][1][lane];
-                        mma_tf32(c, alo[ks], bh0, bh1);
-                        mma_tf32(c, ahi[ks], bl0, bl1);
-                        mma_tf32(c, ahi[ks], bh0, bh1);
-                    }
-                    const int ch = 8 * nt + 2 * tig;
-                    const float2 bb = *reinterpret_cast<const float2 *>(&S.b1s[ch]);
-#pragma unroll
-                    for (int hrow = 0; hrow < 2; ++hrow) {
-                        const int pl = 16 * mt + gid + 8 * hrow;
-                        const int64_t pr = PFN_ROW(pl);
-                        const float2 mm = *reinterpret_cast<const float2 *>(&W.m1[pl][ch]);
-                        const float o0 = fmaxf(mm.x + (c[2 * hrow] + bb.x), 0.0f);
-                        const float o1 = fmaxf(mm.y + (c[2 * hrow + 1] + bb.y), 0.0f);
-                        if (pr < nP) *reinterpret_cast<float2 *>(feats + pr * 64 + ch) = make_float2(o0, o1);
-                    }
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    const int plh = 16 * mt + gid + 8 * hrow - kPfnH * hf;      // pillar within the sub-task
+                    const int64_t pr = PFN_ROW(16 * mt + gid + 8 * hrow);
+                    const float2 mm = *reinterpret_cast<const float2 *>(&W.m1[plh][ch]);
+                    const float o0 = fmaxf(mm.x + (c[2 * hrow] + bb.x), 0.0f);
+                    const float o1 = fmaxf(mm.y + (c[2 * hrow + 1] + bb.y), 0.0f);
+                    if (pr < nP) *reinterpret_cast<float2 *>(feats + pr * 64 + ch) = make_float2(o0, o1);
                 }
             }
+            }   // mt
         }
+        __syncwarp();                                            // the next half re-seeds m1
+        }   // hf
     }
 }
 
@@ -432,18 +474,18 @@ using namespace hvpr;
 
 int hvpr_pfn_init() {
     cudaError_t e;
-    e = cudaFuncSetAttribute(pfn_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PfnSmem));
+    e = cudaFuncSetAttribute(pfn_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PfnSmemT<true>));
     if (e != cudaSuccess) { set_cuda_error(e); return HVPR_ERR_CUDA; }
-    e = cudaFuncSetAttribute(pfn_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PfnSmem));
+    e = cudaFuncSetAttribute(pfn_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PfnSmemT<true>));
     if (e != cudaSuccess) { set_cuda_error(e); return HVPR_ERR_CUDA; }
-    e = cudaFuncSetAttribute(pfn_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PfnSmem));
+    e = cudaFuncSetAttribute(pfn_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PfnSmemT<false>));
     if (e != cudaSuccess) { set_cuda_error(e); return HVPR_ERR_CUDA; }
-    e = cudaFuncSetAttribute(pfn_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PfnSmem));
+    e = cudaFuncSetAttribute(pfn_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PfnSmemT<false>));
     if (e != cudaSuccess) { set_cuda_error(e); return HVPR_ERR_CUDA; }
     return HVPR_OK;
 }
 
-extern "C" size_t hvpr_pfn_packed_bytes(void) { return sizeof(((PfnSmem *)nullptr)->bfrag); }
+extern "C" size_t hvpr_pfn_packed_bytes(void) { return 2 * kPfnFragWords * sizeof(uint32_t); }
 
 extern "C" int hvpr_pfn_pack(const HvprPfnWeights *weights_host, void *packed_dev, void *stream_) {
     if (!weights_host || !packed_dev || (uintptr_t)packed_dev % 16) return HVPR_ERR_ARG;
@@ -466,8 +508,9 @@ extern "C" int hvpr_pfn(const float *voxels, const int32_t *num_points, const in
     if (n_rows_max == 0) return HVPR_OK;
     if (!voxels || !num_points || !coords || !pillar_features) return HVPR_ERR_ARG;
     if (max_points < 1 || max_points > 32) return HVPR_ERR_UNSUPPORTED;
-    const int bps = (launch && launch->blocks_per_sm != 0) ? launch->blocks_per_sm : 2;     // 94 KB of shared memory per block: two fit an SM
     const bool frag_regs = !(launch && launch->variant != 0);
+    // shared memory admits three blocks per SM with the W1a fragments in registers (69 KB per block), two otherwise (77 KB)
+    const int bps = (launch && launch->blocks_per_sm != 0) ? launch->blocks_per_sm : (frag_regs ? 3 : 2);
     if (bps < 1 || bps > 3 || (launch && (launch->variant < 0 || launch->variant > 1))) return HVPR_ERR_ARG;
     if (((uintptr_t)voxels | (uintptr_t)coords | (uintptr_t)scale_out | (uintptr_t)pillar_features | (uintptr_t)weights_packed) % 16) return HVPR_ERR_ARG;
     PfnParams P;
@@ -482,7 +525,7 @@ extern "C" int hvpr_pfn(const float *voxels, const int32_t *num_points, const in
     const int64_t cap = (int64_t)num_sms() * bps;                              // persistent blocks
     const int blocks = (int)(want < cap ? want : cap);
 #define HVPR_PFN_LAUNCH(SC, FR)                                                                                  \
-    pfn_kernel<SC, FR><<<blocks, kPfnThreads, sizeof(PfnSmem), stream>>>(                                         \
+    pfn_kernel<SC, FR><<<blocks, kPfnThreads, sizeof(PfnSmemT<FR>), stream>>>(                                         \
         P, voxels, num_points, coords, n_pillars_dev, n_rows_max, max_points, geom->vs[0], geom->vs[1], geom->vs[2], \
         x_off, y_off, z_off, pillar_features, scale_out, mask_out, (const uint4 *)weights_packed)
     if (scale_out) { if (frag_regs) HVPR_PFN_LAUNCH(true, true); else HVPR_PFN_LAUNCH(true, false); }

@@ -14,14 +14,14 @@ p = fe.plan(B, B * N, N, use_graph=False)
 p.points.copy_(torch.from_numpy(np.concatenate(frames, 0))); p.frame_offsets.copy_(torch.tensor(np.r_[0, np.cumsum([N] * B)], dtype=torch.int32))
 fe.run(); torch.cuda.synchronize()
 vox = p.vox
-def k2(): fe.vfe.run(vox.voxels, vox.num_points, vox.coords, vox.n_pillars_dev, out=p.pillar_features, scale_out=p.pillar_scale, launch=(2, lowreg))
+def k2(): fe.vfe.run(vox.voxels, vox.num_points, vox.coords, vox.n_pillars_dev, out=p.pillar_features, scale_out=p.pillar_scale, launch=(BPS, lowreg))
 res = {}
-for lowreg in (0, 1):
+for BPS, lowreg in ((2, 0), (3, 0), (2, 1), (3, 1)):
     for _ in range(5): k2()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(30): k2()
     e1.record(); torch.cuda.synchronize()
-    res["lowreg%d" % lowreg] = round(e0.elapsed_time(e1) / 30, 4)
+    res["bps%d_lowreg%d" % (BPS, lowreg)] = round(e0.elapsed_time(e1) / 30, 4)
 print("variant", v or "default", "K2 ms", res, "checksum", float(p.pillar_features.double().sum()))
