@@ -24,6 +24,7 @@ SYMBOLS = [
 ]
 
 OVERFLOW = {"continue": 0, "break": 1}
+VOXELIZE_FORCE_HASH = 0x100
 MEM_FP32, MEM_BF16_RESCORE = 0, 1
 
 

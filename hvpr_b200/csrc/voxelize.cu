@@ -4,7 +4,11 @@
 //
 // Parallel restatement (validated against the serial loop in NumPy: oracle/voxelize.py::voxelize_np):
 //   hash    per point: cell = floor((p-lo)/vs) per axis in IEEE fp32 (no FMA, no reciprocal);  dense per-frame table
-//           (a perfect hash for nz=1 pillar grids):  first[cell] = atomicMin(point index), cnt[cell] += 1
+//           (a perfect hash for nz=1 pillar grids):  first[cell] = atomicMin(point index), cnt[cell] += 1.
+//           Grids whose dense table does not fit (nz > 1 at fine resolution; more than 2^31 cells) go through an OPEN-ADDRESSING
+//           table instead: 64-bit cell keys, 2 x max_frame_points slots per frame (load <= 0.5), linear probing with atomicCAS;
+//           every later kernel indexes the table by SLOT, so only the hash kernel and the coordinate decode differ.  Which slot a
+//           cell lands in depends on the race, the outputs (first index / count per cell, ranks) do not.
 //   assign  single-pass exclusive scan of (is_first, cnt) in point order (block aggregates published with a ready bit)
 //           -> first-seen voxel rank + CSR segment offset; caps applied on the rank
 //   fill    unordered CSR fill of point indices per kept voxel
@@ -24,7 +28,8 @@ constexpr int kScanItems = HVPR_SCAN_ITEMS;                       // points per 
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 struct VoxWorkspace {
-    int2 *table;        // [B*cells] {first, cnt}
+    long long *keys;    // hashed mode only: [B*slots] cell id of each slot (-1 = free)
+    int2 *table;        // [B*cells] {first, cnt}   (hashed mode: cells = slots per frame)
     int32_t *cellbuf;   // [n_total]
     unsigned long long *agg;  // [B*blocks_per_frame] block aggregates {sum_cnt : ready flag | n_first}, zeroed by init
     int32_t *ticket;    // [B] scan-block tickets (dispatch order), zeroed by init
@@ -37,10 +42,11 @@ struct VoxWorkspace {
     size_t bytes;
 };
 
-static VoxWorkspace carve(void *base, int64_t n_total, int B, int64_t cells, int max_vox, int64_t blocks_per_frame) {
+static VoxWorkspace carve(void *base, int64_t n_total, int B, int64_t cells, int max_vox, int64_t blocks_per_frame, bool hashed) {
     VoxWorkspace w;
     size_t off = 0;
     auto take = [&](size_t bytes) { void *p = base ? (char *)base + off : nullptr; off += align_up(bytes, 256); return p; };
+    w.keys = hashed ? (long long *)take(sizeof(long long) * (size_t)B * cells) : nullptr;
     w.table = (int2 *)take(sizeof(int2) * (size_t)B * cells);
     w.cellbuf = (int32_t *)take(sizeof(int32_t) * (size_t)n_total);
     w.agg = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)B * blocks_per_frame);
@@ -56,7 +62,7 @@ static VoxWorkspace carve(void *base, int64_t n_total, int B, int64_t cells, int
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void vox_init_kernel(int2 *table, int64_t n_table, int32_t *cell_map, int64_t n_map,
+__global__ void vox_init_kernel(long long *keys, int2 *table, int64_t n_table, int32_t *cell_map, int64_t n_map,
                                 int32_t *cursor, int64_t n_cursor, unsigned long long *agg, int64_t n_agg,
                                 int32_t *frame_nvox, int32_t *istar, int32_t *ticket, int B) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -66,6 +72,8 @@ __global__ void vox_init_kernel(int2 *table, int64_t n_table, int32_t *cell_map,
     int64_t n4 = n_table / 2;
     for (int64_t j = i; j < n4; j += stride) t4[j] = make_int4(INT_MAX, 0, INT_MAX, 0);
     if (i == 0 && (n_table & 1)) table[n_table - 1] = make_int2(INT_MAX, 0);
+    if (keys)
+        for (int64_t j = i; j < n_table; j += stride) keys[j] = -1ll;
     if (cell_map) {
         int4 *m4 = reinterpret_cast<int4 *>(cell_map);
         int64_t nm4 = n_map / 4;
@@ -88,6 +96,28 @@ __device__ __forceinline__ int32_t point_cell(float x, float y, float z, const H
     return ((int32_t)cz * g.grid[1] + (int32_t)cy) * g.grid[0] + (int32_t)cx;
 }
 
+// 64-bit cell id for grids beyond 2^31 cells (same fp32 arithmetic)
+__device__ __forceinline__ long long point_cell64(float x, float y, float z, const HvprGeom &g) {
+    float cx = floorf(__fdiv_rn(__fsub_rn(x, g.lo[0]), g.vs[0]));
+    float cy = floorf(__fdiv_rn(__fsub_rn(y, g.lo[1]), g.vs[1]));
+    float cz = floorf(__fdiv_rn(__fsub_rn(z, g.lo[2]), g.vs[2]));
+    bool ok = (cx >= 0.0f) && (cx < (float)g.grid[0]) && (cy >= 0.0f) && (cy < (float)g.grid[1]) &&
+              (cz >= 0.0f) && (cz < (float)g.grid[2]);
+    if (!ok) return -1ll;
+    return ((long long)cz * g.grid[1] + (long long)cy) * g.grid[0] + (long long)cx;
+}
+// open addressing, linear probing: the slot that holds `cell` in this frame's key table (claims a free one on first sight).
+// slots is a power of two and at least twice the frame's point count, so a free slot always exists.
+__device__ __forceinline__ int32_t hash_slot(long long *keys, int64_t slots, long long cell) {
+    const unsigned long long mask = (unsigned long long)slots - 1ull;
+    unsigned long long s = (((unsigned long long)cell * 0x9E3779B97F4A7C15ull) >> 24) & mask;
+    for (;;) {
+        const long long prev = (long long)atomicCAS(reinterpret_cast<unsigned long long *>(keys + s), ~0ull, (unsigned long long)cell);
+        if (prev == -1ll || prev == cell) return (int32_t)s;
+        s = (s + 1ull) & mask;
+    }
+}
+
 // grid: (blocks over max_frame_points, B).  Point index stored in the table is frame-local.
 // kVoxPPT points per thread, block-strided (coalesced), all loads issued before the first use: the kernel is one
 // dependent chain per point (load -> cell -> two REDs; ncu: long_scoreboard + drain, 11 % issue activity).  Measured for
@@ -97,10 +127,10 @@ __device__ __forceinline__ int32_t point_cell(float x, float y, float z, const H
 #define HVPR_VOX_PPT 2
 #endif
 constexpr int kVoxPPT = HVPR_VOX_PPT;
-template <bool kVec4>
+template <bool kVec4, bool kHashed>
 __global__ void __launch_bounds__(256) vox_hash_kernel(const float *__restrict__ pts, int stride, int xyz_col,
                                                        const int32_t *__restrict__ frame_off, int32_t frame_cap, HvprGeom g,
-                                                       int64_t cells, int2 *table, int32_t *__restrict__ cellbuf) {
+                                                       int64_t cells, long long *keys, int2 *table, int32_t *__restrict__ cellbuf) {
     const int f = blockIdx.y;
     const int32_t start = frame_off[f];
     const int32_t n = min(frame_off[f + 1] - start, frame_cap);      // a frame longer than the caller's bound is cut, identically in every kernel
@@ -127,7 +157,13 @@ __global__ void __launch_bounds__(256) vox_hash_kernel(const float *__restrict__
     for (int k = 0; k < kVoxPPT; ++k) {
         const int32_t i = i0 + k * 256;
         if (i < n) {
-            const int32_t c = point_cell(x[k], y[k], z[k], g);
+            int32_t c;
+            if (kHashed) {
+                const long long c64 = point_cell64(x[k], y[k], z[k], g);
+                c = c64 < 0 ? -1 : hash_slot(keys + (int64_t)f * cells, cells, c64);
+            } else {
+                c = point_cell(x[k], y[k], z[k], g);
+            }
             cellbuf[(int64_t)start + i] = c;
             if (c >= 0) {
                 atomicMin(&tab[c].x, i);
@@ -337,6 +373,7 @@ template <bool kVec4>
 __global__ void __launch_bounds__(256) vox_gather_kernel(const float *__restrict__ pts, int stride, int xyz_col,
                                                          const int32_t *__restrict__ frame_off, int B, HvprGeom g,
                                                          int64_t cells, int max_vox, int max_points,
+                                                         const long long *__restrict__ keys,
                                                          const int32_t *__restrict__ vox_cell,
                                                          const int32_t *__restrict__ seg_off,
                                                          const int32_t *__restrict__ cursor,
@@ -381,9 +418,11 @@ __global__ void __launch_bounds__(256) vox_gather_kernel(const float *__restrict
         if (live == 0) continue;
         const int kept_mine = n < max_points ? n : max_points;
         if (n > 0) {
-            const int32_t cx = cell % g.grid[0];
-            const int32_t cy = (cell / g.grid[0]) % g.grid[1];
-            const int32_t cz = cell / (g.grid[0] * g.grid[1]);
+            // hashed mode: `cell` is a slot of the frame's key table, the key is the cell id
+            const long long cid = keys ? keys[(int64_t)f * cells + cell] : (long long)cell;
+            const int32_t cx = (int32_t)(cid % g.grid[0]);
+            const int32_t cy = (int32_t)((cid / g.grid[0]) % g.grid[1]);
+            const int32_t cz = (int32_t)(cid / ((long long)g.grid[0] * g.grid[1]));
             reinterpret_cast<int4 *>(coords)[row] = make_int4(f, cz, cy, cx);
             num_points[row] = kept_mine;
             if (cell_map) cell_map[(int64_t)f * cells + cell] = (int32_t)row;
@@ -492,11 +531,25 @@ __global__ void frame_offsets_kernel(const float *__restrict__ pts, int64_t n, i
 
 using namespace hvpr;
 
+// the dense {first, count} table is used while it stays below this size; beyond it (or beyond 2^31 cells) the open-addressing table
+constexpr size_t kDenseTableLimit = (size_t)4 << 30;
+static bool dense_allowed(int64_t cells, int n_frames) {
+    return cells <= INT_MAX && (size_t)cells * (size_t)(n_frames > 0 ? n_frames : 1) * sizeof(int2) <= kDenseTableLimit;
+}
+static int64_t hash_slots(int64_t max_frame_points) {           // power of two >= 2 x points of the largest frame
+    int64_t s = 1024;
+    while (s < 2 * max_frame_points) s <<= 1;
+    return s;
+}
+
 extern "C" size_t hvpr_voxelize_workspace_bytes(int64_t n_total, int n_frames, const HvprGeom *geom, int max_voxels) {
     if (!geom || n_total < 0 || n_frames < 0 || max_voxels < 0) return 0;
     int64_t cells = (int64_t)geom->grid[0] * geom->grid[1] * geom->grid[2];
     int64_t bpf = ceil_div64(n_total > 0 ? n_total : 1, kScanTile);
-    return carve(nullptr, n_total, n_frames, cells, max_voxels, bpf).bytes + 256;
+    // enough for either table: the dense one when it is allowed, the open-addressing one always (a frame may hold all n_total points)
+    const size_t hashed = carve(nullptr, n_total, n_frames, hash_slots(n_total), max_voxels, bpf, true).bytes;
+    const size_t dense = dense_allowed(cells, n_frames) ? carve(nullptr, n_total, n_frames, cells, max_voxels, bpf, false).bytes : 0;
+    return (dense > hashed ? dense : hashed) + 256;
 }
 
 extern "C" int hvpr_voxelize(const float *points, int64_t n_total, int pts_stride, int xyz_col,
@@ -510,22 +563,28 @@ extern "C" int hvpr_voxelize(const float *points, int64_t n_total, int pts_strid
     if (n_total > 0 && !points) return HVPR_ERR_ARG;
     if (max_points < 1 || max_points > 32 || max_voxels < 1) return HVPR_ERR_UNSUPPORTED;
     if (n_frames > 64) return HVPR_ERR_UNSUPPORTED;
+    const bool force_hash = (overflow_mode & HVPR_VOXELIZE_FORCE_HASH) != 0;
+    overflow_mode &= ~HVPR_VOXELIZE_FORCE_HASH;
     if (overflow_mode != HVPR_OVERFLOW_CONTINUE && overflow_mode != HVPR_OVERFLOW_BREAK) return HVPR_ERR_ARG;
-    const int64_t cells = (int64_t)geom->grid[0] * geom->grid[1] * geom->grid[2];
-    if (cells <= 0 || cells > INT_MAX || n_total > INT_MAX) return HVPR_ERR_UNSUPPORTED;
+    const int64_t grid_cells = (int64_t)geom->grid[0] * geom->grid[1] * geom->grid[2];
+    if (grid_cells <= 0 || n_total > INT_MAX || geom->grid[0] <= 0 || geom->grid[1] <= 0 || geom->grid[2] <= 0) return HVPR_ERR_UNSUPPORTED;
     if (max_frame_points <= 0 || max_frame_points > n_total) max_frame_points = n_total;
+    const bool hashed = force_hash || !dense_allowed(grid_cells, n_frames);
+    if (hashed && cell_map) return HVPR_ERR_ARG;             // the dense cell -> row map only exists for grids that have a dense table
+    // table stride per frame: the grid's cells, or the slots of the open-addressing table
+    const int64_t cells = hashed ? hash_slots(max_frame_points) : grid_cells;
     const int32_t frame_cap = (int32_t)max_frame_points;     // grids are sized from this bound; the kernels clamp every frame to it
 
     const int64_t bpf_ws = ceil_div64(n_total > 0 ? n_total : 1, kScanTile);
     // 256-B align the caller's pointer
     uintptr_t basep = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
-    VoxWorkspace w = carve((void *)basep, n_total, n_frames, cells, max_voxels, bpf_ws);
+    VoxWorkspace w = carve((void *)basep, n_total, n_frames, cells, max_voxels, bpf_ws, hashed);
     if (w.bytes + (basep - (uintptr_t)workspace) > workspace_bytes) return HVPR_ERR_WORKSPACE;
 
     {
         int64_t work = (int64_t)n_frames * cells / 2;
         int blocks = (int)(ceil_div64(work, 256) < 148 * 8 ? (ceil_div64(work, 256) > 0 ? ceil_div64(work, 256) : 1) : 148 * 8);
-        vox_init_kernel<<<blocks, 256, 0, stream>>>(w.table, (int64_t)n_frames * cells, cell_map,
+        vox_init_kernel<<<blocks, 256, 0, stream>>>(w.keys, w.table, (int64_t)n_frames * cells, cell_map,
                                                    (int64_t)n_frames * cells, w.cursor,
                                                    (int64_t)n_frames * max_voxels, w.agg, (int64_t)n_frames * bpf_ws,
                                                    w.frame_nvox, w.istar, w.ticket, n_frames);
@@ -534,8 +593,13 @@ extern "C" int hvpr_voxelize(const float *points, int64_t n_total, int pts_strid
     const bool vec4 = (pts_stride == 4 && xyz_col == 0 && ((uintptr_t)points % 16 == 0));
     if (max_frame_points > 0) {
         dim3 gridp((unsigned)ceil_div64(max_frame_points, 256 * kVoxPPT), (unsigned)n_frames);
-        if (vec4) vox_hash_kernel<true><<<gridp, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, frame_cap, *geom, cells, w.table, w.cellbuf);
-        else vox_hash_kernel<false><<<gridp, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, frame_cap, *geom, cells, w.table, w.cellbuf);
+        if (hashed) {
+            if (vec4) vox_hash_kernel<true, true><<<gridp, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, frame_cap, *geom, cells, w.keys, w.table, w.cellbuf);
+            else vox_hash_kernel<false, true><<<gridp, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, frame_cap, *geom, cells, w.keys, w.table, w.cellbuf);
+        } else {
+            if (vec4) vox_hash_kernel<true, false><<<gridp, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, frame_cap, *geom, cells, w.keys, w.table, w.cellbuf);
+            else vox_hash_kernel<false, false><<<gridp, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, frame_cap, *geom, cells, w.keys, w.table, w.cellbuf);
+        }
         HVPR_CHECK_LAUNCH();
         const int bpf = (int)ceil_div64(max_frame_points, kScanTile);
         dim3 grids((unsigned)bpf, (unsigned)n_frames);
@@ -550,8 +614,8 @@ extern "C" int hvpr_voxelize(const float *points, int64_t n_total, int pts_strid
         const int64_t runs = ceil_div64(max_voxels, kGatherRun);
         int64_t want = ceil_div64((int64_t)n_frames * ceil_div64(runs, 32 / kGatherRun), 8);   // 8 warps per block, 32 slots per warp
         int blocks = (int)(want < 148 * 16 ? (want > 0 ? want : 1) : 148 * 16);
-        if (vec4) vox_gather_kernel<true><<<blocks, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, n_frames, *geom, cells, max_voxels, max_points, w.vox_cell, w.seg_off, w.cursor, w.csr, w.frame_nvox, voxels, coords, num_points, voxel_offsets, cell_map);
-        else vox_gather_kernel<false><<<blocks, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, n_frames, *geom, cells, max_voxels, max_points, w.vox_cell, w.seg_off, w.cursor, w.csr, w.frame_nvox, voxels, coords, num_points, voxel_offsets, cell_map);
+        if (vec4) vox_gather_kernel<true><<<blocks, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, n_frames, *geom, cells, max_voxels, max_points, w.keys, w.vox_cell, w.seg_off, w.cursor, w.csr, w.frame_nvox, voxels, coords, num_points, voxel_offsets, cell_map);
+        else vox_gather_kernel<false><<<blocks, 256, 0, stream>>>(points, pts_stride, xyz_col, frame_offsets, n_frames, *geom, cells, max_voxels, max_points, w.keys, w.vox_cell, w.seg_off, w.cursor, w.csr, w.frame_nvox, voxels, coords, num_points, voxel_offsets, cell_map);
         HVPR_CHECK_LAUNCH();
     }
     return HVPR_OK;

@@ -162,8 +162,8 @@ class HybridFrontEnd(torch.nn.Module):
         p.spatial = torch.empty((n_frames, 128, ny, nx), dtype=torch.float32, device=dev)
         p.spatial_scale = torch.empty((n_frames, 32, ny, nx), dtype=torch.float32, device=dev)
         # side1 (PFN of the next batch) gets dispatch priority over the canvas fill it shares the SMs with
-        p.side1 = torch.cuda.Stream(device=dev, priority=-1)
-        p.side2, p.copy = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        p.side1 = torch.cuda.Stream(device=dev, priority=int(os.environ.get("HVPR_STREAM_PFN_PRIO", "-1")))
+        p.side2, p.copy = torch.cuda.Stream(device=dev, priority=int(os.environ.get("HVPR_STREAM_K1_PRIO", "0"))), torch.cuda.Stream(device=dev)
         p.ev_copied = [torch.cuda.Event() for _ in range(NS)]
         p.ev_input_free = [torch.cuda.Event() for _ in range(NS)]
         # per-frame pillar offsets of the finished batch: staged on the device inside the graph, read back on their own stream so

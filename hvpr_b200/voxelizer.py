@@ -32,9 +32,13 @@ class VoxelizerOutput:
 class Voxelizer:
     """GPU voxelizer with preallocated buffers for up to `max_frames` frames of `max_total_points` points."""
 
-    def __init__(self, geom: Geometry, overflow: str = "continue", device=None):
+    def __init__(self, geom: Geometry, overflow: str = "continue", device=None, table: str = "auto"):
+        """table: "auto" = dense {first, count} table while it fits (every pillar grid of the reference's configs), else the
+        open-addressing hash table; "hash" forces the latter (no dense cell map is produced then)."""
+        assert table in ("auto", "hash")
         self.geom = geom
         self.overflow = overflow
+        self.table = table
         self.device = torch.device(device if device is not None else "cuda")
         self._geom_c = _lib.make_geom(geom.range_f32, geom.voxel_f32, geom.grid_size)
         self._ws = None
@@ -51,8 +55,13 @@ class Voxelizer:
             self._ws_key = key
         return self._ws
 
+    def uses_hash_table(self, n_frames: int) -> bool:
+        cells = self.geom.cells_per_frame
+        return self.table == "hash" or cells > 2 ** 31 - 1 or cells * max(n_frames, 1) * 8 > (4 << 30)
+
     def alloc_output(self, n_frames: int, with_cell_map: bool = True) -> VoxelizerOutput:
         g, dev = self.geom, self.device
+        with_cell_map = with_cell_map and not self.uses_hash_table(n_frames)
         rows = n_frames * g.max_voxels
         return VoxelizerOutput(
             torch.empty((rows, g.max_points_per_voxel, 4), dtype=torch.float32, device=dev),
@@ -78,7 +87,7 @@ class Voxelizer:
         st = _lib.lib().hvpr_voxelize(
             _lib.ptr(points), n_total, stride, xyz_col, _lib.ptr(frame_offsets), n_frames, int(max_frame_points),
             ctypes.byref(self._geom_c), self.geom.max_points_per_voxel, self.geom.max_voxels,
-            _lib.OVERFLOW[self.overflow], _lib.ptr(out.voxels), _lib.ptr(out.coords), _lib.ptr(out.num_points),
+            _lib.OVERFLOW[self.overflow] | (_lib.VOXELIZE_FORCE_HASH if self.table == "hash" else 0), _lib.ptr(out.voxels), _lib.ptr(out.coords), _lib.ptr(out.num_points),
             _lib.ptr(out.voxel_offsets), _lib.ptr(out.cell_map), _lib.ptr(ws), ws.numel(), _lib.cur_stream())
         _lib.check(st, "hvpr_voxelize")
         return out

@@ -47,7 +47,8 @@ typedef struct HvprGeom {
     int32_t grid[3];  /* nx, ny, nz */
 } HvprGeom;
 
-enum { HVPR_OVERFLOW_CONTINUE = 0, HVPR_OVERFLOW_BREAK = 1 };
+enum { HVPR_OVERFLOW_CONTINUE = 0, HVPR_OVERFLOW_BREAK = 1,
+       HVPR_VOXELIZE_FORCE_HASH = 0x100   /* OR-ed into overflow_mode: use the open-addressing table even when the dense one fits (tests) */ };
 enum { HVPR_MEM_FP32 = 0,          /* exact fp32 SIMT path */
        HVPR_MEM_BF16_RESCORE = 1   /* tcgen05 bf16 GEMM -> candidate set -> exact fp32 re-score (default) */ };
 
@@ -95,7 +96,10 @@ int hvpr_init(void);
  *   num_points    (rows) int32
  *   voxel_offsets (n_frames+1) int32: frame f owns rows [vo[f], vo[f+1]);  vo[n_frames] = total pillar count
  *   cell_map      (n_frames, nz*ny*nx) int32: cell -> row, -1 where empty (consumed by hvpr_bev_fill); may be NULL
- * workspace: hvpr_voxelize_workspace_bytes() bytes, contents undefined on entry.                                     */
+ * workspace: hvpr_voxelize_workspace_bytes() bytes, contents undefined on entry.
+ * Table: dense {first index, count} per cell while that is <= 4 GiB for the batch and the grid has <= 2^31 cells (every pillar grid of
+ * the reference's configs); otherwise an open-addressing hash table with 64-bit cell keys (2 x max_frame_points slots per frame) —
+ * then cell_map must be NULL (there is no dense cell -> row map for such grids).                                          */
 size_t hvpr_voxelize_workspace_bytes(int64_t n_total, int n_frames, const HvprGeom *geom, int max_voxels);
 int hvpr_voxelize(const float *points, int64_t n_total, int pts_stride, int xyz_col,
                   const int32_t *frame_offsets, int n_frames, int64_t max_frame_points,

@@ -35,6 +35,18 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.HvprPfnWeights) == 4 * (160 + 16 + 1024 + 1024 + 64 + 80 + 16 + 512 + 32)
 
 
+def test_voxelizer_workspace_covers_both_table_layouts():
+    """The workspace query is valid for the dense table AND the open-addressing one, and stays small for a grid of 2.7e9 cells."""
+    L = _lib.lib()
+    g2 = _lib.make_geom(G2.range_f32, G2.voxel_f32, G2.grid_size)
+    dense = L.hvpr_voxelize_workspace_bytes(960000, 8, ctypes.byref(g2), 40000)
+    assert dense > 8 * 432 * 496 * 8                                    # holds the dense {first, count} table of 8 frames
+    huge = _lib.make_geom((0.0, -39.68, -3.0), (0.02, 0.02, 0.02), (3456, 3968, 200))
+    hashed = L.hvpr_voxelize_workspace_bytes(960000, 8, ctypes.byref(huge), 40000)
+    assert 0 < hashed < (1 << 30)                                        # 2 x 960k -> 2^21 slots x 16 B x 8 frames + point-sized arrays
+    from hvpr_b200.voxelizer import Voxelizer
+
+
 def test_workspace_query_needs_no_gpu():
     g = _lib.make_geom(G2.range_f32, G2.voxel_f32, G2.grid_size)
     n = _lib.lib().hvpr_voxelize_workspace_bytes(8 * 120000, 8, ctypes.byref(g), 40000)

@@ -153,6 +153,54 @@ def test_voxelize_truncates_frames_longer_than_the_stated_bound():
         assert np.array_equal(out.voxels[:P].cpu().numpy().view(np.int32), rv.view(np.int32))
 
 
+def _voxelize_hash(frames, geom, overflow, table):
+    from hvpr_b200.voxelizer import Voxelizer
+    vz = Voxelizer(geom, overflow, table=table)
+    pts, off = to_dev(frames)
+    out = vz.run(pts, off, len(frames), max(len(f) for f in frames))
+    torch.cuda.synchronize()
+    P = int(out.voxel_offsets[-1])
+    return out, out.voxels[:P].cpu().numpy(), out.coords[:P].cpu().numpy(), out.num_points[:P].cpu().numpy()
+
+
+@pytest.mark.parametrize("mode", ["continue", "break"])
+def test_voxelize_open_addressing_table_equals_dense_table(mode):
+    """The open-addressing hash table (64-bit cell keys, linear probing; used when the dense table does not fit) gives the same bits
+    as the dense table and the oracle — pillar grids with the cap hit (U) and not hit (L), ragged / empty frames."""
+    for g, frames in ((G2, synth.make_batch("U", 120000, G2.point_cloud_range, 2, first_frame=5, edge_cases=True)),
+                      (G1, synth.make_batch("L", 60000, G1.point_cloud_range, 3, first_frame=8, edge_cases=True) + [np.zeros((0, 4), np.float32)])):
+        out_h, v, c, n = _voxelize_hash(frames, g, mode, "hash")
+        assert out_h.cell_map is None
+        rv, rc, rn = ov.voxelize_batch(frames, g.range_f32, g.voxel_f32, 32, g.max_voxels, mode)
+        assert np.array_equal(n, rn) and np.array_equal(c, rc) and np.array_equal(v.view(np.int32), rv.view(np.int32))
+        _, v2, c2, n2 = _voxelize_hash(frames, g, mode, "auto")
+        assert np.array_equal(v.view(np.int32), v2.view(np.int32)) and np.array_equal(c, c2) and np.array_equal(n, n2)
+
+
+def test_voxelize_3d_grid_and_grid_beyond_2_pow_31_cells():
+    """nz > 1: a SECOND-style 3-D voxel grid (dense table and hash table agree with the oracle), and a grid of 2.7e9 cells that only
+    the open-addressing table can hold — checked against the dict-based oracle (no dense table anywhere)."""
+    g3 = Geometry((0.0, -39.68, -3.0, 69.12, 39.68, 1.0), (0.16, 0.16, 0.1), 5, 16000)            # 432 x 496 x 40
+    assert g3.grid_size == (432, 496, 40)
+    frames = synth.make_batch("L", 40000, g3.point_cloud_range, 2, first_frame=3, edge_cases=True)
+    rv, rc, rn = ov.voxelize_batch(frames, g3.range_f32, g3.voxel_f32, 5, 16000, "continue")
+    assert len(set(rc[:, 1].tolist())) > 5                                                         # several z layers are occupied
+    for table in ("auto", "hash"):
+        _, v, c, n = _voxelize_hash(frames, g3, "continue", table)
+        assert np.array_equal(n, rn) and np.array_equal(c, rc) and np.array_equal(v.view(np.int32), rv.view(np.int32)), table
+    huge = Geometry((0.0, -39.68, -3.0, 69.12, 39.68, 1.0), (0.02, 0.02, 0.02), 8, 4000)           # 3456 x 3968 x 200 = 2.74e9 cells
+    nx, ny, nz = huge.grid_size
+    assert nx * ny * nz > 2 ** 31
+    f = synth.make_frame("L", 6000, huge.point_cloud_range, 77, edge_cases=True)
+    f[100:140] = f[100]                                                                            # a crowded cell (cap 8)
+    from hvpr_b200.voxelizer import Voxelizer
+    assert Voxelizer(huge, "continue").uses_hash_table(1)
+    _, v, c, n = _voxelize_hash([f], huge, "continue", "auto")
+    pv, pc, pn = ov.voxelize_py(f, huge.range_f32, huge.voxel_f32, 8, 4000, "continue")
+    assert np.array_equal(n, pn) and np.array_equal(c[:, 1:], pc) and np.array_equal(v.view(np.int32), pv.view(np.int32))
+    assert int(n.max()) == 8 and len(n) == 4000
+
+
 def test_voxelize_collated_points_with_batch_column():
     """batch_dict path: (sum N, 5) [b,x,y,z,r] exactly as collate_batch pads it (dataset.py:161-166)."""
     from hvpr_b200.voxelizer import Voxelizer
