@@ -49,6 +49,24 @@ def launch_cfg(cfg):
     return ctypes.byref(HvprLaunchCfg(int(cfg[0]), int(cfg[1])))
 
 
+class HvprZeroFill(ctypes.Structure):
+    _fields_ = [("ptr", c_void_p * 4), ("bytes", ctypes.c_uint64 * 4), ("n", c_int32)]
+
+
+def zero_fill(tensors):
+    """List of (contiguous, 16-byte aligned) tensors or None -> the zero_fill argument of hvpr_mem_attn."""
+    if not tensors:
+        return None
+    z = HvprZeroFill()
+    assert len(tensors) <= 4
+    for i, t in enumerate(tensors):
+        assert t.is_contiguous()
+        z.ptr[i] = t.data_ptr()
+        z.bytes[i] = t.numel() * t.element_size()
+    z.n = len(tensors)
+    return ctypes.byref(z)
+
+
 class HvprConvArgs(ctypes.Structure):
     _fields_ = [("in_", c_void_p), ("n", c_int32), ("h_in", c_int32), ("w_in", c_int32), ("in_cs", c_int32),
                 ("c_in", c_int32), ("ksize", c_int32), ("stride", c_int32), ("w_packed", c_void_p),
@@ -108,7 +126,7 @@ def lib():
     L.hvpr_mem_pack_bf16.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p]
     L.hvpr_mem_attn.restype = c_int
     L.hvpr_mem_attn.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+                                c_void_p, c_void_p, c_void_p, c_size_t, ctypes.POINTER(HvprZeroFill), c_void_p]
     L.hvpr_mem_train_forward.restype = c_int
     L.hvpr_mem_train_forward.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]
     L.hvpr_mse_loss.restype = c_int

@@ -8,7 +8,7 @@ int hvpr_mem_attn_fp32(const float *, const int32_t *, int64_t, const float *, i
 int hvpr_mem_attn_tc_init();
 size_t hvpr_mem_attn_tc_workspace_bytes(int64_t n_rows_max, int M);
 int hvpr_mem_attn_tc(const float *, const int32_t *, int64_t, const float *, const void *, int, int, int, float *,
-                     int32_t *, void *, size_t, cudaStream_t);
+                     int32_t *, void *, size_t, const HvprZeroFill *, cudaStream_t);
 int hvpr_conv_init();
 int hvpr_mem_train_init();
 int hvpr_mem_pack_bf16_impl(const float *, int, int, void *, cudaStream_t);
@@ -69,17 +69,32 @@ extern "C" int hvpr_mem_pack_bf16(const float *mem_weight, int M, int C, void *m
 extern "C" int hvpr_mem_attn(const float *pillars, const int32_t *n_pillars_dev, int64_t n_rows_max,
                              const float *mem_weight, const void *mem_weight_bf16, int M, int C, int k,
                              int precision_mode, float *readout, int32_t *topk_idx_out, void *workspace,
-                             size_t workspace_bytes, void *stream) {
+                             size_t workspace_bytes, const HvprZeroFill *zero_fill, void *stream) {
     if (n_rows_max < 0 || !mem_weight) return HVPR_ERR_ARG;
-    if (n_rows_max == 0) return HVPR_OK;
+    if (zero_fill) {
+        if (zero_fill->n < 0 || zero_fill->n > 4) return HVPR_ERR_ARG;
+        for (int r = 0; r < zero_fill->n; ++r)
+            if (zero_fill->bytes[r] && (!zero_fill->ptr[r] || ((uintptr_t)zero_fill->ptr[r] | zero_fill->bytes[r]) % 16)) return HVPR_ERR_ARG;
+    }
+    // the tcgen05 kernel zeroes the ranges itself, beside its own work; every other path does it with plain memsets
+    auto memset_ranges = [&]() -> int {
+        if (zero_fill)
+            for (int r = 0; r < zero_fill->n; ++r)
+                if (zero_fill->bytes[r]) HVPR_CHECK_CUDA(cudaMemsetAsync(zero_fill->ptr[r], 0, zero_fill->bytes[r], (cudaStream_t)stream));
+        return HVPR_OK;
+    };
+    if (n_rows_max == 0) return memset_ranges();
     if (!pillars || !readout) return HVPR_ERR_ARG;
-    if (precision_mode == HVPR_MEM_FP32)
+    if (precision_mode == HVPR_MEM_FP32) {
+        const int s = memset_ranges();
+        if (s != HVPR_OK) return s;
         return hvpr_mem_attn_fp32(pillars, n_pillars_dev, n_rows_max, mem_weight, M, C, k, readout, topk_idx_out,
                                   (cudaStream_t)stream);
+    }
     if (precision_mode == HVPR_MEM_BF16_RESCORE) {
         if (!mem_weight_bf16) return HVPR_ERR_ARG;
         return hvpr_mem_attn_tc(pillars, n_pillars_dev, n_rows_max, mem_weight, mem_weight_bf16, M, C, k, readout,
-                                topk_idx_out, workspace, workspace_bytes, (cudaStream_t)stream);
+                                topk_idx_out, workspace, workspace_bytes, zero_fill, (cudaStream_t)stream);
     }
     return HVPR_ERR_ARG;
 }

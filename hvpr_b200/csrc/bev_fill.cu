@@ -40,9 +40,16 @@ constexpr int kBevThreads = 128;   // small blocks: they slot in beside the regi
 #ifndef HVPR_BEV_MINB
 #define HVPR_BEV_MINB 8
 #endif
-__global__ void __launch_bounds__(kBevThreads, HVPR_BEV_MINB) bev_fill_kernel(const __grid_constant__ BevArgs A,
+// kZeroedLanes != 0: the canvas already holds zeros (hvpr_mem_attn's zero_fill wrote them while it computed the readout), so
+// only aligned runs of kZeroedLanes threads (2 / 4 / 8 = 32 / 64 / 128 bytes per channel) that hold a pillar are written —
+// whole DRAM sectors, so that no partially written sector has to be merged with its old contents.  A template parameter: the
+// write-everything form must keep its 64 registers without spills (8 blocks per SM).
+template <int kZeroedLanes>
+__global__ void __launch_bounds__(kBevThreads, kZeroedLanes ? 6 : HVPR_BEV_MINB) bev_fill_kernel(const __grid_constant__ BevArgs A,
                                                        const int32_t *__restrict__ cell_map, int64_t cells,
                                                        int xblocks, int n_frames, int64_t n_items) {
+    constexpr int zeroed_lanes = kZeroedLanes;
+    const unsigned lane_group = zeroed_lanes ? (((1u << zeroed_lanes) - 1u) << ((threadIdx.x & 31) & ~(zeroed_lanes - 1))) : 0u;
     const int64_t groups = cells >> 2;
     int64_t item = blockIdx.x;
     if (item >= n_items) return;
@@ -65,7 +72,10 @@ __global__ void __launch_bounds__(kBevThreads, HVPR_BEV_MINB) bev_fill_kernel(co
         const int c0 = A.chunk_c0[ch], nc = A.chunk_nc[ch];
         float4 *out = reinterpret_cast<float4 *>(s.out + ((int64_t)f * s.Ctot + s.c_off + c0) * cells) + g;
         const bool occupied = (m.x & m.y & m.z & m.w) != -1;   // row ids are >= 0, empties are exactly -1
-        if (!__any_sync(0xffffffffu, occupied)) {
+        const unsigned occ = zeroed_lanes ? __ballot_sync(0xffffffffu, occupied) : (unsigned)__any_sync(0xffffffffu, occupied);
+        if (zeroed_lanes && (occ & lane_group) == 0u) {
+            // nothing to do: these cells are empty and already zero
+        } else if (occ == 0u) {
             if (live) {
                 const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
@@ -151,6 +161,9 @@ extern "C" int hvpr_bev_fill(const float *feat_a, int ca, const float *feat_b, i
     cudaStream_t stream = (cudaStream_t)stream_;
     const int bev_bps = launch ? launch->blocks_per_sm : HVPR_BEV_BPS;
     if (bev_bps < 0 || bev_bps > 16) return HVPR_ERR_ARG;
+    const int variant = launch ? launch->variant : 0;
+    if (variant < 0 || variant > 3) return HVPR_ERR_ARG;
+    const int zeroed_lanes = variant ? (1 << variant) : 0;    // 1 / 2 / 3 -> runs of 2 / 4 / 8 threads = 32 / 64 / 128 bytes
     if (!cell_map || !spatial || !feat_a || ca <= 0 || cb < 0 || cs < 0 || n_frames <= 0 || nx <= 0 || ny <= 0) return HVPR_ERR_ARG;
     if ((cb > 0 && !feat_b) || (cs > 0 && (!feat_s || !spatial_scale))) return HVPR_ERR_ARG;
     const int64_t cells = (int64_t)nx * ny;
@@ -174,9 +187,16 @@ extern "C" int hvpr_bev_fill(const float *feat_a, int ca, const float *feat_b, i
         const int xblocks = (int)ceil_div64(cells / 4, kBevThreads);
         const int64_t n_items = (int64_t)xblocks * n_frames * n;
         const int64_t cap = bev_bps > 0 ? (int64_t)num_sms() * bev_bps : n_items;
-        bev_fill_kernel<<<(unsigned)(n_items < cap ? n_items : cap), kBevThreads, 0, stream>>>(A, cell_map, cells, xblocks, n_frames, n_items);
+        const unsigned nb = (unsigned)(n_items < cap ? n_items : cap);
+        switch (zeroed_lanes) {
+            case 0: bev_fill_kernel<0><<<nb, kBevThreads, 0, stream>>>(A, cell_map, cells, xblocks, n_frames, n_items); break;
+            case 2: bev_fill_kernel<2><<<nb, kBevThreads, 0, stream>>>(A, cell_map, cells, xblocks, n_frames, n_items); break;
+            case 4: bev_fill_kernel<4><<<nb, kBevThreads, 0, stream>>>(A, cell_map, cells, xblocks, n_frames, n_items); break;
+            default: bev_fill_kernel<8><<<nb, kBevThreads, 0, stream>>>(A, cell_map, cells, xblocks, n_frames, n_items); break;
+        }
         HVPR_CHECK_LAUNCH();
     } else {
+        // odd shapes: the scalar kernels rewrite every element (a canvas that is already zero is simply overwritten)
         dim3 grid((unsigned)ceil_div64(cells, 256), (unsigned)n_frames);
         bev_fill_scalar_kernel<<<grid, 256, 0, stream>>>(feat_a, ca, ca + cb, 0, spatial, cell_map, cells);
         HVPR_CHECK_LAUNCH();

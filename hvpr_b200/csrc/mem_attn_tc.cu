@@ -91,9 +91,25 @@ constexpr int kTcOverflow = 99;        // cand_cnt value of a half row that over
 constexpr int kTcCandBufs = 3;         // candidate-list ring between the filter and the tail
 constexpr int kTcSlowScratch = 2048;   // floats per tail warp (global workspace) for the overflow path
 
+#ifndef HVPR_K3_ZF_UNIT
+#define HVPR_K3_ZF_UNIT 8192
+#endif
+constexpr uint32_t kTcZeroBytes = HVPR_K3_ZF_UNIT; // source buffer of the background zero fill (one bulk store each)
+// Background zero fill (HvprZeroFill): the kernel leaves HBM idle (its working set lives in L2 / L1), so lane 0 of the producer warp
+// streams zeros from shared memory into the caller's ranges with bulk async stores (TMA engine: one instruction per 8 KB, no
+// registers, no issue slots of the working warps) while the tiles are processed.  Range r is cut into units[r] pieces of
+// kTcZeroBytes; piece u of the concatenation belongs to CTA u % gridDim.x.
+struct TcZero {
+    uint8_t *ptr[4];
+    uint64_t bytes[4];
+    uint32_t units[4];
+    uint32_t total_units;
+};
+
 struct TcSmem {
     uint8_t w[kTcWStages][kTcChunkBytes];     // 1024-aligned
     uint8_t a[2][kTcATileBytes];
+    alignas(128) uint8_t zeros[kTcZeroBytes];
     uint16_t cand[kTcCandBufs][kTcCandCap][kTcTileM];
     int32_t cand_cnt[kTcCandBufs][2][kTcTileM];
     float tx[9][2 * kTcTileM];                // entries 7..15 of each filter thread's sorted top-16 group maxima (tau exchange)
@@ -154,6 +170,17 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+#ifndef HVPR_K3_ZF_HINT
+#define HVPR_K3_ZF_HINT 1
+#endif
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes, uint64_t policy) {
+#if HVPR_K3_ZF_HINT
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(dst), "r"(smem_u32(src)), "r"(bytes), "l"(policy) : "memory");
+#else
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+#endif
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -580,7 +607,8 @@ const float *__restrict__ pillars,
                                                                     int32_t *__restrict__ topk_idx_out,
                                                                     float *__restrict__ slow_scratch,
                                                                     int32_t *__restrict__ tile_counter,
-                                                                    float *__restrict__ dbg_logits) {
+                                                                    float *__restrict__ dbg_logits,
+                                                                    const __grid_constant__ TcZero Z) {
     // __align__(1024) (128-B swizzle atoms) instead of rounding the pointer up by hand: integer arithmetic on the address makes
     // the compiler lose the shared address space and emit generic LD.E / ST.E for every access to S (group maxima, candidate
     // ring, A-tile stores) in this latency-bound kernel
@@ -621,6 +649,10 @@ const float *__restrict__ pillars,
         next_id = (t2 < ntiles) ? t2 : -1;
     }
     volatile int32_t *tile_ids = S.tile_ids;
+    if (Z.total_units) {
+        for (uint32_t i = tid; i < kTcZeroBytes / 16; i += kTcThreads) reinterpret_cast<uint4 *>(S.zeros)[i] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the bulk-copy engine
+    }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -656,6 +688,33 @@ const float *__restrict__ pillars,
         uint32_t next_load = 0, load_limit = (tile_ids[0] >= 0) ? per_tile : 0u;
         if (lane == 0)
             while (next_load < load_limit && next_load < (uint32_t)(kTcWStages - 1)) issue_load(next_load++);
+        // background zero fill: this CTA's pieces are spread over the chunk iterations it expects to run (a full static share of
+        // the tiles); whatever is left when the tiles run out — all of it for a CTA without work — goes out at the end
+        uint32_t zf_u = blockIdx.x, zf_per_it = 0;
+        uint64_t zf_policy = 0;
+        if (Z.total_units && lane == 0) {
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(zf_policy));
+            const uint32_t mine = Z.total_units > blockIdx.x ? (Z.total_units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+            uint32_t est = ((uint32_t)ntiles / gridDim.x) * per_tile;
+            if (est < 1u) est = 1u;
+            zf_per_it = (mine + est - 1) / est;
+        }
+        auto zf_issue = [&](uint32_t n) {                      // lane 0 only
+            if (zf_u >= Z.total_units) return;
+            for (uint32_t i = 0; i < n && zf_u < Z.total_units; ++i, zf_u += gridDim.x) {
+                uint32_t u = zf_u;
+                uint8_t *base = Z.ptr[0];
+                uint64_t len = Z.bytes[0];
+                bool found = u < Z.units[0];
+#pragma unroll
+                for (int r = 1; r < 4; ++r)
+                    if (!found) { u -= Z.units[r - 1]; base = Z.ptr[r]; len = Z.bytes[r]; found = u < Z.units[r]; }
+                const uint64_t off = (uint64_t)u * kTcZeroBytes;
+                const uint64_t left = len - off;
+                bulk_s2g(base + off, S.zeros, (uint32_t)(left < kTcZeroBytes ? left : kTcZeroBytes), zf_policy);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        };
         uint32_t it = 0, ti = 0;
         TCP_DECL;
         for (;; ++ti) {
@@ -675,6 +734,7 @@ const float *__restrict__ pillars,
                             mbar_test(&S.a_full[ab ^ 1], ((ti + 1) >> 1) & 1) && tile_ids[(ti + 1) & 3] >= 0)
                             load_limit += per_tile;
                         while (next_load < load_limit && next_load < it + kTcWStages) issue_load(next_load++);
+                        if (zf_per_it) zf_issue(zf_per_it);
                     }
                     TCP_BEGIN();
                     mbar_wait(&S.w_full[s], (it / kTcWStages) & 1);
@@ -697,6 +757,11 @@ const float *__restrict__ pillars,
             if (lane == 0) umma_commit(&S.a_empty[ab]);
             __syncwarp();
         }
+        if (Z.total_units && lane == 0) {
+            zf_issue(0xffffffffu);
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // the stores are complete (and S.zeros no longer read) before the CTA may exit
+        }
+        __syncwarp();
         TCP_DUMP(0);
     } else if (warp >= kTcFilterBase) {
         // ===== filter: one accumulator row per thread (4 filter warps) or per thread pair (8 filter warps) ===============
@@ -966,6 +1031,7 @@ const float *__restrict__ pillars,
             named_bar_arrive(kBarCEmpty + cb, kTcFilterThreads + 32 * kTcTailWarps);
             TCP_END(1);
         }
+
         if (tw == 0) { TCP_DUMP(8); }
 #ifdef HVPR_TC_PROFILE
         if (tw == 0 && lane == 0 && dbg_logits) for (int i_ = 0; i_ < 4; ++i_) reinterpret_cast<long long *>(dbg_logits)[(size_t)blockIdx.x * 24 + 10 + i_] = tcp_row_acc[i_];
@@ -1035,7 +1101,7 @@ int hvpr_mem_pack_bf16_impl(const float *W, int M, int C, void *out, cudaStream_
 
 static int tc_launch(const float *pillars, const int32_t *n_pillars_dev, int64_t n_rows_max, const float *W,
                      const void *Wpk, int M, int C, int k, float *readout, int32_t *topk_idx_out, void *workspace,
-                     size_t workspace_bytes, float *dbg_logits, cudaStream_t stream) {
+                     size_t workspace_bytes, float *dbg_logits, const HvprZeroFill *zero_fill, cudaStream_t stream) {
     if (C != kTcK || k != 20 || M < 16 * kTcKPrime || M > kTcMaxChunks * kTcChunkN) return HVPR_ERR_UNSUPPORTED;
     if (((uintptr_t)W | (uintptr_t)Wpk | (uintptr_t)pillars | (uintptr_t)readout) % 16) return HVPR_ERR_ARG;
     if (!workspace || workspace_bytes < hvpr_mem_attn_tc_workspace_bytes(n_rows_max, M)) return HVPR_ERR_WORKSPACE;
@@ -1046,6 +1112,20 @@ static int tc_launch(const float *pillars, const int32_t *n_pillars_dev, int64_t
     cudaError_t me = cudaMemsetAsync(tile_counter, 0, sizeof(int32_t), stream);
     if (me != cudaSuccess) { set_cuda_error(me); return HVPR_ERR_CUDA; }
 #endif
+    TcZero Z = {};
+    if (zero_fill) {
+        if (zero_fill->n < 0 || zero_fill->n > 4) return HVPR_ERR_ARG;
+        uint64_t total = 0;
+        for (int r = 0; r < zero_fill->n; ++r) {
+            if (zero_fill->bytes[r] == 0) continue;
+            if (!zero_fill->ptr[r] || ((uintptr_t)zero_fill->ptr[r] | zero_fill->bytes[r]) % 16) return HVPR_ERR_ARG;
+            const uint64_t units = (zero_fill->bytes[r] + kTcZeroBytes - 1) / kTcZeroBytes;
+            Z.ptr[r] = (uint8_t *)zero_fill->ptr[r]; Z.bytes[r] = zero_fill->bytes[r]; Z.units[r] = (uint32_t)units;
+            total += units;
+        }
+        if (total > 0x7fffffffull) return HVPR_ERR_UNSUPPORTED;
+        Z.total_units = (uint32_t)total;
+    }
     const int nchunks = (M + kTcChunkN - 1) / kTcChunkN;
     int64_t tiles = (n_rows_max + kTcTileM - 1) / kTcTileM;
     const int nsm = num_sms();
@@ -1053,16 +1133,16 @@ static int tc_launch(const float *pillars, const int32_t *n_pillars_dev, int64_t
     if (grid < 1) grid = 1;
     mem_attn_tc_kernel<<<grid, kTcThreads, tc_smem_bytes(), stream>>>(pillars, n_pillars_dev, n_rows_max, W,
                                                                       (const uint8_t *)Wpk, M, nchunks, k, readout,
-                                                                      topk_idx_out, scratch, tile_counter, dbg_logits);
+                                                                      topk_idx_out, scratch, tile_counter, dbg_logits, Z);
     HVPR_CHECK_LAUNCH();
     return HVPR_OK;
 }
 
 int hvpr_mem_attn_tc(const float *pillars, const int32_t *n_pillars_dev, int64_t n_rows_max, const float *W,
                      const void *Wpk, int M, int C, int k, float *readout, int32_t *topk_idx_out, void *workspace,
-                     size_t workspace_bytes, cudaStream_t stream) {
+                     size_t workspace_bytes, const HvprZeroFill *zero_fill, cudaStream_t stream) {
     return tc_launch(pillars, n_pillars_dev, n_rows_max, W, Wpk, M, C, k, readout, topk_idx_out, workspace,
-                     workspace_bytes, nullptr, stream);
+                     workspace_bytes, nullptr, zero_fill, stream);
 }
 
 // debug entry (not part of the public header): also dumps the bf16-GEMM logits (rows, nchunks*256) for unit tests
@@ -1070,5 +1150,5 @@ extern "C" int hvpr_dbg_mem_attn_logits(const float *pillars, int64_t n_rows, co
                                         float *readout, int32_t *topk_idx_out, void *workspace, size_t workspace_bytes,
                                         float *dbg_logits, void *stream) {
     return tc_launch(pillars, nullptr, n_rows, W, Wpk, M, 64, 20, readout, topk_idx_out, workspace, workspace_bytes,
-                     dbg_logits, (cudaStream_t)stream);
+                     dbg_logits, nullptr, (cudaStream_t)stream);
 }

@@ -190,9 +190,12 @@ class HybridFrontEnd(torch.nn.Module):
     def _stage_bev(self, p, slot, after_k3=None, launch=None):      # K3 + K4
         vox = p.voxs[slot]
         m = self.map_to_bev_module
-        m.memory.run(p.pfs[slot], m.k, vox.n_pillars_dev, out=p.readout)
+        fused = m.fused_zero_fill                       # K3 zeroes the canvases beside its own work, K4 writes only occupied runs
+        m.memory.run(p.pfs[slot], m.k, vox.n_pillars_dev, out=p.readout, zero_fill=[p.spatial, p.spatial_scale] if fused else None)
         if after_k3 is not None:
             after_k3()
+        if fused:
+            launch = (launch[0] if launch else 0, fused)
         st = _lib.lib().hvpr_bev_fill(_lib.ptr(p.pfs[slot]), 64, _lib.ptr(p.readout), 64, _lib.ptr(p.pss[slot]), 32,
                                       _lib.ptr(vox.cell_map), p.B, m.nx, m.ny, _lib.ptr(p.spatial),
                                       _lib.ptr(p.spatial_scale), _lib.launch_cfg(launch), _lib.cur_stream())

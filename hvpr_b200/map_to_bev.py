@@ -6,6 +6,7 @@ FORWARD ONLY: it runs under torch.no_grad semantics and its outputs carry no aut
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -44,7 +45,8 @@ class MemoryUnit_Agg(nn.Module):
             self._bf16_key = key
         return self._bf16
 
-    def run(self, pillars, k, n_pillars_dev=None, out=None, topk_idx_out=None):
+    def run(self, pillars, k, n_pillars_dev=None, out=None, topk_idx_out=None, zero_fill=None):
+        """zero_fill: tensors the call leaves all-zero (hvpr_mem_attn's side job — the BEV canvases, see hvpr_bev_fill variant 1..3)."""
         _lib.init_device()
         rows = pillars.shape[0]
         if out is None:
@@ -57,7 +59,7 @@ class MemoryUnit_Agg(nn.Module):
         st = _lib.lib().hvpr_mem_attn(
             _lib.ptr(pillars), _lib.ptr(n_pillars_dev), rows, _lib.ptr(self.weight.detach()), _lib.ptr(bf16),
             self.mem_dim, self.fea_dim, int(k), mode, _lib.ptr(out), _lib.ptr(topk_idx_out),
-            _lib.ptr(self._ws) if nbytes else None, int(nbytes), _lib.cur_stream())
+            _lib.ptr(self._ws) if nbytes else None, int(nbytes), _lib.zero_fill(zero_fill), _lib.cur_stream())
         _lib.check(st, "hvpr_mem_attn")
         return out
 
@@ -152,20 +154,31 @@ class PointPillarScatter_Agg_Memory_1_scale(nn.Module):
         if prec:
             self.memory.precision = prec
         assert self.nz == 1
+        # 0 (default) = hvpr_bev_fill writes every canvas element; 1 / 2 / 3 = hvpr_mem_attn zero-fills the canvases while it runs
+        # and the fill writes only 32 / 64 / 128-byte runs that hold a pillar (HvprLaunchCfg.variant).  Measured:
+        # +2 % for one batch at a time, -6 % in the streaming schedule (the write stream slows the memory kernel) -> opt-in.
+        self.fused_zero_fill = int(model_cfg.get("FUSED_ZERO_FILL", 0)) if hasattr(model_cfg, "get") else 0
+        if os.environ.get("HVPR_FUSED_ZERO_FILL"):          # experiments
+            self.fused_zero_fill = int(os.environ["HVPR_FUSED_ZERO_FILL"])
 
     def run(self, pillar_features, pillar_scale_features, cell_map, B, n_pillars_dev=None, readout=None,
             spatial=None, spatial_scale=None):
         """Memory attention + gather-fill of both canvases on the current stream (graph-capturable)."""
         dev = pillar_features.device
         C, Cs = pillar_features.shape[1], pillar_scale_features.shape[1]
-        readout = self.memory.run(pillar_features, self.k, n_pillars_dev, out=readout)
         if spatial is None:
             spatial = torch.empty((B, 2 * C * self.nz, self.ny, self.nx), dtype=torch.float32, device=dev)
         if spatial_scale is None:
             spatial_scale = torch.empty((B, Cs * self.nz, self.ny, self.nx), dtype=torch.float32, device=dev)
+        # the memory kernel zeroes both canvases beside its own work (it leaves HBM idle); the fill then writes only the
+        # 32-byte runs that hold a pillar.  Same bits as the write-everything form (variant 0), one HBM-bound pass less.
+        fused = self.fused_zero_fill and pillar_features.shape[0] > 0
+        readout = self.memory.run(pillar_features, self.k, n_pillars_dev, out=readout,
+                                  zero_fill=[spatial, spatial_scale] if fused else None)
         st = _lib.lib().hvpr_bev_fill(_lib.ptr(pillar_features), C, _lib.ptr(readout), C,
                                       _lib.ptr(pillar_scale_features), Cs, _lib.ptr(cell_map), B, self.nx, self.ny,
-                                      _lib.ptr(spatial), _lib.ptr(spatial_scale), None, _lib.cur_stream())
+                                      _lib.ptr(spatial), _lib.ptr(spatial_scale),
+                                      _lib.launch_cfg((0, self.fused_zero_fill) if fused else None), _lib.cur_stream())
         _lib.check(st, "hvpr_bev_fill")
         return spatial, spatial_scale, readout
 
@@ -194,7 +207,7 @@ class PointPillarScatter_Agg_Memory_1_scale(nn.Module):
         out = torch.empty((nv, d), dtype=torch.float32, device=pts.device)
         idx = torch.empty((nv, self.k), dtype=torch.int32, device=pts.device)
         st = _lib.lib().hvpr_mem_attn(_lib.ptr(pil), None, nv, _lib.ptr(pts), None, npts, d, int(self.k), _lib.MEM_FP32,
-                                      _lib.ptr(out), _lib.ptr(idx), None, 0, _lib.cur_stream())
+                                      _lib.ptr(out), _lib.ptr(idx), None, 0, None, _lib.cur_stream())
         _lib.check(st, "hvpr_mem_attn(get_score)")
         res = {"output": out, "att": None}
         if return_positive:

@@ -73,7 +73,9 @@ typedef struct HvprPfnWeights {
  *                  registers (fastest alone), 1 = fragments in shared memory (fewer registers: the canvas-fill blocks of
  *                  hvpr_bev_fill fit beside the PFN blocks in the streaming schedule)
  *   hvpr_bev_fill: blocks_per_sm 0 = one 128-thread block per work item (fastest alone), 1..16 = that many persistent
- *                  blocks per SM walking the items with a grid stride; variant unused (0)                              */
+ *                  blocks per SM walking the items with a grid stride; variant 0 = every canvas element is written
+ *                  (feature or 0); 1 / 2 / 3 = the caller guarantees the canvases are ALL-ZERO on entry (hvpr_mem_attn's
+ *                  zero_fill), only aligned runs of 32 / 64 / 128 bytes that hold a pillar are written               */
 typedef struct HvprLaunchCfg {
     int32_t blocks_per_sm;
     int32_t variant;
@@ -130,12 +132,23 @@ int hvpr_pfn(const float *voxels, const int32_t *num_points, const int32_t *coor
  * pillars (rows,64) fp32; mem_weight (M,64) fp32; readout (rows,64) fp32.
  * mem_weight_bf16: (M_pad,64) bf16 copy made by hvpr_mem_pack_bf16 (M_pad = M rounded up to 256); required for
  *                  HVPR_MEM_BF16_RESCORE, ignored for HVPR_MEM_FP32.
- * topk_idx_out: optional (rows,k) int32 — the selected memory items (unordered set), for tests.                      */
+ * topk_idx_out: optional (rows,k) int32 — the selected memory items (unordered set), for tests.
+ * zero_fill: optional side job (NULL = none): in stream order, every listed range is all-zero when the call completes.
+ *            The tcgen05 path is compute-bound and leaves HBM idle, so its TMA-producer thread streams the zeros out
+ *            with bulk async stores while the tiles are processed (the BEV canvases of hvpr_bev_fill's
+ *            canvas-is-zero mode: the 1.1 GB of zeros then cost no time of their own); the fp32 path and the
+ *            no-rows case use cudaMemsetAsync.  The ranges must not overlap anything the call reads or writes.          */
+typedef struct HvprZeroFill {
+    void *ptr[4];       /* device ranges, 16-byte aligned */
+    uint64_t bytes[4];  /* multiples of 16; 0 = unused slot */
+    int32_t n;          /* ranges in use, <= 4 */
+} HvprZeroFill;
 size_t hvpr_mem_attn_workspace_bytes(int64_t n_rows_max, int M, int precision_mode);
 int hvpr_mem_pack_bf16(const float *mem_weight, int M, int C, void *mem_weight_bf16, void *stream);
 int hvpr_mem_attn(const float *pillars, const int32_t *n_pillars_dev, int64_t n_rows_max,
                   const float *mem_weight, const void *mem_weight_bf16, int M, int C, int k, int precision_mode,
-                  float *readout, int32_t *topk_idx_out, void *workspace, size_t workspace_bytes, void *stream);
+                  float *readout, int32_t *topk_idx_out, void *workspace, size_t workspace_bytes,
+                  const HvprZeroFill *zero_fill, void *stream);
 
 /* ---- K4 BEV canvas gather-fill -----------------------------------------------------------------------------------
  * Writes every canvas element exactly once (feature or 0), NCHW, x fastest (pointpillar_scatter.py:192,217-218):

@@ -59,7 +59,7 @@ def test_argument_validation_without_gpu():
     # null pointers / bad sizes are rejected before any CUDA call
     assert L.hvpr_voxelize(None, 10, 4, 0, None, 1, 0, ctypes.byref(g), 32, 100, 0, None, None, None, None, None, None, 0, None) == -1
     assert L.hvpr_bev_fill(None, 64, None, 0, None, 0, None, 1, 432, 496, None, None, None, None) == -1
-    assert L.hvpr_mem_attn(None, None, -1, None, None, 2000, 64, 20, 0, None, None, None, 0, None) == -1
+    assert L.hvpr_mem_attn(None, None, -1, None, None, 2000, 64, 20, 0, None, None, None, 0, None, None) == -1
 
 
 def test_registries_and_state_dict_names():

@@ -421,6 +421,44 @@ def test_mem_attn_module_forward_signature():
     assert rel_err(r["output"], ref)[0] <= TOL_FP32
 
 
+# ------------------------------------------------------------------------------------------------ K3 side job: zero fill
+@pytest.mark.parametrize("mode", ["bf16_rescore", "fp32"])
+def test_mem_attn_zero_fill_side_job(mode):
+    """hvpr_mem_attn(zero_fill=...) leaves every listed range all-zero — ranges that are not multiples of the 8 KB store unit,
+    more units than chunk iterations, a single tile, no live rows at all — never writes past a range, and the readout is the
+    same bits as without the side job."""
+    from hvpr_b200 import _lib, map_to_bev
+    w = hybrid.random_weights(0)
+    mem = map_to_bev.MemoryUnit_Agg(2000, 64, 0.0025).cuda()
+    mem.weight.data.copy_(w["map_to_bev_module.memory.weight"])
+    mem.precision = mode
+    gen = torch.Generator().manual_seed(5)
+    for rows, live in ((70000, None), (100, None), (40000, 0), (300, 129)):
+        x = torch.randn(rows, 64, generator=gen).cuda()
+        n_dev = None if live is None else torch.tensor([live], dtype=torch.int32, device="cuda")
+        base = mem.run(x, 20, n_dev).clone()
+        sizes = (16, 8192 * 3 + 4112, 50_000_000, 8192)               # bytes; every range is guarded by 64 poisoned bytes on both sides
+        bufs = [torch.full((n + 128,), 0xAB, dtype=torch.uint8, device="cuda") for n in sizes]
+        out = mem.run(x, 20, n_dev, zero_fill=[b[64:64 + n] for b, n in zip(bufs, sizes)])
+        torch.cuda.synchronize()
+        nl = rows if live is None else live
+        assert torch.equal(out[:nl], base[:nl]), (rows, live)
+        for b, n in zip(bufs, sizes):
+            assert int(b[64:64 + n].max()) == 0, (rows, live, n)
+            assert bool((b[:64] == 0xAB).all()) and bool((b[64 + n:] == 0xAB).all()), (rows, live, n)
+    # argument checks: misaligned pointer / size, too many ranges
+    L = _lib.lib()
+    z = _lib.HvprZeroFill(); z.n = 5
+    args = lambda zf: (_lib.ptr(x), None, 300, _lib.ptr(mem.weight.detach()), None, 2000, 64, 20, _lib.MEM_FP32, _lib.ptr(out), None, None, 0,
+                       zf, _lib.cur_stream())
+    import ctypes
+    assert L.hvpr_mem_attn(*args(ctypes.byref(z))) == -1
+    z.n = 1; z.ptr[0] = bufs[0].data_ptr() + 4; z.bytes[0] = 16
+    assert L.hvpr_mem_attn(*args(ctypes.byref(z))) == -1
+    z.ptr[0] = bufs[0].data_ptr(); z.bytes[0] = 24
+    assert L.hvpr_mem_attn(*args(ctypes.byref(z))) == -1
+
+
 # ------------------------------------------------------------------------------------------------ K4 BEV fill
 @pytest.mark.parametrize("gname", ["G1", "G2"])
 def test_bev_fill_bitwise(gname):
@@ -457,6 +495,25 @@ def test_bev_fill_bitwise(gname):
                                             _lib.ptr(sp), _lib.ptr(sps), _lib.launch_cfg((bps, 0)), _lib.cur_stream()))
         torch.cuda.synchronize()
         assert torch.equal(sp.cpu().view(3, 128, -1), ref) and torch.equal(sps.cpu().view(3, 32, -1), refs), bps
+    # canvas-is-zero form: only 32 / 64 / 128-byte runs that hold a pillar are written; on zeroed canvases the bits are the same,
+    # with and without the persistent grid
+    for variant in (1, 2, 3):
+        for bps in (0, 2):
+            sp.zero_(); sps.zero_()
+            _lib.check(_lib.lib().hvpr_bev_fill(_lib.ptr(a), 64, _lib.ptr(b_), 64, _lib.ptr(s), 32, _lib.ptr(cm), 3, nx, ny,
+                                                _lib.ptr(sp), _lib.ptr(sps), _lib.launch_cfg((bps, variant)), _lib.cur_stream()))
+            torch.cuda.synchronize()
+            assert torch.equal(sp.cpu().view(3, 128, -1), ref) and torch.equal(sps.cpu().view(3, 32, -1), refs), (variant, bps)
+    # ... and it really leaves empty runs alone (that is the point): a poisoned canvas keeps its poison exactly there
+    sp.fill_(float("nan")); sps.fill_(float("nan"))
+    _lib.check(_lib.lib().hvpr_bev_fill(_lib.ptr(a), 64, _lib.ptr(b_), 64, _lib.ptr(s), 32, _lib.ptr(cm), 3, nx, ny,
+                                        _lib.ptr(sp), _lib.ptr(sps), _lib.launch_cfg((0, 1)), _lib.cur_stream()))
+    torch.cuda.synchronize()
+    occ8 = (cm.view(3, -1, 8) >= 0).any(-1).cpu()                            # 8 cells = 32 bytes per channel
+    got = sp.cpu().view(3, 128, -1, 8)
+    assert bool(torch.isnan(got[:, 0][~occ8]).all()) and not bool(torch.isnan(got[:, 0][occ8]).any())
+    assert _lib.lib().hvpr_bev_fill(_lib.ptr(a), 64, _lib.ptr(b_), 64, _lib.ptr(s), 32, _lib.ptr(cm), 3, nx, ny,
+                                    _lib.ptr(sp), _lib.ptr(sps), _lib.launch_cfg((0, 4)), _lib.cur_stream()) == -1
     for bad in (17, -1):       # the launch shape is validated per call (there is no process-wide knob any more)
         assert _lib.lib().hvpr_bev_fill(_lib.ptr(a), 64, _lib.ptr(b_), 64, _lib.ptr(s), 32, _lib.ptr(cm), 3, nx, ny,
                                         _lib.ptr(sp), _lib.ptr(sps), _lib.launch_cfg((bad, 0)), _lib.cur_stream()) == -1
@@ -666,6 +723,48 @@ def test_streaming_mode_is_bit_identical_to_single_stream():
         torch.cuda.synchronize()
         assert torch.equal(sp.spatial, ref[b][0]) and torch.equal(sp.spatial_scale, ref[b][1]), (i, b)
         assert torch.equal(cnt, ref[b][2].cpu())
+
+
+@pytest.mark.parametrize("variant", [1, 3])
+def test_fused_zero_fill_front_end_is_bit_identical(variant):
+    """FUSED_ZERO_FILL: the memory kernel zero-fills both canvases as a side job and the fill writes only occupied runs — same
+    canvases, bit for bit, as the write-everything path; plain, graph-captured and streaming, with poisoned canvases in front."""
+    g = G1
+    B, N = 2, 40000
+    w = hybrid.random_weights(9)
+    batches = [synth.make_batch("L", N, g.point_cloud_range, B, first_frame=10 * i) for i in range(2)]
+    fe = _frontend(g, w)
+    p = fe.plan(B, B * N, N, use_graph=False)
+    ref = []
+    for fr in batches:
+        pts, off = to_dev(fr)
+        p.points.copy_(pts); p.frame_offsets.copy_(off)
+        fe.run(); torch.cuda.synchronize()
+        ref.append((p.spatial.clone(), p.spatial_scale.clone()))
+    fe2 = _frontend(g, w)
+    fe2.map_to_bev_module.fused_zero_fill = variant
+    for use_graph in (False, True):
+        p2 = fe2.plan(B, B * N, N, use_graph=use_graph)
+        for rep in range(2):
+            for fr, r in zip(batches, ref):
+                pts, off = to_dev(fr)
+                p2.points.copy_(pts); p2.frame_offsets.copy_(off)
+                p2.spatial.fill_(float("nan")); p2.spatial_scale.fill_(float("nan"))
+                fe2.run(); torch.cuda.synchronize()
+                assert torch.equal(p2.spatial, r[0]) and torch.equal(p2.spatial_scale, r[1]), (use_graph, rep)
+    sp = fe2.plan_stream(B, B * N, N)
+    host = [(torch.from_numpy(np.concatenate(fr, 0)).pin_memory(),
+             torch.tensor(np.r_[0, np.cumsum([len(f) for f in fr])], dtype=torch.int32).pin_memory()) for fr in batches]
+    cnt = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
+    order = [0, 1, 1, 0, 0, 1]
+    fe2.stream_prime(host[order[0]], host[order[1]])
+    for i, b in enumerate(order):
+        nb = order[i + 2] if i + 2 < len(order) else 0
+        sp.spatial.fill_(float("nan")); sp.spatial_scale.fill_(float("nan"))
+        torch.cuda.synchronize()
+        fe2.stream_step(host[nb][0], host[nb][1], cnt)
+        torch.cuda.synchronize()
+        assert torch.equal(sp.spatial, ref[b][0]) and torch.equal(sp.spatial_scale, ref[b][1]), (i, b)
 
 
 def test_two_front_ends_two_streams_with_different_launch_shapes():
