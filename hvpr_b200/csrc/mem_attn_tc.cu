@@ -390,7 +390,16 @@ __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, co
     TCP_ROW_START;
     const int sub = lane & 15, hb = lane & 16;                // channel quad / first candidate slot of this half
     const char *__restrict__ Wq = reinterpret_cast<const char *>(W) + sub * 16;     // this lane's 16-byte piece of every memory row
-#define HVPR_WROW(j) reinterpret_cast<const float4 *>(Wq + (size_t)(j) * (kTcK * 4))
+    // address of memory row j's piece as one PTX multiply-add on the per-lane base (SASS: LEA + LEA.HI.X); written in C the
+    // compiler keeps W in uniform registers and spends four instructions per gather (IMAD.WIDE, LOP3, IADD3, IADD3.X: 64 per
+    // pillar row).  A pitch hidden from ptxas (register / constant bank) gives IMAD.WIDE + IADD3 + IMAD.X: three.
+    const unsigned long long Wq64 = reinterpret_cast<unsigned long long>(Wq);
+    auto wrow = [&](uint32_t j) -> const float4 * {
+        unsigned long long a;
+        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(j), "n"(kTcK * 4), "l"(Wq64));
+        return reinterpret_cast<const float4 *>(a);
+    };
+#define HVPR_WROW(j) wrow((uint32_t)(j))
     const float4 p4 = __ldg(reinterpret_cast<const float4 *>(prow) + sub);
     // slots past cnt replay candidate 0 (an L1 hit) so that all gathers are unconditional and issue back to back:
     // any branch here makes the compiler merge registers per group and serialises the L2 round trips
@@ -449,15 +458,25 @@ __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, co
     TCP_ROW_T(1);
     // top-k by rank: every lane reads all 32 keys (broadcast) and counts the larger ones — 32 independent compares instead of
     // (cnt - k) dependent warp-min / ballot / find-first rounds; equal keys (exact fp32 ties) rank by lane
-    const uint32_t key = (lane < cnt) ? float_key(logit) : 0u;            // absent slots rank last (a real key is never 0: -NaN aside)
-    bc[1][lane] = key;
+    // The compares run as subtractions whose SIGN bits are funnel-shifted into a mask (packed FADD2 + SHF per key, one POPC at the
+    // end: 1.5 instructions per key on two pipes, against ISETP + add + predicated move in one dependent chain): bc[1] holds the
+    // NEGATED logits, d = logit_lane - logit_j is negative exactly when j is larger (no FTZ: the sign of a difference is exact).
+    // Absent slots hold -inf as their logit (+inf stored): they rank last and are never counted as larger.
+    const float lg = (lane < cnt) ? logit : -INFINITY;
+    bc[1][lane] = __float_as_uint(-lg);
     __syncwarp();
-    int rank = 0;
+    uint32_t gt0 = 0u, gt1 = 0u;
+    const float2 lg2 = make_float2(lg, lg);
 #pragma unroll
     for (int m4 = 0; m4 < 8; ++m4) {
-        const uint4 kk = *reinterpret_cast<const uint4 *>(&bc[1][4 * m4]);
-        rank += (kk.x > key) ? 1 : 0; rank += (kk.y > key) ? 1 : 0; rank += (kk.z > key) ? 1 : 0; rank += (kk.w > key) ? 1 : 0;
+        const float4 nk = *reinterpret_cast<const float4 *>(&bc[1][4 * m4]);
+        const float2 d0 = add2(make_float2(nk.x, nk.y), lg2), d1 = add2(make_float2(nk.z, nk.w), lg2);
+        gt0 = __funnelshift_l(__float_as_uint(d0.x), gt0, 1); gt1 = __funnelshift_l(__float_as_uint(d1.x), gt1, 1);
+        gt0 = __funnelshift_l(__float_as_uint(d0.y), gt0, 1); gt1 = __funnelshift_l(__float_as_uint(d1.y), gt1, 1);
     }
+    int rank = __popc(gt0) + __popc(gt1);
+    // keys for the tie-break and the maximum: -0 and +0 compare equal above, so they must share a key (x + 0 maps -0 to +0)
+    const uint32_t key = (lane < cnt) ? float_key(__fadd_rn(logit, 0.0f)) : 0u;   // absent slots: smallest key (a real key is never 0: -NaN aside)
     bool valid = (lane < cnt) && rank < k;
     if (__popc(__ballot_sync(0xffffffffu, valid)) != k) {      // an exact fp32 tie straddles the cut: equal keys rank by lane
         const uint32_t same = __match_any_sync(0xffffffffu, key);
