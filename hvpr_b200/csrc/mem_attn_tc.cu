@@ -485,11 +485,15 @@ __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, co
     }
     const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
     const float mx = key_float(kmax);
-    const float ex = valid ? expf(logit - mx) : 0.0f;
+    // exp and 1/sum through the SFU approximations (ex2.approx / rcp.approx, ~2 ulp: 2e-7 against the 1e-4 tolerance) — expf and
+    // an IEEE reciprocal cost ~20 more instructions per row in range reduction, Newton steps and their slow-path branches
+    const float ex = valid ? __expf(logit - mx) : 0.0f;
     float sum = ex;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float a = ex * __frcp_rn(sum);                       // sum >= 1 (the maximum contributes exp(0)); a 0 / sum division takes the slow path
+    float rs;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(sum));   // sum >= 1 (the maximum contributes exp(0))
+    const float a = ex * rs;
     __syncwarp();                                              // every lane has read the keys before the weights overwrite them
     TCP_ROW_T(2);
     float2 oa = make_float2(0.0f, 0.0f), ob = oa;
@@ -1031,21 +1035,22 @@ const float *__restrict__ pillars,
             // tile t's MMAs are complete (its candidates exist), so its A buffer is free: stage tile ti + 2 into it
             stage_tile(tile_ids[(ti + 2) & 3], ti + 2);
             for (int r = tw; r < kTcTileM; r += kTcTailWarps) {
-                const int64_t grow = (int64_t)t * kTcTileM + r;
-                if (grow >= nP) break;
+                const uint32_t grow = (uint32_t)t * kTcTileM + (uint32_t)r;     // < 2^31 rows: 32-bit row arithmetic, one widening multiply per pointer
+                if ((int64_t)grow >= nP) break;
                 const int cnt_a = S.cand_cnt[cb][0][r], cnt_b = S.cand_cnt[cb][1][r];
                 const int cnt = (cnt_a > kTcHalfCap || cnt_b > kTcHalfCap) ? 2 * kTcCandCap : cnt_a + cnt_b;   // a half row overflowed -> full scan
-                const float *prow = pillars + grow * kTcK;
-                int32_t *idx_row = topk_idx_out ? topk_idx_out + grow * k : nullptr;
+                const float *prow = pillars + (uint64_t)grow * kTcK;
+                int32_t *idx_row = nullptr;
+                if (topk_idx_out) idx_row = topk_idx_out + (uint64_t)grow * (uint32_t)k;
 #ifdef HVPR_TC_PROFILE
                 if (lane == 0 && dbg_logits) atomicAdd(reinterpret_cast<unsigned long long *>(dbg_logits) + (size_t)blockIdx.x * 24 + ((cnt >= k && cnt <= 32) ? 19 : (cnt > 32 && cnt <= kTcCandCap) ? 20 : 21), 1ull);
 #endif
                 if (cnt >= k && cnt <= 32)
-                    tail_fast_row(prow, W, k, cnt, cnt_a, &S.cand[cb][0][r], S.bcast[tw], &S.tr[tw][0][0], readout + grow * kTcK, idx_row, lane TCP_ROW_PASS);
+                    tail_fast_row(prow, W, k, cnt, cnt_a, &S.cand[cb][0][r], S.bcast[tw], &S.tr[tw][0][0], readout + (uint64_t)grow * kTcK, idx_row, lane TCP_ROW_PASS);
                 else if (cnt > 32 && cnt <= kTcCandCap)
-                    tail_medium_row(prow, W, k, cnt, cnt_a, &S.cand[cb][0][r], readout + grow * kTcK, idx_row, lane);
+                    tail_medium_row(prow, W, k, cnt, cnt_a, &S.cand[cb][0][r], readout + (uint64_t)grow * kTcK, idx_row, lane);
                 else
-                    tail_slow_row(prow, W, M, k, scratch, readout + grow * kTcK, idx_row, lane);
+                    tail_slow_row(prow, W, M, k, scratch, readout + (uint64_t)grow * kTcK, idx_row, lane);
             }
             named_bar_arrive(kBarCEmpty + cb, kTcFilterThreads + 32 * kTcTailWarps);
             TCP_END(1);
@@ -1122,6 +1127,7 @@ static int tc_launch(const float *pillars, const int32_t *n_pillars_dev, int64_t
                      const void *Wpk, int M, int C, int k, float *readout, int32_t *topk_idx_out, void *workspace,
                      size_t workspace_bytes, float *dbg_logits, const HvprZeroFill *zero_fill, cudaStream_t stream) {
     if (C != kTcK || k != 20 || M < 16 * kTcKPrime || M > kTcMaxChunks * kTcChunkN) return HVPR_ERR_UNSUPPORTED;
+    if (n_rows_max > (int64_t)0x7fffff00) return HVPR_ERR_UNSUPPORTED;     // the kernel indexes rows with 32 bits
     if (((uintptr_t)W | (uintptr_t)Wpk | (uintptr_t)pillars | (uintptr_t)readout) % 16) return HVPR_ERR_ARG;
     if (!workspace || workspace_bytes < hvpr_mem_attn_tc_workspace_bytes(n_rows_max, M)) return HVPR_ERR_WORKSPACE;
     float *scratch = (float *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
