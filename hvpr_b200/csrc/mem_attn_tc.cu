@@ -65,8 +65,19 @@ constexpr int kTcKPrime = 24;          // tau = kTcKPrime-th largest group maxim
 #ifndef HVPR_K3_TAIL_LOWREG
 #define HVPR_K3_TAIL_LOWREG 0   // 1: the tail fetches candidate rows twice instead of caching them (for builds with < 128 registers per thread)
 #endif
+// Shipped shape (round 2, after the tail lost ~15 % of its instructions): EIGHT filter warps (two threads per accumulator row)
+// + 11 tail warps + the producer/MMA warp = 640 threads launched at 96 registers; the two filter warpgroups then hand registers
+// back (setmaxnreg.dec 64) and the three warpgroups that hold tail warps take them (setmaxnreg.inc 112): 0.296 -> 0.284 ms against
+// 4 filter + 11 tail warps at 128.  The registers a warpgroup may take are the ones the CTA was LAUNCHED with and others released:
+// 8 * 32 * (96 - FILTER_REGS) >= 12 * 32 * (TAIL_REGS - 96), or the inc waits forever (64 / 112 and 56 / 120 are the legal pairs).
+#ifndef HVPR_K3_FILTER_WARPS
+#define HVPR_K3_FILTER_WARPS 8
+#endif
 #ifndef HVPR_K3_SETMAXNREG
-#define HVPR_K3_SETMAXNREG 0
+#define HVPR_K3_SETMAXNREG (HVPR_K3_FILTER_WARPS == 8)
+#endif
+#if HVPR_K3_FILTER_WARPS == 8 && !defined(HVPR_K3_MAXREG)
+#define HVPR_K3_MAXREG 96
 #endif
 #ifndef HVPR_K3_FILTER_REGS
 #define HVPR_K3_FILTER_REGS 64
@@ -74,8 +85,8 @@ constexpr int kTcKPrime = 24;          // tau = kTcKPrime-th largest group maxim
 #ifndef HVPR_K3_TAIL_REGS
 #define HVPR_K3_TAIL_REGS 112
 #endif
-#ifndef HVPR_K3_FILTER_WARPS
-#define HVPR_K3_FILTER_WARPS 4
+#if HVPR_K3_FILTER_WARPS == 8 && HVPR_K3_SETMAXNREG
+static_assert(8 * (96 - HVPR_K3_FILTER_REGS) >= 12 * (HVPR_K3_TAIL_REGS - 96), "setmaxnreg.inc would wait for registers nobody releases");
 #endif
 constexpr int kTcFilterWarps = HVPR_K3_FILTER_WARPS;   // 4: one thread per row; 8: warp 4 + q + 4 * half owns columns [128 * half, +128) of every chunk
 static_assert(kTcFilterWarps == 4 || kTcFilterWarps == 8, "filter warps: one or two per TMEM lane quadrant");
