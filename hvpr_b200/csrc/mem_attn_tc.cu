@@ -397,7 +397,7 @@ __device__ __forceinline__ int cand_at(const uint16_t *__restrict__ cand_col /* 
 }
 __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, const float *__restrict__ W, int k, int cnt, int cnt_a,
                                               const uint16_t *__restrict__ cand_col /* stride kTcTileM */, uint32_t (*bc)[32], float *__restrict__ tr,
-                                              float *__restrict__ out_row, int32_t *__restrict__ idx_row, int lane TCP_ROW_ARG) {
+                                              float *__restrict__ out_row, int32_t *__restrict__ idx_base, uint32_t grow, int lane TCP_ROW_ARG) {
     TCP_ROW_START;
     const int sub = lane & 15, hb = lane & 16;                // channel quad / first candidate slot of this half
     const char *__restrict__ Wq = reinterpret_cast<const char *>(W) + sub * 16;     // this lane's 16-byte piece of every memory row
@@ -547,7 +547,8 @@ __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, co
     o4.z += __shfl_xor_sync(0xffffffffu, o4.z, 16); o4.w += __shfl_xor_sync(0xffffffffu, o4.w, 16);
     if (lane < 16) reinterpret_cast<float4 *>(out_row)[sub] = o4;
     TCP_ROW_T(3);
-    if (idx_row) {
+    if (idx_base) {                                            // tests only: the pointer arithmetic stays inside the branch
+        int32_t *idx_row = idx_base + (uint64_t)grow * (uint32_t)k;
         const uint32_t kept = __ballot_sync(0xffffffffu, valid);
         if (valid) idx_row[__popc(kept & ((1u << lane) - 1u))] = my_j;
     }
@@ -1051,17 +1052,16 @@ const float *__restrict__ pillars,
                 const int cnt_a = S.cand_cnt[cb][0][r], cnt_b = S.cand_cnt[cb][1][r];
                 const int cnt = (cnt_a > kTcHalfCap || cnt_b > kTcHalfCap) ? 2 * kTcCandCap : cnt_a + cnt_b;   // a half row overflowed -> full scan
                 const float *prow = pillars + (uint64_t)grow * kTcK;
-                int32_t *idx_row = nullptr;
-                if (topk_idx_out) idx_row = topk_idx_out + (uint64_t)grow * (uint32_t)k;
+                auto idx_row_of = [&]() -> int32_t * { return topk_idx_out ? topk_idx_out + (uint64_t)grow * (uint32_t)k : nullptr; };
 #ifdef HVPR_TC_PROFILE
                 if (lane == 0 && dbg_logits) atomicAdd(reinterpret_cast<unsigned long long *>(dbg_logits) + (size_t)blockIdx.x * 24 + ((cnt >= k && cnt <= 32) ? 19 : (cnt > 32 && cnt <= kTcCandCap) ? 20 : 21), 1ull);
 #endif
                 if (cnt >= k && cnt <= 32)
-                    tail_fast_row(prow, W, k, cnt, cnt_a, &S.cand[cb][0][r], S.bcast[tw], &S.tr[tw][0][0], readout + (uint64_t)grow * kTcK, idx_row, lane TCP_ROW_PASS);
+                    tail_fast_row(prow, W, k, cnt, cnt_a, &S.cand[cb][0][r], S.bcast[tw], &S.tr[tw][0][0], readout + (uint64_t)grow * kTcK, topk_idx_out, grow, lane TCP_ROW_PASS);
                 else if (cnt > 32 && cnt <= kTcCandCap)
-                    tail_medium_row(prow, W, k, cnt, cnt_a, &S.cand[cb][0][r], readout + (uint64_t)grow * kTcK, idx_row, lane);
+                    tail_medium_row(prow, W, k, cnt, cnt_a, &S.cand[cb][0][r], readout + (uint64_t)grow * kTcK, idx_row_of(), lane);
                 else
-                    tail_slow_row(prow, W, M, k, scratch, readout + (uint64_t)grow * kTcK, idx_row, lane);
+                    tail_slow_row(prow, W, M, k, scratch, readout + (uint64_t)grow * kTcK, idx_row_of(), lane);
             }
             named_bar_arrive(kBarCEmpty + cb, kTcFilterThreads + 32 * kTcTailWarps);
             TCP_END(1);
