@@ -499,16 +499,14 @@ __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, co
     // exp and 1/sum through the SFU approximations (ex2.approx / rcp.approx, ~2 ulp: 2e-7 against the 1e-4 tolerance) — expf and
     // an IEEE reciprocal cost ~20 more instructions per row in range reduction, Newton steps and their slow-path branches
     const float ex = valid ? __expf(logit - mx) : 0.0f;
-    float sum = ex;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    float rs;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(sum));   // sum >= 1 (the maximum contributes exp(0))
-    const float a = ex * rs;
     __syncwarp();                                              // every lane has read the keys before the weights overwrite them
     TCP_ROW_T(2);
+    // The readout runs on the UNNORMALISED weights and is scaled by 1 / sum at the end: the sum of the 32 weights falls out of the
+    // broadcast reads the readout does anyway (16 per half + one more exchange between the halves), instead of a five-deep
+    // dependent shuffle chain in front of it
     float2 oa = make_float2(0.0f, 0.0f), ob = oa;
-    bc[1][lane] = __float_as_uint(a);                          // 0 for dropped / absent candidates
+    float hsum = 0.0f;
+    bc[1][lane] = __float_as_uint(ex);                         // 0 for dropped / absent candidates
     __syncwarp();
 #if HVPR_K3_TAIL_LOWREG
     // pass 2: readout over the kept rows (weight 0 = dropped or absent slot: no load)
@@ -526,6 +524,7 @@ __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, co
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             const float ac = __uint_as_float(xx[c]);
+            hsum += ac;
             oa = fma2(make_float2(w[c].x, w[c].y), make_float2(ac, ac), oa);
             ob = fma2(make_float2(w[c].z, w[c].w), make_float2(ac, ac), ob);
         }
@@ -535,6 +534,7 @@ __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, co
     for (int c4 = 0; c4 < 4; ++c4) {
         const uint4 aa = *reinterpret_cast<const uint4 *>(&bc[1][hb + 4 * c4]);
         const float av[4] = {__uint_as_float(aa.x), __uint_as_float(aa.y), __uint_as_float(aa.z), __uint_as_float(aa.w)};
+        hsum += (av[0] + av[1]) + (av[2] + av[3]);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             oa = fma2(make_float2(w4[4 * c4 + u].x, w4[4 * c4 + u].y), make_float2(av[u], av[u]), oa);
@@ -545,6 +545,10 @@ __device__ __forceinline__ void tail_fast_row(const float *__restrict__ prow, co
     float4 o4 = make_float4(oa.x, oa.y, ob.x, ob.y);
     o4.x += __shfl_xor_sync(0xffffffffu, o4.x, 16); o4.y += __shfl_xor_sync(0xffffffffu, o4.y, 16);
     o4.z += __shfl_xor_sync(0xffffffffu, o4.z, 16); o4.w += __shfl_xor_sync(0xffffffffu, o4.w, 16);
+    hsum += __shfl_xor_sync(0xffffffffu, hsum, 16);
+    float rs;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(hsum));  // sum >= 1 (the maximum contributes exp(0))
+    o4.x *= rs; o4.y *= rs; o4.z *= rs; o4.w *= rs;
     if (lane < 16) reinterpret_cast<float4 *>(out_row)[sub] = o4;
     TCP_ROW_T(3);
     if (idx_base) {                                            // tests only: the pointer arithmetic stays inside the branch
