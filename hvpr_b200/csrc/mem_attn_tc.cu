@@ -67,8 +67,9 @@ constexpr int kTcKPrime = 24;          // tau = kTcKPrime-th largest group maxim
 #endif
 // Shipped shape (round 2, after the tail lost ~15 % of its instructions): EIGHT filter warps (two threads per accumulator row)
 // + 11 tail warps + the producer/MMA warp = 640 threads launched at 96 registers; the two filter warpgroups then hand registers
-// back (setmaxnreg.dec 64) and the three warpgroups that hold tail warps take them (setmaxnreg.inc 112): 0.296 -> 0.284 ms against
-// 4 filter + 11 tail warps at 128.  The registers a warpgroup may take are the ones the CTA was LAUNCHED with and others released:
+// back (setmaxnreg.dec 56) and the three warpgroups that hold tail warps take them (setmaxnreg.inc 120): 0.296 -> 0.284 ms against
+// 4 filter + 11 tail warps at 128 with the 64 / 112 split; the tail is the critical role in this shape (tools/dev/tcprof.py: busy
+// for the whole CTA life, filter ~35 % slack), so it gets the larger share — 56 / 120 is another 1 % (no spills left in the tail).  The registers a warpgroup may take are the ones the CTA was LAUNCHED with and others released:
 // 8 * 32 * (96 - FILTER_REGS) >= 12 * 32 * (TAIL_REGS - 96), or the inc waits forever (64 / 112 and 56 / 120 are the legal pairs).
 #ifndef HVPR_K3_FILTER_WARPS
 #define HVPR_K3_FILTER_WARPS 8
@@ -80,10 +81,10 @@ constexpr int kTcKPrime = 24;          // tau = kTcKPrime-th largest group maxim
 #define HVPR_K3_MAXREG 96
 #endif
 #ifndef HVPR_K3_FILTER_REGS
-#define HVPR_K3_FILTER_REGS 64
+#define HVPR_K3_FILTER_REGS 56
 #endif
 #ifndef HVPR_K3_TAIL_REGS
-#define HVPR_K3_TAIL_REGS 112
+#define HVPR_K3_TAIL_REGS 120
 #endif
 #if HVPR_K3_FILTER_WARPS == 8 && HVPR_K3_SETMAXNREG
 static_assert(8 * (96 - HVPR_K3_FILTER_REGS) >= 12 * (HVPR_K3_TAIL_REGS - 96), "setmaxnreg.inc would wait for registers nobody releases");
