@@ -30,7 +30,19 @@ def test_library_exports_every_header_symbol():
     assert _lib.lib().hvpr_strerror(0) == b"ok" and b"workspace" in _lib.lib().hvpr_strerror(-3)
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    # the ctypes mirrors against the C compiler's view of include/hvpr_b200.h
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hvpr_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(HvprGeom), sizeof(HvprPfnWeights), sizeof(HvprLaunchCfg), '
+                   'sizeof(HvprZeroFill), offsetof(HvprZeroFill, bytes), offsetof(HvprZeroFill, n), sizeof(HvprConvArgs), offsetof(HvprLaunchCfg, variant)); return 0; }\n')
+    exe = tmp_path / "layout"
+    import subprocess
+    subprocess.run(["gcc", "-I", os.path.join(os.path.dirname(_lib._HERE), "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    Z = _lib.HvprZeroFill
+    assert got == [ctypes.sizeof(_lib.HvprGeom), ctypes.sizeof(_lib.HvprPfnWeights), ctypes.sizeof(_lib.HvprLaunchCfg), ctypes.sizeof(Z),
+                   Z.bytes.offset, Z.n.offset, ctypes.sizeof(_lib.HvprConvArgs), _lib.HvprLaunchCfg.variant.offset], got
     assert ctypes.sizeof(_lib.HvprGeom) == 36
     assert ctypes.sizeof(_lib.HvprPfnWeights) == 4 * (160 + 16 + 1024 + 1024 + 64 + 80 + 16 + 512 + 32)
 
