@@ -87,7 +87,8 @@ constexpr int kTcKPrime = 24;          // tau = kTcKPrime-th largest group maxim
 #define HVPR_K3_TAIL_REGS 120
 #endif
 #if HVPR_K3_FILTER_WARPS == 8 && HVPR_K3_SETMAXNREG
-static_assert(8 * (96 - HVPR_K3_FILTER_REGS) >= 12 * (HVPR_K3_TAIL_REGS - 96), "setmaxnreg.inc would wait for registers nobody releases");
+static_assert(8 * (HVPR_K3_MAXREG - HVPR_K3_FILTER_REGS) >= (HVPR_K3_TAIL_WARPS + 1) * (HVPR_K3_TAIL_REGS - HVPR_K3_MAXREG),
+              "setmaxnreg.inc would wait for registers nobody releases");
 #endif
 constexpr int kTcFilterWarps = HVPR_K3_FILTER_WARPS;   // 4: one thread per row; 8: warp 4 + q + 4 * half owns columns [128 * half, +128) of every chunk
 static_assert(kTcFilterWarps == 4 || kTcFilterWarps == 8, "filter warps: one or two per TMEM lane quadrant");
