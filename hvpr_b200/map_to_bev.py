@@ -52,6 +52,10 @@ class MemoryUnit_Agg(nn.Module):
         if out is None:
             out = torch.empty((rows, self.fea_dim), dtype=torch.float32, device=pillars.device)
         mode = {"fp32": _lib.MEM_FP32, "bf16_rescore": _lib.MEM_BF16_RESCORE}[self.precision]
+        # the tcgen05 kernel is built for the shipped cfg (k = 20, 64 features, 384 <= M <= 2048); any other memory shape runs the
+        # exact fp32 CUDA kernel (any M >= k, k <= 32) — still on the GPU, same results up to fp32 summation order
+        if mode == _lib.MEM_BF16_RESCORE and not (int(k) == 20 and self.fea_dim == 64 and 384 <= self.mem_dim <= 2048):
+            mode = _lib.MEM_FP32
         bf16 = self._packed_bf16() if mode == _lib.MEM_BF16_RESCORE else None
         nbytes = _lib.lib().hvpr_mem_attn_workspace_bytes(rows, self.mem_dim, mode)
         if nbytes and (self._ws is None or self._ws.numel() < nbytes or self._ws.device != pillars.device):

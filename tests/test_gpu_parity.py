@@ -421,6 +421,23 @@ def test_mem_attn_module_forward_signature():
     assert rel_err(r["output"], ref)[0] <= TOL_FP32
 
 
+@pytest.mark.parametrize("mem_dim,k", [(500, 10), (200, 20), (2000, 8), (3000, 20)])
+def test_mem_attn_module_other_memory_shapes_use_the_exact_kernel(mem_dim, k):
+    """Memory sizes / k outside the tcgen05 kernel's build (k = 20, 384 <= M <= 2048) are served by the exact fp32 CUDA kernel
+    without the caller having to switch `precision` (memory_module.py:60-77 for any mem_dim / k)."""
+    from hvpr_b200.map_to_bev import MemoryUnit_Agg
+    gen = torch.Generator().manual_seed(mem_dim + k)
+    pil = torch.randn(777, 64, generator=gen).relu()
+    W = (torch.rand(mem_dim, 64, generator=gen) - 0.5) / 4
+    m = MemoryUnit_Agg(mem_dim, 64).cuda().eval()
+    assert m.precision == "bf16_rescore"
+    with torch.no_grad():
+        m.weight.copy_(W)
+        r = m(pil.cuda(), None, k)
+        ref = hybrid.memory_attention(pil, W, k)
+    tie_aware_readout_check(r["output"], ref, pil, W, TOL_FP32, k=k)
+
+
 # ------------------------------------------------------------------------------------------------ K3 side job: zero fill
 @pytest.mark.parametrize("mode", ["bf16_rescore", "fp32"])
 def test_mem_attn_zero_fill_side_job(mode):
