@@ -160,7 +160,7 @@ class PointPillarScatter_Agg_Memory_1_scale(nn.Module):
         assert self.nz == 1
         # 0 (default) = hvpr_bev_fill writes every canvas element; 1 / 2 / 3 = hvpr_mem_attn zero-fills the canvases while it runs
         # and the fill writes only 32 / 64 / 128-byte runs that hold a pillar (HvprLaunchCfg.variant).  Measured:
-        # +2 % for one batch at a time, -6 % in the streaming schedule (the write stream slows the memory kernel) -> opt-in.
+        # -1 % for one batch at a time, -9 % in the streaming schedule (the write stream slows the tail-bound memory kernel) -> opt-in.
         self.fused_zero_fill = int(model_cfg.get("FUSED_ZERO_FILL", 0)) if hasattr(model_cfg, "get") else 0
         if os.environ.get("HVPR_FUSED_ZERO_FILL"):          # experiments
             self.fused_zero_fill = int(os.environ["HVPR_FUSED_ZERO_FILL"])

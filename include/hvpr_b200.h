@@ -136,8 +136,9 @@ int hvpr_pfn(const float *voxels, const int32_t *num_points, const int32_t *coor
  * zero_fill: optional side job (NULL = none): in stream order, every listed range is all-zero when the call completes.
  *            The tcgen05 path is compute-bound and leaves HBM idle, so its TMA-producer thread streams the zeros out
  *            with bulk async stores while the tiles are processed (the BEV canvases of hvpr_bev_fill's
- *            canvas-is-zero mode: the 1.1 GB of zeros then cost no time of their own); the fp32 path and the
- *            no-rows case use cudaMemsetAsync.  The ranges must not overlap anything the call reads or writes.          */
+ *            canvas-is-zero mode); measured, the write stream slows the latency-bound kernel by more than the fill
+ *            saves, so nothing in the shipped pipeline uses it; the fp32 path and the no-rows case
+ *            use cudaMemsetAsync.  The ranges must not overlap anything the call reads or writes.          */
 typedef struct HvprZeroFill {
     void *ptr[4];       /* device ranges, 16-byte aligned */
     uint64_t bytes[4];  /* multiples of 16; 0 = unused slot */
