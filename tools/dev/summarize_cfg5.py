@@ -9,9 +9,8 @@ names = [r[ki].split('(')[0].replace('void ', '').replace('hvpr::', '') for r in
 vals = [float(r[vi].replace(',', '')) / 1e3 for r in rows]
 # one detector step = the launches from one vox_init_kernel to the next
 starts = [i for i, n in enumerate(names) if n.startswith('vox_init_kernel')]
-# bench.py also launches library kernels between steps (head-bias calibration, accuracy check): take the leanest window
-wins = [(starts[i], starts[i + 1]) for i in range(len(starts) - 1)]
-a, b = min(wins, key=lambda w: w[1] - w[0]) if wins else (starts[-1], len(names))
+# bench.py calibrates the head bias after the first step (library kernels, a re-plan): take the LAST complete step
+a, b = (starts[-2], starts[-1]) if len(starts) >= 2 else (starts[-1], len(names))
 agg = collections.OrderedDict()
 skipped = 0
 for n, v in zip(names[a:b], vals[a:b]):
